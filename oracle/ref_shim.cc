@@ -1,0 +1,99 @@
+// oracle/ref_shim.cc -- TEST INFRASTRUCTURE ONLY.
+//
+// A thin extern "C" shim (our code) around the UNMODIFIED reference ICM library
+// (/root/reference/src/ICM/icm.{hh,cc}, compiled by oracle/Makefile into
+// oracle/_ref/obj/icm.o).  It lets the python tests call the real ICM_t /
+// ICM_Training_t through ctypes to pin oracle/icm_oracle.c and the CUDA path.
+// Nothing here is part of the product.
+
+#include "icm.hh"
+#include <string>
+#include <vector>
+#include <cstring>
+
+namespace {
+// ICM_t keeps its tables protected (icm.hh:118-129); a derived peeker exposes them.
+struct Peek : public ICM_t {
+  int nodes() const { return num_nodes; }
+  int len() const { return model_len; }
+  int depth() const { return model_depth; }
+  int period() const { return periodicity; }
+  const ICM_Score_Node_t* row(int p) const { return score[p]; }
+};
+}  // namespace
+
+extern "C" {
+
+void* ref_icm_read(const char* path) {
+  ICM_t* m = new ICM_t();
+  m->Read(const_cast<char*>(path));
+  return m;
+}
+
+void* ref_icm_build_indep(double gc, const char** stops, int n_stops) {
+  ICM_t* m = new ICM_t(3, 2, 3);
+  std::vector<const char*> v(stops, stops + n_stops);
+  m->Build_Indep_WO_Stops(gc, v);
+  return m;
+}
+
+void ref_icm_free(void* h) { delete static_cast<ICM_t*>(h); }
+
+void ref_icm_dims(void* h, int* dims /*len, depth, period, nodes*/) {
+  const Peek* p = static_cast<const Peek*>(static_cast<ICM_t*>(h));
+  dims[0] = p->len(); dims[1] = p->depth(); dims[2] = p->period(); dims[3] = p->nodes();
+}
+
+// mip: int16[period*nodes], prob: float[period*nodes*4]
+void ref_icm_tables(void* h, short* mip, float* prob) {
+  const Peek* p = static_cast<const Peek*>(static_cast<ICM_t*>(h));
+  for (int f = 0; f < p->period(); f++)
+    for (int i = 0; i < p->nodes(); i++) {
+      mip[f * p->nodes() + i] = p->row(f)[i].mut_info_pos;
+      memcpy(prob + 4 * (size_t)(f * p->nodes() + i), p->row(f)[i].prob, 4 * sizeof(float));
+    }
+}
+
+double ref_full_window_prob(void* h, const char* w, int frame) {
+  return static_cast<ICM_t*>(h)->Full_Window_Prob(w, frame);
+}
+double ref_partial_window_prob(void* h, int predict_pos, const char* s, int frame) {
+  return static_cast<ICM_t*>(h)->Partial_Window_Prob(predict_pos, s, frame);
+}
+double ref_score_string(void* h, const char* s, int len, int frame) {
+  return static_cast<ICM_t*>(h)->Score_String(s, len, frame);
+}
+void ref_cumulative_score(void* h, const char* s, int len, int frame, double* out) {
+  std::string str(s, len);
+  std::vector<double> v;
+  static_cast<ICM_t*>(h)->Cumulative_Score(str, v, frame);
+  for (int i = 0; i < len; i++) out[i] = v[i];
+}
+void ref_frame_score(void* h, const char* s, int len, int frame, double* out) {
+  std::string str(s, len);
+  std::vector<double> v;
+  static_cast<ICM_t*>(h)->Frame_Score(str, v, frame);
+  for (int i = 0; i < len; i++) out[i] = v[i];
+}
+
+// Train an ICM on n NUL-terminated strings (already lower-cased / reversed by the
+// caller, as build-icm.cc:111-118 does) and write it in binary form to `path`.
+void* ref_icm_train(const char** strings, int n, int w, int d, int p) {
+  ICM_Training_t* m = new ICM_Training_t(w, d, p);
+  std::vector<char*> data;
+  for (int i = 0; i < n; i++) data.push_back(strdup(strings[i]));
+  m->Train_Model(data);
+  for (int i = 0; i < n; i++) free(data[i]);
+  return static_cast<ICM_t*>(m);
+}
+void ref_icm_train_free(void* h) { delete static_cast<ICM_Training_t*>(static_cast<ICM_t*>(h)); }
+
+int ref_icm_write(void* h, const char* path) {
+  FILE* fp = fopen(path, "wb");
+  if (!fp) return -1;
+  static_cast<ICM_t*>(h)->Output(fp, true);
+  fclose(fp);
+  return 0;
+}
+
+}  // extern "C"
