@@ -1651,7 +1651,9 @@ static void  Score_Orfs_Errors
 	       if (gmg_last_hdr != Fasta_Header) {
 		    gmg_last_hdr = Fasta_Header;
 		    fprintf(gmg_fp, "R %d %s\n", Sequence_Len, Fasta_Header);
-		    if (getenv("GMG_DUMP_FS") != NULL)
+#ifdef GMG_DUMP_HAS_FS
+		    static int gmg_reads = 0; gmg_reads++;
+		    if (getenv("GMG_DUMP_FS") != NULL && gmg_reads <= atoi(getenv("GMG_DUMP_FS")))
 			 for (int gf = 0; gf < 6; gf++) {
 			      fprintf(gmg_fp, "F %d", gf);
 			      for (int gi = 0; gi < Sequence_Len; gi++) {
@@ -1660,6 +1662,7 @@ static void  Score_Orfs_Errors
 			      }
 			      fprintf(gmg_fp, "\n");
 			 }
+#endif
 	       }
 	       fprintf(gmg_fp, "O %d %d %d %d %d\n", orf_list[i].Get_Frame(), orf_list[i].Get_Stop_Position(),
 		       orf_list[i].Get_Orf_Len(), orf_list[i].Get_Gene_Len(), (int)start_list.size());
