@@ -1,0 +1,142 @@
+// glimmer_mg_b200/csrc/gmg_internal.cuh -- shared definitions of libgmgicm.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gmg_icm.h"
+
+#define GMG_MAX_W 32      // window bases held in one 64-bit register
+#define GMG_MAX_DEPTH 12
+#define GMG_PAD_WORDS 4   // 64-bit words of zero padding before/after the packed bases
+
+void gmg_set_error(const char* fmt, ...);
+
+#define GMG_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      gmg_set_error("CUDA error %s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define GMG_CHECK(cond, ...)     \
+  do {                           \
+    if (!(cond)) {               \
+      gmg_set_error(__VA_ARGS__); \
+      return 1;                  \
+    }                            \
+  } while (0)
+
+// device view of an ICM: only what the walks need.
+//  mip   int8 [P][inner]   branch position of the nodes on levels 0..D-1 (levels that can be
+//                          descended from); -1/-2 = stop here.
+//  prob  float [P][N][4]   natural-log probabilities with cut nodes (mut_info_pos == -2)
+//                          pre-resolved to their parent's row (icm.cc:592-597, 829-830), so a
+//                          walk needs no fix-up step.
+struct DevIcm {
+  int W, D, P, N, inner;
+  const int8_t* mip;
+  const float* prob;
+};
+
+struct gmg_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int sm_count;
+  int64_t launches;
+  // scratch (grown on demand, reused across calls)
+  void* scratch[8];
+  size_t scratch_bytes[8];
+  double* h_penalty;  // pinned staging
+};
+
+struct gmg_icm {
+  gmg_ctx* ctx;
+  int W, D, P, N;
+  std::vector<int16_t> mip;  // [P][N]   host mirror, exactly as ICM_t::score[][].mut_info_pos
+  std::vector<float> prob;   // [P][N][4] exactly as ICM_t::score[][].prob
+  int8_t* d_mip;
+  float* d_prob;
+  DevIcm dev;
+};
+
+struct gmg_seqset {
+  gmg_ctx* ctx;
+  int64_t n;                 // sequences
+  int64_t total;             // bases
+  std::vector<int64_t> off;  // host copy, n+1
+  int64_t* d_off;            // n+1
+  uint64_t* d_words_base;    // allocation incl. padding
+  uint64_t* d_words;         // 2-bit bases, base i at bits 2*(i%32) of word i/32
+  int32_t* d_blk2seq;        // sequence holding base 32*b
+  uint8_t* d_qual;           // per-base quality (input file values) or NULL
+  unsigned long long* d_gc;  // {gc count}
+  // ORFs
+  int64_t n_orfs;
+  gmg_orf* d_orfs;
+  int64_t* d_orf_off;        // n+1
+  int32_t* d_orf_seq;        // sequence index of every ORF
+  std::vector<int64_t> orf_off;
+  // starts of the last scoring call
+  int64_t n_starts;
+  gmg_start* d_starts;
+  int64_t* d_start_off;      // n_orfs+1
+  int64_t uncertified;
+  size_t cap_orfs, cap_starts;
+};
+
+// scratch slots
+enum { SCR_PLANES = 0, SCR_CUM = 1, SCR_TMP = 2, SCR_TMP2 = 3, SCR_FLAGS = 4, SCR_TMP3 = 5, SCR_QUAL = 6, SCR_TMP4 = 7 };
+int gmg_scratch(gmg_ctx* ctx, int slot, size_t bytes, void** out);
+
+// ---- device helpers ---------------------------------------------------------------------
+
+// bases [p0, p0+32) as one 64-bit value (base p0 at bits 0..1); p0 may be negative down to
+// -32*GMG_PAD_WORDS and run past the end by the same amount (zero padding).
+__device__ __forceinline__ uint64_t gmg_extract32(const uint64_t* __restrict__ words, int64_t p0) {
+  int64_t w = p0 >> 5;  // arithmetic shift: floor
+  int sh = (int)(p0 & 31) * 2;
+  uint64_t lo = __ldg(words + w);
+  if (sh == 0) return lo;
+  uint64_t hi = __ldg(words + w + 1);
+  return (lo >> sh) | (hi << (64 - sh));
+}
+
+__device__ __forceinline__ int gmg_base_at(const uint64_t* __restrict__ words, int64_t p) {
+  return (int)((__ldg(words + (p >> 5)) >> ((p & 31) * 2)) & 3);
+}
+
+// One ICM walk (Full_Window_Prob icm.cc:557-610 / Partial_Window_Prob icm.cc:807-842 unified):
+//  ctx   window bases: window position k at bits 2*k (k = 0 .. W-1; W-1 = predicted base)
+//  lim   smallest window position whose base is available (0 = full window)
+// mipf / probf already offset to the period's table.
+__device__ __forceinline__ float gmg_walk(const int8_t* __restrict__ mipf, const float* __restrict__ probf,
+                                          uint64_t ctx, int W, int D, int lim) {
+  int node = 0;
+  for (int i = 0; i < D; i++) {
+    int pos = mipf[node];
+    if (pos < lim) break;  // -1 leaf, -2 cut, or context base not available
+    node = 4 * node + (int)((ctx >> (2 * pos)) & 3) + 1;
+  }
+  return __ldg(probf + 4 * (size_t)node + (int)((ctx >> (2 * (W - 1))) & 3));
+}
+
+// reverse the order of the low W bases of v (base i <-> base W-1-i)
+__device__ __forceinline__ uint64_t gmg_reverse_bases(uint64_t v, int W) {
+  // reverse all 32 2-bit groups, then shift down
+  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+  v = ((v >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((v & 0x0F0F0F0F0F0F0F0Full) << 4);
+  v = ((v >> 8) & 0x00FF00FF00FF00FFull) | ((v & 0x00FF00FF00FF00FFull) << 8);
+  v = ((v >> 16) & 0x0000FFFF0000FFFFull) | ((v & 0x0000FFFF0000FFFFull) << 16);
+  v = (v >> 32) | (v << 32);
+  return v >> (2 * (32 - W));
+}
+
+// kernel launchers implemented across the .cu files
+int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc);

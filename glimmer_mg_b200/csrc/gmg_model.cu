@@ -1,0 +1,389 @@
+// glimmer_mg_b200/csrc/gmg_model.cu -- context, error channel and the ICM_t container:
+// build-icm binary format reader/writer, Build_Indep_WO_Stops, device upload.
+//
+// Reference behaviour mirrored (paths relative to /root/reference/src/):
+//   ICM_t::ICM_t / Input / Output / Output_Node / Write_Header   ICM/icm.cc:24-45, 614-803, 961-998
+//   ICM_t::Build_Indep_WO_Stops                                   ICM/icm.cc:65-216
+//   Set_Ignore_Score_Len                                          Glimmer/glimmer_base.cc:2597-2633
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gmg_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gmg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* gmg_last_error(void) { return g_err; }
+extern "C" int gmg_abi_version(void) { return GMG_ABI_VERSION; }
+
+extern "C" int gmg_ctx_create(int device, void* stream, gmg_ctx** out) {
+  GMG_CHECK(out != NULL, "gmg_ctx_create: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    gmg_set_error("gmg_ctx_create: no usable CUDA device (%s); libgmgicm has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 1;
+  }
+  GMG_CHECK(device >= 0 && device < n, "gmg_ctx_create: device %d out of range (have %d)", device, n);
+  GMG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GMG_CUDA(cudaGetDeviceProperties(&prop, device));
+  GMG_CHECK(prop.major >= 10, "gmg_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+            device, prop.major, prop.minor);
+  gmg_ctx* c = new gmg_ctx();
+  memset(c, 0, sizeof *c);
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+  } else {
+    GMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 8; i++)
+    if (c->scratch[i]) cudaFree(c->scratch[i]);
+  if (c->h_penalty) cudaFreeHost(c->h_penalty);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int gmg_ctx_sync(gmg_ctx* c) {
+  GMG_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int64_t gmg_ctx_launch_count(const gmg_ctx* c) { return c->launches; }
+
+extern "C" int gmg_ctx_memcpy_d2h(gmg_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+  GMG_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GMG_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gmg_ctx_memcpy_h2d(gmg_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+  GMG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+  GMG_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int gmg_scratch(gmg_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 256;
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      GMG_CUDA(cudaFree(ctx->scratch[slot]));
+      ctx->scratch[slot] = NULL;
+      ctx->scratch_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    GMG_CUDA(cudaMalloc(&ctx->scratch[slot], want));
+    ctx->scratch_bytes[slot] = want;
+  }
+  *out = ctx->scratch[slot];
+  return 0;
+}
+
+extern "C" void gmg_params_default(gmg_params* p, int metagenomic) {
+  memset(p, 0, sizeof *p);
+  p->min_gene_len = 75;
+  p->allow_truncated = metagenomic ? 1 : 0;
+  p->min_indel_orf_len = 15;
+  p->indel_quality_threshold = 18;
+  p->indel_max = 2;
+  p->ignore_score_len = INT_MAX;
+  p->indel_suffix_score_threshold = -12.0;
+  p->n_start = 3;
+  strcpy(p->start_codon[0], "atg");
+  strcpy(p->start_codon[1], "gtg");
+  strcpy(p->start_codon[2], "ttg");
+  p->n_stop = 3;
+  strcpy(p->stop_codon[0], "taa");
+  strcpy(p->stop_codon[1], "tag");
+  strcpy(p->stop_codon[2], "tga");
+}
+
+extern "C" int gmg_ignore_score_len(double gc, const gmg_params* p) {
+  double lambda = 0.0;
+  for (int i = 0; i < p->n_stop; i++) {
+    double x = 1.0;
+    for (int j = 0; j < 3; j++) {
+      char ch = p->stop_codon[i][j];
+      x *= (ch == 'c' || ch == 'g') ? gc / 2.0 : (1.0 - gc) / 2.0;
+    }
+    lambda += x;
+  }
+  if (lambda == 0.0) return INT_MAX;
+  return (int)(long)floor(3.0 * log(2.0 * 1000000 * lambda) / lambda);
+}
+
+// ------------------------------------------------------------------------------------------
+
+static int base_code(char ch) {
+  // Subscript(Filter(ch)) (icm.cc:2008-2027, gene.cc:1139-1175)
+  switch (ch | 0x20) {
+    case 'a': return 0;
+    case 'c': return 1;
+    case 'g': return 2;
+    case 't': return 3;
+    case 'r': return 2;
+    case 'y': return 1;
+    case 's': return 1;
+    case 'w': return 3;
+    case 'm': return 1;
+    case 'k': return 3;
+    case 'b': return 1;
+    case 'd': return 2;
+    case 'h': return 1;
+    case 'v': return 1;
+    default: return 1;
+  }
+}
+
+static int num_nodes_for(int d) {
+  long n = 1, pw = 1;
+  for (int i = 0; i < d; i++) {
+    pw *= 4;
+    n += pw;
+  }
+  return (int)n;
+}
+
+static int icm_upload(gmg_icm* m) {
+  gmg_ctx* ctx = m->ctx;
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  const int P = m->P, N = m->N, D = m->D;
+  const int inner = (D == 0) ? 1 : num_nodes_for(D - 1);  // nodes on levels 0..D-1
+  std::vector<int8_t> mip8((size_t)P * inner);
+  std::vector<float> eff((size_t)P * N * 4);
+  for (int f = 0; f < P; f++) {
+    for (int i = 0; i < inner; i++) {
+      int v = m->mip[(size_t)f * N + i];
+      mip8[(size_t)f * inner + i] = (int8_t)(v < -2 ? -2 : v);
+    }
+    for (int i = 0; i < N; i++) {
+      // cut node -> parent's probabilities (the reference steps back one level only)
+      int src = (m->mip[(size_t)f * N + i] < -1 && i > 0) ? (i - 1) / 4 : i;
+      memcpy(&eff[((size_t)f * N + i) * 4], &m->prob[((size_t)f * N + src) * 4], 4 * sizeof(float));
+    }
+  }
+  GMG_CUDA(cudaMalloc(&m->d_mip, mip8.size() + 16));
+  GMG_CUDA(cudaMalloc(&m->d_prob, eff.size() * sizeof(float) + 16));
+  GMG_CUDA(cudaMemcpyAsync(m->d_mip, mip8.data(), mip8.size(), cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(m->d_prob, eff.data(), eff.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  m->dev.W = m->W;
+  m->dev.D = D;
+  m->dev.P = P;
+  m->dev.N = N;
+  m->dev.inner = inner;
+  m->dev.mip = m->d_mip;
+  m->dev.prob = m->d_prob;
+  return 0;
+}
+
+static int icm_validate(int w, int d, int p, int n) {
+  GMG_CHECK(w >= 1 && w <= GMG_MAX_W, "ICM model_len %d unsupported (1..%d)", w, GMG_MAX_W);
+  GMG_CHECK(d >= 0 && d <= GMG_MAX_DEPTH && d < w + 1, "ICM model_depth %d unsupported (0..%d)", d, GMG_MAX_DEPTH);
+  GMG_CHECK(p >= 1 && p <= 16, "ICM periodicity %d unsupported", p);
+  GMG_CHECK(n == num_nodes_for(d), "ICM num_nodes %d does not match depth %d", n, d);
+  return 0;
+}
+
+extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int16_t* h_mip, const float* h_prob,
+                                   gmg_icm** out) {
+  GMG_CHECK(ctx && out && h_mip && h_prob, "gmg_icm_from_tables: NULL argument");
+  int n = num_nodes_for(d);
+  if (icm_validate(w, d, p, n)) return 1;
+  gmg_icm* m = new gmg_icm();
+  m->ctx = ctx;
+  m->W = w; m->D = d; m->P = p; m->N = n;
+  m->mip.assign(h_mip, h_mip + (size_t)p * n);
+  m->prob.assign(h_prob, h_prob + (size_t)p * n * 4);
+  m->d_mip = NULL;
+  m->d_prob = NULL;
+  for (size_t i = 0; i < m->mip.size(); i++)
+    if (m->mip[i] >= w - 1 && w > 1) {
+      gmg_set_error("ICM node %zu has mut_info_pos %d outside the context window (len %d)", i, m->mip[i], w);
+      delete m;
+      return 1;
+    }
+  if (icm_upload(m)) {
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" int gmg_icm_load(gmg_ctx* ctx, const char* path, gmg_icm** out) {
+  GMG_CHECK(ctx && path && out, "gmg_icm_load: NULL argument");
+  FILE* fp = fopen(path, "rb");
+  GMG_CHECK(fp != NULL, "ERROR:  Could not open file  %s", path);
+  char line[150];
+  int32_t param[6];
+  if (fread(line, 1, 150, fp) != 150) {
+    fclose(fp);
+    gmg_set_error("ERROR reading ICM header");
+    return 1;
+  }
+  if (fread(param, sizeof(int32_t), 6, fp) != 6) {
+    fclose(fp);
+    gmg_set_error("ERROR reading parameters");
+    return 1;
+  }
+  if (param[0] != 200) {
+    fclose(fp);
+    gmg_set_error("Bad ICM version = %d  should be %d", param[0], 200);
+    return 1;
+  }
+  if (param[1] != 150) {
+    fclose(fp);
+    gmg_set_error("Bad ID_STRING_LEN = %d  should be %d", param[1], 150);
+    return 1;
+  }
+  const int w = param[2], d = param[3], p = param[4], n = param[5];
+  if (icm_validate(w, d, p, n)) {
+    fclose(fp);
+    return 1;
+  }
+  std::vector<int16_t> mip((size_t)p * n, 0);
+  std::vector<float> prob((size_t)p * n * 4, 0.0f);
+  int period = -1, prev = 0;
+  int32_t id;
+  while (fread(&id, sizeof id, 1, fp) == 1) {
+    if (id < 0) break;
+    if (id == 0) period++;
+    if (period < 0 || period >= p || id >= n) {
+      fclose(fp);
+      gmg_set_error("ERROR reading icm node = %d  period = %d", id, period);
+      return 1;
+    }
+    size_t at = (size_t)period * n + id;
+    if (fread(&prob[at * 4], sizeof(float), 4, fp) != 4) {
+      fclose(fp);
+      gmg_set_error("ERROR reading icm node = %d  period = %d", id, period);
+      return 1;
+    }
+    if (fread(&mip[at], sizeof(int16_t), 1, fp) != 1) {
+      fclose(fp);
+      gmg_set_error("ERROR reading mut_info_pos for node = %d  period = %d", id, period);
+      return 1;
+    }
+    if (id != 0 && prev != id - 1)
+      for (int i = prev + 1; i < id; i++) mip[(size_t)period * n + i] = -2;
+    if (id == 0 && period > 0)
+      for (int i = prev + 1; i < n; i++) mip[(size_t)(period - 1) * n + i] = -2;
+    prev = id;
+  }
+  fclose(fp);
+  GMG_CHECK(period == p - 1, "ERROR:  Too few nodes for periodicity = %d", p);
+  for (int i = prev + 1; i < n; i++) mip[(size_t)period * n + i] = -2;
+  return gmg_icm_from_tables(ctx, w, d, p, mip.data(), prob.data(), out);
+}
+
+extern "C" int gmg_icm_write(const gmg_icm* m, const char* path) {
+  GMG_CHECK(m && path, "gmg_icm_write: NULL argument");
+  FILE* fp = fopen(path, "wb");
+  GMG_CHECK(fp != NULL, "ERROR:  Could not open file  %s", path);
+  char line[150];
+  memset(line, 0, sizeof line);
+  snprintf(line, sizeof line, ">ver = %.2f  len = %d  depth = %d  periodicity = %d  nodes = %d\n", 2.00, m->W, m->D,
+           m->P, m->N);
+  int32_t param[6] = {200, 150, m->W, m->D, m->P, m->N};
+  bool ok = fwrite(line, 1, 150, fp) == 150 && fwrite(param, sizeof(int32_t), 6, fp) == 6;
+  for (int f = 0; ok && f < m->P; f++)
+    for (int32_t i = 0; ok && i < m->N; i++) {
+      size_t at = (size_t)f * m->N + i;
+      if (i != 0 && m->mip[at] < -1) continue;  // cut nodes are not stored
+      ok = fwrite(&i, sizeof i, 1, fp) == 1 && fwrite(&m->prob[at * 4], sizeof(float), 4, fp) == 4 &&
+           fwrite(&m->mip[at], sizeof(int16_t), 1, fp) == 1;
+    }
+  int32_t end_marker = -1;
+  ok = ok && fwrite(&end_marker, sizeof end_marker, 1, fp) == 1;
+  ok = (fclose(fp) == 0) && ok;
+  GMG_CHECK(ok, "ERROR writing ICM file %s", path);
+  return 0;
+}
+
+extern "C" int gmg_icm_dims(const gmg_icm* m, int32_t dims[4]) {
+  GMG_CHECK(m && dims, "gmg_icm_dims: NULL argument");
+  dims[0] = m->W; dims[1] = m->D; dims[2] = m->P; dims[3] = m->N;
+  return 0;
+}
+
+extern "C" int gmg_icm_tables(const gmg_icm* m, int16_t* h_mip, float* h_prob) {
+  GMG_CHECK(m, "gmg_icm_tables: NULL model");
+  if (h_mip) memcpy(h_mip, m->mip.data(), m->mip.size() * sizeof(int16_t));
+  if (h_prob) memcpy(h_prob, m->prob.data(), m->prob.size() * sizeof(float));
+  return 0;
+}
+
+extern "C" void gmg_icm_free(gmg_icm* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  if (m->d_mip) cudaFree(m->d_mip);
+  if (m->d_prob) cudaFree(m->d_prob);
+  delete m;
+}
+
+// Independent-nucleotide codon model without stop codons, stored as a period-3 depth-2
+// ICM in the reversed orientation the gene models use (icm.cc:65-216).  The table is tiny
+// (63 nodes) and is built once per run on the host in FP64 exactly like the reference
+// (its float accumulators round at every += ; glibc log), then uploaded.
+extern "C" int gmg_icm_build_indep(gmg_ctx* ctx, double gc, const char* const* stops, int n_stops, gmg_icm** out) {
+  GMG_CHECK(ctx && out, "gmg_icm_build_indep: NULL argument");
+  double base_prob[4], codon_prob[64];
+  base_prob[1] = base_prob[2] = gc / 2.0;
+  base_prob[0] = base_prob[3] = 0.5 - base_prob[1];
+  for (int c = 0; c < 64; c++) codon_prob[c] = base_prob[(c >> 4) & 3] * base_prob[(c >> 2) & 3] * base_prob[c & 3];
+  for (int i = 0; i < n_stops; i++) {
+    // the model runs 3'->5', so the stop codon enters reversed
+    int j = base_code(stops[i][0]) + 4 * base_code(stops[i][1]) + 16 * base_code(stops[i][2]);
+    codon_prob[j] = 1e-20;
+  }
+  double sum = 0.0;
+  for (int c = 0; c < 64; c++) sum += codon_prob[c];
+  for (int c = 0; c < 64; c++) codon_prob[c] /= sum;
+
+  const int N = 21;
+  std::vector<int16_t> mip(3 * N, 0);
+  std::vector<float> acc(3 * N * 4, 0.0f);
+  static const int pw[3] = {1, 4, 16};
+  for (int f = 0; f < 3; f++) {
+    const int d1 = pw[(3 - f) % 3], d2 = pw[(4 - f) % 3], d3 = pw[(5 - f) % 3];
+    mip[f * N] = (f == 1) ? -1 : 1;
+    for (int c = 0; c < 64; c++) acc[(f * N) * 4 + (c / d1) % 4] += codon_prob[c];
+    for (int b = 0; b < 4; b++) mip[f * N + 1 + b] = (f == 2) ? -1 : 0;
+    if (f != 1)
+      for (int c = 0; c < 64; c++) acc[(f * N + 1 + (c / d2) % 4) * 4 + (c / d1) % 4] += codon_prob[c];
+    if (f == 0) {
+      for (int b = 0; b < 16; b++) mip[f * N + 5 + b] = -1;
+      for (int c = 0; c < 64; c++) acc[(f * N + 5 + 4 * ((c / d2) % 4) + (c / d3) % 4) * 4 + (c / d1) % 4] += codon_prob[c];
+    }
+  }
+  std::vector<float> prob(3 * N * 4);
+  for (int i = 0; i < 3 * N; i++) {
+    double s = 0.0;
+    for (int k = 0; k < 4; k++) s += acc[i * 4 + k];
+    for (int k = 0; k < 4; k++) prob[i * 4 + k] = (float)(s == 0.0 ? 0.0 : log(acc[i * 4 + k] / s));
+  }
+  return gmg_icm_from_tables(ctx, 3, 2, 3, mip.data(), prob.data(), out);
+}

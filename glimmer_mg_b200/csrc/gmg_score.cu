@@ -1,0 +1,1454 @@
+// glimmer_mg_b200/csrc/gmg_score.cu -- the scoring kernels.
+//
+//   K1  k1_planes          per-position six-frame ICM tree walks            (Score_All_Frames glimmer-mg.cc:1468,
+//                                                                            ICM_t::Frame_Score icm.cc:485)
+//   K2  k2_prefix          per-(strand, reading-frame class) prefix sums of gene - indep log-odds, previous /
+//                          next in-frame stop tables, 454 quality synthesis, FP64 exactness certificate
+//                                                                           (Cumulative_Frame_Score glimmer-mg.cc:561,
+//                                                                            Save_Prev_Stops :675, Set_Quality_454 :1865)
+//   K3  k3_mg_starts       per-ORF start enumeration incl. indel / substitution branches
+//                                                                           (Score_Orf_Starts :1693, Score_Indels :1513)
+//       k3_g3_starts       whole-genome variant on extracted ORF strings    (Score_Orfs glimmer3.cc:1275)
+//   plus the device ORF finder (Find_Orfs glimmer_base.cc:638) and the scalar operator surface
+//   (Score_String / Cumulative_Score / Frame_Score icm.cc:864/354/485).
+//
+// Data layout (all offsets are global base indices p = off[seq] + q, q = position in the sequence):
+//   words   2-bit bases, 32 per 64-bit word
+//   planes  float [6][total]   gene-ICM log-prob of base p for reading-frame class c:
+//              plane c   (forward strand): model period (c - q) mod 3, context = the W-1 bases to the RIGHT of q
+//              plane 3+c (reverse strand): model period (1 + q - c) mod 3, context = complement of the W-1
+//                                          bases to the LEFT of q
+//           a forward ORF whose last base has index e = hi-1 reads plane (hi mod 3); a reverse ORF whose first
+//           base has index a reads plane 3 + (a mod 3); both read CONTIGUOUS runs.
+//   cum     double [6][total]  forward planes: suffix sums  sum_{q' >= q} (gene - indep); reverse planes: prefix sums.
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "gmg_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+
+__device__ __forceinline__ int mod3(int x) {
+  int r = x % 3;
+  return r < 0 ? r + 3 : r;
+}
+
+struct SeqView {
+  int64_t a;  // global index of the first base
+  int len;
+};
+
+__device__ __forceinline__ SeqView locate(const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
+                                          int64_t p, int32_t* seq_out) {
+  int32_t s = __ldg(blk2seq + (p >> 5));
+  while (p >= __ldg(off + s + 1)) s++;
+  SeqView v;
+  v.a = __ldg(off + s);
+  v.len = (int)(__ldg(off + s + 1) - v.a);
+  *seq_out = s;
+  return v;
+}
+
+// window register for the forward strand at global position p: window position k <-> base p + W-1-k
+__device__ __forceinline__ uint64_t ctx_fwd(const uint64_t* __restrict__ words, int64_t p, int W) {
+  return gmg_reverse_bases(gmg_extract32(words, p), W);
+}
+// reverse strand: window position k <-> complement of base p - (W-1) + k
+__device__ __forceinline__ uint64_t ctx_rev(const uint64_t* __restrict__ words, int64_t p, int W) {
+  return ~gmg_extract32(words, p - (W - 1));
+}
+// plain string order (Score_String etc.): window position k <-> base p - (W-1) + k
+__device__ __forceinline__ uint64_t ctx_str(const uint64_t* __restrict__ words, int64_t p, int W) {
+  return gmg_extract32(words, p - (W - 1));
+}
+
+__device__ __forceinline__ float icm_fwd(const DevIcm& m, const uint64_t* __restrict__ words, int64_t p, int q, int end,
+                                         int f) {
+  // `end` = exclusive end (in sequence coordinates) of the available context
+  int lim = q + m.W - end;
+  return gmg_walk(m.mip + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_fwd(words, p, m.W), m.W, m.D,
+                  lim > 0 ? lim : 0);
+}
+__device__ __forceinline__ float icm_rev(const DevIcm& m, const uint64_t* __restrict__ words, int64_t p, int q,
+                                         int begin, int f) {
+  int lim = m.W - 1 - (q - begin);
+  return gmg_walk(m.mip + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_rev(words, p, m.W), m.W, m.D,
+                  lim > 0 ? lim : 0);
+}
+__device__ __forceinline__ float icm_str(const DevIcm& m, const uint64_t* __restrict__ words, int64_t p, int q, int f) {
+  int lim = m.W - 1 - q;
+  return gmg_walk(m.mip + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_str(words, p, m.W), m.W, m.D,
+                  lim > 0 ? lim : 0);
+}
+
+// codon (5'->3' on the given strand) whose 3' base is at sequence position q (forward) / whose 3' base is at q
+// reading the reverse strand, as a 6-bit code b0*16 + b1*4 + b2
+__device__ __forceinline__ int codon_fwd_ending_at(const uint64_t* __restrict__ words, int64_t a, int q) {
+  // bases q-2, q-1, q
+  return gmg_base_at(words, a + q - 2) * 16 + gmg_base_at(words, a + q - 1) * 4 + gmg_base_at(words, a + q);
+}
+__device__ __forceinline__ int codon_rev_starting_at(const uint64_t* __restrict__ words, int64_t a, int q) {
+  // reverse-strand codon occupying q, q+1, q+2 read 5'->3': c(q+2), c(q+1), c(q)
+  return (3 - gmg_base_at(words, a + q + 2)) * 16 + (3 - gmg_base_at(words, a + q + 1)) * 4 +
+         (3 - gmg_base_at(words, a + q));
+}
+
+struct CodonSets {
+  unsigned long long start_mask;  // bit c set: 6-bit codon c is a start codon
+  unsigned long long stop_mask;
+  unsigned char which[64];        // index of the first matching start codon (Can_Be order)
+};
+
+struct DevParams {
+  int min_gene_len, allow_truncated, allow_indels, allow_subs, min_indel_orf_len, indel_q_thresh, indel_max,
+      ignore_score_len, have_quality_file;
+  double indel_suffix_thresh;
+};
+
+static int code_of(char ch) {
+  switch (ch | 0x20) {
+    case 'a': return 0;
+    case 'c': return 1;
+    case 'g': return 2;
+    case 't': return 3;
+    default: return -1;
+  }
+}
+
+static int make_codon_sets(const gmg_params* p, CodonSets* cs, DevParams* dp) {
+  memset(cs, 0, sizeof *cs);
+  GMG_CHECK(p->n_start >= 0 && p->n_start <= 8 && p->n_stop >= 0 && p->n_stop <= 8, "bad start/stop codon count");
+  memset(cs->which, 0xFF, sizeof cs->which);
+  for (int i = 0; i < p->n_start; i++) {
+    int a = code_of(p->start_codon[i][0]), b = code_of(p->start_codon[i][1]), c = code_of(p->start_codon[i][2]);
+    GMG_CHECK(a >= 0 && b >= 0 && c >= 0, "start codon '%s': only a/c/g/t codons are supported", p->start_codon[i]);
+    int code = a * 16 + b * 4 + c;
+    if (!(cs->start_mask >> code & 1)) cs->which[code] = (unsigned char)i;
+    cs->start_mask |= 1ull << code;
+  }
+  for (int i = 0; i < p->n_stop; i++) {
+    int a = code_of(p->stop_codon[i][0]), b = code_of(p->stop_codon[i][1]), c = code_of(p->stop_codon[i][2]);
+    GMG_CHECK(a >= 0 && b >= 0 && c >= 0, "stop codon '%s': only a/c/g/t codons are supported", p->stop_codon[i]);
+    cs->stop_mask |= 1ull << (a * 16 + b * 4 + c);
+  }
+  GMG_CHECK(p->indel_max >= 0 && p->indel_max <= 2, "indel_max %d unsupported (0..2)", p->indel_max);
+  dp->min_gene_len = p->min_gene_len;
+  dp->allow_truncated = p->allow_truncated;
+  dp->allow_indels = p->allow_indels;
+  dp->allow_subs = p->allow_subs;
+  dp->min_indel_orf_len = p->min_indel_orf_len;
+  dp->indel_q_thresh = p->indel_quality_threshold;
+  dp->indel_max = p->indel_max;
+  dp->ignore_score_len = p->ignore_score_len;
+  dp->have_quality_file = p->have_quality_file;
+  dp->indel_suffix_thresh = p->indel_suffix_score_threshold;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: per-position six-frame walks of the gene ICM.
+//
+// One thread per base, six independent walks per thread (ILP hides the dependent shared-memory
+// lookups); the branch-position bytes of the descendable levels (P * (4^D-1)/3 bytes = 16 KB at the
+// defaults) are staged in shared memory, the leaf probabilities are one 4-byte read-only gather per
+// walk from the L2-resident table.  Stores are one full 128-byte line per warp and plane.
+
+template <int NW>
+__device__ __forceinline__ void walk_many(const int8_t* const* mipf, const float* const* probf, const uint64_t* ctx,
+                                          const int* lim, int W, int D, float* out) {
+  int node[NW];
+  bool live[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    node[w] = 0;
+    live[w] = true;
+  }
+  for (int i = 0; i < D; i++) {
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      int pos = live[w] ? (int)mipf[w][node[w]] : -1;
+      live[w] = live[w] && (pos >= lim[w]);
+      int b = (int)((ctx[w] >> (2 * (pos & 31))) & 3);
+      node[w] = live[w] ? 4 * node[w] + b + 1 : node[w];
+      any |= live[w];
+    }
+    if (!any) break;
+  }
+#pragma unroll
+  for (int w = 0; w < NW; w++) out[w] = __ldg(probf[w] + 4 * (size_t)node[w] + (int)((ctx[w] >> (2 * (W - 1))) & 3));
+}
+
+__global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __restrict__ words,
+                                                 const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
+                                                 int64_t total, float* __restrict__ planes) {
+  extern __shared__ int8_t s_mip[];
+  const int nmip = gene.P * gene.inner;
+  for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip[i] = gene.mip[i];
+  __syncthreads();
+
+  const int W = gene.W, D = gene.D;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s;
+    SeqView sv = locate(off, blk2seq, p, &s);
+    const int q = (int)(p - sv.a);
+    uint64_t cf = ctx_fwd(words, p, W), cr = ctx_rev(words, p, W);
+    int lf = q + W - sv.len;
+    lf = lf > 0 ? lf : 0;
+    int lr = W - 1 - q;
+    lr = lr > 0 ? lr : 0;
+    const int8_t* mipf[6];
+    const float* probf[6];
+    uint64_t ctx[6];
+    int lim[6];
+    float v[6];
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      mipf[f] = mipf[3 + f] = s_mip + f * gene.inner;
+      probf[f] = probf[3 + f] = gene.prob + (size_t)f * gene.N * 4;
+      ctx[f] = cf;
+      ctx[3 + f] = cr;
+      lim[f] = lf;
+      lim[3 + f] = lr;
+    }
+    walk_many<6>(mipf, probf, ctx, lim, W, D, v);
+    // forward: period f belongs to class (f + q) mod 3;  reverse: period f belongs to class (1 + q - f) mod 3
+    const int r = q % 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      int ff = c - r;
+      ff = ff < 0 ? ff + 3 : ff;  // (c - q) mod 3
+      int fr = 1 + r - c;
+      fr = fr < 0 ? fr + 3 : (fr >= 3 ? fr - 3 : fr);  // (1 + q - c) mod 3
+      planes[(size_t)c * total + p] = ff == 0 ? v[0] : (ff == 1 ? v[1] : v[2]);
+      planes[(size_t)(3 + c) * total + p] = fr == 0 ? v[3] : (fr == 1 ? v[4] : v[5]);
+    }
+  }
+}
+
+static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** planes_out) {
+  GMG_CHECK(gene->P == 3, "six-frame scoring needs a periodicity-3 gene model (got %d)", gene->P);
+  void* planes = NULL;
+  if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
+  *planes_out = (float*)planes;
+  if (s->total == 0) return 0;
+  size_t smem = (size_t)gene->dev.P * gene->dev.inner;
+  GMG_CHECK(smem <= 200 * 1024, "gene model too deep for the shared-memory walk table (%zu bytes)", smem);
+  if (smem > 48 * 1024)
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t need = (s->total + 255) / 256;
+  int64_t cap = (int64_t)ctx->sm_count * 8;
+  int grid = (int)(need < cap ? need : cap);
+  k1_planes<<<grid, 256, smem, ctx->stream>>>(gene->dev, s->d_words, s->d_off, s->d_blk2seq, s->total, (float*)planes);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gmg_k1_score_planes(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s) {
+  GMG_CHECK(ctx && gene && s, "gmg_k1_score_planes: NULL argument");
+  float* planes;
+  return launch_k1(ctx, gene, s, &planes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame_Scores surface (Score_All_Frames): FS[f][q] = gene - indep as doubles, reference layout.
+
+__global__ void __launch_bounds__(256) k_frame_scores(DevIcm indep, const uint64_t* __restrict__ words,
+                                                      const int64_t* __restrict__ off,
+                                                      const int32_t* __restrict__ blk2seq, int64_t total,
+                                                      const float* __restrict__ planes, double* __restrict__ fs) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  int32_t s;
+  SeqView sv = locate(off, blk2seq, p, &s);
+  const int q = (int)(p - sv.a);
+  double* row = fs + 6 * sv.a;
+  for (int f = 0; f < 3; f++) {
+    float g = planes[(size_t)mod3(f + q) * total + p];
+    float n = icm_fwd(indep, words, p, q, sv.len, f);
+    row[(size_t)f * sv.len + q] = (double)g - (double)n;
+    g = planes[(size_t)(3 + mod3(1 + q - f)) * total + p];
+    n = icm_rev(indep, words, p, q, 0, f);
+    row[(size_t)(3 + f) * sv.len + q] = (double)g - (double)n;
+  }
+}
+
+extern "C" int gmg_score_all_frames(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, gmg_seqset* s,
+                                    double* out, int out_on_device) {
+  GMG_CHECK(ctx && gene && indep && s && out, "gmg_score_all_frames: NULL argument");
+  GMG_CHECK(indep->P == 3, "independent model must have periodicity 3");
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  if (s->total == 0) return 0;
+  double* d_fs = out;
+  if (!out_on_device) {
+    void* tmp;
+    if (gmg_scratch(ctx, SCR_CUM, (size_t)6 * s->total * sizeof(double), &tmp)) return 1;
+    d_fs = (double*)tmp;
+  }
+  k_frame_scores<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off,
+                                                                             s->d_blk2seq, s->total, planes, d_fs);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  if (!out_on_device) {
+    GMG_CUDA(cudaMemcpyAsync(out, d_fs, (size_t)6 * s->total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scalar operator surface: Score_String / Cumulative_Score / Frame_Score.
+// One warp per string; lanes evaluate 32 consecutive positions, lane order is preserved when the
+// FP64 sum is accumulated so the result has the reference's serial rounding (icm.cc:886-900).
+
+// mode 0: Score_String (one double per string), 1: Cumulative_Score, 2: Frame_Score
+__global__ void __launch_bounds__(128) k_string_scores(DevIcm m, const uint64_t* __restrict__ words,
+                                                       const int64_t* __restrict__ off, int64_t n, int frame0,
+                                                       int mode, double* __restrict__ out) {
+  int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n) return;
+  const int64_t a = off[s];
+  const int len = (int)(off[s + 1] - a);
+  if (m.P == 1) frame0 = 0;
+  double total = 0.0;
+  for (int base = 0; base < len; base += 32) {
+    int q = base + lane;
+    double x = 0.0;
+    if (q < len) {
+      int f = (mode == 2) ? frame0 : (frame0 + q) % m.P;
+      x = (double)icm_str(m, words, a + q, q, f);
+      if (mode == 2) out[a + q] = x;
+    }
+    if (mode != 2) {
+      // ordered accumulation: position base+0, base+1, ... exactly like the serial loop
+      double run = total;
+      double mine = 0.0;
+      int cnt = min(32, len - base);
+      for (int l = 0; l < cnt; l++) {
+        double xl = __shfl_sync(0xffffffffu, x, l);
+        run += xl;
+        if (l == lane) mine = run;
+      }
+      total = run;
+      if (mode == 1 && q < len) out[a + q] = mine;
+    }
+  }
+  if (mode == 0 && lane == 0) out[s] = total;
+}
+
+static int string_scores(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, int mode, double* h_out) {
+  GMG_CHECK(ctx && m && s && h_out, "string score: NULL argument");
+  GMG_CHECK(frame >= 0 && (frame < m->P || m->P == 1), "frame %d out of range for periodicity %d", frame, m->P);
+  if (s->n == 0) return 0;
+  size_t n_out = (mode == 0) ? (size_t)s->n : (size_t)s->total;
+  if (n_out == 0) return 0;
+  void* d_out;
+  if (gmg_scratch(ctx, SCR_CUM, n_out * sizeof(double), &d_out)) return 1;
+  int64_t threads = s->n * 32;
+  k_string_scores<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(m->dev, s->d_words, s->d_off, s->n, frame,
+                                                                             mode, (double*)d_out);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  GMG_CUDA(cudaMemcpyAsync(h_out, d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int gmg_icm_score_strings(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out) {
+  return string_scores(ctx, m, s, frame, 0, h_out);
+}
+extern "C" int gmg_icm_cumulative_score(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out) {
+  return string_scores(ctx, m, s, frame, 1, h_out);
+}
+extern "C" int gmg_icm_frame_score(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out) {
+  return string_scores(ctx, m, s, frame, 2, h_out);
+}
+
+extern "C" int gmg_icm_full_window_prob(gmg_ctx* ctx, const gmg_icm* m, const char* w, int frame, double* out) {
+  GMG_CHECK(ctx && m && w && out, "gmg_icm_full_window_prob: NULL argument");
+  int64_t off[2] = {0, m->W};
+  gmg_seqset* s = NULL;
+  if (gmg_seqset_create(ctx, w, off, 1, NULL, &s)) return 1;
+  std::vector<double> v(m->W);
+  int rc = string_scores(ctx, m, s, frame, 2, v.data());
+  gmg_seqset_free(s);
+  if (rc == 0) *out = v[m->W - 1];
+  return rc;
+}
+
+extern "C" int gmg_icm_partial_window_prob(gmg_ctx* ctx, const gmg_icm* m, int predict_pos, const char* str, int frame,
+                                           double* out) {
+  GMG_CHECK(ctx && m && str && out && predict_pos >= 0, "gmg_icm_partial_window_prob: bad argument");
+  int64_t off[2] = {0, predict_pos + 1};
+  gmg_seqset* s = NULL;
+  if (gmg_seqset_create(ctx, str, off, 1, NULL, &s)) return 1;
+  std::vector<double> v(predict_pos + 1);
+  int rc = string_scores(ctx, m, s, frame, 2, v.data());
+  gmg_seqset_free(s);
+  if (rc == 0) *out = v[predict_pos];
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device ORF finder (Find_Orfs, glimmer_base.cc:638-817; linear sequences, no ignore regions).
+//
+// Every ORF is created by the stop codon that closes it, so one thread per base handles the (at most
+// two) ORFs closed at that base and walks back codon by codon to the previous in-frame stop -- total
+// work = total ORF length.  The thread of a sequence's last base also emits the three Finish_Orfs
+// reverse ORFs and the three virtual forward stops past the end, in the reference's order.  Two
+// passes (count, block scan, write) give the reference's output order deterministically.
+
+__device__ bool orf_fwd_closed_at(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool virt,
+                                  const CodonSets& cs, const DevParams& P, gmg_orf* o) {
+  // i = index of the last base of the closing (possibly virtual) stop codon
+  if (!virt) {
+    if (i < 2 || !((cs.stop_mask >> codon_fwd_ending_at(words, a, i)) & 1)) return false;
+  }
+  int first_start = INT_MAX;
+  int prev = 0;  // 1-based first base of the previous stop, 0 = none
+  for (int t = i - 3; t >= 2; t -= 3) {
+    if (t >= L) continue;  // virtual closing stop: codons hanging past the end do not exist
+    int c = codon_fwd_ending_at(words, a, t);
+    if ((cs.stop_mask >> c) & 1) {
+      prev = t - 1;
+      break;
+    }
+    if ((cs.start_mask >> c) & 1) first_start = t - 1;
+  }
+  int gene_len, orf_len;
+  if (prev == 0) {
+    int pos = i - 1;
+    orf_len = pos - 1;
+    orf_len -= orf_len % 3;
+    gene_len = (first_start == INT_MAX) ? 0 : pos - first_start;
+    if (P.allow_truncated && gene_len < P.min_gene_len) gene_len = orf_len;
+  } else {
+    gene_len = (int)((long long)i - first_start - 1);
+    orf_len = i - prev - 4;
+  }
+  if (!(gene_len >= P.min_gene_len || ((P.allow_indels || P.allow_subs) && orf_len >= P.min_indel_orf_len)))
+    return false;
+  o->stop_position = i - 1;
+  o->frame = 1 + (i % 3 + 1) % 3;
+  o->gene_len = gene_len;
+  o->orf_len = orf_len;
+  return true;
+}
+
+// reverse ORF closed at i (real reverse stop whose highest base is i), or with finish = true the
+// Finish_Orfs ORF of frame class fr = i % 3 where i is the last position of that class (< L).
+__device__ bool orf_rev_closed_at(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool finish,
+                                  const CodonSets& cs, const DevParams& P, gmg_orf* o) {
+  int t0 = i - 3;
+  if (!finish) {
+    if (i < 2 || !((cs.stop_mask >> codon_rev_starting_at(words, a, i - 2)) & 1)) return false;
+  } else {
+    t0 = i;  // scan starts at the last codon of this class
+  }
+  int last_start = 0, prev = 0;
+  for (int t = t0; t >= 2; t -= 3) {
+    int c = codon_rev_starting_at(words, a, t - 2);
+    if ((cs.stop_mask >> c) & 1) {
+      prev = t - 1;
+      break;
+    }
+    if (last_start == 0 && ((cs.start_mask >> c) & 1)) last_start = t - 1;
+  }
+  int gene_len, orf_len, orf_stop;
+  if (!finish) {
+    if (prev == 0) {
+      if (!P.allow_truncated) {
+        gene_len = 0;
+        orf_stop = 0;  // glimmer_base.cc:513,999-1003: orf_stop keeps its initial value
+      } else {
+        orf_stop = (i - 1) % 3;
+        if (orf_stop > 0) orf_stop -= 3;
+        gene_len = last_start - orf_stop;
+      }
+    } else {
+      orf_stop = prev;
+      gene_len = last_start - orf_stop;
+    }
+    orf_len = i - orf_stop - 4;
+  } else {
+    const int fr = i % 3;
+    orf_stop = prev ? prev : (fr == 0 ? -1 : (fr == 1 ? 0 : -2));
+    orf_len = L - orf_stop - 2;
+    orf_len -= orf_len % 3;
+    gene_len = (last_start == 0) ? 0 : last_start - orf_stop;
+    if (P.allow_truncated && gene_len < P.min_gene_len) gene_len = orf_len;
+  }
+  if (!(gene_len >= P.min_gene_len || ((P.allow_indels || P.allow_subs) && orf_len >= P.min_indel_orf_len)))
+    return false;
+  o->stop_position = orf_stop;
+  o->frame = -1 - (i % 3 + 1) % 3;
+  o->gene_len = gene_len;
+  o->orf_len = orf_len;
+  return true;
+}
+
+// all ORFs created by base p, in reference order; returns the count (<= 8)
+__device__ int orfs_at(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                       const int32_t* __restrict__ blk2seq, int64_t p, const CodonSets& cs, const DevParams& P,
+                       gmg_orf* out, int32_t* seq_out) {
+  int32_t s;
+  SeqView sv = locate(off, blk2seq, p, &s);
+  *seq_out = s;
+  const int L = sv.len, q = (int)(p - sv.a);
+  if (L < P.min_gene_len) return 0;
+  int n = 0;
+  if (orf_fwd_closed_at(words, sv.a, L, q, false, cs, P, out + n)) n++;
+  if (orf_rev_closed_at(words, sv.a, L, q, false, cs, P, out + n)) n++;
+  if (q == L - 1) {
+    for (int fr = 0; fr < 3; fr++) {
+      // last index of class fr that is < L
+      int i = L - 1 - mod3(L - 1 - fr);
+      if (i < 0) i = fr;  // degenerate; the walk loop is empty
+      // the frame number only depends on fr, which equals i % 3 when i >= 0
+      gmg_orf tmp;
+      bool keep = orf_rev_closed_at(words, sv.a, L, i, true, cs, P, &tmp);
+      if (keep) {
+        tmp.frame = -1 - (fr + 1) % 3;
+        out[n++] = tmp;
+      }
+    }
+    if (P.allow_truncated)
+      for (int i = L; i < L + 3; i++)
+        if (orf_fwd_closed_at(words, sv.a, L, i, true, cs, P, out + n)) n++;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(256) k_orf_count(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                   const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
+                                                   DevParams P, int64_t* __restrict__ block_counts) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  gmg_orf tmp[8];
+  int32_t s;
+  int n = (p < total) ? orfs_at(words, off, blk2seq, p, cs, P, tmp, &s) : 0;
+  __shared__ int wsum[8];
+  int v = n;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; w++) t += wsum[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_orf_write(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                   const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
+                                                   DevParams P, const int64_t* __restrict__ block_base,
+                                                   gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  gmg_orf tmp[8];
+  int32_t s = 0;
+  int n = (p < total) ? orfs_at(words, off, blk2seq, p, cs, P, tmp, &s) : 0;
+  // block-level exclusive scan of n
+  __shared__ int wsum[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < wid; w++) wbase += wsum[w];
+  int64_t slot = block_base[blockIdx.x] + wbase + incl - n;
+  for (int k = 0; k < n; k++) {
+    orfs[slot + k] = tmp[k];
+    orf_seq[slot + k] = s;
+  }
+}
+
+// first ORF of every sequence (orf_seq is sorted): lower bound
+__global__ void k_orf_offsets(const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t n_seq,
+                              int64_t* __restrict__ orf_off) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_seq) return;
+  int64_t lo = 0, hi = n_orfs;  // first index with orf_seq >= s
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (orf_seq[mid] < s) lo = mid + 1;
+    else hi = mid;
+  }
+  orf_off[s] = lo;
+}
+
+__global__ void k_orf_seq_from_off(const int64_t* __restrict__ orf_off, int64_t n_seq, int64_t n_orfs,
+                                   int32_t* __restrict__ orf_seq) {
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_orfs) return;
+  int64_t lo = 0, hi = n_seq;  // largest s with orf_off[s] <= o
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (orf_off[mid] <= o) lo = mid;
+    else hi = mid;
+  }
+  orf_seq[o] = (int32_t)lo;
+}
+
+static int exclusive_sum_i64(gmg_ctx* ctx, int64_t* d_in, int64_t* d_out, int64_t n) {
+  size_t tmp_bytes = 0;
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_in, d_out, n, ctx->stream));
+  void* tmp;
+  if (gmg_scratch(ctx, SCR_TMP4, tmp_bytes, &tmp)) return 1;
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, n, ctx->stream));
+  ctx->launches += 2;
+  return 0;
+}
+
+static int ensure_orf_capacity(gmg_seqset* s, int64_t n_orfs) {
+  if ((size_t)n_orfs > s->cap_orfs || !s->d_orfs) {
+    if (s->d_orfs) cudaFree(s->d_orfs);
+    if (s->d_orf_seq) cudaFree(s->d_orf_seq);
+    if (s->d_start_off) cudaFree(s->d_start_off);
+    s->d_orfs = NULL; s->d_orf_seq = NULL; s->d_start_off = NULL;
+    size_t cap = (size_t)n_orfs + (size_t)n_orfs / 8 + 64;
+    GMG_CUDA(cudaMalloc(&s->d_orfs, cap * sizeof(gmg_orf)));
+    GMG_CUDA(cudaMalloc(&s->d_orf_seq, cap * sizeof(int32_t)));
+    GMG_CUDA(cudaMalloc(&s->d_start_off, (cap + 1) * sizeof(int64_t)));
+    s->cap_orfs = cap;
+  }
+  if (!s->d_orf_off) GMG_CUDA(cudaMalloc(&s->d_orf_off, (size_t)(s->n + 2) * sizeof(int64_t)));
+  return 0;
+}
+
+extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, int64_t* n_orfs) {
+  GMG_CHECK(ctx && s && p, "gmg_find_orfs: NULL argument");
+  CodonSets cs;
+  DevParams dp;
+  if (make_codon_sets(p, &cs, &dp)) return 1;
+  s->n_orfs = 0;
+  s->n_starts = 0;
+  if (s->total == 0) {
+    if (ensure_orf_capacity(s, 0)) return 1;
+    GMG_CUDA(cudaMemsetAsync(s->d_orf_off, 0, (size_t)(s->n + 1) * sizeof(int64_t), ctx->stream));
+    s->orf_off.assign((size_t)s->n + 1, 0);
+    if (n_orfs) *n_orfs = 0;
+    return 0;
+  }
+  int64_t nblk = (s->total + 255) / 256;
+  void* d_counts;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(2 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
+  int64_t* counts = (int64_t*)d_counts;
+  int64_t* bases = counts + nblk + 1;
+  GMG_CUDA(cudaMemsetAsync(counts + nblk, 0, sizeof(int64_t), ctx->stream));
+  k_orf_count<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, counts);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  if (exclusive_sum_i64(ctx, counts, bases, nblk + 1)) return 1;
+  int64_t total_orfs = 0;
+  GMG_CUDA(cudaMemcpyAsync(&total_orfs, bases + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ensure_orf_capacity(s, total_orfs)) return 1;
+  k_orf_write<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, bases,
+                                                      s->d_orfs, s->d_orf_seq);
+  k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
+  ctx->launches += 2;
+  GMG_CUDA(cudaGetLastError());
+  s->n_orfs = total_orfs;
+  s->orf_off.clear();
+  if (n_orfs) *n_orfs = total_orfs;
+  return 0;
+}
+
+extern "C" int gmg_get_orfs(gmg_ctx* ctx, gmg_seqset* s, gmg_orf* h_orfs, int64_t* h_orf_off) {
+  GMG_CHECK(ctx && s, "gmg_get_orfs: NULL argument");
+  if (h_orfs && s->n_orfs)
+    GMG_CUDA(cudaMemcpyAsync(h_orfs, s->d_orfs, (size_t)s->n_orfs * sizeof(gmg_orf), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_orf_off && s->d_orf_off)
+    GMG_CUDA(cudaMemcpyAsync(h_orf_off, s->d_orf_off, (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int gmg_set_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_orf* h_orfs, const int64_t* h_orf_off) {
+  GMG_CHECK(ctx && s && h_orf_off, "gmg_set_orfs: NULL argument");
+  int64_t n_orfs = h_orf_off[s->n];
+  GMG_CHECK(n_orfs >= 0 && h_orf_off[0] == 0, "gmg_set_orfs: bad offsets");
+  GMG_CHECK(n_orfs == 0 || h_orfs, "gmg_set_orfs: NULL ORF table");
+  if (ensure_orf_capacity(s, n_orfs)) return 1;
+  if (n_orfs)
+    GMG_CUDA(cudaMemcpyAsync(s->d_orfs, h_orfs, (size_t)n_orfs * sizeof(gmg_orf), cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(s->d_orf_off, h_orf_off, (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  if (n_orfs) {
+    k_orf_seq_from_off<<<(unsigned)((n_orfs + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_off, s->n, n_orfs, s->d_orf_seq);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->n_orfs = n_orfs;
+  s->n_starts = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Start-list emission shared by the glimmer3 and glimmer-mg kernels.
+
+struct Emit {
+  gmg_start* out;  // NULL = counting pass
+  int64_t n;
+};
+
+__device__ __forceinline__ void emit_start(Emit& e, int j, int pos, double score, int which, int truncated, int first,
+                                           int n_err, const int* err_pos, const int* err_type, int ignore_len) {
+  if (e.out) {
+    gmg_start st;
+    st.j = j;
+    st.pos = pos;
+    // long-ORF boost (glimmer-mg.cc:1649-1651, glimmer3.cc:1464-1466): Max(0.0, score)
+    st.score = (j > ignore_len && 0.0 > score) ? 0.0 : score;
+    st.which = which;
+    st.truncated = truncated;
+    st.first = first;
+    st.n_err = n_err;
+    st.err_pos[0] = n_err > 0 ? err_pos[0] : 0;
+    st.err_pos[1] = n_err > 1 ? err_pos[1] : 0;
+    st.err_type[0] = n_err > 0 ? err_type[0] : 0;
+    st.err_type[1] = n_err > 1 ? err_type[1] : 0;
+    e.out[e.n] = st;
+  }
+  e.n++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (glimmer3): Score_Orfs start enumeration on the extracted ORF string (glimmer3.cc:1275-1466).
+//
+// One warp per ORF.  buff[j] = S[hi-1-j] (forward) / complement S[lo+j] (reverse); the gene ICM and the
+// independent model are accumulated SEPARATELY in FP64 in j order with the period cycling 1,2,0
+// (Cumulative_Score icm.cc:354-405).  Positions j >= W-1 read the K1 planes; the first W-1 positions
+// use partial windows that only see the ORF string (icm.cc:376-388), recomputed here.
+// Lanes evaluate 32 consecutive j; the running sums are formed by an ordered in-warp accumulation, so
+// every prefix has exactly the reference's serial rounding -- no reassociation.
+
+struct G3Geom {
+  int frame, lo, hi, len, k0, trunc;
+};
+
+__device__ __forceinline__ G3Geom g3_geom(const gmg_orf& o, int L, const DevParams& P) {
+  G3Geom g;
+  g.frame = o.frame;
+  g.len = o.orf_len;
+  if (o.frame > 0) {
+    g.hi = o.stop_position - 1;
+    if (g.hi <= 0) g.hi += L;
+    g.lo = g.hi - g.len;
+    g.trunc = (g.lo < 3 && P.allow_truncated);
+    g.k0 = o.stop_position - g.len - 2;
+  } else {
+    g.lo = o.stop_position + 2;
+    if (g.lo >= L) g.lo -= L;
+    g.hi = g.lo + g.len;
+    g.trunc = (L - g.hi < 3 && P.allow_truncated);
+    g.k0 = o.stop_position + g.len + 4;
+  }
+  return g;
+}
+
+// is j a start position of this ORF string?  returns which (>=0), -1 = only by the truncated rule, -2 = no
+__device__ __forceinline__ int g3_codon_which(const uint64_t* __restrict__ words, int64_t a, const G3Geom& g, int j,
+                                              const CodonSets& cs) {
+  // codon register after shifting in buff[m-1] .. buff[j]: buff[j+2], buff[j+1], buff[j]; complete iff j <= m-3
+  if (j > g.len - 3) return -1;
+  int c;
+  if (g.frame > 0) c = codon_fwd_ending_at(words, a, g.hi - 1 - j);  // S[p-2], S[p-1], S[p], p = hi-1-j
+  else c = codon_rev_starting_at(words, a, g.lo + j);                 // c(S[q+2]), c(S[q+1]), c(S[q]), q = lo+j
+  return ((cs.start_mask >> c) & 1) ? (int)cs.which[c] : -1;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                    const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                    const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                    int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
+                                                    gmg_start* __restrict__ starts) {
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (oi >= n_orfs) return;
+  const gmg_orf o = orfs[oi];
+  const int32_t s = orf_seq[oi];
+  const int64_t a = off[s];
+  const int L = (int)(off[s + 1] - a);
+  const G3Geom g = g3_geom(o, L, P);
+  const int m = g.len;
+  const int lowest_j = min(3, P.min_gene_len - 3);
+
+  // pass A: positions that emit (descending j), needs only codons.  first_j = largest qualifying j.
+  // A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and
+  // (codon is a start || (nothing emitted yet && truncated)).
+  int n_emit = 0;        // total records
+  int first_j = -1;      // j of the first (largest-j) emitting position
+  int first_double = 0;  // first position emits two records (truncated + real start codon)
+  {
+    // largest j % 3 == 0 that is <= m-1
+    int jtop = (m - 1) - ((m - 1) % 3);
+    int found_first = -1, cnt = 0;
+    for (int jb = jtop; jb >= lowest_j; jb -= 96) {
+      int j = jb - 3 * lane;
+      bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
+      int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
+      bool is_codon = ok && w >= 0;
+      // truncated rule can only apply to the very first candidate position examined (first_pos == 0)
+      unsigned cm = __ballot_sync(0xffffffffu, is_codon);
+      unsigned okm = __ballot_sync(0xffffffffu, ok);
+      if (found_first < 0) {
+        if (g.trunc && okm) {
+          int l0 = __ffs(okm) - 1;  // first ok lane = largest j
+          found_first = jb - 3 * l0;
+          first_double = (cm >> l0) & 1;
+          cnt += 1 + first_double;
+          cm &= ~(1u << l0);
+          cnt += __popc(cm);
+        } else if (!g.trunc && cm) {
+          int l0 = __ffs(cm) - 1;
+          found_first = jb - 3 * l0;
+          cnt += __popc(cm);
+        }
+      } else {
+        cnt += __popc(cm);
+      }
+    }
+    n_emit = cnt;
+    first_j = found_first;
+  }
+  if (!kWrite) {
+    if (lane == 0) counts[oi] = n_emit;
+    return;
+  }
+  if (n_emit == 0) return;
+  gmg_start* out = starts + start_off[oi];
+
+  // pass B: ordered FP64 accumulation of gene / indep along j, emitting score[j-1] for start position j.
+  const int W = gene.W;
+  const int cls = (g.frame > 0) ? (g.hi % 3) : (g.lo % 3);
+  const float* plane = planes + (size_t)((g.frame > 0 ? 0 : 3) + cls) * total;
+  double run_g = 0.0, run_n = 0.0;
+  int emitted_below = 0;  // records of start positions < current chunk (ascending j)
+  const int j_last = first_j - 1;  // scores are needed up to index first_j - 1
+  for (int base = 0; base <= j_last; base += 32) {
+    const int j = base + lane;
+    float xg = 0.f, xn = 0.f;
+    if (j <= j_last) {
+      const int f = (1 + j) % 3;
+      if (g.frame > 0) {
+        const int q = g.hi - 1 - j;
+        xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f) : __ldg(plane + a + q);
+        xn = icm_fwd(indep, words, a + q, q, g.hi, f);
+      } else {
+        const int q = g.lo + j;
+        xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f) : __ldg(plane + a + q);
+        xn = icm_rev(indep, words, a + q, q, g.lo, f);
+      }
+    }
+    // ordered accumulation (lane 0 first) -> my_g / my_n = score[j] / indep_score[j]
+    double my_g = 0.0, my_n = 0.0;
+    const int cnt = min(32, j_last + 1 - base);
+    for (int l = 0; l < cnt; l++) {
+      run_g += (double)__shfl_sync(0xffffffffu, xg, l);
+      run_n += (double)__shfl_sync(0xffffffffu, xn, l);
+      if (l == lane) {
+        my_g = run_g;
+        my_n = run_n;
+      }
+    }
+    // start position js = j + 1 uses score[j]
+    const int js = j + 1;
+    bool cand = (j <= j_last) && (js % 3 == 0) && (js >= lowest_j) && (js <= m - 1) && (js + 3 >= P.min_gene_len);
+    int w = cand ? g3_codon_which(words, a, g, js, cs) : -2;
+    bool is_first = cand && (js == first_j);
+    bool emits = cand && (w >= 0 || (is_first && g.trunc));
+    int nrec = emits ? ((is_first && g.trunc && w >= 0) ? 2 : 1) : 0;
+    // records are stored in DESCENDING j order: slot = n_emit - (records at positions <= js)
+    int incl = nrec;
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (emits) {
+      const int slot = n_emit - (emitted_below + incl);
+      const double sc = my_g - my_n;
+      const int kpos = (g.frame > 0) ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
+      Emit e;
+      e.out = out;
+      e.n = slot;
+      if (is_first && g.trunc) {
+        if (w >= 0) {
+          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+          emit_start(e, js + 2, kpos, sc, w, 0, 0, 0, NULL, NULL, P.ignore_score_len);
+        } else {
+          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+        }
+      } else {
+        emit_start(e, js + 2, kpos, sc, w, 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
+      }
+    }
+    emitted_below += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (glimmer-mg): per-sequence prefix sums, stop tables, quality synthesis, exactness certificate.
+// One warp per sequence.
+
+// lowest set bit exponent of a finite non-zero double (x is an integer multiple of 2^ret)
+__device__ __forceinline__ int low_bit_exp(double x) {
+  long long b = __double_as_longlong(x);
+  int e = (int)((b >> 52) & 0x7FF);
+  unsigned long long mant = (unsigned long long)b & 0xFFFFFFFFFFFFFull;
+  if (e == 0) return -1074 + (mant ? __ffsll((long long)mant) - 1 : 0);
+  mant |= 1ull << 52;
+  return e - 1075 + (__ffsll((long long)mant) - 1);
+}
+
+__global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* __restrict__ words,
+                                                 const int64_t* __restrict__ off, int64_t n_seq, int64_t total,
+                                                 const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                 const uint8_t* __restrict__ qual_in, double* __restrict__ cum,
+                                                 int32_t* __restrict__ fwd_prev, int32_t* __restrict__ rev_next,
+                                                 uint8_t* __restrict__ qual, uint8_t* __restrict__ cert) {
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_seq) return;
+  const int64_t a = off[s];
+  const int L = (int)(off[s + 1] - a);
+  if (L == 0) {
+    if (lane == 0) cert[s] = 1;
+    return;
+  }
+  int gmin = 4096;
+  double asum = 0.0;
+
+  // ---- left-to-right: reverse-strand prefix sums, previous forward stops, quality ----
+  {
+    double carry[3] = {0.0, 0.0, 0.0};
+    int last_stop[3] = {0, 1, -1};  // Save_Prev_Stops init (glimmer-mg.cc:684)
+    for (int base = 0; base < L; base += 32) {
+      const int q = base + lane;
+      const bool in = q < L;
+      double x[3] = {0.0, 0.0, 0.0};
+      if (in) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int f = mod3(1 + q - c);
+          const float gval = planes[(size_t)(3 + c) * total + a + q];
+          const float nval = icm_rev(indep, words, a + q, q, 0, f);
+          x[c] = (double)gval - (double)nval;
+          if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
+          asum += fabs(x[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double v = x[c];
+        for (int d = 1; d < 32; d <<= 1) {
+          double t = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += t;
+        }
+        v += carry[c];
+        if (in) cum[(size_t)(3 + c) * total + a + q] = v;
+        carry[c] = __shfl_sync(0xffffffffu, v, 31);
+      }
+      // previous forward stop per frame class q % 3 (index of the stop's last base)
+      int st = -0x40000000;
+      if (in && q >= 2 && ((cs.stop_mask >> codon_fwd_ending_at(words, a, q)) & 1)) st = q;
+      int v = st;
+      for (int d = 3; d < 32; d *= 2) {  // class-restricted max-scan: same class = multiples of 3 apart
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = max(v, t);
+      }
+      const int cl = q % 3;
+      int prevv = max(v, cl == 0 ? last_stop[0] : (cl == 1 ? last_stop[1] : last_stop[2]));
+      // carries must only replace the init values when a real stop was seen
+      if (v < 0) prevv = (cl == 0 ? last_stop[0] : (cl == 1 ? last_stop[1] : last_stop[2]));
+      if (in) fwd_prev[a + q] = prevv;
+      // new carries: value at the last lane of each class in this chunk
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        // highest lane l with (base + l) % 3 == c and base + l < L
+        int top = min(31, L - 1 - base);
+        int l = top - mod3(base + top - c);
+        int nv = __shfl_sync(0xffffffffu, prevv, l < 0 ? 0 : l);
+        if (l >= 0) last_stop[c] = nv;
+      }
+      // Set_Quality_454 (glimmer-mg.cc:1865-1906): last base of a homopolymer run of length r gets
+      // 31 - 5*min(r,5), every other base 31.  Clean_Quality_454 (:519-546) when a quality file is given.
+      if (in && qual) {
+        const int b = gmg_base_at(words, a + q);
+        const bool last_of_run = (q == L - 1) || (gmg_base_at(words, a + q + 1) != b);
+        int qv;
+        if (qual_in) {
+          qv = qual_in[a + q];
+          if (qv <= 0) qv = 1;
+          if (!last_of_run && qv < P.indel_q_thresh + 1) qv = P.indel_q_thresh + 1;
+          qv = min(qv, 255);
+        } else if (!last_of_run) {
+          qv = 31;
+        } else {
+          int r = 1;
+          while (r < 5 && q - r >= 0 && gmg_base_at(words, a + q - r) == b) r++;
+          qv = 31 - 5 * r;
+        }
+        qual[a + q] = (uint8_t)qv;
+      }
+    }
+  }
+  // ---- right-to-left: forward-strand suffix sums, next reverse stops ----
+  {
+    double carry[3] = {0.0, 0.0, 0.0};
+    // Save_Prev_Stops reverse init (glimmer-mg.cc:706-708) per class r = (L-1-q) % 3: {L-1, L-2, L}
+    int next_stop[3] = {L - 1, L - 2, L};
+    for (int base = 0; base < L; base += 32) {
+      const int q = L - 1 - (base + lane);  // lane 0 = rightmost
+      const bool in = q >= 0;
+      double x[3] = {0.0, 0.0, 0.0};
+      if (in) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int f = mod3(c - q);
+          const float gval = planes[(size_t)c * total + a + q];
+          const float nval = icm_fwd(indep, words, a + q, q, L, f);
+          x[c] = (double)gval - (double)nval;
+          if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
+          asum += fabs(x[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double v = x[c];
+        for (int d = 1; d < 32; d <<= 1) {
+          double t = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += t;
+        }
+        v += carry[c];
+        if (in) cum[(size_t)c * total + a + q] = v;
+        carry[c] = __shfl_sync(0xffffffffu, v, 31);
+      }
+      int st = 0x40000000;
+      if (in && q <= L - 3 && ((cs.stop_mask >> codon_rev_starting_at(words, a, q)) & 1)) st = q;
+      int v = st;
+      for (int d = 3; d < 32; d *= 2) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = min(v, t);
+      }
+      const int r = (base + lane) % 3;  // (L-1-q) % 3
+      const int init = (r == 0 ? next_stop[0] : (r == 1 ? next_stop[1] : next_stop[2]));
+      // a stop at or right of q inside this chunk is always nearer than the carried one
+      const int nextv = (v >= 0x40000000) ? init : v;
+      if (in) rev_next[a + q] = nextv;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        int top = min(31, L - 1 - base);  // highest valid lane
+        int l = top - mod3(base + top - c);
+        int nv = __shfl_sync(0xffffffffu, nextv, l < 0 ? 0 : l);
+        if (l >= 0) next_stop[c] = nv;
+      }
+    }
+  }
+  // ---- certificate: every partial sum of every plane is exactly representable ----
+  for (int d = 16; d > 0; d >>= 1) {
+    gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, d));
+    asum += __shfl_xor_sync(0xffffffffu, asum, d);
+  }
+  if (lane == 0) {
+    // all terms are multiples of 2^gmin and |any partial sum| <= asum: exact iff asum < 2^(gmin+52)
+    // (one binade of margin for the rounding of asum itself)
+    bool ok = (gmin == 4096) || (asum < ldexp(1.0, gmin + 52));
+    cert[s] = ok ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (glimmer-mg): Score_Orf_Starts / Score_Indels / Pass_Stop_Penalty recursion, one thread per ORF,
+// explicit stack (depth <= 1 + indel_max + sub).  score[j] of any branch is a difference of two entries of
+// the K2 prefix-sum planes (bit-identical to the reference's serial Cumulative_Frame_Score whenever the
+// sequence's certificate holds -- see DESIGN.md).
+
+struct MgSeq {
+  const uint64_t* words;
+  int64_t a;
+  int L;
+  int64_t total;
+  const double* cum;
+  const int32_t* fwd_prev;
+  const int32_t* rev_next;
+  const uint8_t* qual;
+  const double* penalty;   // [256] log(pe/2) - log(1-pe), pe = 10^(-q/10)   (host glibc, Score_Indels :1520-1521)
+  const double* stop_pen;  // [4]   Pass_Stop_Penalty without a quality file, index = 2*a1 + a2
+  const double* codon_p;   // [256] 1 - 10^(-q/10)
+};
+
+struct MgCall {
+  int lo, hi, m;       // geometry of this call (1-based lo/hi as in the reference)
+  int j;               // loop cursor
+  int phase;           // 0: before deletion branch, 1: before insertion branch, 2: codon test
+  int suffix_j;
+  int first_pos;
+  int trunc;
+  int n_err;
+  int err_pos[2], err_type[2];
+  double suffix_score;
+  double cbase;        // cumulative value subtracted to get score[] of this call
+};
+
+__device__ __forceinline__ double mg_cum_f(const MgSeq& S, int c, int q) {  // suffix sum from q (0 past the end)
+  return (q >= S.L || q < 0) ? 0.0 : S.cum[(size_t)c * S.total + S.a + q];
+}
+__device__ __forceinline__ double mg_cum_r(const MgSeq& S, int c, int q) {  // prefix sum through q (0 before 0)
+  return (q < 0 || q >= S.L) ? 0.0 : S.cum[(size_t)(3 + c) * S.total + S.a + q];
+}
+
+// score[j] of a call (Cumulative_Frame_Score glimmer-mg.cc:561-604)
+__device__ __forceinline__ double mg_score(const MgSeq& S, int frame, const MgCall& c, int j) {
+  if (frame > 0) {
+    const int cls = mod3(c.hi);
+    return mg_cum_f(S, cls, c.hi - 1 - j) - c.cbase;
+  } else {
+    const int cls = mod3(c.lo - 1);
+    return mg_cum_r(S, cls, c.lo - 1 + j) - c.cbase;
+  }
+}
+
+__device__ __forceinline__ void mg_open_call(const MgSeq& S, const DevParams& P, int frame, int end_point,
+                                             MgCall& c) {
+  const int L = S.L;
+  if (frame > 0) {
+    c.hi = end_point;
+    const int e = end_point - 1;
+    c.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
+    c.m = c.hi - c.lo;
+    c.trunc = (c.lo < 3 && P.allow_truncated);
+    c.cbase = mg_cum_f(S, mod3(c.hi), c.hi);
+  } else {
+    c.lo = end_point;
+    const int e = end_point - 1;
+    c.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
+    c.m = c.hi - c.lo;
+    c.trunc = (L - (c.hi - 1) < 3 && P.allow_truncated);
+    c.cbase = mg_cum_r(S, mod3(c.lo - 1), c.lo - 2);
+  }
+  if (c.m < 0) c.m = 0;
+  c.j = c.m - 1;
+  c.phase = 0;
+  c.first_pos = 0;
+}
+
+__device__ double mg_pass_stop_penalty(const MgSeq& S, const DevParams& P, int frame, int lo, int hi) {
+  int i0, i1, i2;
+  if (frame > 0) { i0 = lo - 3; i1 = lo - 2; i2 = lo - 1; }
+  else { i0 = hi + 1; i1 = hi; i2 = hi - 1; }
+  const int want = (frame > 0) ? 0 : 3;  // 'a' forward, 't' reverse
+  const bool a1 = (i1 >= 0 && i1 < S.L) && gmg_base_at(S.words, S.a + i1) == want;
+  const bool a2 = (i2 >= 0 && i2 < S.L) && gmg_base_at(S.words, S.a + i2) == want;
+  if (!P.have_quality_file) return S.stop_pen[2 * (int)a1 + (int)a2];
+  double cp[3];
+  const int idx[3] = {i0, i1, i2};
+  for (int t = 0; t < 3; t++) cp[t] = (idx[t] >= 0 && idx[t] < S.L) ? S.codon_p[S.qual[S.a + idx[t]]] : 0.999;
+  double p_stop = cp[0];
+  p_stop *= a1 ? (2.0 / 3.0 * cp[1] + 1.0 / 3.0) : cp[1];
+  p_stop *= a2 ? (2.0 / 3.0 * cp[2] + 1.0 / 3.0) : cp[2];
+  return log(1.0 - p_stop) - log(p_stop);
+}
+
+__device__ void mg_orf_starts(const MgSeq& S, const DevParams& P, const CodonSets& cs, const gmg_orf& o, Emit& e) {
+  const int frame = o.frame;
+  const int lowest_j = min(3, P.min_gene_len - 3);
+  MgCall st[5];
+  int sp = 0;
+  mg_open_call(S, P, frame, frame > 0 ? o.stop_position - 1 : o.stop_position + 3, st[0]);
+  st[0].suffix_score = 0.0;
+  st[0].suffix_j = 0;
+  st[0].n_err = 0;
+  bool fresh = true;  // the call on top of the stack has not run its substitution pre-step yet
+  while (sp >= 0) {
+    MgCall& c = st[sp];
+    if (fresh) {
+      fresh = false;
+      // substitution through the previous stop (glimmer-mg.cc:1771-1806)
+      if (P.allow_subs && c.n_err < 1) {
+        int eep, epos;
+        if (frame > 0) { eep = c.lo - 3; epos = c.lo - 2; }
+        else { eep = c.hi + 3; epos = c.hi + 2; }
+        if (eep >= 0 && eep - 2 < S.L) {
+          double ess = c.suffix_score + mg_pass_stop_penalty(S, P, frame, c.lo, c.hi);
+          if (c.m > 0) ess += mg_score(S, frame, c, c.m - 1) - 0.0;
+          MgCall& nc = st[sp + 1];
+          mg_open_call(S, P, frame, eep, nc);
+          nc.suffix_score = ess;
+          nc.suffix_j = c.suffix_j + c.m;
+          nc.n_err = c.n_err + 1;
+          nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
+          nc.err_pos[c.n_err] = epos;
+          nc.err_type[c.n_err] = 2;
+          sp++;
+          fresh = true;
+          continue;
+        }
+      }
+    }
+    if (c.j < lowest_j) {
+      sp--;
+      continue;
+    }
+    const int j = c.j;
+    const int k = (frame > 0) ? c.lo + c.m - 2 - j : c.lo + j + 2;
+    const int bidx = (frame > 0) ? c.hi - 1 - j : c.lo - 1 + j;
+    if (c.phase < 2) {
+      bool branch = false;
+      if (P.allow_indels && c.n_err < P.indel_max) {
+        const int qv = S.qual[S.a + bidx];
+        if (qv <= P.indel_q_thresh) {
+          const double pen = S.penalty[qv];
+          const int esj = c.suffix_j + j + 2 - (j % 3);
+          while (c.phase < 2 && !branch) {
+            const int ph = c.phase++;
+            const double ess = c.suffix_score + mg_score(S, frame, c, ph == 0 ? j : j - 1) - 0.0 + pen;
+            if (ess > P.indel_suffix_thresh) {
+              int eep, epos;
+              if (ph == 0) {  // deletion
+                eep = (frame > 0) ? k + (j % 3) : k - (j % 3);
+                epos = (frame > 0) ? k + 3 : k - 1;
+              } else {        // insertion
+                eep = (frame > 0) ? k - (2 - (j % 3)) : k + 2 - (j % 3);
+                epos = (frame > 0) ? k + 2 : k - 2;
+              }
+              MgCall& nc = st[sp + 1];
+              mg_open_call(S, P, frame, eep, nc);
+              nc.suffix_score = ess;
+              nc.suffix_j = esj;
+              nc.n_err = c.n_err + 1;
+              nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
+              nc.err_pos[c.n_err] = epos;
+              nc.err_type[c.n_err] = (ph == 0) ? 1 : 0;
+              branch = true;
+            }
+          }
+        }
+      }
+      if (branch) {
+        sp++;
+        fresh = true;
+        continue;
+      }
+      c.phase = 2;
+    }
+    // codon test at j (glimmer-mg.cc:1819-1856)
+    if (j % 3 == 0) {
+      int which = -1;
+      if (j <= c.m - 3) {
+        const int cd = (frame > 0) ? codon_fwd_ending_at(S.words, S.a, bidx) : codon_rev_starting_at(S.words, S.a, bidx);
+        if ((cs.start_mask >> cd) & 1) which = cs.which[cd];
+      }
+      if ((which >= 0 || (c.first_pos == 0 && c.trunc)) && j + 3 + c.suffix_j >= P.min_gene_len) {
+        const double sc = (mg_score(S, frame, c, j - 1) - 0.0) + c.suffix_score;
+        int first = (c.first_pos == 0);
+        if (which >= 0 && c.first_pos == 0 && c.trunc) {
+          emit_start(e, j + 2 + c.suffix_j, k, sc, -1, 1, first, c.n_err, c.err_pos, c.err_type, P.ignore_score_len);
+          first = 0;
+        }
+        emit_start(e, j + 2 + c.suffix_j, k, sc, which, which < 0, first, c.n_err, c.err_pos, c.err_type,
+                   P.ignore_score_len);
+        if (c.first_pos == 0) c.first_pos = k;
+      }
+    }
+    c.j--;
+    c.phase = 0;
+  }
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128) k3_mg_starts(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                    const gmg_orf* __restrict__ orfs,
+                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                    const double* __restrict__ cum, const int32_t* __restrict__ fwd_prev,
+                                                    const int32_t* __restrict__ rev_next, const uint8_t* __restrict__ qual,
+                                                    const double* __restrict__ tables, CodonSets cs, DevParams P,
+                                                    int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
+                                                    gmg_start* __restrict__ starts) {
+  const int64_t oi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (oi >= n_orfs) return;
+  const int32_t s = orf_seq[oi];
+  MgSeq S;
+  S.words = words;
+  S.a = off[s];
+  S.L = (int)(off[s + 1] - S.a);
+  S.total = total;
+  S.cum = cum;
+  S.fwd_prev = fwd_prev;
+  S.rev_next = rev_next;
+  S.qual = qual;
+  S.penalty = tables;
+  S.stop_pen = tables + 256;
+  S.codon_p = tables + 260;
+  Emit e;
+  e.out = kWrite ? starts + start_off[oi] : NULL;
+  e.n = 0;
+  mg_orf_starts(S, P, cs, orfs[oi], e);
+  if (!kWrite) counts[oi] = e.n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host drivers of the two scoring halves
+
+static int ensure_start_capacity(gmg_seqset* s, int64_t n) {
+  if ((size_t)n > s->cap_starts || !s->d_starts) {
+    if (s->d_starts) cudaFree(s->d_starts);
+    s->d_starts = NULL;
+    size_t cap = (size_t)n + (size_t)n / 8 + 64;
+    GMG_CUDA(cudaMalloc(&s->d_starts, cap * sizeof(gmg_start)));
+    s->cap_starts = cap;
+  }
+  return 0;
+}
+
+__global__ void k_count_zero_flags(const uint8_t* __restrict__ cert, int64_t n, unsigned long long* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned bad = (i < n && cert[i] == 0) ? 1u : 0u;
+  bad = __popc(__ballot_sync(0xffffffffu, bad));
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, gmg_seqset* s,
+                                 const gmg_params* p, int64_t* n_starts) {
+  GMG_CHECK(ctx && gene && indep && s && p, "gmg_score_orfs_g3: NULL argument");
+  GMG_CHECK(gene->P == 3 && indep->P == 3, "glimmer3 scoring needs periodicity-3 models");
+  CodonSets cs;
+  DevParams dp;
+  if (make_codon_sets(p, &cs, &dp)) return 1;
+  s->n_starts = 0;
+  s->uncertified = 0;
+  if (n_starts) *n_starts = 0;
+  if (s->n_orfs == 0) return 0;
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  void* d_counts;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 1) * sizeof(int64_t), &d_counts)) return 1;
+  int64_t* counts = (int64_t*)d_counts;
+  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, sizeof(int64_t), ctx->stream));
+  unsigned grid = (unsigned)((s->n_orfs * 32 + 127) / 128);
+  k3_g3_starts<false><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs,
+                                                     s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp, counts, NULL, NULL);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
+  int64_t total_starts = 0;
+  GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ensure_start_capacity(s, total_starts)) return 1;
+  k3_g3_starts<true><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq,
+                                                    s->n_orfs, s->total, planes, cs, dp, NULL, s->d_start_off, s->d_starts);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  s->n_starts = total_starts;
+  if (n_starts) *n_starts = total_starts;
+  return 0;
+}
+
+extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, gmg_seqset* s,
+                                 const gmg_params* p, int64_t* n_starts) {
+  GMG_CHECK(ctx && gene && indep && s && p, "gmg_score_orfs_mg: NULL argument");
+  GMG_CHECK(gene->P == 3 && indep->P == 3, "glimmer-mg scoring needs periodicity-3 models");
+  CodonSets cs;
+  DevParams dp;
+  if (make_codon_sets(p, &cs, &dp)) return 1;
+  GMG_CHECK(!(p->have_quality_file && !s->d_qual), "have_quality_file set but the seqset has no quality values");
+  s->n_starts = 0;
+  s->uncertified = 0;
+  if (n_starts) *n_starts = 0;
+  if (s->n_orfs == 0) return 0;
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  // K2
+  void *d_cum, *d_tab, *d_qual, *d_cert;
+  if (gmg_scratch(ctx, SCR_CUM, (size_t)6 * s->total * sizeof(double), &d_cum)) return 1;
+  if (gmg_scratch(ctx, SCR_TMP, (size_t)2 * s->total * sizeof(int32_t), &d_tab)) return 1;
+  if (gmg_scratch(ctx, SCR_QUAL, (size_t)s->total, &d_qual)) return 1;
+  if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n + 64 + 520 * sizeof(double), &d_cert)) return 1;
+  int32_t* fwd_prev = (int32_t*)d_tab;
+  int32_t* rev_next = fwd_prev + s->total;
+  // penalty tables (host libm, FP64): indices 0..255 indel penalty, 256..259 stop penalty, 260..515 codon_p
+  double* d_tables = (double*)d_cert;
+  uint8_t* cert = (uint8_t*)(d_tables + 516);
+  if (!ctx->h_penalty) GMG_CUDA(cudaMallocHost(&ctx->h_penalty, 516 * sizeof(double)));
+  for (int q = 0; q < 256; q++) {
+    double pe = pow(10.0, -(double)q / 10.0);
+    ctx->h_penalty[q] = log(pe / 2.0) - log(1.0 - pe);
+    ctx->h_penalty[260 + q] = 1.0 - pe;
+  }
+  for (int t = 0; t < 4; t++) {
+    const double dpv = 0.999;
+    double ps = dpv;
+    ps *= (t & 2) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
+    ps *= (t & 1) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
+    ctx->h_penalty[256 + t] = log(1.0 - ps) - log(ps);
+  }
+  GMG_CUDA(cudaMemcpyAsync(d_tables, ctx->h_penalty, 516 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const bool need_qual = p->allow_indels || p->have_quality_file;
+  unsigned g2 = (unsigned)((s->n * 32 + 127) / 128);
+  k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, cs, dp,
+                                         p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
+                                         need_qual ? (uint8_t*)d_qual : NULL, cert);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  // K3: count, scan, write
+  void* d_counts;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
+  int64_t* counts = (int64_t*)d_counts;
+  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
+  unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
+  k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                   (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                   counts, NULL, NULL);
+  k_count_zero_flags<<<(unsigned)((s->n + 255) / 256), 256, 0, ctx->stream>>>(cert, s->n,
+                                                                             (unsigned long long*)(counts + s->n_orfs + 1));
+  ctx->launches += 2;
+  GMG_CUDA(cudaGetLastError());
+  if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
+  int64_t total_starts = 0, bad = 0;
+  GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(&bad, counts + s->n_orfs + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->uncertified = bad;
+  if (ensure_start_capacity(s, total_starts)) return 1;
+  k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                  (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                  NULL, s->d_start_off, s->d_starts);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  s->n_starts = total_starts;
+  if (n_starts) *n_starts = total_starts;
+  return 0;
+}
+
+extern "C" int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_start_off) {
+  GMG_CHECK(ctx && s, "gmg_get_starts: NULL argument");
+  if (h_starts && s->n_starts)
+    GMG_CUDA(cudaMemcpyAsync(h_starts, s->d_starts, (size_t)s->n_starts * sizeof(gmg_start), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  if (h_start_off) {
+    if (s->n_orfs)
+      GMG_CUDA(cudaMemcpyAsync(h_start_off, s->d_start_off, (size_t)(s->n_orfs + 1) * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    else
+      h_start_off[0] = 0;
+  }
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int64_t gmg_uncertified_count(const gmg_seqset* s) { return s ? s->uncertified : 0; }

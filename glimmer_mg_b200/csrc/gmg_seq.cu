@@ -1,0 +1,194 @@
+// glimmer_mg_b200/csrc/gmg_seq.cu -- sequence batches: ASCII -> Filter -> 2-bit pack in HBM.
+//
+// Reference behaviour mirrored (paths relative to /root/reference/src/):
+//   Filter                 Common/gene.cc:1139-1175   (every non-acgt IUPAC code -> one fixed base,
+//                                                      anything else incl. 'n' -> 'c')
+//   tolower(Filter(c))     Glimmer/glimmer-mg.cc:381-382, glimmer3.cc:270-271
+//   Set_GC_Fraction        Glimmer/glimmer_base.cc:2564-2595
+#include <string.h>
+
+#include "gmg_internal.cuh"
+
+// 2-bit code of tolower(Filter(ch)): a=0 c=1 g=2 t=3 (ALPHA_STRING "acgt", icm.hh:30)
+__device__ __forceinline__ unsigned filter_code(unsigned ch) {
+  switch (ch | 0x20u) {
+    case 'a': return 0;
+    case 'g': case 'r': case 'd': return 2;
+    case 't': case 'w': case 'k': return 3;
+    default: return 1;  // c, y, s, m, b, h, v and everything else
+  }
+}
+
+// one thread packs 32 bases (32 ASCII bytes = two 16-byte loads) into one 64-bit word and
+// counts its g/c; a warp therefore reads 1 KB contiguous and writes 256 B contiguous.
+__global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii, int64_t total,
+                                              uint64_t* __restrict__ words, unsigned long long* __restrict__ gc) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nwords = (total + 31) >> 5;
+  unsigned my_gc = 0;
+  if (w < nwords) {
+    int64_t base = w << 5;
+    uint64_t v = 0;
+    if (base + 32 <= total && ((reinterpret_cast<uintptr_t>(ascii + base) & 15) == 0)) {
+      const uint4* src = reinterpret_cast<const uint4*>(ascii + base);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint4 q = __ldg(src + h);
+        unsigned r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            unsigned code = filter_code((r[k] >> (8 * b)) & 0xFF);
+            my_gc += (code == 1 || code == 2);
+            v |= (uint64_t)code << (2 * (h * 16 + k * 4 + b));
+          }
+      }
+    } else {
+      for (int b = 0; b < 32 && base + b < total; b++) {
+        unsigned code = filter_code(ascii[base + b]);
+        my_gc += (code == 1 || code == 2);
+        v |= (uint64_t)code << (2 * b);
+      }
+    }
+    words[w] = v;
+  }
+  // block reduction of the GC count -> one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) my_gc += __shfl_down_sync(0xffffffffu, my_gc, o);
+  if ((threadIdx.x & 31) == 0 && my_gc) atomicAdd(gc, (unsigned long long)my_gc);
+}
+
+__global__ void k_unpack(const uint64_t* __restrict__ words, int64_t total, char* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = "acgt"[gmg_base_at(words, i)];
+}
+
+// sequence that holds base 32*b (binary search over the offsets; run once per batch)
+__global__ void k_blk2seq(const int64_t* __restrict__ off, int64_t n, int64_t nblk, int32_t* __restrict__ blk2seq) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  int64_t p = b << 5;
+  int64_t lo = 0, hi = n;  // largest s with off[s] <= p
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= p) lo = mid;
+    else hi = mid;
+  }
+  blk2seq[b] = (int32_t)lo;
+}
+
+int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc) {
+  int64_t nwords = (total + 31) >> 5;
+  if (nwords == 0) return 0;
+  k_pack<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(d_ascii, total, d_words, d_gc);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off, int64_t n, const void* d_qual,
+                        gmg_seqset** out) {
+  GMG_CHECK(n >= 0 && n < (1ll << 31), "gmg_seqset_create: %lld sequences unsupported", (long long)n);
+  for (int64_t i = 0; i < n; i++)
+    GMG_CHECK(h_off[i + 1] >= h_off[i], "gmg_seqset_create: offsets not monotone at %lld", (long long)i);
+  GMG_CHECK(n == 0 || h_off[0] == 0, "gmg_seqset_create: offsets must start at 0");
+  gmg_seqset* s = new gmg_seqset();
+  s->ctx = ctx;
+  s->n = n;
+  s->total = n ? h_off[n] : 0;
+  s->off.assign(h_off, h_off + n + 1);
+  if (n == 0) s->off.assign(1, 0);
+  s->d_off = NULL; s->d_words_base = NULL; s->d_words = NULL; s->d_blk2seq = NULL; s->d_qual = NULL; s->d_gc = NULL;
+  s->n_orfs = 0; s->d_orfs = NULL; s->d_orf_off = NULL; s->d_orf_seq = NULL;
+  s->n_starts = 0; s->d_starts = NULL; s->d_start_off = NULL; s->uncertified = 0;
+  s->cap_orfs = s->cap_starts = 0;
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  int64_t nwords = (s->total + 31) >> 5;
+  int64_t nblk = nwords > 0 ? nwords : 1;
+  size_t wbytes = (size_t)(nwords + 2 * GMG_PAD_WORDS) * sizeof(uint64_t);
+  GMG_CUDA(cudaMalloc(&s->d_words_base, wbytes));
+  GMG_CUDA(cudaMemsetAsync(s->d_words_base, 0, wbytes, ctx->stream));
+  s->d_words = s->d_words_base + GMG_PAD_WORDS;
+  GMG_CUDA(cudaMalloc(&s->d_off, (size_t)(s->n + 1) * sizeof(int64_t)));
+  GMG_CUDA(cudaMemcpyAsync(s->d_off, s->off.data(), (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  GMG_CUDA(cudaMalloc(&s->d_blk2seq, (size_t)nblk * sizeof(int32_t)));
+  GMG_CUDA(cudaMalloc(&s->d_gc, sizeof(unsigned long long)));
+  GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, sizeof(unsigned long long), ctx->stream));
+  if (s->total > 0) {
+    if (gmg_launch_pack(ctx, (const uint8_t*)d_ascii, s->total, s->d_words, s->d_gc)) return 1;
+    k_blk2seq<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d_off, s->n, nblk, s->d_blk2seq);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+    if (d_qual) {
+      GMG_CUDA(cudaMalloc(&s->d_qual, (size_t)s->total));
+      GMG_CUDA(cudaMemcpyAsync(s->d_qual, d_qual, (size_t)s->total, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  *out = s;
+  return 0;
+}
+
+extern "C" int gmg_seqset_create_device(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off, int64_t n,
+                                        const void* d_qual, gmg_seqset** out) {
+  GMG_CHECK(ctx && h_off && out, "gmg_seqset_create_device: NULL argument");
+  return seqset_build(ctx, d_ascii, h_off, n, d_qual, out);
+}
+
+extern "C" int gmg_seqset_create(gmg_ctx* ctx, const char* h_ascii, const int64_t* h_off, int64_t n,
+                                 const uint8_t* h_qual, gmg_seqset** out) {
+  GMG_CHECK(ctx && h_off && out, "gmg_seqset_create: NULL argument");
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  int64_t total = n ? h_off[n] : 0;
+  void* d_ascii = NULL;
+  void* d_q = NULL;
+  if (total > 0) {
+    GMG_CHECK(h_ascii != NULL, "gmg_seqset_create: NULL sequence data");
+    if (gmg_scratch(ctx, SCR_TMP, (size_t)total + 64, &d_ascii)) return 1;
+    GMG_CUDA(cudaMemcpyAsync(d_ascii, h_ascii, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    if (h_qual) {
+      if (gmg_scratch(ctx, SCR_TMP2, (size_t)total + 64, &d_q)) return 1;
+      GMG_CUDA(cudaMemcpyAsync(d_q, h_qual, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  int rc = seqset_build(ctx, d_ascii, h_off, n, d_q, out);
+  if (rc == 0) GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller
+  return rc;
+}
+
+extern "C" void gmg_seqset_free(gmg_seqset* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  void* ptrs[] = {s->d_off, s->d_words_base, s->d_blk2seq, s->d_qual, s->d_gc, s->d_orfs, s->d_orf_off,
+                  s->d_orf_seq, s->d_starts, s->d_start_off};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+}
+
+extern "C" int64_t gmg_seqset_total_bases(const gmg_seqset* s) { return s ? s->total : 0; }
+
+extern "C" int gmg_seqset_gc_fraction(gmg_seqset* s, double* gc) {
+  GMG_CHECK(s && gc, "gmg_seqset_gc_fraction: NULL argument");
+  unsigned long long ct = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ct, s->d_gc, sizeof ct, cudaMemcpyDeviceToHost, s->ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  // the reference counts in `unsigned int` and divides as double (glimmer_base.cc:2571-2590)
+  *gc = (double)(unsigned int)ct / (double)(unsigned int)s->total;
+  return 0;
+}
+
+extern "C" int gmg_seqset_unpack(gmg_seqset* s, char* h_out) {
+  GMG_CHECK(s && h_out, "gmg_seqset_unpack: NULL argument");
+  if (s->total == 0) return 0;
+  gmg_ctx* ctx = s->ctx;
+  void* d = NULL;
+  if (gmg_scratch(ctx, SCR_TMP, (size_t)s->total, &d)) return 1;
+  k_unpack<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(s->d_words, s->total, (char*)d);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  GMG_CUDA(cudaMemcpyAsync(h_out, d, (size_t)s->total, cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}

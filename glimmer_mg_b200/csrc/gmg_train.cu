@@ -1,0 +1,353 @@
+// glimmer_mg_b200/csrc/gmg_train.cu -- ICM_Training_t: context counting on the device (K4), the
+// level-synchronous tree construction around it.
+//
+// Reference behaviour mirrored (paths relative to /root/reference/src/ICM/):
+//   Train_Model                     icm.cc:1356-1463   root counts, root probs (float arithmetic), root MI position
+//   Complete_Tree                   icm.cc:1061-1186   per level: count, MI position with the 3 % right bias, prune
+//   Count_Char_Pairs                icm.cc:1841-1870   (level 0)
+//   Count_Char_Pairs_Restricted     icm.cc:1190-1229   (level >= 1)
+//   Get_Training_Node               icm.cc:1233-1256
+//   Get_Mutual_Info                 icm.cc:1900-1954
+//   Interpolate_Probs               icm.cc:1260-1330
+//   Take_Logs                       icm.cc:1334-1352   (logf: float overload)
+//
+// K4 is the hot part (~90 % of build-icm): every window of every training string walks `level` steps
+// down the tree built so far and adds 1 to W-1 pair counters of the node it lands in.  The level's
+// count slab [P][4^level][W-1][16] int32 is what gets all-reduced across GPUs; mutual information,
+// interpolation and logs are O(nodes) FP64/float arithmetic whose rounding decides the tree topology,
+// so they run on the host with the same libm the reference uses (parallel over nodes -- every node's
+// arithmetic is independent, so this is bit-identical to the serial loop).
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include <thread>
+
+#include "gmg_internal.cuh"
+
+struct gmg_trainer {
+  gmg_ctx* ctx;
+  gmg_seqset* seqs;
+  int W, D, P, N, reverse;
+  std::vector<int16_t> mip;  // [P][N]
+  std::vector<float> prob;   // [P][N][4] probabilities (logs only after finish)
+  int8_t* d_mip;             // [P][N] current tree (levels not built yet are -1)
+  int32_t* d_counts;         // slab of the level being counted
+  size_t counts_cap;
+  std::vector<int32_t> h_counts;
+  int next_level;
+};
+
+static inline int64_t level_nodes(int level) {
+  int64_t n = 1;
+  for (int i = 0; i < level; i++) n *= 4;
+  return n;
+}
+static inline int64_t first_node_of(int level) { return (level_nodes(level) - 1) / 3; }
+
+// One thread per window.  kSmem: the slab (times `copies` replicas to spread same-address conflicts)
+// lives in shared memory and is flushed once per CTA; otherwise global reductions.
+template <bool kSmem>
+__global__ void __launch_bounds__(512) k4_count(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                const int32_t* __restrict__ blk2seq, int64_t total, int W, int P,
+                                                int N, int reverse, int level, int first_node, int nodes_on_level,
+                                                const int8_t* __restrict__ mip, int* __restrict__ counts,
+                                                int slab, int copies) {
+  extern __shared__ int s_cnt[];
+  if (kSmem) {
+    for (int i = threadIdx.x; i < slab * copies; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+  }
+  int* mine = kSmem ? s_cnt + ((threadIdx.x >> 5) % copies) * slab : counts;
+  const int wp = W % P;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s = __ldg(blk2seq + (p >> 5));
+    while (p >= __ldg(off + s + 1)) s++;
+    const int64_t a = __ldg(off + s);
+    const int len = (int)(__ldg(off + s + 1) - a);
+    const int q = (int)(p - a);
+    uint64_t ctx;
+    int t;  // window start in the (possibly reversed) training string
+    if (!reverse) {
+      if (q + W > len) continue;
+      t = q;
+      ctx = gmg_extract32(words, p);  // window position k <-> s[q + k]
+    } else {
+      if (q - (W - 1) < 0) continue;
+      t = len - 1 - q;
+      ctx = gmg_reverse_bases(gmg_extract32(words, p - (W - 1)), W);  // window position k <-> s[q - k]
+    }
+    const int f = (wp + t) % P;
+    int node = 0;
+    bool ok = true;
+    const int8_t* mf = mip + (size_t)f * N;
+    for (int i = 0; i < level; i++) {
+      int j = mf[node];
+      if (j < 0) {
+        ok = false;
+        break;
+      }
+      node = 4 * node + (int)((ctx >> (2 * j)) & 3) + 1;
+    }
+    if (!ok) continue;
+    const int last = (int)((ctx >> (2 * (W - 1))) & 3);
+    int* row = mine + ((size_t)f * nodes_on_level + (node - first_node)) * (W - 1) * 16 + last;
+    for (int i = 0; i < W - 1; i++) {
+      int b = (int)((ctx >> (2 * i)) & 3);
+      atomicAdd(row + i * 16 + 4 * b, 1);
+    }
+  }
+  if (kSmem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < slab; i += blockDim.x) {
+      int v = 0;
+      for (int c = 0; c < copies; c++) v += s_cnt[c * slab + i];
+      if (v) atomicAdd(counts + i, v);
+    }
+  }
+}
+
+extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_trainer** out) {
+  GMG_CHECK(ctx && s && out, "gmg_trainer_create: NULL argument");
+  GMG_CHECK(w >= 2 && w <= GMG_MAX_W, "training: model_len %d unsupported (2..%d)", w, GMG_MAX_W);
+  GMG_CHECK(d >= 1 && d <= GMG_MAX_DEPTH && d <= w - 1, "training: model_depth %d unsupported", d);
+  GMG_CHECK(p >= 1 && p <= 16, "training: periodicity %d unsupported", p);
+  gmg_trainer* t = new gmg_trainer();
+  t->ctx = ctx;
+  t->seqs = s;
+  t->W = w; t->D = d; t->P = p; t->reverse = reverse;
+  t->N = (int)((level_nodes(d + 1) - 1) / 3);
+  t->mip.assign((size_t)p * t->N, 0);
+  t->prob.assign((size_t)p * t->N * 4, 0.0f);
+  t->d_mip = NULL;
+  t->d_counts = NULL;
+  t->counts_cap = 0;
+  t->next_level = 0;
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  GMG_CUDA(cudaMalloc(&t->d_mip, (size_t)p * t->N));
+  GMG_CUDA(cudaMemsetAsync(t->d_mip, 0xFF, (size_t)p * t->N, ctx->stream));
+  size_t cap = (size_t)p * level_nodes(d) * (w - 1) * 16;
+  GMG_CUDA(cudaMalloc(&t->d_counts, cap * sizeof(int32_t)));
+  t->counts_cap = cap;
+  *out = t;
+  return 0;
+}
+
+extern "C" void gmg_trainer_free(gmg_trainer* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->d_mip) cudaFree(t->d_mip);
+  if (t->d_counts) cudaFree(t->d_counts);
+  delete t;
+}
+
+extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_counts, int64_t* n_counts) {
+  GMG_CHECK(t, "gmg_trainer_count_level: NULL trainer");
+  GMG_CHECK(level == t->next_level && level <= t->D, "gmg_trainer_count_level: level %d out of order (next %d)", level,
+            t->next_level);
+  gmg_ctx* ctx = t->ctx;
+  gmg_seqset* s = t->seqs;
+  const int64_t nl = level_nodes(level);
+  const int64_t slab = (int64_t)t->P * nl * (t->W - 1) * 16;
+  GMG_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)slab * sizeof(int32_t), ctx->stream));
+  if (s->total > 0) {
+    const size_t smem_budget = 200 * 1024;
+    const bool use_smem = (size_t)slab * sizeof(int) <= smem_budget;
+    const int threads = 512;
+    if (use_smem) {
+      int copies = (int)(smem_budget / ((size_t)slab * sizeof(int)));
+      if (copies > threads / 32) copies = threads / 32;
+      if (copies < 1) copies = 1;
+      size_t smem = (size_t)slab * copies * sizeof(int);
+      GMG_CUDA(cudaFuncSetAttribute(k4_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int64_t need = (s->total + threads - 1) / threads;
+      int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);
+      k4_count<true><<<grid, threads, smem, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, t->W, t->P, t->N,
+                                                          t->reverse, level, (int)first_node_of(level), (int)nl, t->d_mip,
+                                                          t->d_counts, (int)slab, copies);
+    } else {
+      int64_t need = (s->total + threads - 1) / threads;
+      int64_t cap = (int64_t)ctx->sm_count * 4;
+      int grid = (int)(need < cap ? need : cap);
+      k4_count<false><<<grid, threads, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, t->W, t->P, t->N,
+                                                        t->reverse, level, (int)first_node_of(level), (int)nl, t->d_mip,
+                                                        t->d_counts, (int)slab, 1);
+    }
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
+  if (d_counts) *d_counts = t->d_counts;
+  if (n_counts) *n_counts = slab;
+  return 0;
+}
+
+// Get_Mutual_Info for a 4x4 table (icm.cc:1900-1954)
+static double mutual_info16(const int32_t* ct, int sum) {
+  if (sum == 0) return 0.0;
+  double left[4] = {0, 0, 0, 0}, right[4] = {0, 0, 0, 0}, mi = 0.0;
+  for (int i = 0, k = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++, k++) {
+      left[i] += ct[k];
+      right[j] += ct[k];
+    }
+  for (int i = 0; i < 4; i++) {
+    left[i] /= sum;
+    right[i] /= sum;
+  }
+  for (int i = 0, k = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++, k++) {
+      double pr = double(ct[k]) / sum;
+      if (pr != 0.0 && left[i] != 0.0 && right[j] != 0.0) mi += pr * log(pr / (left[i] * right[j]));
+    }
+  return mi;
+}
+
+static const float kChi2Val[7] = {2.37f, 4.11f, 6.25f, 7.81f, 9.35f, 11.3f, 12.8f};          // icm.hh:36-37
+static const float kChi2Sig[7] = {0.50f, 0.75f, 0.90f, 0.95f, 0.975f, 0.99f, 0.995f};         // icm.hh:39-40
+
+// position choice for one node; returns max_pos (no pruning applied) and best_info
+static int choose_position(const int32_t* node_counts, int W, int sum, double* best_out) {
+  int max_pos = 0;
+  double best = mutual_info16(node_counts, sum);
+  for (int i = 1; i < W - 1; i++) {
+    double next = mutual_info16(node_counts + 16 * i, sum);
+    if (next >= best) {
+      best = next;
+      max_pos = i;
+    } else if (next >= best / (1.0 + 0.03))  // MUT_INFO_BIAS: prefer positions to the right
+      max_pos = i;
+  }
+  *best_out = best;
+  return max_pos;
+}
+
+static void interpolate_probs(float* pr, const float* pp, const int ct[4]) {
+  double total = 0.0;
+  for (int i = 0; i < 4; i++) total += ct[i];
+  for (int i = 0; i < 4; i++) pr[i] = (float)((ct[i] + 0.001 * pp[i]) / (total + 0.001));
+  if (total >= 400) return;
+  double chi2 = 0.0;
+  for (int i = 0; i < 4; i++) {
+    double expected = total * pp[i];
+    if (expected > 0.0) chi2 += pow(ct[i] - expected, 2.0) / expected;
+  }
+  int i;
+  for (i = 0; i < 7 && kChi2Val[i] < chi2; i++)
+    ;
+  double lambda;
+  if (i == 0) lambda = 0.0;
+  else if (i == 7) lambda = 1.0;
+  else
+    lambda = kChi2Sig[i - 1] +
+             ((chi2 - kChi2Val[i - 1]) / (kChi2Val[i] - kChi2Val[i - 1])) * (kChi2Sig[i] - kChi2Sig[i - 1]);
+  lambda *= total / 400;
+  if (lambda > 1.0) lambda = 1.0;
+  for (int k = 0; k < 4; k++) {
+    pr[k] = (float)(pr[k] * lambda);                  // two float stores, like the reference (icm.cc:1324-1326)
+    pr[k] = (float)(pr[k] + (1.0 - lambda) * pp[k]);
+  }
+}
+
+extern "C" int gmg_trainer_finish_level(gmg_trainer* t, int level) {
+  GMG_CHECK(t, "gmg_trainer_finish_level: NULL trainer");
+  GMG_CHECK(level == t->next_level && level <= t->D, "gmg_trainer_finish_level: level %d out of order", level);
+  gmg_ctx* ctx = t->ctx;
+  const int W = t->W, P = t->P, N = t->N;
+  const int64_t nl = level_nodes(level), first = first_node_of(level);
+  const int64_t slab = (int64_t)P * nl * (W - 1) * 16;
+  t->h_counts.resize((size_t)slab);
+  GMG_CUDA(cudaMemcpyAsync(t->h_counts.data(), t->d_counts, (size_t)slab * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int32_t* C = t->h_counts.data();
+  const int64_t n_items = (int64_t)P * nl;
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t it = lo; it < hi; it++) {
+      const int f = (int)(it / nl);
+      const int64_t local = it % nl;
+      const int sub = (int)(first + local);
+      const int32_t* nc = C + (size_t)it * (W - 1) * 16;
+      int16_t* mp = &t->mip[(size_t)f * N + sub];
+      float* pr = &t->prob[((size_t)f * N + sub) * 4];
+      if (level > 0 && t->mip[(size_t)f * N + (sub - 1) / 4] < 0) {
+        *mp = -2;  // stopped at the parent (icm.cc:1104-1109)
+        continue;
+      }
+      int final_ct[4] = {0, 0, 0, 0}, sum = 0;
+      for (int i = 0, k = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++, k++) {
+          sum += nc[k];
+          final_ct[j] += nc[k];
+        }
+      double best;
+      int max_pos = choose_position(nc, W, sum, &best);
+      if (level == 0) {
+        // float arithmetic (icm.cc:1411-1413)
+        for (int j = 0; j < 4; j++) pr[j] = ((float)final_ct[j] + float(0.001 / 4)) / float(sum + 0.001);
+        *mp = (int16_t)max_pos;
+      } else {
+        if (best <= 1e-4 && sum < 400) max_pos = -1;  // MUT_INFO_EPSILON, SAMPLE_SIZE_BOUND
+        *mp = (int16_t)max_pos;
+        interpolate_probs(pr, &t->prob[((size_t)f * N + (sub - 1) / 4) * 4], final_ct);
+      }
+    }
+  };
+  unsigned hw = std::thread::hardware_concurrency();
+  int nthreads = (int)(hw ? hw : 1);
+  if (nthreads > 32) nthreads = 32;
+  if (n_items < 256) nthreads = 1;
+  if (nthreads <= 1) {
+    work(0, n_items);
+  } else {
+    std::vector<std::thread> pool;
+    int64_t chunk = (n_items + nthreads - 1) / nthreads;
+    for (int i = 0; i < nthreads; i++) {
+      int64_t lo = i * chunk, hi = lo + chunk < n_items ? lo + chunk : n_items;
+      if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto& th : pool) th.join();
+  }
+  // publish this level's branch positions to the device tree
+  std::vector<int8_t> lvl((size_t)nl);
+  for (int f = 0; f < P; f++) {
+    for (int64_t i = 0; i < nl; i++) {
+      int v = t->mip[(size_t)f * N + first + i];
+      lvl[(size_t)i] = (int8_t)(v < -2 ? -2 : v);
+    }
+    GMG_CUDA(cudaMemcpyAsync(t->d_mip + (size_t)f * N + first, lvl.data(), (size_t)nl, cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  t->next_level = level + 1;
+  return 0;
+}
+
+extern "C" int gmg_trainer_finish(gmg_trainer* t, gmg_icm** out) {
+  GMG_CHECK(t && out, "gmg_trainer_finish: NULL argument");
+  GMG_CHECK(t->next_level == t->D + 1, "gmg_trainer_finish: only %d of %d levels built", t->next_level, t->D + 1);
+  std::vector<float> logs(t->prob.size());
+  for (size_t i = 0; i < logs.size(); i++) logs[i] = (t->prob[i] > 0.0f) ? logf(t->prob[i]) : -FLT_MAX;
+  return gmg_icm_from_tables(t->ctx, t->W, t->D, t->P, t->mip.data(), logs.data(), out);
+}
+
+extern "C" int gmg_icm_train(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_allreduce_fn ar,
+                             void* user, gmg_icm** out) {
+  gmg_trainer* t = NULL;
+  if (gmg_trainer_create(ctx, s, w, d, p, reverse, &t)) return 1;
+  int rc = 0;
+  for (int level = 0; level <= d && rc == 0; level++) {
+    void* dptr = NULL;
+    int64_t n = 0;
+    rc = gmg_trainer_count_level(t, level, &dptr, &n);
+    if (rc == 0 && ar) {
+      if (ar(user, dptr, n, (void*)ctx->stream)) {
+        gmg_set_error("gmg_icm_train: all-reduce callback failed at level %d", level);
+        rc = 1;
+      }
+    }
+    if (rc == 0) rc = gmg_trainer_finish_level(t, level);
+  }
+  if (rc == 0) rc = gmg_trainer_finish(t, out);
+  gmg_trainer_free(t);
+  return rc;
+}

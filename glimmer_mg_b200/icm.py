@@ -1,0 +1,467 @@
+"""ctypes host mirror of the reference's ICM operator surface over libgmgicm.so.
+
+Names follow the reference (``/root/reference/src/ICM/icm.hh``): ``ICM.Read`` / ``Output`` /
+``Score_String`` / ``Cumulative_Score`` / ``Frame_Score`` / ``Full_Window_Prob`` /
+``Partial_Window_Prob`` / ``Build_Indep_WO_Stops``; ``ICMTraining.Train_Model``.  The batched calls
+(``SeqSet.score_all_frames`` = ``Score_All_Frames`` glimmer-mg.cc:1468, ``find_orfs`` = ``Find_Orfs``
+glimmer_base.cc:638, ``score_orfs_mg`` = ``Score_Orfs_Errors`` glimmer-mg.cc:1605, ``score_orfs_g3`` =
+``Score_Orfs`` glimmer3.cc:1275) are the device-side equivalents of the drivers' scoring half.
+
+Errors: the reference prints to stderr and exits (icm.cc:635-657); here every failing C-ABI call raises
+:class:`GmgError` with the same message text.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class GmgError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libgmgicm.so")
+
+
+class _Params(C.Structure):
+    _fields_ = [("min_gene_len", C.c_int32), ("allow_truncated", C.c_int32), ("allow_indels", C.c_int32),
+                ("allow_subs", C.c_int32), ("min_indel_orf_len", C.c_int32),
+                ("indel_quality_threshold", C.c_int32), ("indel_max", C.c_int32), ("ignore_score_len", C.c_int32),
+                ("indel_suffix_score_threshold", C.c_double), ("have_quality_file", C.c_int32),
+                ("n_start", C.c_int32), ("n_stop", C.c_int32), ("start_codon", (C.c_char * 4) * 8),
+                ("stop_codon", (C.c_char * 4) * 8)]
+
+
+ORF_DTYPE = np.dtype([("frame", "<i4"), ("stop_position", "<i4"), ("orf_len", "<i4"), ("gene_len", "<i4")])
+START_DTYPE = np.dtype([("j", "<i4"), ("pos", "<i4"), ("score", "<f8"), ("which", "<i4"), ("truncated", "<i4"),
+                        ("first", "<i4"), ("n_err", "<i4"), ("err_pos", "<i4", (2,)), ("err_type", "<i4", (2,))])
+assert START_DTYPE.itemsize == 48 and ORF_DTYPE.itemsize == 16
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+_lib = None
+
+
+def lib():
+    """Load libgmgicm.so.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise GmgError(f"{path} not found: build it with `make -C glimmer_mg_b200/csrc` "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    P = C.POINTER
+    sig = {
+        "gmg_abi_version": (i32, []),
+        "gmg_last_error": (C.c_char_p, []),
+        "gmg_ctx_create": (i32, [i32, vp, P(vp)]),
+        "gmg_ctx_destroy": (None, [vp]),
+        "gmg_ctx_sync": (i32, [vp]),
+        "gmg_ctx_launch_count": (i64, [vp]),
+        "gmg_ctx_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+        "gmg_ctx_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
+        "gmg_params_default": (None, [P(_Params), i32]),
+        "gmg_ignore_score_len": (i32, [C.c_double, P(_Params)]),
+        "gmg_icm_load": (i32, [vp, C.c_char_p, P(vp)]),
+        "gmg_icm_from_tables": (i32, [vp, i32, i32, i32, vp, vp, P(vp)]),
+        "gmg_icm_build_indep": (i32, [vp, C.c_double, P(C.c_char_p), i32, P(vp)]),
+        "gmg_icm_write": (i32, [vp, C.c_char_p]),
+        "gmg_icm_dims": (i32, [vp, vp]),
+        "gmg_icm_tables": (i32, [vp, vp, vp]),
+        "gmg_icm_free": (None, [vp]),
+        "gmg_seqset_create": (i32, [vp, vp, vp, i64, vp, P(vp)]),
+        "gmg_seqset_create_device": (i32, [vp, vp, vp, i64, vp, P(vp)]),
+        "gmg_seqset_free": (None, [vp]),
+        "gmg_seqset_total_bases": (i64, [vp]),
+        "gmg_seqset_gc_fraction": (i32, [vp, P(C.c_double)]),
+        "gmg_seqset_unpack": (i32, [vp, vp]),
+        "gmg_icm_score_strings": (i32, [vp, vp, vp, i32, vp]),
+        "gmg_icm_cumulative_score": (i32, [vp, vp, vp, i32, vp]),
+        "gmg_icm_frame_score": (i32, [vp, vp, vp, i32, vp]),
+        "gmg_icm_full_window_prob": (i32, [vp, vp, C.c_char_p, i32, P(C.c_double)]),
+        "gmg_icm_partial_window_prob": (i32, [vp, vp, i32, C.c_char_p, i32, P(C.c_double)]),
+        "gmg_score_all_frames": (i32, [vp, vp, vp, vp, vp, i32]),
+        "gmg_k1_score_planes": (i32, [vp, vp, vp]),
+        "gmg_find_orfs": (i32, [vp, vp, P(_Params), P(i64)]),
+        "gmg_get_orfs": (i32, [vp, vp, vp, vp]),
+        "gmg_set_orfs": (i32, [vp, vp, vp, vp]),
+        "gmg_score_orfs_g3": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
+        "gmg_score_orfs_mg": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
+        "gmg_get_starts": (i32, [vp, vp, vp, vp]),
+        "gmg_uncertified_count": (i64, [vp]),
+        "gmg_trainer_create": (i32, [vp, vp, i32, i32, i32, i32, P(vp)]),
+        "gmg_trainer_free": (None, [vp]),
+        "gmg_trainer_count_level": (i32, [vp, i32, P(vp), P(i64)]),
+        "gmg_trainer_finish_level": (i32, [vp, i32]),
+        "gmg_trainer_finish": (i32, [vp, P(vp)]),
+        "gmg_icm_train": (i32, [vp, vp, i32, i32, i32, i32, ALLREDUCE_FN, vp, P(vp)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError = the library does not export what include/gmg_icm.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise GmgError(lib().gmg_last_error().decode(errors="replace"))
+
+
+class Params:
+    """Options of the scoring half (glimmer-mg / glimmer3 command-line state)."""
+
+    def __init__(self, metagenomic=True, **kw):
+        self.c = _Params()
+        lib().gmg_params_default(C.byref(self.c), 1 if metagenomic else 0)
+        for k, v in kw.items():
+            self.set(k, v)
+
+    def set(self, k, v):
+        if k in ("start_codons", "stop_codons"):
+            arr = self.c.start_codon if k == "start_codons" else self.c.stop_codon
+            for i, s in enumerate(v):
+                arr[i].value = s.lower().encode()
+            setattr(self.c, "n_start" if k == "start_codons" else "n_stop", len(v))
+        else:
+            setattr(self.c, k, v)
+
+    def __getattr__(self, k):
+        return getattr(self.__dict__["c"], k)
+
+    @property
+    def stop_codons(self):
+        return [self.c.stop_codon[i].value.decode() for i in range(self.c.n_stop)]
+
+    def set_ignore_score_len(self, gc):
+        """Set_Ignore_Score_Len (glimmer_base.cc:2597)."""
+        self.c.ignore_score_len = lib().gmg_ignore_score_len(gc, C.byref(self.c))
+        return self.c.ignore_score_len
+
+
+class Context:
+    """One per GPU: device, stream, scratch.  ``stream`` may be a raw cudaStream_t (int) -- e.g.
+    ``torch.cuda.current_stream().cuda_stream`` -- so that torch events bracket our kernels."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        _check(lib().gmg_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        self.device = device
+
+    def sync(self):
+        _check(lib().gmg_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(lib().gmg_ctx_launch_count(self.h))
+
+    def d2h(self, dptr, count, dtype):
+        out = np.zeros(count, dtype)
+        _check(lib().gmg_ctx_memcpy_d2h(self.h, out.ctypes.data, C.c_void_p(dptr), out.nbytes))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().gmg_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ascii_concat(seqs):
+    """list of bytes/str -> (uint8 array, int64 offsets)."""
+    bs = [s if isinstance(s, (bytes, bytearray)) else s.encode() for s in seqs]
+    off = np.zeros(len(bs) + 1, np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    data = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(0, np.uint8)
+    return data, off
+
+
+class SeqSet:
+    """A batch of sequences packed 2 bits/base in HBM (Filter + lower-case applied on the device)."""
+
+    def __init__(self, ctx, seqs=None, ascii=None, offsets=None, qual=None, device_ptr=None, device_qual=None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        if seqs is not None:
+            ascii, offsets = _ascii_concat(seqs)
+        self.off = np.ascontiguousarray(offsets, np.int64)
+        self.n = len(self.off) - 1
+        if device_ptr is not None:
+            _check(lib().gmg_seqset_create_device(ctx.h, C.c_void_p(device_ptr), self.off.ctypes.data, self.n,
+                                                  C.c_void_p(device_qual) if device_qual else None, C.byref(self.h)))
+        else:
+            a = np.ascontiguousarray(ascii, np.uint8)
+            q = None if qual is None else np.ascontiguousarray(qual, np.uint8)
+            _check(lib().gmg_seqset_create(ctx.h, a.ctypes.data, self.off.ctypes.data, self.n,
+                                           None if q is None else q.ctypes.data, C.byref(self.h)))
+        self.total = int(self.off[-1])
+        self.n_orfs = 0
+        self.n_starts = 0
+
+    def close(self):
+        if self.h:
+            lib().gmg_seqset_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gc_fraction(self):
+        gc = C.c_double()
+        _check(lib().gmg_seqset_gc_fraction(self.h, C.byref(gc)))
+        return gc.value
+
+    def unpack(self):
+        out = np.zeros(self.total, np.uint8)
+        _check(lib().gmg_seqset_unpack(self.h, out.ctypes.data))
+        return out.tobytes()
+
+    # ---- Score_All_Frames ----
+    def score_all_frames(self, gene, indep):
+        """-> list of [6, len_i] float64 arrays (Frame_Scores, glimmer-mg.cc:140,1468)."""
+        out = np.zeros(6 * self.total, np.float64)
+        _check(lib().gmg_score_all_frames(self.ctx.h, gene.h, indep.h, self.h, out.ctypes.data, 0))
+        res = []
+        for i in range(self.n):
+            a, b = int(self.off[i]), int(self.off[i + 1])
+            res.append(out[6 * a:6 * b].reshape(6, b - a))
+        return res
+
+    def k1_score_planes(self, gene):
+        _check(lib().gmg_k1_score_planes(self.ctx.h, gene.h, self.h))
+
+    # ---- ORFs ----
+    def find_orfs(self, params):
+        n = C.c_int64()
+        _check(lib().gmg_find_orfs(self.ctx.h, self.h, C.byref(params.c), C.byref(n)))
+        self.n_orfs = n.value
+        return self.n_orfs
+
+    def get_orfs(self):
+        orfs = np.zeros(self.n_orfs, ORF_DTYPE)
+        off = np.zeros(self.n + 1, np.int64)
+        _check(lib().gmg_get_orfs(self.ctx.h, self.h, orfs.ctypes.data, off.ctypes.data))
+        return orfs, off
+
+    def set_orfs(self, orfs, orf_off):
+        orfs = np.ascontiguousarray(orfs, ORF_DTYPE)
+        orf_off = np.ascontiguousarray(orf_off, np.int64)
+        _check(lib().gmg_set_orfs(self.ctx.h, self.h, orfs.ctypes.data, orf_off.ctypes.data))
+        self.n_orfs = int(orf_off[-1])
+
+    # ---- scoring halves ----
+    def score_orfs_g3(self, gene, indep, params):
+        n = C.c_int64()
+        _check(lib().gmg_score_orfs_g3(self.ctx.h, gene.h, indep.h, self.h, C.byref(params.c), C.byref(n)))
+        self.n_starts = n.value
+        return self.n_starts
+
+    def score_orfs_mg(self, gene, indep, params):
+        n = C.c_int64()
+        _check(lib().gmg_score_orfs_mg(self.ctx.h, gene.h, indep.h, self.h, C.byref(params.c), C.byref(n)))
+        self.n_starts = n.value
+        return self.n_starts
+
+    def get_starts(self):
+        starts = np.zeros(self.n_starts, START_DTYPE)
+        off = np.zeros(self.n_orfs + 1, np.int64)
+        _check(lib().gmg_get_starts(self.ctx.h, self.h, starts.ctypes.data, off.ctypes.data))
+        return starts, off
+
+    @property
+    def uncertified(self):
+        return int(lib().gmg_uncertified_count(self.h))
+
+
+class ICM:
+    """ICM_t (icm.hh:116-213)."""
+
+    def __init__(self, ctx, handle=None):
+        self.ctx = ctx
+        self.h = handle if handle is not None else C.c_void_p()
+
+    # -- construction --
+    @classmethod
+    def Read(cls, ctx, path):
+        """ICM_t::Read (icm.cc:846)."""
+        h = C.c_void_p()
+        _check(lib().gmg_icm_load(ctx.h, os.fsencode(path), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_tables(cls, ctx, w, d, p, mip, prob):
+        mip = np.ascontiguousarray(mip, np.int16)
+        prob = np.ascontiguousarray(prob, np.float32)
+        h = C.c_void_p()
+        _check(lib().gmg_icm_from_tables(ctx.h, w, d, p, mip.ctypes.data, prob.ctypes.data, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def Build_Indep_WO_Stops(cls, ctx, gc_frac, stop_codons=("taa", "tag", "tga")):
+        """ICM_t(3,2,3).Build_Indep_WO_Stops (icm.cc:65)."""
+        arr = (C.c_char_p * len(stop_codons))(*[s.encode() for s in stop_codons])
+        h = C.c_void_p()
+        _check(lib().gmg_icm_build_indep(ctx.h, gc_frac, arr, len(stop_codons), C.byref(h)))
+        return cls(ctx, h)
+
+    def Output(self, path, binary_form=True):
+        """ICM_t::Output (icm.cc:729); only the binary form exists here."""
+        if not binary_form:
+            raise GmgError("text-form ICM output is not implemented (debug-only in the reference)")
+        _check(lib().gmg_icm_write(self.h, os.fsencode(path)))
+
+    def close(self):
+        if self.h:
+            lib().gmg_icm_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- accessors --
+    def dims(self):
+        d = np.zeros(4, np.int32)
+        _check(lib().gmg_icm_dims(self.h, d.ctypes.data))
+        return tuple(int(x) for x in d)
+
+    def Get_Model_Len(self):
+        return self.dims()[0]
+
+    def Get_Periodicity(self):
+        return self.dims()[2]
+
+    def tables(self):
+        w, d, p, n = self.dims()
+        mip = np.zeros((p, n), np.int16)
+        prob = np.zeros((p, n, 4), np.float32)
+        _check(lib().gmg_icm_tables(self.h, mip.ctypes.data, prob.ctypes.data))
+        return mip, prob
+
+    # -- scoring surface --
+    def _one(self, s):
+        return SeqSet(self.ctx, seqs=[s])
+
+    def Full_Window_Prob(self, window, frame):
+        out = C.c_double()
+        w = window if isinstance(window, bytes) else window.encode()
+        _check(lib().gmg_icm_full_window_prob(self.ctx.h, self.h, w, frame, C.byref(out)))
+        return out.value
+
+    def Partial_Window_Prob(self, predict_pos, string, frame):
+        out = C.c_double()
+        s = string if isinstance(string, bytes) else string.encode()
+        _check(lib().gmg_icm_partial_window_prob(self.ctx.h, self.h, predict_pos, s, frame, C.byref(out)))
+        return out.value
+
+    def Score_String(self, string, frame=0, length=None):
+        s = string if isinstance(string, bytes) else string.encode()
+        if length is not None:
+            s = s[:length]
+        return float(self.score_strings([s], frame)[0])
+
+    def score_strings(self, strings, frame=0):
+        """Score_String of many strings in one launch."""
+        ss = strings if isinstance(strings, SeqSet) else SeqSet(self.ctx, seqs=strings)
+        out = np.zeros(ss.n, np.float64)
+        _check(lib().gmg_icm_score_strings(self.ctx.h, self.h, ss.h, frame, out.ctypes.data))
+        return out
+
+    def Cumulative_Score(self, string, frame):
+        ss = self._one(string)
+        out = np.zeros(ss.total, np.float64)
+        _check(lib().gmg_icm_cumulative_score(self.ctx.h, self.h, ss.h, frame, out.ctypes.data))
+        return out
+
+    def Frame_Score(self, string, frame):
+        ss = self._one(string)
+        out = np.zeros(ss.total, np.float64)
+        _check(lib().gmg_icm_frame_score(self.ctx.h, self.h, ss.h, frame, out.ctypes.data))
+        return out
+
+
+def build_indep_wo_stops(ctx, gc, stops=("taa", "tag", "tga")):
+    return ICM.Build_Indep_WO_Stops(ctx, gc, stops)
+
+
+class ICMTraining:
+    """ICM_Training_t (icm.hh:190-213)."""
+
+    def __init__(self, ctx, model_len=12, model_depth=7, periodicity=3):
+        self.ctx = ctx
+        self.w, self.d, self.p = model_len, model_depth, periodicity
+
+    def Train_Model(self, data, reverse=False, allreduce=None):
+        """Train_Model (icm.cc:1356).  ``data``: training strings (or a SeqSet); ``reverse`` = build-icm -r.
+        ``allreduce(dptr, count, stream)``: sums ``count`` int32 at device address ``dptr`` across ranks
+        (ordered on ``stream``) -- the one exchange step of multi-GPU training."""
+        ss = data if isinstance(data, SeqSet) else SeqSet(self.ctx, seqs=data)
+        h = C.c_void_p()
+        if allreduce is None:
+            cb = C.cast(None, ALLREDUCE_FN)
+        else:
+            def _cb(user, dptr, count, stream):
+                try:
+                    allreduce(dptr, count, stream)
+                    return 0
+                except Exception:  # pragma: no cover
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = ALLREDUCE_FN(_cb)
+        _check(lib().gmg_icm_train(self.ctx.h, ss.h, self.w, self.d, self.p, 1 if reverse else 0, cb, None, C.byref(h)))
+        return ICM(self.ctx, h)
+
+    # split form, for callers that want to drive the levels themselves
+    def levels(self, data, reverse=False):
+        ss = data if isinstance(data, SeqSet) else SeqSet(self.ctx, seqs=data)
+        t = C.c_void_p()
+        _check(lib().gmg_trainer_create(self.ctx.h, ss.h, self.w, self.d, self.p, 1 if reverse else 0, C.byref(t)))
+        return _Trainer(self.ctx, t, ss, self.d)
+
+
+class _Trainer:
+    def __init__(self, ctx, h, ss, depth):
+        self.ctx, self.h, self.ss, self.depth = ctx, h, ss, depth
+
+    def count_level(self, level):
+        ptr, n = C.c_void_p(), C.c_int64()
+        _check(lib().gmg_trainer_count_level(self.h, level, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def finish_level(self, level):
+        _check(lib().gmg_trainer_finish_level(self.h, level))
+
+    def finish(self):
+        h = C.c_void_p()
+        _check(lib().gmg_trainer_finish(self.h, C.byref(h)))
+        return ICM(self.ctx, h)
+
+    def close(self):
+        if self.h:
+            lib().gmg_trainer_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

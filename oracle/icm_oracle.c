@@ -749,7 +749,7 @@ int orc_mg_score_orfs(const orc_icm* gene, const orc_icm* indep, const char* seq
     int end_point = (orfs[i].frame > 0) ? orfs[i].stop_position - 1 : orfs[i].stop_position + 3;
     score_orf_starts(&c, orfs[i].frame, &S, end_point, 0, 0, none);
     for (int s = start_off[i]; s < S.n; s++) /* boost long ORFs (:1649-1651) */
-      if (S.v[s].j > p->ignore_score_len && !(S.v[s].score > 0.0)) S.v[s].score = 0.0;
+      if (S.v[s].j > p->ignore_score_len && 0.0 > S.v[s].score) S.v[s].score = 0.0; /* Max(0.0, score) */
   }
   start_off[n_orf] = S.n;
   *starts = S.v;
@@ -836,7 +836,7 @@ int orc_g3_score_orfs(const orc_icm* gene, const orc_icm* indep, const char* seq
       else k--;
     }
     for (int s = start_off[i]; s < S.n; s++)
-      if (S.v[s].j > p->ignore_score_len && !(S.v[s].score > 0.0)) S.v[s].score = 0.0;
+      if (S.v[s].j > p->ignore_score_len && 0.0 > S.v[s].score) S.v[s].score = 0.0; /* Max(0.0, score) */
   }
   start_off[n_orf] = S.n;
   *starts = S.v;

@@ -31,7 +31,7 @@ def boost(starts, ignore_score_len):
     """long-ORF boost (glimmer-mg.cc:1649-1651) applied to dumped (pre-boost) starts."""
     out = []
     for (j, pos, sc, w, tr, fi, er) in starts:
-        if j > ignore_score_len and not (np.uint64(sc).view(np.float64) > 0):
+        if j > ignore_score_len and 0.0 > np.uint64(sc).view(np.float64):
             sc = 0
         out.append((j, pos, sc, w, tr, fi, er))
     return out

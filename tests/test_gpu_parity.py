@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libgmgicm.so) against the oracle
+(oracle/icm_oracle.c), the reference's golden vectors and dumps of the unmodified reference.
+
+Bar: bit-exact for every integer / index output AND for every FP64 score (the sums are formed in
+the reference's order, or certified exact -- DESIGN.md); trained models byte-identical.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from dumps import boost, parse_dump, starts_as_tuples
+
+pytestmark = pytest.mark.gpu
+G = O.GOLDEN
+
+
+@pytest.fixture(scope="module")
+def gm():
+    import glimmer_mg_b200 as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def ctx(gm):
+    c = gm.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def reads():
+    return O.read_fasta(os.path.join(G, "seqs.fa.gz"))
+
+
+@pytest.fixture(scope="module")
+def genome():
+    return O.read_fasta(os.path.join(G, "NC_000915.fna.gz"))[0][1]
+
+
+def _gc_oracle(seqs):
+    return O.lib().orc_gc_fraction(O.cstr_array(seqs), (C.c_int * len(seqs))(*[len(s) for s in seqs]), len(seqs))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def test_model_io_and_tables(gm, ctx, tmp_path):
+    for name in ("NC_000915.icm", "cluster-4.icm", "seqs.cluster-4.run1.filt.gicm"):
+        path = os.path.join(G, name)
+        m = gm.ICM.Read(ctx, path)
+        o = O.lib().orc_icm_read(path.encode())
+        mip, prob = m.tables()
+        omip, oprob = O.icm_tables(o)
+        assert (mip == omip).all() and (prob.view(np.uint32) == oprob.view(np.uint32)).all()
+        out = str(tmp_path / "w.icm")
+        m.Output(out)
+        assert open(out, "rb").read() == open(path, "rb").read()
+    with pytest.raises(gm.GmgError):
+        gm.ICM.Read(ctx, str(tmp_path / "missing.icm"))
+    bad = tmp_path / "bad.icm"
+    bad.write_bytes(b"x" * 100)
+    with pytest.raises(gm.GmgError, match="ERROR reading ICM header"):
+        gm.ICM.Read(ctx, str(bad))
+
+
+def test_build_indep_wo_stops(gm, ctx):
+    for gc, stops in ((0.3887516210824964, ("taa", "tag", "tga")), (0.5, ("taa", "tag", "tga")),
+                      (0.66, ("taa", "tag"))):
+        m = gm.ICM.Build_Indep_WO_Stops(ctx, gc, stops)
+        mip, prob = m.tables()
+        omip, oprob = O.icm_tables(O.build_indep(gc, stops))
+        assert (mip == omip).all() and (prob.view(np.uint32) == oprob.view(np.uint32)).all()
+
+
+def test_filter_pack_gc(gm, ctx):
+    rng = np.random.default_rng(1)
+    alphabet = np.frombuffer(b"acgtACGTnNrRyYsSwWmMkKbBdDhHvVxX*-", np.uint8)
+    seqs = [alphabet[rng.integers(0, len(alphabet), n)].tobytes() for n in (0, 1, 31, 32, 33, 64, 1000, 5, 0, 777)]
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    assert ss.unpack() == b"".join(O.filter_lower(s) for s in seqs)
+    assert ss.gc_fraction() == _gc_oracle(seqs)
+
+
+@pytest.mark.parametrize("k", [4, 5])
+def test_score_string_known_answers(gm, ctx, reads, k):
+    m = gm.ICM.Read(ctx, os.path.join(G, f"cluster-{k}.icm"))
+    gold = [l.split() for l in open(os.path.join(G, f"icm-{k}.scores.tmp"))]
+    got = m.score_strings([s for _, s in reads], 0)
+    om = O.lib().orc_icm_read(os.path.join(G, f"cluster-{k}.icm").encode())
+    for (h, s), (gh, gv), v in zip(reads, gold, got):
+        assert "%.4f" % v == "%.4f" % float(gv)
+        assert v == O.lib().orc_score_string(om, s, len(s), 0)
+
+
+def test_scalar_surface_matches_oracle(gm, ctx, reads):
+    path = os.path.join(G, "NC_000915.icm")
+    m = gm.ICM.Read(ctx, path)
+    om = O.lib().orc_icm_read(path.encode())
+    L = O.lib()
+    for _, s0 in reads[:6]:
+        s = O.filter_lower(s0)
+        for f in range(3):
+            a = np.zeros(len(s))
+            L.orc_frame_score(om, s, len(s), f, a.ctypes.data)
+            assert (_bits(m.Frame_Score(s0, f)) == _bits(a)).all()
+            L.orc_cumulative_score(om, s, len(s), f, a.ctypes.data)
+            assert (_bits(m.Cumulative_Score(s0, f)) == _bits(a)).all()
+        for n in (1, 5, 11, 12, 13, 40):
+            assert m.Score_String(s0, 1, n) == L.orc_score_string(om, s, n, 1)
+        assert m.Full_Window_Prob(s[20:32], 2) == L.orc_full_window_prob(om, s[20:32], 2)
+        assert m.Partial_Window_Prob(7, s, 1) == L.orc_partial_window_prob(om, 7, s, 1)
+    assert len(m.score_strings([b""], 0)) == 1 and m.score_strings([b""], 0)[0] == 0.0
+
+
+def test_score_all_frames_bit_exact(gm, ctx, reads):
+    path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, path)
+    og = O.lib().orc_icm_read(path.encode())
+    seqs = [s for _, s in reads[:60]]
+    seqs += [b"", b"a", b"acgtacgtacg", b"acgtacgtacgt", seqs[0][:13], seqs[1][:100], b"n" * 40]  # ragged / short
+    gc = _gc_oracle(seqs)
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    oi = O.build_indep(gc)
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    fs = ss.score_all_frames(gene, indep)
+    for s0, got in zip(seqs, fs):
+        want = O.score_all_frames(og, oi, O.filter_lower(s0))
+        assert got.shape == want.shape
+        assert (_bits(got) == _bits(want)).all()
+    # golden Frame_Scores of the unmodified reference (first 25 reads)
+    recs = parse_dump(os.path.join(G, "mg_plain_120.dump.gz"))
+    gc = _gc_oracle([s for _, s in reads[:120]])
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    fs = gm.SeqSet(ctx, seqs=[s for _, s in reads[:25]]).score_all_frames(gene, indep)
+    byhdr = {r["hdr"]: r for r in recs}
+    n = 0
+    for (h, _), got in zip(reads[:25], fs):
+        if h in byhdr and byhdr[h]["fs"]:
+            for f in range(6):
+                assert (_bits(got[f]) == byhdr[h]["fs"][f]).all()
+            n += 1
+    assert n >= 20
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(allow_indels=1), dict(allow_subs=1), dict(allow_truncated=0)])
+def test_find_orfs_reads(gm, ctx, reads, flags):
+    seqs = [s for _, s in reads[:150]] + [b"", b"acgt" * 10, b"atg" + b"aaa" * 30 + b"taa"]
+    p = gm.Params(True, **flags)
+    op = O.params(True, **flags)
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    n = ss.find_orfs(p)
+    orfs, off = ss.get_orfs()
+    assert off[-1] == n
+    for i, s0 in enumerate(seqs):
+        want = O.find_orfs(O.filter_lower(s0), op)
+        got = orfs[off[i]:off[i + 1]]
+        assert got.tolist() == want.tolist(), i
+
+
+@pytest.mark.parametrize("truncated", [0, 1])
+def test_find_orfs_genome(gm, ctx, genome, truncated):
+    s0 = genome[:400000]
+    p = gm.Params(False, allow_truncated=truncated)
+    op = O.params(False, allow_truncated=truncated)
+    ss = gm.SeqSet(ctx, seqs=[s0])
+    ss.find_orfs(p)
+    orfs, off = ss.get_orfs()
+    want = O.find_orfs(O.filter_lower(s0), op)
+    assert orfs.tolist() == want.tolist()
+
+
+@pytest.mark.parametrize("tag,n,flags", [("plain", 120, {}), ("indel", 40, dict(allow_indels=1)),
+                                         ("sub", 80, dict(allow_subs=1))])
+def test_mg_start_lists_match_reference_dump(gm, ctx, reads, tag, n, flags):
+    """glimmer-mg -u 1.0 -m NC_000915.icm [-i|-s]: ORFs and raw start_list of every ORF identical to the
+    unmodified reference (order, j, pos, which, flags, error lists and FP64 score BITS)."""
+    recs = parse_dump(os.path.join(G, f"mg_{tag}_{n}.dump.gz"))
+    sub = reads[:n]
+    gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+    ss = gm.SeqSet(ctx, seqs=[s for _, s in sub])
+    gc = ss.gc_fraction()
+    assert gc == _gc_oracle([s for _, s in sub])
+    p = gm.Params(True, **flags)
+    p.set_ignore_score_len(gc)
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc, p.stop_codons)
+    ss.find_orfs(p)
+    ss.score_orfs_mg(gene, indep, p)
+    assert ss.uncertified == 0
+    orfs, ooff = ss.get_orfs()
+    starts, soff = ss.get_starts()
+    byhdr = {r["hdr"]: r for r in recs}
+    total = 0
+    for i, (h, _) in enumerate(sub):
+        r = byhdr.get(h)
+        mine = orfs[ooff[i]:ooff[i + 1]]
+        if r is None:
+            assert len(mine) == 0
+            continue
+        assert [o["o"] for o in r["orfs"]] == [tuple(x) for x in mine.tolist()]
+        for k, o in enumerate(r["orfs"]):
+            oi = ooff[i] + k
+            got = starts_as_tuples(starts[soff[oi]:soff[oi + 1]])
+            assert got == boost(o["starts"], p.ignore_score_len), (h, o["o"])
+            total += len(got)
+    assert total > 1000
+
+
+def test_mg_start_lists_match_oracle_more_reads(gm, ctx, reads):
+    """A larger differential run against the oracle, indel mode with a quality 'file'."""
+    rng = np.random.default_rng(7)
+    sub = [s for _, s in reads[300:380]] + [b"", b"acg"]
+    quals = [rng.integers(1, 41, len(s)).astype(np.uint8) for s in sub]
+    gene_path = os.path.join(G, "seqs.cluster-5.run1.filt.gicm")
+    gene = gm.ICM.Read(ctx, gene_path)
+    og = O.lib().orc_icm_read(gene_path.encode())
+    ss = gm.SeqSet(ctx, seqs=sub, qual=np.concatenate(quals))
+    gc = ss.gc_fraction()
+    for flags in (dict(allow_indels=1, have_quality_file=1), dict(allow_indels=1, allow_subs=1)):
+        p = gm.Params(True, **flags)
+        p.set_ignore_score_len(gc)
+        op = O.params(True, **flags)
+        op.ignore_score_len = p.ignore_score_len
+        indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+        oi = O.build_indep(gc)
+        ss.find_orfs(p)
+        ss.score_orfs_mg(gene, indep, p)
+        orfs, ooff = ss.get_orfs()
+        starts, soff = ss.get_starts()
+        for i, s0 in enumerate(sub):
+            s = O.filter_lower(s0)
+            want_orfs = O.find_orfs(s, op)
+            assert orfs[ooff[i]:ooff[i + 1]].tolist() == want_orfs.tolist()
+            q = quals[i].astype(np.int32) if flags.get("have_quality_file") else None
+            woff, wst = O.mg_score_orfs(og, oi, s, op, want_orfs, q)
+            for k in range(len(want_orfs)):
+                o = ooff[i] + k
+                assert starts_as_tuples(starts[soff[o]:soff[o + 1]]) == starts_as_tuples(wst[woff[k]:woff[k + 1]])
+
+
+def test_g3_start_lists_match_reference_dump(gm, ctx, genome):
+    recs = parse_dump(os.path.join(G, "g3_300k.dump.gz"))
+    s0 = genome[:(300000 // 70) * 70]
+    gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+    ss = gm.SeqSet(ctx, seqs=[s0])
+    gc = ss.gc_fraction()
+    p = gm.Params(False)
+    p.set_ignore_score_len(gc)
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    ss.find_orfs(p)
+    ss.score_orfs_g3(gene, indep, p)
+    orfs, _ = ss.get_orfs()
+    starts, soff = ss.get_starts()
+    mine = {tuple(o): starts_as_tuples(starts[soff[i]:soff[i + 1]]) for i, o in enumerate(orfs.tolist())}
+    assert len(recs[0]["orfs"]) > 2000
+    for o in recs[0]["orfs"]:
+        assert mine[o["o"]] == o["starts"], o["o"]
+
+
+@pytest.mark.parametrize("truncated", [0, 1])
+def test_g3_full_genome_matches_oracle(gm, ctx, genome, truncated):
+    path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, path)
+    og = O.lib().orc_icm_read(path.encode())
+    ss = gm.SeqSet(ctx, seqs=[genome])
+    gc = ss.gc_fraction()
+    p = gm.Params(False, allow_truncated=truncated)
+    p.set_ignore_score_len(gc)
+    op = O.params(False, allow_truncated=truncated)
+    op.ignore_score_len = p.ignore_score_len
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    oi = O.build_indep(gc)
+    ss.find_orfs(p)
+    ss.score_orfs_g3(gene, indep, p)
+    orfs, _ = ss.get_orfs()
+    starts, soff = ss.get_starts()
+    s = O.filter_lower(genome)
+    want_orfs = O.find_orfs(s, op)
+    assert orfs.tolist() == want_orfs.tolist()
+    woff, wst = O.g3_score_orfs(og, oi, s, op, want_orfs)
+    assert (soff == woff).all()
+    for f in ("j", "pos", "which", "truncated", "first"):
+        assert (starts[f] == wst[f]).all(), f
+    assert (_bits(starts["score"]) == _bits(wst["score"])).all()
+
+
+def _train_strings(name):
+    return [s.lower() for _, s in O.read_fasta(os.path.join(G, name))]
+
+
+@pytest.mark.parametrize("fasta,depth,period", [("seqs.cluster-4.run1.filt.gene.fasta.gz", 7, 3),
+                                                ("seqs.cluster-5.run1.filt.gene.fasta.gz", 7, 3),
+                                                ("seqs.cluster-5.run1.filt.gene.fasta.gz", 3, 1),
+                                                ("NC_000915.train.gz", 7, 3)])
+def test_training_byte_identical_to_oracle(gm, ctx, tmp_path, fasta, depth, period):
+    """build-icm -r: the model file written from the device-counted tree equals the oracle's (and therefore,
+    by tests/test_oracle.py, the reference's) byte for byte."""
+    strs = _train_strings(fasta)
+    m = gm.ICMTraining(ctx, 12, depth, period).Train_Model(strs, reverse=True)
+    rev = [s[::-1] for s in strs]
+    o = O.lib().orc_icm_train(O.cstr_array(rev), len(rev), 12, depth, period)
+    a, b = str(tmp_path / "a.icm"), str(tmp_path / "b.icm")
+    m.Output(a)
+    O.lib().orc_icm_write(o, b.encode())
+    assert open(a, "rb").read() == open(b, "rb").read()
+    # not reversed, strings pre-reversed on the host: same model
+    m2 = gm.ICMTraining(ctx, 12, depth, period).Train_Model(rev, reverse=False)
+    m2.Output(a)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_count_level_matches_oracle(gm, ctx):
+    """K4 in isolation: the count slab of every level equals Count_Char_Pairs(_Restricted) of the oracle."""
+    strs = [s[::-1] for s in _train_strings("seqs.cluster-5.run1.filt.gene.fasta.gz")]
+    arr = O.cstr_array(strs)
+    omip, _ = O.icm_tables(O.lib().orc_icm_train(arr, len(strs), 12, 7, 3))  # the finished tree
+    om = O.lib().orc_icm_new(12, 7, 3)
+    tr = gm.ICMTraining(ctx, 12, 7, 3).levels(strs, reverse=False)
+    for level in range(0, 8):
+        ptr, n = tr.count_level(level)
+        nl = 4 ** level
+        first = (nl - 1) // 3
+        assert n == 3 * nl * 11 * 16
+        got = ctx.d2h(ptr, n, np.int32).reshape(3, nl, 11, 16)
+        full = np.zeros(3 * 21845 * 11 * 16, np.int32)
+        O.lib().orc_count_level(om, arr, len(strs), level, full.ctypes.data)
+        assert (got == full.reshape(3, 21845, 11, 16)[:, first:first + nl]).all(), level
+        tr.finish_level(level)
+        for f in range(3):  # give the oracle's walk this level's branch positions
+            for i in range(first, first + nl):
+                om.contents.mip[f * 21845 + i] = int(omip[f, i])
+    m = tr.finish()
+    assert (m.tables()[0] == omip).all()
