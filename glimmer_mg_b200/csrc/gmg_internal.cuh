@@ -12,6 +12,8 @@
 #define GMG_MAX_W 32      // window bases held in one 64-bit register
 #define GMG_MAX_DEPTH 12
 #define GMG_PAD_WORDS 4   // 64-bit words of zero padding before/after the packed bases
+#define GMG_NPROF 8
+#define GMG_PROF_RING 64
 
 void gmg_set_error(const char* fmt, ...);
 
@@ -44,6 +46,18 @@ struct DevIcm {
   const float* prob;
 };
 
+// "marker-indexed" view of the same ICM for the K1 fast path (W <= 16, D <= 8): node on level l with
+// in-level index i is addressed by m = 4^l + i (a leading 1 marks the level), so a child is
+// m' = 4 m + base with no "+1" and no per-level offsets, and one funnel shift descends one level.
+//  msh    uint8 [P][2 * 4^(D-1)]  30 - 2 * mut_info_pos of the descendable nodes (left shift that brings the
+//                                 branch base to the top two bits of the 32-bit window register); 255 = stop
+//  mprob  float [P][2 * 4^D][4]   log-probabilities, cut nodes pre-resolved to their parent's row
+struct DevIcmFast {
+  int valid, W, D, P, inner_m, leaves_m;
+  const uint8_t* msh;
+  const float* mprob;
+};
+
 struct gmg_ctx {
   int device;
   cudaStream_t stream;
@@ -54,7 +68,17 @@ struct gmg_ctx {
   void* scratch[8];
   size_t scratch_bytes[8];
   double* h_penalty;  // pinned staging
+  // per-kernel device timing (gmg_ctx_profile): event pairs around the launches of each kernel class
+  int prof_on;
+  int prof_n[GMG_NPROF];
+  cudaEvent_t prof_ev[GMG_NPROF][GMG_PROF_RING][2];
+  double prof_ms[GMG_NPROF];
+  int64_t prof_launches[GMG_NPROF];
 };
+
+// kernel classes of gmg_ctx_profile_read (values are part of the C-ABI, see gmg_icm.h)
+int gmg_prof_begin(gmg_ctx* ctx, int cls);
+void gmg_prof_end(gmg_ctx* ctx, int cls);
 
 struct gmg_icm {
   gmg_ctx* ctx;
@@ -64,6 +88,9 @@ struct gmg_icm {
   int8_t* d_mip;
   float* d_prob;
   DevIcm dev;
+  uint8_t* d_msh;
+  float* d_mprob;
+  DevIcmFast fast;
 };
 
 struct gmg_seqset {
@@ -76,7 +103,7 @@ struct gmg_seqset {
   uint64_t* d_words;         // 2-bit bases, base i at bits 2*(i%32) of word i/32
   int32_t* d_blk2seq;        // sequence holding base 32*b
   uint8_t* d_qual;           // per-base quality (input file values) or NULL
-  unsigned long long* d_gc;  // {gc count}
+  unsigned long long* d_gc;  // {gc count, ORFs of the last g3 scoring call that took the ordered-sum fallback}
   // ORFs
   int64_t n_orfs;
   gmg_orf* d_orfs;

@@ -51,8 +51,25 @@ extern "C" int gmg_ctx_create(int device, void* stream, gmg_ctx** out) {
     GMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  // seqset / ORF / start buffers come from the device's stream-ordered pool; keep freed blocks cached
+  // so that steady-state batches allocate without touching the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = c;
   return 0;
+}
+
+extern "C" int gmg_host_alloc(size_t bytes, void** out) {
+  GMG_CHECK(out, "gmg_host_alloc: out is NULL");
+  GMG_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+
+extern "C" void gmg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
@@ -61,8 +78,62 @@ extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
   for (int i = 0; i < 8; i++)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->h_penalty) cudaFreeHost(c->h_penalty);
+  for (int k = 0; k < GMG_NPROF; k++)
+    for (int i = 0; i < GMG_PROF_RING; i++)
+      for (int e = 0; e < 2; e++)
+        if (c->prof_ev[k][i][e]) cudaEventDestroy(c->prof_ev[k][i][e]);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// ---- per-kernel device timing ---------------------------------------------------------------
+static int prof_drain(gmg_ctx* c, int cls) {
+  if (c->prof_n[cls] == 0) return 0;
+  GMG_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->prof_n[cls]; i++) {
+    float ms = 0.f;
+    GMG_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[cls][i][0], c->prof_ev[cls][i][1]));
+    c->prof_ms[cls] += ms;
+  }
+  c->prof_n[cls] = 0;
+  return 0;
+}
+
+int gmg_prof_begin(gmg_ctx* c, int cls) {
+  if (!c->prof_on) return 0;
+  if (c->prof_n[cls] == GMG_PROF_RING && prof_drain(c, cls)) return 1;
+  cudaEvent_t* ev = c->prof_ev[cls][c->prof_n[cls]];
+  if (!ev[0]) {
+    GMG_CUDA(cudaEventCreate(&ev[0]));
+    GMG_CUDA(cudaEventCreate(&ev[1]));
+  }
+  GMG_CUDA(cudaEventRecord(ev[0], c->stream));
+  return 0;
+}
+
+void gmg_prof_end(gmg_ctx* c, int cls) {
+  if (!c->prof_on) return;
+  cudaEventRecord(c->prof_ev[cls][c->prof_n[cls]][1], c->stream);
+  c->prof_n[cls]++;
+  c->prof_launches[cls]++;
+}
+
+extern "C" int gmg_ctx_profile(gmg_ctx* c, int enable) {
+  GMG_CHECK(c, "gmg_ctx_profile: NULL context");
+  for (int k = 0; k < GMG_NPROF; k++)
+    if (prof_drain(c, k)) return 1;
+  c->prof_on = enable ? 1 : 0;
+  return 0;
+}
+
+extern "C" int gmg_ctx_profile_read(gmg_ctx* c, int cls, double* ms, int64_t* launches) {
+  GMG_CHECK(c && cls >= 0 && cls < GMG_NPROF, "gmg_ctx_profile_read: bad argument");
+  if (prof_drain(c, cls)) return 1;
+  if (ms) *ms = c->prof_ms[cls];
+  if (launches) *launches = c->prof_launches[cls];
+  c->prof_ms[cls] = 0.0;
+  c->prof_launches[cls] = 0;
+  return 0;
 }
 
 extern "C" int gmg_ctx_sync(gmg_ctx* c) {
@@ -189,6 +260,43 @@ static int icm_upload(gmg_icm* m) {
   GMG_CUDA(cudaMemcpyAsync(m->d_mip, mip8.data(), mip8.size(), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(m->d_prob, eff.data(), eff.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  // marker-indexed tables of the K1 fast path
+  m->fast.valid = 0;
+  if (m->W <= 16 && D >= 1 && D <= 8) {
+    size_t inner_m = 2, leaves_m = 8;  // 2 * 4^(D-1), 2 * 4^D
+    for (int i = 1; i < D; i++) inner_m *= 4;
+    leaves_m = inner_m * 4;
+    std::vector<uint8_t> msh((size_t)P * inner_m, 255);
+    std::vector<float> mprob((size_t)P * leaves_m * 4, 0.0f);
+    for (int f = 0; f < P; f++) {
+      size_t first = 0, width = 1;  // dense index of the level's first node, nodes on the level
+      for (int l = 0; l <= D; l++) {
+        for (size_t i = 0; i < width; i++) {
+          const size_t n = first + i, mk = width + i;
+          if (l < D) {
+            int v = m->mip[(size_t)f * N + n];
+            msh[(size_t)f * inner_m + mk] = (uint8_t)(v >= 0 ? 30 - 2 * v : 255);
+          }
+          memcpy(&mprob[((size_t)f * leaves_m + mk) * 4], &eff[((size_t)f * N + n) * 4], 4 * sizeof(float));
+        }
+        first += width;
+        width *= 4;
+      }
+    }
+    GMG_CUDA(cudaMalloc(&m->d_msh, msh.size() + 16));
+    GMG_CUDA(cudaMalloc(&m->d_mprob, mprob.size() * sizeof(float) + 16));
+    GMG_CUDA(cudaMemcpyAsync(m->d_msh, msh.data(), msh.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaMemcpyAsync(m->d_mprob, mprob.data(), mprob.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->fast.valid = 1;
+    m->fast.W = m->W;
+    m->fast.D = D;
+    m->fast.P = P;
+    m->fast.inner_m = (int)inner_m;
+    m->fast.leaves_m = (int)leaves_m;
+    m->fast.msh = m->d_msh;
+    m->fast.mprob = m->d_mprob;
+  }
   m->dev.W = m->W;
   m->dev.D = D;
   m->dev.P = P;
@@ -219,6 +327,8 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->prob.assign(h_prob, h_prob + (size_t)p * n * 4);
   m->d_mip = NULL;
   m->d_prob = NULL;
+  m->d_msh = NULL;
+  m->d_mprob = NULL;
   for (size_t i = 0; i < m->mip.size(); i++)
     if (m->mip[i] >= w - 1 && w > 1) {
       gmg_set_error("ICM node %zu has mut_info_pos %d outside the context window (len %d)", i, m->mip[i], w);
@@ -341,6 +451,8 @@ extern "C" void gmg_icm_free(gmg_icm* m) {
   cudaSetDevice(m->ctx->device);
   if (m->d_mip) cudaFree(m->d_mip);
   if (m->d_prob) cudaFree(m->d_prob);
+  if (m->d_msh) cudaFree(m->d_msh);
+  if (m->d_mprob) cudaFree(m->d_mprob);
   delete m;
 }
 

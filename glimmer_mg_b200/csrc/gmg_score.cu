@@ -231,12 +231,116 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
   }
 }
 
+// K1 fast path (W <= 16, D <= 8; the build-icm defaults are 12 / 7): marker-indexed tables (DevIcmFast), 32-bit
+// window registers, one LDS + one compare + two funnel/shift instructions per tree level and walk.
+//   window register: window position k at bits 2k for BOTH strands (the forward strand's bases are
+//   order-reversed once per thread with BREV + a pair swap), so both strands share one shift table.
+// One CTA of 1024 threads, two per SM (48 KB of shift tables per SM leaves ~180 KB of L1 for the leaf gathers).
+template <int kD>  // kD > 0: depth known at compile time (table offsets fold into the LDS immediates); 0: runtime depth
+__global__ void __launch_bounds__(1024, 2) k1_planes_fast(DevIcmFast gm, const uint32_t* __restrict__ w32,
+                                                          const int64_t* __restrict__ off,
+                                                          const int32_t* __restrict__ blk2seq, int64_t total,
+                                                          float* __restrict__ planes) {
+  extern __shared__ uint8_t s_sh[];
+  {
+    const int n16 = (3 * gm.inner_m) >> 4;  // inner_m is a multiple of 16 for D >= 3; tail handled below
+    const uint4* src = reinterpret_cast<const uint4*>(gm.msh);
+    uint4* dst = reinterpret_cast<uint4*>(s_sh);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = (n16 << 4) + threadIdx.x; i < 3 * gm.inner_m; i += blockDim.x) s_sh[i] = gm.msh[i];
+  }
+  __syncthreads();
+  const int W = gm.W, D = kD > 0 ? kD : gm.D;
+  const int inner_m = kD > 0 ? (2 << (2 * (kD > 0 ? kD - 1 : 0))) : gm.inner_m;
+  const int wsh = 32 - 2 * W, psh = 2 * (W - 1);
+  const uint8_t* sh0 = s_sh;
+  const uint8_t* sh1 = s_sh + inner_m;
+  const uint8_t* sh2 = s_sh + 2 * inner_m;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s;
+    SeqView sv = locate(off, blk2seq, p, &s);
+    const int q = (int)(p - sv.a);
+    // forward: bases p .. p+15; reverse: bases p-(W-1) .. p+16-W (16 bases starting W-1 to the left)
+    const int64_t pr = p - (W - 1);
+    const uint32_t* wf = w32 + (p >> 4);
+    const uint32_t* wr = w32 + (pr >> 4);
+    const uint32_t rawf = __funnelshift_r(__ldg(wf), __ldg(wf + 1), 2 * (int)(p & 15));
+    const uint32_t rawr = __funnelshift_r(__ldg(wr), __ldg(wr + 1), 2 * (int)(pr & 15));
+    uint32_t cf = __brev(rawf);
+    cf = ((cf >> 1) & 0x55555555u) | ((cf & 0x55555555u) << 1);
+    cf >>= wsh;                  // window position k <-> base p + W-1-k
+    const uint32_t cr = ~rawr;   // window position k <-> complement of base p - (W-1) + k
+    int lf = q + W - sv.len;     // first available window position (0 = full window)
+    lf = lf > 0 ? lf : 0;
+    int lr = W - 1 - q;
+    lr = lr > 0 ? lr : 0;
+    const unsigned lshf = 30 - 2 * lf, lshr = 30 - 2 * lr;  // a node may be descended iff its shift <= this
+    uint32_t m0 = 1, m1 = 1, m2 = 1, m3 = 1, m4 = 1, m5 = 1;
+    bool a0 = true, a1 = true, a2 = true, a3 = true, a4 = true, a5 = true;
+#pragma unroll
+    for (int l = 0; l < D; l++) {
+      const unsigned s0 = sh0[m0], s1 = sh1[m1], s2 = sh2[m2], s3 = sh0[m3], s4 = sh1[m4], s5 = sh2[m5];
+      a0 = a0 && (s0 <= lshf);
+      a1 = a1 && (s1 <= lshf);
+      a2 = a2 && (s2 <= lshf);
+      a3 = a3 && (s3 <= lshr);
+      a4 = a4 && (s4 <= lshr);
+      a5 = a5 && (s5 <= lshr);
+      const uint32_t n0 = __funnelshift_l(cf << (s0 & 31), m0, 2), n1 = __funnelshift_l(cf << (s1 & 31), m1, 2),
+                     n2 = __funnelshift_l(cf << (s2 & 31), m2, 2), n3 = __funnelshift_l(cr << (s3 & 31), m3, 2),
+                     n4 = __funnelshift_l(cr << (s4 & 31), m4, 2), n5 = __funnelshift_l(cr << (s5 & 31), m5, 2);
+      m0 = a0 ? n0 : m0;
+      m1 = a1 ? n1 : m1;
+      m2 = a2 ? n2 : m2;
+      m3 = a3 ? n3 : m3;
+      m4 = a4 ? n4 : m4;
+      m5 = a5 ? n5 : m5;
+    }
+    const uint32_t bf = (cf >> psh) & 3u, br = (cr >> psh) & 3u;
+    const float* pb0 = gm.mprob;
+    const float* pb1 = gm.mprob + (size_t)gm.leaves_m * 4;
+    const float* pb2 = gm.mprob + (size_t)gm.leaves_m * 8;
+    const float v0 = __ldg(pb0 + (m0 * 4 + bf)), v1 = __ldg(pb1 + (m1 * 4 + bf)), v2 = __ldg(pb2 + (m2 * 4 + bf));
+    const float v3 = __ldg(pb0 + (m3 * 4 + br)), v4 = __ldg(pb1 + (m4 * 4 + br)), v5 = __ldg(pb2 + (m5 * 4 + br));
+    // forward: period f belongs to class (f + q) mod 3, i.e. class c holds period (c - q) mod 3
+    // reverse: period f belongs to class (1 + q - f) mod 3, i.e. class c holds period (1 + q - c) mod 3
+    const int r = q % 3;
+    float* o = planes + p;
+    const size_t T = (size_t)total;
+    o[0]     = r == 0 ? v0 : (r == 1 ? v2 : v1);
+    o[T]     = r == 0 ? v1 : (r == 1 ? v0 : v2);
+    o[2 * T] = r == 0 ? v2 : (r == 1 ? v1 : v0);
+    o[3 * T] = r == 0 ? v4 : (r == 1 ? v5 : v3);
+    o[4 * T] = r == 0 ? v3 : (r == 1 ? v4 : v5);
+    o[5 * T] = r == 0 ? v5 : (r == 1 ? v3 : v4);
+  }
+}
+
 static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** planes_out) {
   GMG_CHECK(gene->P == 3, "six-frame scoring needs a periodicity-3 gene model (got %d)", gene->P);
   void* planes = NULL;
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
   *planes_out = (float*)planes;
   if (s->total == 0) return 0;
+  if (gene->fast.valid) {
+    size_t smem = (size_t)3 * gene->fast.inner_m;
+    if (smem > 48 * 1024)
+      GMG_CUDA(cudaFuncSetAttribute(k1_planes_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t need = (s->total + 1023) / 1024;
+    int64_t cap = (int64_t)ctx->sm_count * 2;
+    int grid = (int)(need < cap ? need : cap);
+    if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
+    if (gene->fast.D == 7)
+      k1_planes_fast<7><<<grid, 1024, smem, ctx->stream>>>(gene->fast, (const uint32_t*)s->d_words, s->d_off,
+                                                           s->d_blk2seq, s->total, (float*)planes);
+    else
+      k1_planes_fast<0><<<grid, 1024, smem, ctx->stream>>>(gene->fast, (const uint32_t*)s->d_words, s->d_off,
+                                                           s->d_blk2seq, s->total, (float*)planes);
+    gmg_prof_end(ctx, GMG_PROF_K1);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+    return 0;
+  }
   size_t smem = (size_t)gene->dev.P * gene->dev.inner;
   GMG_CHECK(smem <= 200 * 1024, "gene model too deep for the shared-memory walk table (%zu bytes)", smem);
   if (smem > 48 * 1024)
@@ -244,7 +348,9 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   int64_t need = (s->total + 255) / 256;
   int64_t cap = (int64_t)ctx->sm_count * 8;
   int grid = (int)(need < cap ? need : cap);
+  if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
   k1_planes<<<grid, 256, smem, ctx->stream>>>(gene->dev, s->d_words, s->d_off, s->d_blk2seq, s->total, (float*)planes);
+  gmg_prof_end(ctx, GMG_PROF_K1);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   return 0;
@@ -292,8 +398,10 @@ extern "C" int gmg_score_all_frames(gmg_ctx* ctx, const gmg_icm* gene, const gmg
     if (gmg_scratch(ctx, SCR_CUM, (size_t)6 * s->total * sizeof(double), &tmp)) return 1;
     d_fs = (double*)tmp;
   }
+  if (gmg_prof_begin(ctx, GMG_PROF_FS)) return 1;
   k_frame_scores<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off,
                                                                              s->d_blk2seq, s->total, planes, d_fs);
+  gmg_prof_end(ctx, GMG_PROF_FS);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   if (!out_on_device) {
@@ -612,17 +720,17 @@ static int exclusive_sum_i64(gmg_ctx* ctx, int64_t* d_in, int64_t* d_out, int64_
 
 static int ensure_orf_capacity(gmg_seqset* s, int64_t n_orfs) {
   if ((size_t)n_orfs > s->cap_orfs || !s->d_orfs) {
-    if (s->d_orfs) cudaFree(s->d_orfs);
-    if (s->d_orf_seq) cudaFree(s->d_orf_seq);
-    if (s->d_start_off) cudaFree(s->d_start_off);
+    if (s->d_orfs) cudaFreeAsync(s->d_orfs, s->ctx->stream);
+    if (s->d_orf_seq) cudaFreeAsync(s->d_orf_seq, s->ctx->stream);
+    if (s->d_start_off) cudaFreeAsync(s->d_start_off, s->ctx->stream);
     s->d_orfs = NULL; s->d_orf_seq = NULL; s->d_start_off = NULL;
     size_t cap = (size_t)n_orfs + (size_t)n_orfs / 8 + 64;
-    GMG_CUDA(cudaMalloc(&s->d_orfs, cap * sizeof(gmg_orf)));
-    GMG_CUDA(cudaMalloc(&s->d_orf_seq, cap * sizeof(int32_t)));
-    GMG_CUDA(cudaMalloc(&s->d_start_off, (cap + 1) * sizeof(int64_t)));
+    GMG_CUDA(cudaMallocAsync(&s->d_orfs, cap * sizeof(gmg_orf), s->ctx->stream));
+    GMG_CUDA(cudaMallocAsync(&s->d_orf_seq, cap * sizeof(int32_t), s->ctx->stream));
+    GMG_CUDA(cudaMallocAsync(&s->d_start_off, (cap + 1) * sizeof(int64_t), s->ctx->stream));
     s->cap_orfs = cap;
   }
-  if (!s->d_orf_off) GMG_CUDA(cudaMalloc(&s->d_orf_off, (size_t)(s->n + 2) * sizeof(int64_t)));
+  if (!s->d_orf_off) GMG_CUDA(cudaMallocAsync(&s->d_orf_off, (size_t)(s->n + 2) * sizeof(int64_t), s->ctx->stream));
   return 0;
 }
 
@@ -646,7 +754,9 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   int64_t* counts = (int64_t*)d_counts;
   int64_t* bases = counts + nblk + 1;
   GMG_CUDA(cudaMemsetAsync(counts + nblk, 0, sizeof(int64_t), ctx->stream));
+  if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
   k_orf_count<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, counts);
+  gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   if (exclusive_sum_i64(ctx, counts, bases, nblk + 1)) return 1;
@@ -654,8 +764,10 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   GMG_CUDA(cudaMemcpyAsync(&total_orfs, bases + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_orf_capacity(s, total_orfs)) return 1;
+  if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
   k_orf_write<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, bases,
                                                       s->d_orfs, s->d_orf_seq);
+  gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
   GMG_CUDA(cudaGetLastError());
@@ -771,75 +883,38 @@ __device__ __forceinline__ int g3_codon_which(const uint64_t* __restrict__ words
   return ((cs.start_mask >> c) & 1) ? (int)cs.which[c] : -1;
 }
 
-template <bool kWrite>
-__global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
-                                                    const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
-                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                    const float* __restrict__ planes, CodonSets cs, DevParams P,
-                                                    int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
-                                                    gmg_start* __restrict__ starts) {
-  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Independent-model lookup: the model of Build_Indep_WO_Stops is an ICM_t(3,2,3), so a full window is one of 64
+// base triples per period.  lut[(strand*3 + f)*64 + raw] with raw = b(q0) | b(q0+1) << 2 | b(q0+2) << 4 of the three
+// sequence bases the window covers (forward strand: q0 = q, reverse strand: q0 = q - 2), filled once per CTA.
+__device__ __forceinline__ void fill_indep_lut(const DevIcm& indep, float* lut) {
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) {
+    const int raw = i & 63, f = (i >> 6) % 3, strand = i / 192;
+    uint64_t ctx;
+    if (strand == 0) ctx = (uint64_t)(((raw >> 4) & 3) | (((raw >> 2) & 3) << 2) | ((raw & 3) << 4));  // reversed order
+    else ctx = (uint64_t)((~raw) & 63);                                                                // complemented
+    lut[i] = gmg_walk(indep.mip + (size_t)f * indep.inner, indep.prob + (size_t)f * indep.N * 4, ctx, 3, indep.D, 0);
+  }
+}
+
+// Pass B of k3_g3_starts: gene / indep running sums along j and emission of the start records.
+//   kOrdered = true : lane-ordered serial accumulation, the reference's association (icm.cc:390-402).
+//   kOrdered = false: warp-parallel inclusive scans.  Returns (to every lane) whether the sums are CERTIFIED to
+//                     be bit-identical to the serial ones: every term is a float, i.e. an integer multiple of
+//                     2^(e_min - 150) (e_min = smallest biased exponent among the non-zero terms), so when
+//                     sum |term| < 2^(e_min - 150 + 52) every partial sum of ANY association is exactly
+//                     representable in FP64 and no addition rounds.  The caller re-runs uncertified ORFs ordered.
+template <bool kOrdered>
+__device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
+                              const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
+                              const float* __restrict__ plane, const CodonSets& cs, const DevParams& P, int first_j,
+                              int n_emit, gmg_start* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  if (oi >= n_orfs) return;
-  const gmg_orf o = orfs[oi];
-  const int32_t s = orf_seq[oi];
-  const int64_t a = off[s];
-  const int L = (int)(off[s + 1] - a);
-  const G3Geom g = g3_geom(o, L, P);
-  const int m = g.len;
+  const int W = gene.W, m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
-
-  // pass A: positions that emit (descending j), needs only codons.  first_j = largest qualifying j.
-  // A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and
-  // (codon is a start || (nothing emitted yet && truncated)).
-  int n_emit = 0;        // total records
-  int first_j = -1;      // j of the first (largest-j) emitting position
-  int first_double = 0;  // first position emits two records (truncated + real start codon)
-  {
-    // largest j % 3 == 0 that is <= m-1
-    int jtop = (m - 1) - ((m - 1) % 3);
-    int found_first = -1, cnt = 0;
-    for (int jb = jtop; jb >= lowest_j; jb -= 96) {
-      int j = jb - 3 * lane;
-      bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
-      int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
-      bool is_codon = ok && w >= 0;
-      // truncated rule can only apply to the very first candidate position examined (first_pos == 0)
-      unsigned cm = __ballot_sync(0xffffffffu, is_codon);
-      unsigned okm = __ballot_sync(0xffffffffu, ok);
-      if (found_first < 0) {
-        if (g.trunc && okm) {
-          int l0 = __ffs(okm) - 1;  // first ok lane = largest j
-          found_first = jb - 3 * l0;
-          first_double = (cm >> l0) & 1;
-          cnt += 1 + first_double;
-          cm &= ~(1u << l0);
-          cnt += __popc(cm);
-        } else if (!g.trunc && cm) {
-          int l0 = __ffs(cm) - 1;
-          found_first = jb - 3 * l0;
-          cnt += __popc(cm);
-        }
-      } else {
-        cnt += __popc(cm);
-      }
-    }
-    n_emit = cnt;
-    first_j = found_first;
-  }
-  if (!kWrite) {
-    if (lane == 0) counts[oi] = n_emit;
-    return;
-  }
-  if (n_emit == 0) return;
-  gmg_start* out = starts + start_off[oi];
-
-  // pass B: ordered FP64 accumulation of gene / indep along j, emitting score[j-1] for start position j.
-  const int W = gene.W;
-  const int cls = (g.frame > 0) ? (g.hi % 3) : (g.lo % 3);
-  const float* plane = planes + (size_t)((g.frame > 0 ? 0 : 3) + cls) * total;
-  double run_g = 0.0, run_n = 0.0;
-  int emitted_below = 0;  // records of start positions < current chunk (ascending j)
+  const bool use_lut = (indep.W == 3);
+  double run_g = 0.0, run_n = 0.0, asum = 0.0;
+  unsigned emin = 0x7F800000u;
+  int emitted_below = 0;           // records of start positions below the current chunk (ascending j)
   const int j_last = first_j - 1;  // scores are needed up to index first_j - 1
   for (int base = 0; base <= j_last; base += 32) {
     const int j = base + lane;
@@ -849,23 +924,46 @@ __global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, c
       if (g.frame > 0) {
         const int q = g.hi - 1 - j;
         xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f) : __ldg(plane + a + q);
-        xn = icm_fwd(indep, words, a + q, q, g.hi, f);
+        if (use_lut && j >= 2) xn = lut[f * 64 + (int)(gmg_extract32(words, a + q) & 63)];
+        else xn = icm_fwd(indep, words, a + q, q, g.hi, f);
       } else {
         const int q = g.lo + j;
         xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f) : __ldg(plane + a + q);
-        xn = icm_rev(indep, words, a + q, q, g.lo, f);
+        if (use_lut && j >= 2) xn = lut[(3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63)];
+        else xn = icm_rev(indep, words, a + q, q, g.lo, f);
       }
     }
-    // ordered accumulation (lane 0 first) -> my_g / my_n = score[j] / indep_score[j]
-    double my_g = 0.0, my_n = 0.0;
-    const int cnt = min(32, j_last + 1 - base);
-    for (int l = 0; l < cnt; l++) {
-      run_g += (double)__shfl_sync(0xffffffffu, xg, l);
-      run_n += (double)__shfl_sync(0xffffffffu, xn, l);
-      if (l == lane) {
-        my_g = run_g;
-        my_n = run_n;
+    double my_g, my_n;
+    if (kOrdered) {
+      // position base+0, base+1, ... exactly like the serial loop
+      my_g = my_n = 0.0;
+      const int cnt = min(32, j_last + 1 - base);
+      for (int l = 0; l < cnt; l++) {
+        run_g += (double)__shfl_sync(0xffffffffu, xg, l);
+        run_n += (double)__shfl_sync(0xffffffffu, xn, l);
+        if (l == lane) {
+          my_g = run_g;
+          my_n = run_n;
+        }
       }
+    } else {
+      const unsigned eg = __float_as_uint(xg) & 0x7F800000u, en = __float_as_uint(xn) & 0x7F800000u;
+      if (xg != 0.f) emin = min(emin, eg);
+      if (xn != 0.f) emin = min(emin, en);
+      asum += fmax(fabs((double)xg), fabs((double)xn));
+      double vg = (double)xg, vn = (double)xn;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double tg = __shfl_up_sync(0xffffffffu, vg, d), tn = __shfl_up_sync(0xffffffffu, vn, d);
+        if (lane >= d) {
+          vg += tg;
+          vn += tn;
+        }
+      }
+      my_g = run_g + vg;
+      my_n = run_n + vn;
+      run_g = __shfl_sync(0xffffffffu, my_g, 31);
+      run_n = __shfl_sync(0xffffffffu, my_n, 31);
     }
     // start position js = j + 1 uses score[j]
     const int js = j + 1;
@@ -899,6 +997,90 @@ __global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, c
       }
     }
     emitted_below += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (kOrdered) return true;
+  for (int d = 16; d > 0; d >>= 1) {
+    emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
+    asum += __shfl_xor_sync(0xffffffffu, asum, d);
+  }
+  // asum over-counts by at most its own rounding (< 2^-40 relative); one binade of margin (52, not 53)
+  const int gexp = (int)(emin >> 23) - 150;
+  return emin != 0u && asum < ldexp(1.0, gexp + 52);
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                    const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                    const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                    int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
+                                                    gmg_start* __restrict__ starts,
+                                                    unsigned long long* __restrict__ n_ordered) {
+  __shared__ float s_lut[384];
+  if (kWrite) {
+    if (indep.W == 3) fill_indep_lut(indep, s_lut);
+    __syncthreads();
+  }
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (oi >= n_orfs) return;
+  const gmg_orf o = orfs[oi];
+  const int32_t s = orf_seq[oi];
+  const int64_t a = off[s];
+  const int L = (int)(off[s + 1] - a);
+  const G3Geom g = g3_geom(o, L, P);
+  const int m = g.len;
+  const int lowest_j = min(3, P.min_gene_len - 3);
+
+  // pass A: positions that emit (descending j), needs only codons.  first_j = largest qualifying j.
+  // A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and
+  // (codon is a start || (nothing emitted yet && truncated)).
+  int n_emit = 0;        // total records
+  int first_j = -1;      // j of the first (largest-j) emitting position
+  {
+    // largest j % 3 == 0 that is <= m-1
+    int jtop = (m - 1) - ((m - 1) % 3);
+    int found_first = -1, cnt = 0;
+    for (int jb = jtop; jb >= lowest_j; jb -= 96) {
+      int j = jb - 3 * lane;
+      bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
+      int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
+      bool is_codon = ok && w >= 0;
+      // truncated rule can only apply to the very first candidate position examined (first_pos == 0)
+      unsigned cm = __ballot_sync(0xffffffffu, is_codon);
+      unsigned okm = __ballot_sync(0xffffffffu, ok);
+      if (found_first < 0) {
+        if (g.trunc && okm) {
+          int l0 = __ffs(okm) - 1;  // first ok lane = largest j
+          found_first = jb - 3 * l0;
+          cnt += 1 + ((cm >> l0) & 1);
+          cm &= ~(1u << l0);
+          cnt += __popc(cm);
+        } else if (!g.trunc && cm) {
+          int l0 = __ffs(cm) - 1;
+          found_first = jb - 3 * l0;
+          cnt += __popc(cm);
+        }
+      } else {
+        cnt += __popc(cm);
+      }
+    }
+    n_emit = cnt;
+    first_j = found_first;
+  }
+  if (!kWrite) {
+    if (lane == 0) counts[oi] = n_emit;
+    return;
+  }
+  if (n_emit == 0) return;
+  gmg_start* out = starts + start_off[oi];
+
+  // pass B: FP64 sums of gene / indep along j, emitting score[j-1] for start position j
+  const int cls = (g.frame > 0) ? (g.hi % 3) : (g.lo % 3);
+  const float* plane = planes + (size_t)((g.frame > 0 ? 0 : 3) + cls) * total;
+  if (!g3_accumulate<false>(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out)) {
+    g3_accumulate<true>(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out);
+    if (lane == 0) atomicAdd(n_ordered, 1ull);
   }
 }
 
@@ -1307,10 +1489,10 @@ __global__ void __launch_bounds__(128) k3_mg_starts(const uint64_t* __restrict__
 
 static int ensure_start_capacity(gmg_seqset* s, int64_t n) {
   if ((size_t)n > s->cap_starts || !s->d_starts) {
-    if (s->d_starts) cudaFree(s->d_starts);
+    if (s->d_starts) cudaFreeAsync(s->d_starts, s->ctx->stream);
     s->d_starts = NULL;
     size_t cap = (size_t)n + (size_t)n / 8 + 64;
-    GMG_CUDA(cudaMalloc(&s->d_starts, cap * sizeof(gmg_start)));
+    GMG_CUDA(cudaMallocAsync(&s->d_starts, cap * sizeof(gmg_start), s->ctx->stream));
     s->cap_starts = cap;
   }
   return 0;
@@ -1336,13 +1518,16 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   if (s->n_orfs == 0) return 0;
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
+  GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
   void* d_counts;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 1) * sizeof(int64_t), &d_counts)) return 1;
   int64_t* counts = (int64_t*)d_counts;
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, sizeof(int64_t), ctx->stream));
   unsigned grid = (unsigned)((s->n_orfs * 32 + 127) / 128);
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
   k3_g3_starts<false><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs,
-                                                     s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp, counts, NULL, NULL);
+                                                     s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp, counts, NULL, NULL, NULL);
+  gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
@@ -1350,8 +1535,11 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_start_capacity(s, total_starts)) return 1;
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
   k3_g3_starts<true><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq,
-                                                    s->n_orfs, s->total, planes, cs, dp, NULL, s->d_start_off, s->d_starts);
+                                                    s->n_orfs, s->total, planes, cs, dp, NULL, s->d_start_off, s->d_starts,
+                                                    s->d_gc + 1);
+  gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   s->n_starts = total_starts;
@@ -1400,9 +1588,11 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaMemcpyAsync(d_tables, ctx->h_penalty, 516 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   const bool need_qual = p->allow_indels || p->have_quality_file;
   unsigned g2 = (unsigned)((s->n * 32 + 127) / 128);
+  if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
   k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, cs, dp,
                                          p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
                                          need_qual ? (uint8_t*)d_qual : NULL, cert);
+  gmg_prof_end(ctx, GMG_PROF_K2);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   // K3: count, scan, write
@@ -1411,9 +1601,11 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   int64_t* counts = (int64_t*)d_counts;
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
   unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
   k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
                                                    (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
                                                    counts, NULL, NULL);
+  gmg_prof_end(ctx, GMG_PROF_K3);
   k_count_zero_flags<<<(unsigned)((s->n + 255) / 256), 256, 0, ctx->stream>>>(cert, s->n,
                                                                              (unsigned long long*)(counts + s->n_orfs + 1));
   ctx->launches += 2;
@@ -1425,9 +1617,11 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   s->uncertified = bad;
   if (ensure_start_capacity(s, total_starts)) return 1;
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
   k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
                                                   (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
                                                   NULL, s->d_start_off, s->d_starts);
+  gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   s->n_starts = total_starts;
@@ -1452,3 +1646,12 @@ extern "C" int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, 
 }
 
 extern "C" int64_t gmg_uncertified_count(const gmg_seqset* s) { return s ? s->uncertified : 0; }
+
+extern "C" int gmg_ordered_fallback_count(gmg_seqset* s, int64_t* out) {
+  GMG_CHECK(s && out, "gmg_ordered_fallback_count: NULL argument");
+  unsigned long long v = 0;
+  GMG_CUDA(cudaMemcpyAsync(&v, s->d_gc + 1, sizeof v, cudaMemcpyDeviceToHost, s->ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  *out = (int64_t)v;
+  return 0;
+}

@@ -80,7 +80,9 @@ __global__ void k_blk2seq(const int64_t* __restrict__ off, int64_t n, int64_t nb
 int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc) {
   int64_t nwords = (total + 31) >> 5;
   if (nwords == 0) return 0;
+  if (gmg_prof_begin(ctx, GMG_PROF_PACK)) return 1;
   k_pack<<<(unsigned)((nwords + 255) / 256), 256, 0, ctx->stream>>>(d_ascii, total, d_words, d_gc);
+  gmg_prof_end(ctx, GMG_PROF_PACK);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   return 0;
@@ -106,22 +108,22 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
   int64_t nwords = (s->total + 31) >> 5;
   int64_t nblk = nwords > 0 ? nwords : 1;
   size_t wbytes = (size_t)(nwords + 2 * GMG_PAD_WORDS) * sizeof(uint64_t);
-  GMG_CUDA(cudaMalloc(&s->d_words_base, wbytes));
+  GMG_CUDA(cudaMallocAsync(&s->d_words_base, wbytes, s->ctx->stream));
   GMG_CUDA(cudaMemsetAsync(s->d_words_base, 0, wbytes, ctx->stream));
   s->d_words = s->d_words_base + GMG_PAD_WORDS;
-  GMG_CUDA(cudaMalloc(&s->d_off, (size_t)(s->n + 1) * sizeof(int64_t)));
+  GMG_CUDA(cudaMallocAsync(&s->d_off, (size_t)(s->n + 1) * sizeof(int64_t), s->ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(s->d_off, s->off.data(), (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            ctx->stream));
-  GMG_CUDA(cudaMalloc(&s->d_blk2seq, (size_t)nblk * sizeof(int32_t)));
-  GMG_CUDA(cudaMalloc(&s->d_gc, sizeof(unsigned long long)));
-  GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, sizeof(unsigned long long), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_blk2seq, (size_t)nblk * sizeof(int32_t), s->ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_gc, 2 * sizeof(unsigned long long), s->ctx->stream));
+  GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if (s->total > 0) {
     if (gmg_launch_pack(ctx, (const uint8_t*)d_ascii, s->total, s->d_words, s->d_gc)) return 1;
     k_blk2seq<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d_off, s->n, nblk, s->d_blk2seq);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
     if (d_qual) {
-      GMG_CUDA(cudaMalloc(&s->d_qual, (size_t)s->total));
+      GMG_CUDA(cudaMallocAsync(&s->d_qual, (size_t)s->total, s->ctx->stream));
       GMG_CUDA(cudaMemcpyAsync(s->d_qual, d_qual, (size_t)s->total, cudaMemcpyDeviceToDevice, ctx->stream));
     }
   }
@@ -159,11 +161,10 @@ extern "C" int gmg_seqset_create(gmg_ctx* ctx, const char* h_ascii, const int64_
 extern "C" void gmg_seqset_free(gmg_seqset* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
   void* ptrs[] = {s->d_off, s->d_words_base, s->d_blk2seq, s->d_qual, s->d_gc, s->d_orfs, s->d_orf_off,
                   s->d_orf_seq, s->d_starts, s->d_start_off};
   for (void* p : ptrs)
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s->ctx->stream);
   delete s;
 }
 

@@ -155,6 +155,7 @@ extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_count
     const size_t smem_budget = 200 * 1024;
     const bool use_smem = (size_t)slab * sizeof(int) <= smem_budget;
     const int threads = 512;
+    if (gmg_prof_begin(ctx, GMG_PROF_K4)) return 1;
     if (use_smem) {
       int copies = (int)(smem_budget / ((size_t)slab * sizeof(int)));
       if (copies > threads / 32) copies = threads / 32;
@@ -174,6 +175,7 @@ extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_count
                                                         t->reverse, level, (int)first_node_of(level), (int)nl, t->d_mip,
                                                         t->d_counts, (int)slab, 1);
     }
+    gmg_prof_end(ctx, GMG_PROF_K4);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
   }

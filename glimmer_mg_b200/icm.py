@@ -64,6 +64,10 @@ def lib():
         "gmg_ctx_destroy": (None, [vp]),
         "gmg_ctx_sync": (i32, [vp]),
         "gmg_ctx_launch_count": (i64, [vp]),
+        "gmg_ctx_profile": (i32, [vp, i32]),
+        "gmg_ctx_profile_read": (i32, [vp, i32, P(C.c_double), P(i64)]),
+        "gmg_host_alloc": (i32, [C.c_size_t, P(vp)]),
+        "gmg_host_free": (None, [vp]),
         "gmg_ctx_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
         "gmg_ctx_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
         "gmg_params_default": (None, [P(_Params), i32]),
@@ -95,6 +99,7 @@ def lib():
         "gmg_score_orfs_mg": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
         "gmg_get_starts": (i32, [vp, vp, vp, vp]),
         "gmg_uncertified_count": (i64, [vp]),
+        "gmg_ordered_fallback_count": (i32, [vp, P(i64)]),
         "gmg_trainer_create": (i32, [vp, vp, i32, i32, i32, i32, P(vp)]),
         "gmg_trainer_free": (None, [vp]),
         "gmg_trainer_count_level": (i32, [vp, i32, P(vp), P(i64)]),
@@ -152,6 +157,7 @@ class Context:
 
     def __init__(self, device=0, stream=None):
         self.h = C.c_void_p()
+        self._pinned = {}
         _check(lib().gmg_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)))
         self.device = device
 
@@ -162,13 +168,44 @@ class Context:
     def launches(self):
         return int(lib().gmg_ctx_launch_count(self.h))
 
+    PROF = {"k1": 0, "k2": 1, "k3": 2, "k4": 3, "orf": 4, "pack": 5, "fs": 6}
+
+    def profile(self, enable=True):
+        """Bracket every hot-kernel launch with CUDA events on the context's stream."""
+        _check(lib().gmg_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self, kernel):
+        """-> (summed device ms, launches) of one kernel class since the last read."""
+        ms, n = C.c_double(), C.c_int64()
+        _check(lib().gmg_ctx_profile_read(self.h, self.PROF[kernel], C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def d2h(self, dptr, count, dtype):
         out = np.zeros(count, dtype)
         _check(lib().gmg_ctx_memcpy_d2h(self.h, out.ctypes.data, C.c_void_p(dptr), out.nbytes))
         return out
 
+    def pinned(self, name, count, dtype):
+        """A page-locked host array (gmg_host_alloc) owned by the context and reused by name: D2H copies into
+        it run at PCIe rate.  The returned view is overwritten by the next request for the same name."""
+        dtype = np.dtype(dtype)
+        need = max(1, count) * dtype.itemsize
+        buf = self._pinned.get(name)
+        if buf is None or buf[1] < need:
+            if buf is not None:
+                lib().gmg_host_free(buf[0])
+            cap = need + need // 4 + 4096
+            ptr = C.c_void_p()
+            _check(lib().gmg_host_alloc(cap, C.byref(ptr)))
+            buf = (ptr, cap, (C.c_uint8 * cap).from_address(ptr.value))
+            self._pinned[name] = buf
+        return np.frombuffer(buf[2], dtype=dtype, count=count)
+
     def close(self):
         if self.h:
+            for ptr, _, _ in self._pinned.values():
+                lib().gmg_host_free(ptr)
+            self._pinned = {}
             lib().gmg_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -253,9 +290,15 @@ class SeqSet:
         self.n_orfs = n.value
         return self.n_orfs
 
-    def get_orfs(self):
-        orfs = np.zeros(self.n_orfs, ORF_DTYPE)
-        off = np.zeros(self.n + 1, np.int64)
+    def get_orfs(self, pinned=False):
+        """ORF table + per-sequence offsets.  pinned=True returns views of the context's page-locked staging
+        buffers (valid until the next pinned get_orfs on this context)."""
+        if pinned:
+            orfs = self.ctx.pinned("orfs", self.n_orfs, ORF_DTYPE)
+            off = self.ctx.pinned("orf_off", self.n + 1, np.int64)
+        else:
+            orfs = np.zeros(self.n_orfs, ORF_DTYPE)
+            off = np.zeros(self.n + 1, np.int64)
         _check(lib().gmg_get_orfs(self.ctx.h, self.h, orfs.ctypes.data, off.ctypes.data))
         return orfs, off
 
@@ -278,11 +321,21 @@ class SeqSet:
         self.n_starts = n.value
         return self.n_starts
 
-    def get_starts(self):
-        starts = np.zeros(self.n_starts, START_DTYPE)
-        off = np.zeros(self.n_orfs + 1, np.int64)
+    def get_starts(self, pinned=False):
+        if pinned:
+            starts = self.ctx.pinned("starts", self.n_starts, START_DTYPE)
+            off = self.ctx.pinned("start_off", self.n_orfs + 1, np.int64)
+        else:
+            starts = np.zeros(self.n_starts, START_DTYPE)
+            off = np.zeros(self.n_orfs + 1, np.int64)
         _check(lib().gmg_get_starts(self.ctx.h, self.h, starts.ctypes.data, off.ctypes.data))
         return starts, off
+
+    @property
+    def ordered_fallbacks(self):
+        n = C.c_int64()
+        _check(lib().gmg_ordered_fallback_count(self.h, C.byref(n)))
+        return n.value
 
     @property
     def uncertified(self):

@@ -82,6 +82,22 @@ void gmg_ctx_destroy(gmg_ctx* ctx);
 int gmg_ctx_sync(gmg_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gmg_ctx_launch_count(const gmg_ctx* ctx);
+/* Per-kernel device timing for bench.py's roofline: while enabled, CUDA events on the context's
+ * stream bracket every launch of the hot kernels.  gmg_ctx_profile_read synchronises the stream and
+ * returns (and resets) the summed duration and launch count of one kernel class. */
+#define GMG_PROF_K1 0   /* k1_planes: six-frame tree walks */
+#define GMG_PROF_K2 1   /* k2_prefix: prefix sums / stop tables / quality */
+#define GMG_PROF_K3 2   /* k3_*_starts: start enumeration (count + write passes) */
+#define GMG_PROF_K4 3   /* k4_count: training context counts */
+#define GMG_PROF_ORF 4  /* ORF finder */
+#define GMG_PROF_PACK 5 /* Filter + 2-bit pack */
+#define GMG_PROF_FS 6   /* Frame_Scores surface (gene - indep as FP64) */
+int gmg_ctx_profile(gmg_ctx* ctx, int enable);
+int gmg_ctx_profile_read(gmg_ctx* ctx, int kernel_class, double* ms, int64_t* launches);
+/* page-locked host memory (cudaMallocHost) for callers without a CUDA runtime of their own: input
+ * and output buffers allocated here make the H2D / D2H copies of the calls below run at PCIe rate */
+int gmg_host_alloc(size_t bytes, void** out);
+void gmg_host_free(void* p);
 /* plain copies on the context's stream (for callers without a CUDA runtime of their own); both sync */
 int gmg_ctx_memcpy_d2h(gmg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int gmg_ctx_memcpy_h2d(gmg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
@@ -169,6 +185,10 @@ int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_
  * DESIGN.md "exactness certificate"); their scores are within 1e-12 relative instead of
  * bit-identical. */
 int64_t gmg_uncertified_count(const gmg_seqset* s);
+/* gmg_score_orfs_g3 forms its FP64 sums with warp-parallel scans where an exactness certificate proves
+ * them bit-identical to the reference's serial sums, and re-does every other ORF in the reference's
+ * order; this returns how many ORFs of the last call took that ordered path (results are exact either way). */
+int gmg_ordered_fallback_count(gmg_seqset* s, int64_t* out);
 
 /* ---- training: ICM_Training_t ---------------------------------------------------------- */
 /* strings as given to Train_Model (icm.cc:1356): the seqset holds the training strings in

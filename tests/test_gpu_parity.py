@@ -146,6 +146,23 @@ def test_score_all_frames_bit_exact(gm, ctx, reads):
     assert n >= 20
 
 
+@pytest.mark.parametrize("w,d", [(12, 5), (12, 2), (16, 8), (18, 4), (9, 7)])
+def test_score_all_frames_other_model_shapes(gm, ctx, reads, w, d):
+    """K1 beyond the build-icm defaults: runtime-depth fast path (w <= 16, d <= 8) and the generic kernel (w > 16)."""
+    strs = [s[::-1] for s in _train_strings("seqs.cluster-5.run1.filt.gene.fasta.gz")]
+    om = O.lib().orc_icm_train(O.cstr_array(strs), len(strs), w, d, 3)
+    omip, oprob = O.icm_tables(om)
+    gene = gm.ICM.from_tables(ctx, w, d, 3, omip, oprob)
+    seqs = [s for _, s in reads[100:130]] + [b"acgtacgtacgtacgtacgt"[:n] for n in (1, 8, 9, 15, 16, 17, 18, 19, 20)]
+    gc = _gc_oracle(seqs)
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    oi = O.build_indep(gc)
+    fs = gm.SeqSet(ctx, seqs=seqs).score_all_frames(gene, indep)
+    for s0, got in zip(seqs, fs):
+        want = O.score_all_frames(om, oi, O.filter_lower(s0))
+        assert (_bits(got) == _bits(want)).all()
+
+
 @pytest.mark.parametrize("flags", [dict(), dict(allow_indels=1), dict(allow_subs=1), dict(allow_truncated=0)])
 def test_find_orfs_reads(gm, ctx, reads, flags):
     seqs = [s for _, s in reads[:150]] + [b"", b"acgt" * 10, b"atg" + b"aaa" * 30 + b"taa"]
@@ -285,6 +302,8 @@ def test_g3_full_genome_matches_oracle(gm, ctx, genome, truncated):
     for f in ("j", "pos", "which", "truncated", "first"):
         assert (starts[f] == wst[f]).all(), f
     assert (_bits(starts["score"]) == _bits(wst["score"])).all()
+    # the warp-parallel (certified exact) sums must be the common case, the ordered re-run the exception
+    assert ss.ordered_fallbacks <= len(orfs) // 20
 
 
 def _train_strings(name):
