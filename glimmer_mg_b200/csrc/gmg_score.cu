@@ -508,28 +508,43 @@ extern "C" int gmg_icm_partial_window_prob(gmg_ctx* ctx, const gmg_icm* m, int p
 // ------------------------------------------------------------------------------------------------
 // Device ORF finder (Find_Orfs, glimmer_base.cc:638-817; linear sequences, no ignore regions).
 //
-// Every ORF is created by the stop codon that closes it, so one thread per base handles the (at most
-// two) ORFs closed at that base and walks back codon by codon to the previous in-frame stop -- total
-// work = total ORF length.  The thread of a sequence's last base also emits the three Finish_Orfs
-// reverse ORFs and the three virtual forward stops past the end, in the reference's order.  Two
-// passes (count, block scan, write) give the reference's output order deterministically.
+// Every ORF is created by the stop codon that closes it.  A warp owns 32 consecutive bases; for every base
+// that closes an ORF (at most one forward and one reverse stop, plus the Finish_Orfs reverse ORFs and the
+// three virtual forward stops at a sequence's last base) the WHOLE warp searches backwards for the previous
+// in-frame stop, 32 codons per step (ballot + find-first), so the cost of a long ORF is shared by 32 lanes
+// instead of serialising one.  Two passes (count, block scan, write) give the reference's output order
+// deterministically: by closing base; forward before reverse; then the end-of-sequence extras.
 
-__device__ bool orf_fwd_closed_at(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool virt,
-                                  const CodonSets& cs, const DevParams& P, gmg_orf* o) {
-  // i = index of the last base of the closing (possibly virtual) stop codon
-  if (!virt) {
-    if (i < 2 || !((cs.stop_mask >> codon_fwd_ending_at(words, a, i)) & 1)) return false;
-  }
+// 6-bit code of the codon whose three sequence bases are q0, q0+1, q0+2 read on the forward strand
+__device__ __forceinline__ int codon6_at(const uint64_t* __restrict__ words, int64_t g) {
+  const int raw = (int)(gmg_extract32(words, g) & 63);  // b(q0) | b(q0+1) << 2 | b(q0+2) << 4
+  return ((raw & 3) << 4) | (raw & 12) | (raw >> 4);
+}
+
+// forward ORF closed by the (possibly virtual) stop codon whose last base is i.  Warp-uniform arguments and
+// result; all 32 lanes must call.
+__device__ bool orf_fwd_closed_warp(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool virt,
+                                    const CodonSets& cs, const DevParams& P, gmg_orf* o) {
+  const int lane = threadIdx.x & 31;
   int first_start = INT_MAX;
   int prev = 0;  // 1-based first base of the previous stop, 0 = none
-  for (int t = i - 3; t >= 2; t -= 3) {
-    if (t >= L) continue;  // virtual closing stop: codons hanging past the end do not exist
-    int c = codon_fwd_ending_at(words, a, t);
-    if ((cs.stop_mask >> c) & 1) {
-      prev = t - 1;
-      break;
+  for (int tb = i - 3; tb >= 2; tb -= 96) {
+    const int t = tb - 3 * lane;
+    bool is_stop = false, is_start = false;
+    if (t >= 2 && t < L) {  // virtual closing stop: codons hanging past the end do not exist
+      const int c = codon6_at(words, a + t - 2);
+      is_stop = (cs.stop_mask >> c) & 1;
+      is_start = (cs.start_mask >> c) & 1;
     }
-    if ((cs.start_mask >> c) & 1) first_start = t - 1;
+    const unsigned stopm = __ballot_sync(0xffffffffu, is_stop);
+    unsigned startm = __ballot_sync(0xffffffffu, is_start);
+    if (stopm) {
+      const int sl = __ffs(stopm) - 1;
+      prev = tb - 3 * sl - 1;
+      startm &= (1u << sl) - 1u;
+    }
+    if (startm) first_start = tb - 3 * (31 - __clz(startm)) - 1;  // farthest from i = nearest to the previous stop
+    if (stopm) break;
   }
   int gene_len, orf_len;
   if (prev == 0) {
@@ -553,22 +568,29 @@ __device__ bool orf_fwd_closed_at(const uint64_t* __restrict__ words, int64_t a,
 
 // reverse ORF closed at i (real reverse stop whose highest base is i), or with finish = true the
 // Finish_Orfs ORF of frame class fr = i % 3 where i is the last position of that class (< L).
-__device__ bool orf_rev_closed_at(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool finish,
-                                  const CodonSets& cs, const DevParams& P, gmg_orf* o) {
-  int t0 = i - 3;
-  if (!finish) {
-    if (i < 2 || !((cs.stop_mask >> codon_rev_starting_at(words, a, i - 2)) & 1)) return false;
-  } else {
-    t0 = i;  // scan starts at the last codon of this class
-  }
+__device__ bool orf_rev_closed_warp(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool finish,
+                                    const CodonSets& cs, const DevParams& P, gmg_orf* o) {
+  const int lane = threadIdx.x & 31;
+  const int t0 = finish ? i : i - 3;
   int last_start = 0, prev = 0;
-  for (int t = t0; t >= 2; t -= 3) {
-    int c = codon_rev_starting_at(words, a, t - 2);
-    if ((cs.stop_mask >> c) & 1) {
-      prev = t - 1;
-      break;
+  for (int tb = t0; tb >= 2; tb -= 96) {
+    const int t = tb - 3 * lane;
+    bool is_stop = false, is_start = false;
+    if (t >= 2) {
+      const int c = 63 - codon6_at(words, a + t - 2);  // complement ...
+      const int rc = ((c & 3) << 4) | (c & 12) | (c >> 4);  // ... read in the other direction
+      is_stop = (cs.stop_mask >> rc) & 1;
+      is_start = (cs.start_mask >> rc) & 1;
     }
-    if (last_start == 0 && ((cs.start_mask >> c) & 1)) last_start = t - 1;
+    const unsigned stopm = __ballot_sync(0xffffffffu, is_stop);
+    unsigned startm = __ballot_sync(0xffffffffu, is_start);
+    if (stopm) {
+      const int sl = __ffs(stopm) - 1;
+      prev = tb - 3 * sl - 1;
+      startm &= (1u << sl) - 1u;
+    }
+    if (last_start == 0 && startm) last_start = tb - 3 * (__ffs(startm) - 1) - 1;  // nearest to i
+    if (stopm) break;
   }
   int gene_len, orf_len, orf_stop;
   if (!finish) {
@@ -603,81 +625,108 @@ __device__ bool orf_rev_closed_at(const uint64_t* __restrict__ words, int64_t a,
   return true;
 }
 
-// all ORFs created by base p, in reference order; returns the count (<= 8)
-__device__ int orfs_at(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                       const int32_t* __restrict__ blk2seq, int64_t p, const CodonSets& cs, const DevParams& P,
-                       gmg_orf* out, int32_t* seq_out) {
-  int32_t s;
-  SeqView sv = locate(off, blk2seq, p, &s);
-  *seq_out = s;
-  const int L = sv.len, q = (int)(p - sv.a);
-  if (L < P.min_gene_len) return 0;
-  int n = 0;
-  if (orf_fwd_closed_at(words, sv.a, L, q, false, cs, P, out + n)) n++;
-  if (orf_rev_closed_at(words, sv.a, L, q, false, cs, P, out + n)) n++;
-  if (q == L - 1) {
-    for (int fr = 0; fr < 3; fr++) {
-      // last index of class fr that is < L
-      int i = L - 1 - mod3(L - 1 - fr);
-      if (i < 0) i = fr;  // degenerate; the walk loop is empty
-      // the frame number only depends on fr, which equals i % 3 when i >= 0
-      gmg_orf tmp;
-      bool keep = orf_rev_closed_at(words, sv.a, L, i, true, cs, P, &tmp);
-      if (keep) {
-        tmp.frame = -1 - (fr + 1) % 3;
-        out[n++] = tmp;
-      }
-    }
-    if (P.allow_truncated)
-      for (int i = L; i < L + 3; i++)
-        if (orf_fwd_closed_at(words, sv.a, L, i, true, cs, P, out + n)) n++;
-  }
-  return n;
-}
-
-__global__ void __launch_bounds__(256) k_orf_count(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                   const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
-                                                   DevParams P, int64_t* __restrict__ block_counts) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  gmg_orf tmp[8];
-  int32_t s;
-  int n = (p < total) ? orfs_at(words, off, blk2seq, p, cs, P, tmp, &s) : 0;
-  __shared__ int wsum[8];
-  int v = n;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < 8; w++) t += wsum[w];
-    block_counts[blockIdx.x] = t;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_orf_write(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                   const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
-                                                   DevParams P, const int64_t* __restrict__ block_base,
-                                                   gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  gmg_orf tmp[8];
-  int32_t s = 0;
-  int n = (p < total) ? orfs_at(words, off, blk2seq, p, cs, P, tmp, &s) : 0;
-  // block-level exclusive scan of n
+// kWrite = false: per-CTA ORF counts.  kWrite = true: ORF records at block_base[blockIdx] + in-block rank.
+template <bool kWrite>
+__global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                              const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
+                                              DevParams P, int64_t* __restrict__ block_counts,
+                                              int64_t* __restrict__ warp_pack, const int64_t* __restrict__ block_base,
+                                              gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
   __shared__ int wsum[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int incl = n;
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // what this lane's base closes
+  int64_t a = 0;
+  int L = 0, q = 0;
+  int32_t sq = 0;
+  bool cf = false, cr = false, last = false;
+  if (p < total) {
+    SeqView sv = locate(off, blk2seq, p, &sq);
+    a = sv.a;
+    L = sv.len;
+    q = (int)(p - a);
+    if (L >= P.min_gene_len) {
+      if (q >= 2) {
+        const int c = codon6_at(words, p - 2);
+        cf = (cs.stop_mask >> c) & 1;
+        const int cc = 63 - c;
+        cr = (cs.stop_mask >> (((cc & 3) << 4) | (cc & 12) | (cc >> 4))) & 1;
+      }
+      last = (q == L - 1);
+    }
   }
-  if (lane == 31) wsum[wid] = incl;
-  __syncthreads();
-  int wbase = 0;
-  for (int w = 0; w < wid; w++) wbase += wsum[w];
-  int64_t slot = block_base[blockIdx.x] + wbase + incl - n;
-  for (int k = 0; k < n; k++) {
-    orfs[slot + k] = tmp[k];
-    orf_seq[slot + k] = s;
+  const unsigned mf = __ballot_sync(0xffffffffu, cf), mr = __ballot_sync(0xffffffffu, cr),
+                 ml = __ballot_sync(0xffffffffu, last);
+  // write pass: this warp's first slot = block base + the ORFs of the block's earlier warps (packed, 8 bits each)
+  int64_t base = 0;
+  if (kWrite) {
+    base = block_base[blockIdx.x];
+    const unsigned long long pack = (unsigned long long)warp_pack[blockIdx.x];
+    for (int w = 0; w < wid; w++) base += (int)((pack >> (8 * w)) & 0xFF);
+  }
+  int n = 0;  // warp-uniform count of ORFs found so far
+  unsigned any = mf | mr | ml;
+  while (any) {
+    const int l = __ffs(any) - 1;
+    any &= any - 1;
+    const int64_t al = __shfl_sync(0xffffffffu, a, l);
+    const int Ll = __shfl_sync(0xffffffffu, L, l), ql = __shfl_sync(0xffffffffu, q, l);
+    const int32_t sl = __shfl_sync(0xffffffffu, sq, l);
+    gmg_orf o;
+    if ((mf >> l) & 1)
+      if (orf_fwd_closed_warp(words, al, Ll, ql, false, cs, P, &o)) {
+        if (kWrite && lane == 0) {
+          orfs[base + n] = o;
+          orf_seq[base + n] = sl;
+        }
+        n++;
+      }
+    if ((mr >> l) & 1)
+      if (orf_rev_closed_warp(words, al, Ll, ql, false, cs, P, &o)) {
+        if (kWrite && lane == 0) {
+          orfs[base + n] = o;
+          orf_seq[base + n] = sl;
+        }
+        n++;
+      }
+    if ((ml >> l) & 1) {
+      for (int fr = 0; fr < 3; fr++) {
+        int i = Ll - 1 - mod3(Ll - 1 - fr);  // last index of class fr that is < L
+        if (i < 0) i = fr;                   // degenerate; the search loop is empty
+        if (orf_rev_closed_warp(words, al, Ll, i, true, cs, P, &o)) {
+          o.frame = -1 - (fr + 1) % 3;  // only depends on fr (= i % 3 when i >= 0)
+          if (kWrite && lane == 0) {
+            orfs[base + n] = o;
+            orf_seq[base + n] = sl;
+          }
+          n++;
+        }
+      }
+      if (P.allow_truncated)
+        for (int i = Ll; i < Ll + 3; i++)
+          if (orf_fwd_closed_warp(words, al, Ll, i, true, cs, P, &o)) {
+            if (kWrite && lane == 0) {
+              orfs[base + n] = o;
+              orf_seq[base + n] = sl;
+            }
+            n++;
+          }
+    }
+  }
+  if (!kWrite) {
+    // a warp closes at most 2 * 32 + 6 ORFs, so eight warp counts pack into one 64-bit word
+    if (lane == 0) wsum[wid] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      unsigned long long pack = 0;
+      for (int w = 0; w < 8; w++) {
+        t += wsum[w];
+        pack |= (unsigned long long)wsum[w] << (8 * w);
+      }
+      block_counts[blockIdx.x] = t;
+      warp_pack[blockIdx.x] = (int64_t)pack;
+    }
   }
 }
 
@@ -750,12 +799,14 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   }
   int64_t nblk = (s->total + 255) / 256;
   void* d_counts;
-  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(2 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(3 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
   int64_t* counts = (int64_t*)d_counts;
   int64_t* bases = counts + nblk + 1;
+  int64_t* packs = bases + nblk + 1;
   GMG_CUDA(cudaMemsetAsync(counts + nblk, 0, sizeof(int64_t), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orf_count<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, counts);
+  k_orfs<false><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, counts,
+                                                         packs, NULL, NULL, NULL);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -765,8 +816,8 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_orf_capacity(s, total_orfs)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orf_write<<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, bases,
-                                                      s->d_orfs, s->d_orf_seq);
+  k_orfs<true><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, NULL,
+                                                        packs, bases, s->d_orfs, s->d_orf_seq);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
@@ -1008,6 +1059,138 @@ __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const flo
   return emin != 0u && asum < ldexp(1.0, gexp + 52);
 }
 
+// Pass B, fast form: every lane sums a run of 8 consecutive j serially, one warp scan joins the 32 runs (256
+// positions per step).  Any association gives the reference's bits when the certificate of g3_accumulate holds;
+// returns false (caller re-runs the ORF in the reference's order) when it does not.
+__device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
+                                   const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
+                                   const float* __restrict__ plane, const CodonSets& cs, const DevParams& P,
+                                   int first_j, int n_emit, gmg_start* __restrict__ out) {
+  if (indep.W != 3) return false;
+  const int lane = threadIdx.x & 31;
+  const int W = gene.W, m = g.len;
+  const int lowest_j = min(3, P.min_gene_len - 3);
+  const bool fwd = g.frame > 0;
+  const int bound = fwd ? g.hi : g.lo;
+  double run_g = 0.0, run_n = 0.0, asum = 0.0;
+  unsigned emin = 0x7F800000u;
+  int emitted_below = 0;
+  const int j_last = first_j - 1;
+  // partial-window head of the ORF string: lane j evaluates position j (j < W-1 <= 31), all lanes in parallel;
+  // the runs of lanes 0.. pick their values up by shuffle in the first step
+  float hg = 0.f, hn = 0.f;
+  if (lane < W - 1 && lane <= j_last) {
+    const int q = fwd ? g.hi - 1 - lane : g.lo + lane;
+    const int f = (1 + lane) % 3;
+    hg = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
+    if (lane < 2) hn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
+  }
+  for (int base = 0; base <= j_last; base += 256) {
+    const int j0 = base + 8 * lane;
+    const int r0 = j0 % 3;
+    const int k0 = r0 == 0 ? 2 : (r0 == 1 ? 1 : 0);  // j % 3 == 2 at k = k0, k0 + 3, k0 + 6
+    double lg = 0.0, ln = 0.0;
+    double sg[3] = {0.0, 0.0, 0.0}, sn[3] = {0.0, 0.0, 0.0};
+    {
+      const bool in0 = j0 <= j_last;
+      const int q0 = fwd ? g.hi - 1 - j0 : g.lo + j0;
+      // forward: bases q0-7 .. q0+2 (position q0-k needs q0-k .. q0-k+2); reverse: q0-2 .. q0+7
+      const uint32_t win = in0 ? (uint32_t)gmg_extract32(words, a + (fwd ? q0 - 7 : q0 - 2)) : 0u;
+      const float* pl = plane + a + q0;
+      const float* lt = lut + (fwd ? 0 : 192);
+      int f = (1 + j0) % 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int j = j0 + k;
+        float xg = 0.f, xn = 0.f;
+        if (base == 0) {  // warp-uniform
+          xg = __shfl_sync(0xffffffffu, hg, j & 31);
+          xn = __shfl_sync(0xffffffffu, hn, j & 31);
+        }
+        if (j <= j_last) {
+          if (j >= W - 1) xg = __ldg(fwd ? pl - k : pl + k);
+          if (j >= 2) xn = lt[f * 64 + (int)((win >> (fwd ? 2 * (7 - k) : 2 * k)) & 63u)];
+        } else {
+          xg = xn = 0.f;
+        }
+        if (xg != 0.f) emin = min(emin, __float_as_uint(xg) & 0x7F800000u);
+        if (xn != 0.f) emin = min(emin, __float_as_uint(xn) & 0x7F800000u);
+        asum += (double)fmaxf(fabsf(xg), fabsf(xn));
+        lg += (double)xg;
+        ln += (double)xn;
+        if (k % 3 == k0) {
+          sg[k / 3] = lg;
+          sn[k / 3] = ln;
+        }
+        f = (f == 2) ? 0 : f + 1;
+      }
+    }
+    // join the runs: exclusive prefix of the run totals over the lanes
+    double vg = lg, vn = ln;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double tg = __shfl_up_sync(0xffffffffu, vg, d), tn = __shfl_up_sync(0xffffffffu, vn, d);
+      if (lane >= d) {
+        vg += tg;
+        vn += tn;
+      }
+    }
+    double eg = __shfl_up_sync(0xffffffffu, vg, 1), en = __shfl_up_sync(0xffffffffu, vn, 1);
+    if (lane == 0) eg = en = 0.0;
+    eg += run_g;
+    en += run_n;
+    run_g += __shfl_sync(0xffffffffu, vg, 31);
+    run_n += __shfl_sync(0xffffffffu, vn, 31);
+    // start position js = j + 1 (js % 3 == 0) uses score[j]
+    int wv[3], nrec[3], lane_total = 0;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int k = k0 + 3 * t, js = j0 + k + 1;
+      const bool cand = (k < 8) && (js - 1 <= j_last) && (js >= lowest_j) && (js <= m - 1) && (js + 3 >= P.min_gene_len);
+      const int w = cand ? g3_codon_which(words, a, g, js, cs) : -2;
+      const bool is_first = cand && (js == first_j);
+      const bool emits = cand && (w >= 0 || (is_first && g.trunc));
+      wv[t] = w;
+      nrec[t] = emits ? ((is_first && g.trunc && w >= 0) ? 2 : 1) : 0;
+      lane_total += nrec[t];
+    }
+    int incl = lane_total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int below = emitted_below + incl - lane_total;  // records at start positions below this lane's run
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      if (nrec[t]) {
+        const int js = j0 + k0 + 3 * t + 1;
+        below += nrec[t];
+        // records are stored in DESCENDING j order: slot = n_emit - (records at positions <= js)
+        Emit e;
+        e.out = out;
+        e.n = n_emit - below;
+        const double sc = (eg + sg[t]) - (en + sn[t]);
+        const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
+        const bool is_first = (js == first_j);
+        if (is_first && g.trunc) {
+          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+          if (wv[t] >= 0) emit_start(e, js + 2, kpos, sc, wv[t], 0, 0, 0, NULL, NULL, P.ignore_score_len);
+        } else {
+          emit_start(e, js + 2, kpos, sc, wv[t], 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
+        }
+      }
+    }
+    emitted_below += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
+    asum += __shfl_xor_sync(0xffffffffu, asum, d);
+  }
+  const int gexp = (int)(emin >> 23) - 150;
+  return emin != 0u && asum < ldexp(1.0, gexp + 52);
+}
+
 template <bool kWrite>
 __global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
                                                     const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
@@ -1078,7 +1261,7 @@ __global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, c
   // pass B: FP64 sums of gene / indep along j, emitting score[j-1] for start position j
   const int cls = (g.frame > 0) ? (g.hi % 3) : (g.lo % 3);
   const float* plane = planes + (size_t)((g.frame > 0 ? 0 : 3) + cls) * total;
-  if (!g3_accumulate<false>(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out)) {
+  if (!g3_accumulate_fast(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out)) {
     g3_accumulate<true>(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out);
     if (lane == 0) atomicAdd(n_ordered, 1ull);
   }
