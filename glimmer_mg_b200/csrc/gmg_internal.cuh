@@ -40,10 +40,14 @@ void gmg_set_error(const char* fmt, ...);
 //  prob  float [P][N][4]   natural-log probabilities with cut nodes (mut_info_pos == -2)
 //                          pre-resolved to their parent's row (icm.cc:592-597, 829-830), so a
 //                          walk needs no fix-up step.
+//  lut3  float [2][3][64]  only for W == 3 models (the independent model): the full-window value of
+//                          every base triple, [strand][period][b(q0) | b(q0+1) << 2 | b(q0+2) << 4] where q0 is
+//                          the lowest of the three sequence positions the window covers; NULL otherwise.
 struct DevIcm {
   int W, D, P, N, inner;
   const int8_t* mip;
   const float* prob;
+  const float* lut3;
 };
 
 // "marker-indexed" view of the same ICM for the K1 fast path (W <= 16, D <= 8): node on level l with
@@ -90,6 +94,7 @@ struct gmg_icm {
   DevIcm dev;
   uint8_t* d_msh;
   float* d_mprob;
+  float* d_lut3;
   DevIcmFast fast;
 };
 
@@ -101,7 +106,7 @@ struct gmg_seqset {
   int64_t* d_off;            // n+1
   uint64_t* d_words_base;    // allocation incl. padding
   uint64_t* d_words;         // 2-bit bases, base i at bits 2*(i%32) of word i/32
-  int32_t* d_blk2seq;        // sequence holding base 32*b
+  int32_t* d_blk2seq;        // sequence holding base 32*b; bit 31 = interior block (see k_blk2seq)
   uint8_t* d_qual;           // per-base quality (input file values) or NULL
   unsigned long long* d_gc;  // {gc count, ORFs of the last g3 scoring call that took the ordered-sum fallback}
   // ORFs

@@ -297,6 +297,28 @@ static int icm_upload(gmg_icm* m) {
     m->fast.msh = m->d_msh;
     m->fast.mprob = m->d_mprob;
   }
+  // full-window lookup table of W == 3 models (Build_Indep_WO_Stops makes an ICM_t(3,2,3))
+  m->dev.lut3 = NULL;
+  if (m->W == 3 && P == 3) {
+    std::vector<float> lut(384);
+    for (int i = 0; i < 384; i++) {
+      const int raw = i & 63, f = (i >> 6) % 3, strand = i / 192;
+      // forward strand: window position k <-> base q0 + 2 - k; reverse strand: complement of base q0 + k
+      const unsigned ctx = strand == 0 ? (unsigned)(((raw >> 4) & 3) | (((raw >> 2) & 3) << 2) | ((raw & 3) << 4))
+                                       : (unsigned)((~raw) & 63);
+      int node = 0;
+      for (int l = 0; l < D; l++) {
+        const int pos = m->mip[(size_t)f * N + node];
+        if (pos < 0) break;
+        node = 4 * node + (int)((ctx >> (2 * pos)) & 3) + 1;
+      }
+      lut[i] = eff[((size_t)f * N + node) * 4 + ((ctx >> 4) & 3)];
+    }
+    GMG_CUDA(cudaMalloc(&m->d_lut3, 384 * sizeof(float)));
+    GMG_CUDA(cudaMemcpyAsync(m->d_lut3, lut.data(), 384 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->dev.lut3 = m->d_lut3;
+  }
   m->dev.W = m->W;
   m->dev.D = D;
   m->dev.P = P;
@@ -329,6 +351,7 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->d_prob = NULL;
   m->d_msh = NULL;
   m->d_mprob = NULL;
+  m->d_lut3 = NULL;
   for (size_t i = 0; i < m->mip.size(); i++)
     if (m->mip[i] >= w - 1 && w > 1) {
       gmg_set_error("ICM node %zu has mut_info_pos %d outside the context window (len %d)", i, m->mip[i], w);
@@ -453,6 +476,7 @@ extern "C" void gmg_icm_free(gmg_icm* m) {
   if (m->d_prob) cudaFree(m->d_prob);
   if (m->d_msh) cudaFree(m->d_msh);
   if (m->d_mprob) cudaFree(m->d_mprob);
+  if (m->d_lut3) cudaFree(m->d_lut3);
   delete m;
 }
 

@@ -14,16 +14,17 @@
 //
 // Data layout (all offsets are global base indices p = off[seq] + q, q = position in the sequence):
 //   words   2-bit bases, 32 per 64-bit word
-//   planes  float [6][total]   gene-ICM log-prob of base p for reading-frame class c:
-//              plane c   (forward strand): model period (c - q) mod 3, context = the W-1 bases to the RIGHT of q
-//              plane 3+c (reverse strand): model period (1 + q - c) mod 3, context = complement of the W-1
-//                                          bases to the LEFT of q
-//           a forward ORF whose last base has index e = hi-1 reads plane (hi mod 3); a reverse ORF whose first
-//           base has index a reads plane 3 + (a mod 3); both read CONTIGUOUS runs.
+//   planes  float [6][total]   gene-ICM log-prob of base p under model period f (Frame_Score, icm.cc:485):
+//              plane f   (forward strand): context = the W-1 bases to the RIGHT of q
+//              plane 3+f (reverse strand): context = complement of the W-1 bases to the LEFT of q
+//           position j of an ORF string uses period (1 + j) mod 3 (Cumulative_Score icm.cc:354); in terms of the
+//           reading-frame class c of the K2 sums (forward ORFs with hi mod 3 == c, reverse ORFs with lo mod 3 == c)
+//           a forward class-c sum takes period (c - q) mod 3 at position q, a reverse one (1 + q - c) mod 3.
 //   cum     double [6][total]  forward planes: suffix sums  sum_{q' >= q} (gene - indep); reverse planes: prefix sums.
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cub/device/device_scan.cuh>
@@ -45,7 +46,7 @@ struct SeqView {
 
 __device__ __forceinline__ SeqView locate(const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
                                           int64_t p, int32_t* seq_out) {
-  int32_t s = __ldg(blk2seq + (p >> 5));
+  int32_t s = __ldg(blk2seq + (p >> 5)) & 0x7FFFFFFF;
   while (p >= __ldg(off + s + 1)) s++;
   SeqView v;
   v.a = __ldg(off + s);
@@ -86,16 +87,19 @@ __device__ __forceinline__ float icm_str(const DevIcm& m, const uint64_t* __rest
                   lim > 0 ? lim : 0);
 }
 
-// codon (5'->3' on the given strand) whose 3' base is at sequence position q (forward) / whose 3' base is at q
-// reading the reverse strand, as a 6-bit code b0*16 + b1*4 + b2
-__device__ __forceinline__ int codon_fwd_ending_at(const uint64_t* __restrict__ words, int64_t a, int q) {
-  // bases q-2, q-1, q
-  return gmg_base_at(words, a + q - 2) * 16 + gmg_base_at(words, a + q - 1) * 4 + gmg_base_at(words, a + q);
+// 6-bit code (b0*16 + b1*4 + b2) of the forward-strand codon whose three bases start at global index g
+__device__ __forceinline__ int codon6_at(const uint64_t* __restrict__ words, int64_t g) {
+  const int raw = (int)(gmg_extract32(words, g) & 63);  // b(g) | b(g+1) << 2 | b(g+2) << 4
+  return ((raw & 3) << 4) | (raw & 12) | (raw >> 4);
 }
+// forward codon whose 3' base is at sequence position q: S[q-2], S[q-1], S[q]
+__device__ __forceinline__ int codon_fwd_ending_at(const uint64_t* __restrict__ words, int64_t a, int q) {
+  return codon6_at(words, a + q - 2);
+}
+// reverse-strand codon occupying q, q+1, q+2 read 5'->3': c(q+2), c(q+1), c(q)
 __device__ __forceinline__ int codon_rev_starting_at(const uint64_t* __restrict__ words, int64_t a, int q) {
-  // reverse-strand codon occupying q, q+1, q+2 read 5'->3': c(q+2), c(q+1), c(q)
-  return (3 - gmg_base_at(words, a + q + 2)) * 16 + (3 - gmg_base_at(words, a + q + 1)) * 4 +
-         (3 - gmg_base_at(words, a + q));
+  const int c = 63 - codon6_at(words, a + q);
+  return ((c & 3) << 4) | (c & 12) | (c >> 4);
 }
 
 struct CodonSets {
@@ -217,17 +221,8 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
       lim[3 + f] = lr;
     }
     walk_many<6>(mipf, probf, ctx, lim, W, D, v);
-    // forward: period f belongs to class (f + q) mod 3;  reverse: period f belongs to class (1 + q - f) mod 3
-    const int r = q % 3;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      int ff = c - r;
-      ff = ff < 0 ? ff + 3 : ff;  // (c - q) mod 3
-      int fr = 1 + r - c;
-      fr = fr < 0 ? fr + 3 : (fr >= 3 ? fr - 3 : fr);  // (1 + q - c) mod 3
-      planes[(size_t)c * total + p] = ff == 0 ? v[0] : (ff == 1 ? v[1] : v[2]);
-      planes[(size_t)(3 + c) * total + p] = fr == 0 ? v[3] : (fr == 1 ? v[4] : v[5]);
-    }
+    for (int f = 0; f < 6; f++) planes[(size_t)f * total + p] = v[f];
   }
 }
 
@@ -302,17 +297,142 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_fast(DevIcmFast gm, const u
     const float* pb2 = gm.mprob + (size_t)gm.leaves_m * 8;
     const float v0 = __ldg(pb0 + (m0 * 4 + bf)), v1 = __ldg(pb1 + (m1 * 4 + bf)), v2 = __ldg(pb2 + (m2 * 4 + bf));
     const float v3 = __ldg(pb0 + (m3 * 4 + br)), v4 = __ldg(pb1 + (m4 * 4 + br)), v5 = __ldg(pb2 + (m5 * 4 + br));
-    // forward: period f belongs to class (f + q) mod 3, i.e. class c holds period (c - q) mod 3
-    // reverse: period f belongs to class (1 + q - f) mod 3, i.e. class c holds period (1 + q - c) mod 3
-    const int r = q % 3;
     float* o = planes + p;
     const size_t T = (size_t)total;
-    o[0]     = r == 0 ? v0 : (r == 1 ? v2 : v1);
-    o[T]     = r == 0 ? v1 : (r == 1 ? v0 : v2);
-    o[2 * T] = r == 0 ? v2 : (r == 1 ? v1 : v0);
-    o[3 * T] = r == 0 ? v4 : (r == 1 ? v5 : v3);
-    o[4 * T] = r == 0 ? v3 : (r == 1 ? v4 : v5);
-    o[5 * T] = r == 0 ? v5 : (r == 1 ? v3 : v4);
+    o[0] = v0;
+    o[T] = v1;
+    o[2 * T] = v2;
+    o[3 * T] = v3;
+    o[4 * T] = v4;
+    o[5 * T] = v5;
+  }
+}
+
+// K1, period-phased form (the default): the CTA walks its contiguous chunk of bases three times, once per
+// model period, so that only ONE period's leaf table (256 KB of `mprob` for the default depth 7) is live in
+// the SM's L1 at a time -- measured (tools/gpu/ubench_gather.cu): random 4-byte gathers cost 11 cycles per
+// warp and SM from an L1-resident 256 KB table against 28 from the L2-resident 1.5 MB one.  Per phase a thread
+// keeps six walks in flight (three bases x two strands).  One 1024-thread CTA per SM, 8 KB of shift table.
+// one phase-step of k1_planes_phased for kU bases per thread (2 kU walks in flight).  kInterior: every base is
+// at least 32 bases from both ends of its sequence (warp-uniform), so all windows are full and the stop test
+// degenerates to "is this node descendable".
+template <int kD, int kU, bool kInterior>
+__device__ __forceinline__ void k1_phase_step(const DevIcmFast& gm, const uint8_t* s_sh, const uint32_t* __restrict__ w32,
+                                              const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
+                                              const float* __restrict__ pb, float* __restrict__ of,
+                                              float* __restrict__ orv, int64_t p0, int64_t c0, int64_t c1, int nt) {
+  const int W = gm.W, D = kD > 0 ? kD : gm.D;
+  const int wsh = 32 - 2 * W, psh = 2 * (W - 1);
+  uint32_t cf[kU], cr[kU], mf[kU], mr[kU];
+  unsigned lshf[kU], lshr[kU];
+  bool af[kU], ar[kU], ok[kU];
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    const int64_t p = p0 + (int64_t)nt * u;
+    ok[u] = p < c1;
+    const int64_t pp = ok[u] ? p : c0;  // harmless in-range stand-in
+    const int64_t pr = pp - (W - 1);
+    const uint32_t* wf = w32 + (pp >> 4);
+    const uint32_t* wr = w32 + (pr >> 4);
+    const uint32_t rawf = __funnelshift_r(__ldg(wf), __ldg(wf + 1), 2 * (int)(pp & 15));
+    const uint32_t rawr = __funnelshift_r(__ldg(wr), __ldg(wr + 1), 2 * (int)(pr & 15));
+    uint32_t c = __brev(rawf);
+    c = ((c >> 1) & 0x55555555u) | ((c & 0x55555555u) << 1);
+    cf[u] = c >> wsh;   // window position k <-> base p + W-1-k
+    cr[u] = ~rawr;      // window position k <-> complement of base p - (W-1) + k
+    if (kInterior) {
+      lshf[u] = lshr[u] = 30;
+    } else {
+      int32_t s;
+      SeqView sv = locate(off, blk2seq, pp, &s);
+      const int q = (int)(pp - sv.a);
+      int lf = q + W - sv.len;  // first available window position (0 = full window)
+      lf = lf > 0 ? lf : 0;
+      int lr = W - 1 - q;
+      lr = lr > 0 ? lr : 0;
+      lshf[u] = 30 - 2 * lf;  // a node may be descended iff its shift <= this
+      lshr[u] = 30 - 2 * lr;
+    }
+    mf[u] = mr[u] = 1;
+    af[u] = ar[u] = true;
+  }
+#pragma unroll
+  for (int l = 0; l < D; l++) {
+    unsigned sf[kU], sr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      sf[u] = s_sh[mf[u]];
+      sr[u] = s_sh[mr[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      af[u] = af[u] && (sf[u] <= (kInterior ? 30u : lshf[u]));
+      ar[u] = ar[u] && (sr[u] <= (kInterior ? 30u : lshr[u]));
+      const uint32_t nf = __funnelshift_l(cf[u] << (sf[u] & 31), mf[u], 2);
+      const uint32_t nr = __funnelshift_l(cr[u] << (sr[u] & 31), mr[u], 2);
+      mf[u] = af[u] ? nf : mf[u];
+      mr[u] = ar[u] ? nr : mr[u];
+    }
+  }
+  float vf[kU], vr[kU];
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    vf[u] = __ldg(pb + (mf[u] * 4 + ((cf[u] >> psh) & 3u)));
+    vr[u] = __ldg(pb + (mr[u] * 4 + ((cr[u] >> psh) & 3u)));
+  }
+#pragma unroll
+  for (int u = 0; u < kU; u++)
+    if (ok[u]) {
+      of[p0 + (int64_t)nt * u] = vf[u];
+      orv[p0 + (int64_t)nt * u] = vr[u];
+    }
+}
+
+// K1, period-phased form (the default): the CTA walks its contiguous chunk of bases three times, once per
+// model period, so that only ONE period's leaf table (256 KB of `mprob` for the default depth 7) is live in
+// the SM's L1 at a time -- measured (tools/gpu/ubench_gather.cu): random 4-byte gathers cost 11 cycles per
+// warp and SM from an L1-resident 256 KB table against 28 from the L2-resident 1.5 MB one.  Per phase a thread
+// keeps 2 kU walks in flight (kU bases x two strands); 8 KB of shift table per CTA.
+template <int kD, int kU>
+__global__ void __launch_bounds__(1024, 2) k1_planes_phased(DevIcmFast gm, const uint32_t* __restrict__ w32,
+                                                            const int64_t* __restrict__ off,
+                                                            const int32_t* __restrict__ blk2seq, int64_t total,
+                                                            float* __restrict__ planes) {
+  extern __shared__ uint8_t s_sh[];
+  const int inner_m = gm.inner_m;
+  // contiguous chunk of this CTA (a multiple of 32 bases: warps are aligned with the blocks of blk2seq)
+  const int nt = blockDim.x;
+  int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + 31) / 32 * 32;
+  const int64_t c0 = (int64_t)blockIdx.x * per;
+  const int64_t c1 = c0 + per < total ? c0 + per : total;
+  for (int f = 0; f < 3; f++) {
+    __syncthreads();
+    {
+      const uint8_t* src8 = gm.msh + (size_t)f * inner_m;
+      if ((inner_m & 15) == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(src8);
+        uint4* dst = reinterpret_cast<uint4*>(s_sh);
+        for (int i = threadIdx.x; i < (inner_m >> 4); i += blockDim.x) dst[i] = __ldg(src + i);
+      } else {
+        for (int i = threadIdx.x; i < inner_m; i += blockDim.x) s_sh[i] = src8[i];
+      }
+    }
+    __syncthreads();
+    const float* pb = gm.mprob + (size_t)f * gm.leaves_m * 4;
+    float* of = planes + (size_t)f * total;
+    float* orv = planes + (size_t)(3 + f) * total;
+    for (int64_t p0 = c0 + threadIdx.x; p0 < c1; p0 += (int64_t)kU * nt) {
+      // the warp's kU 32-base blocks (c0 and nt are multiples of 32): all interior?
+      bool interior = true;
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int64_t p = p0 + (int64_t)nt * u;
+        interior = interior && (p < c1) && (__ldg(blk2seq + (p >> 5)) < 0);
+      }
+      if (interior) k1_phase_step<kD, kU, true>(gm, s_sh, w32, off, blk2seq, pb, of, orv, p0, c0, c1, nt);
+      else k1_phase_step<kD, kU, false>(gm, s_sh, w32, off, blk2seq, pb, of, orv, p0, c0, c1, nt);
+    }
   }
 }
 
@@ -322,6 +442,34 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
   *planes_out = (float*)planes;
   if (s->total == 0) return 0;
+  static const bool phased = !(getenv("GMG_K1_UNPHASED") && atoi(getenv("GMG_K1_UNPHASED")));
+  if (gene->fast.valid && phased) {
+    size_t smem = (size_t)gene->fast.inner_m;
+    if (smem > 48 * 1024)  // only depth 8
+      GMG_CUDA(cudaFuncSetAttribute(k1_planes_phased<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int nt = getenv("GMG_K1_THREADS") ? atoi(getenv("GMG_K1_THREADS")) : 1024;
+    static const int per_sm = getenv("GMG_K1_CTAS") ? atoi(getenv("GMG_K1_CTAS")) : 2;
+    static const int ku = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 1;
+    int64_t need = (s->total + ku * nt - 1) / (ku * nt);
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    int grid = (int)(need < cap ? need : cap);
+    if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
+    const uint32_t* w32 = (const uint32_t*)s->d_words;
+#define GMG_K1_LAUNCH(KD, KU) \
+  k1_planes_phased<KD, KU><<<grid, nt, smem, ctx->stream>>>(gene->fast, w32, s->d_off, s->d_blk2seq, s->total, (float*)planes)
+    if (gene->fast.D == 7) {
+      if (ku == 1) GMG_K1_LAUNCH(7, 1);
+      else if (ku == 3) GMG_K1_LAUNCH(7, 3);
+      else GMG_K1_LAUNCH(7, 2);
+    } else {
+      GMG_K1_LAUNCH(0, 2);
+    }
+#undef GMG_K1_LAUNCH
+    gmg_prof_end(ctx, GMG_PROF_K1);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (gene->fast.valid) {
     size_t smem = (size_t)3 * gene->fast.inner_m;
     if (smem > 48 * 1024)
@@ -376,10 +524,10 @@ __global__ void __launch_bounds__(256) k_frame_scores(DevIcm indep, const uint64
   const int q = (int)(p - sv.a);
   double* row = fs + 6 * sv.a;
   for (int f = 0; f < 3; f++) {
-    float g = planes[(size_t)mod3(f + q) * total + p];
+    float g = planes[(size_t)f * total + p];
     float n = icm_fwd(indep, words, p, q, sv.len, f);
     row[(size_t)f * sv.len + q] = (double)g - (double)n;
-    g = planes[(size_t)(3 + mod3(1 + q - f)) * total + p];
+    g = planes[(size_t)(3 + f) * total + p];
     n = icm_rev(indep, words, p, q, 0, f);
     row[(size_t)(3 + f) * sv.len + q] = (double)g - (double)n;
   }
@@ -514,12 +662,6 @@ extern "C" int gmg_icm_partial_window_prob(gmg_ctx* ctx, const gmg_icm* m, int p
 // in-frame stop, 32 codons per step (ballot + find-first), so the cost of a long ORF is shared by 32 lanes
 // instead of serialising one.  Two passes (count, block scan, write) give the reference's output order
 // deterministically: by closing base; forward before reverse; then the end-of-sequence extras.
-
-// 6-bit code of the codon whose three sequence bases are q0, q0+1, q0+2 read on the forward strand
-__device__ __forceinline__ int codon6_at(const uint64_t* __restrict__ words, int64_t g) {
-  const int raw = (int)(gmg_extract32(words, g) & 63);  // b(q0) | b(q0+1) << 2 | b(q0+2) << 4
-  return ((raw & 3) << 4) | (raw & 12) | (raw >> 4);
-}
 
 // forward ORF closed by the (possibly virtual) stop codon whose last base is i.  Warp-uniform arguments and
 // result; all 32 lanes must call.
@@ -934,19 +1076,6 @@ __device__ __forceinline__ int g3_codon_which(const uint64_t* __restrict__ words
   return ((cs.start_mask >> c) & 1) ? (int)cs.which[c] : -1;
 }
 
-// Independent-model lookup: the model of Build_Indep_WO_Stops is an ICM_t(3,2,3), so a full window is one of 64
-// base triples per period.  lut[(strand*3 + f)*64 + raw] with raw = b(q0) | b(q0+1) << 2 | b(q0+2) << 4 of the three
-// sequence bases the window covers (forward strand: q0 = q, reverse strand: q0 = q - 2), filled once per CTA.
-__device__ __forceinline__ void fill_indep_lut(const DevIcm& indep, float* lut) {
-  for (int i = threadIdx.x; i < 384; i += blockDim.x) {
-    const int raw = i & 63, f = (i >> 6) % 3, strand = i / 192;
-    uint64_t ctx;
-    if (strand == 0) ctx = (uint64_t)(((raw >> 4) & 3) | (((raw >> 2) & 3) << 2) | ((raw & 3) << 4));  // reversed order
-    else ctx = (uint64_t)((~raw) & 63);                                                                // complemented
-    lut[i] = gmg_walk(indep.mip + (size_t)f * indep.inner, indep.prob + (size_t)f * indep.N * 4, ctx, 3, indep.D, 0);
-  }
-}
-
 // Pass B of k3_g3_starts: gene / indep running sums along j and emission of the start records.
 //   kOrdered = true : lane-ordered serial accumulation, the reference's association (icm.cc:390-402).
 //   kOrdered = false: warp-parallel inclusive scans.  Returns (to every lane) whether the sums are CERTIFIED to
@@ -957,12 +1086,13 @@ __device__ __forceinline__ void fill_indep_lut(const DevIcm& indep, float* lut) 
 template <bool kOrdered>
 __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
                               const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
-                              const float* __restrict__ plane, const CodonSets& cs, const DevParams& P, int first_j,
+                              const float* __restrict__ plane, int64_t total, const CodonSets& cs, const DevParams& P,
+                              int first_j,
                               int n_emit, gmg_start* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int W = gene.W, m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
-  const bool use_lut = (indep.W == 3);
+  const bool use_lut = (lut != NULL);
   double run_g = 0.0, run_n = 0.0, asum = 0.0;
   unsigned emin = 0x7F800000u;
   int emitted_below = 0;           // records of start positions below the current chunk (ascending j)
@@ -974,12 +1104,12 @@ __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const flo
       const int f = (1 + j) % 3;
       if (g.frame > 0) {
         const int q = g.hi - 1 - j;
-        xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f) : __ldg(plane + a + q);
+        xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f) : __ldg(plane + (size_t)f * total + a + q);
         if (use_lut && j >= 2) xn = lut[f * 64 + (int)(gmg_extract32(words, a + q) & 63)];
         else xn = icm_fwd(indep, words, a + q, q, g.hi, f);
       } else {
         const int q = g.lo + j;
-        xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f) : __ldg(plane + a + q);
+        xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f) : __ldg(plane + (size_t)f * total + a + q);
         if (use_lut && j >= 2) xn = lut[(3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63)];
         else xn = icm_rev(indep, words, a + q, q, g.lo, f);
       }
@@ -1059,34 +1189,44 @@ __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const flo
   return emin != 0u && asum < ldexp(1.0, gexp + 52);
 }
 
-// Pass B, fast form: every lane sums a run of 8 consecutive j serially, one warp scan joins the 32 runs (256
-// positions per step).  Any association gives the reference's bits when the certificate of g3_accumulate holds;
-// returns false (caller re-runs the ORF in the reference's order) when it does not.
-__device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
-                                   const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
-                                   const float* __restrict__ plane, const CodonSets& cs, const DevParams& P,
-                                   int first_j, int n_emit, gmg_start* __restrict__ out) {
-  if (indep.W != 3) return false;
-  const int lane = threadIdx.x & 31;
+// Pass B, fast form.  A group of G lanes owns one ORF (32 / G ORFs per warp: most ORFs are a few hundred bases, so
+// a whole warp per ORF would mostly idle).  Every lane sums a run of 8 consecutive j serially, one G-wide scan
+// joins the runs (8 G positions per step).  Any association gives the reference's bits when the certificate of
+// g3_accumulate holds; the group's result is false (caller re-runs the ORF in the reference's order) when it
+// does not.  Must be called by all 32 lanes; `active` = this lane's group has an ORF to do.
+template <int G>
+__device__ bool g3_accumulate_group(bool active, const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
+                                    const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
+                                    const float* __restrict__ plane, int64_t total, const CodonSets& cs,
+                                    const DevParams& P, int first_j, int n_emit, gmg_start* __restrict__ out) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int gl = (threadIdx.x & 31) % G;  // lane within the group
   const int W = gene.W, m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
   const bool fwd = g.frame > 0;
   const int bound = fwd ? g.hi : g.lo;
+  const int j_last = active ? first_j - 1 : -1;
+  // partial-window head of the ORF string (positions j < W-1 <= 2 G): group lane gl evaluates j = gl and G + gl
+  float h0 = 0.f, h1 = 0.f, hn = 0.f;
+  {
+    const int j1 = G + gl;
+    if (gl < W - 1 && gl <= j_last) {
+      const int q = fwd ? g.hi - 1 - gl : g.lo + gl;
+      const int f = (1 + gl) % 3;
+      h0 = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
+      if (gl < 2) hn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
+    }
+    if (j1 < W - 1 && j1 <= j_last) {
+      const int q = fwd ? g.hi - 1 - j1 : g.lo + j1;
+      const int f = (1 + j1) % 3;
+      h1 = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
+    }
+  }
   double run_g = 0.0, run_n = 0.0, asum = 0.0;
   unsigned emin = 0x7F800000u;
   int emitted_below = 0;
-  const int j_last = first_j - 1;
-  // partial-window head of the ORF string: lane j evaluates position j (j < W-1 <= 31), all lanes in parallel;
-  // the runs of lanes 0.. pick their values up by shuffle in the first step
-  float hg = 0.f, hn = 0.f;
-  if (lane < W - 1 && lane <= j_last) {
-    const int q = fwd ? g.hi - 1 - lane : g.lo + lane;
-    const int f = (1 + lane) % 3;
-    hg = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
-    if (lane < 2) hn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
-  }
-  for (int base = 0; base <= j_last; base += 256) {
-    const int j0 = base + 8 * lane;
+  for (int base = 0; __any_sync(FULL, base <= j_last); base += 8 * G) {
+    const int j0 = base + 8 * gl;
     const int r0 = j0 % 3;
     const int k0 = r0 == 0 ? 2 : (r0 == 1 ? 1 : 0);  // j % 3 == 2 at k = k0, k0 + 3, k0 + 6
     double lg = 0.0, ln = 0.0;
@@ -1096,19 +1236,21 @@ __device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, cons
       const int q0 = fwd ? g.hi - 1 - j0 : g.lo + j0;
       // forward: bases q0-7 .. q0+2 (position q0-k needs q0-k .. q0-k+2); reverse: q0-2 .. q0+7
       const uint32_t win = in0 ? (uint32_t)gmg_extract32(words, a + (fwd ? q0 - 7 : q0 - 2)) : 0u;
-      const float* pl = plane + a + q0;
+      const float* pl = plane + a + q0;  // + f * total selects the period's plane
       const float* lt = lut + (fwd ? 0 : 192);
       int f = (1 + j0) % 3;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int j = j0 + k;
         float xg = 0.f, xn = 0.f;
-        if (base == 0) {  // warp-uniform
-          xg = __shfl_sync(0xffffffffu, hg, j & 31);
-          xn = __shfl_sync(0xffffffffu, hn, j & 31);
+        if (base == 0) {  // warp-uniform: head value of position j is held by group lane j % G, round j / G
+          const int hl = j % G;
+          const float t0 = __shfl_sync(FULL, h0, hl, G), t1 = __shfl_sync(FULL, h1, hl, G), tn = __shfl_sync(FULL, hn, hl, G);
+          xg = j < G ? t0 : t1;
+          xn = j < 2 ? tn : 0.f;
         }
         if (j <= j_last) {
-          if (j >= W - 1) xg = __ldg(fwd ? pl - k : pl + k);
+          if (j >= W - 1) xg = __ldg((fwd ? pl - k : pl + k) + (size_t)f * total);
           if (j >= 2) xn = lt[f * 64 + (int)((win >> (fwd ? 2 * (7 - k) : 2 * k)) & 63u)];
         } else {
           xg = xn = 0.f;
@@ -1125,22 +1267,22 @@ __device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, cons
         f = (f == 2) ? 0 : f + 1;
       }
     }
-    // join the runs: exclusive prefix of the run totals over the lanes
+    // join the runs: exclusive prefix of the run totals over the group's lanes
     double vg = lg, vn = ln;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double tg = __shfl_up_sync(0xffffffffu, vg, d), tn = __shfl_up_sync(0xffffffffu, vn, d);
-      if (lane >= d) {
+    for (int d = 1; d < G; d <<= 1) {
+      const double tg = __shfl_up_sync(FULL, vg, d, G), tn = __shfl_up_sync(FULL, vn, d, G);
+      if (gl >= d) {
         vg += tg;
         vn += tn;
       }
     }
-    double eg = __shfl_up_sync(0xffffffffu, vg, 1), en = __shfl_up_sync(0xffffffffu, vn, 1);
-    if (lane == 0) eg = en = 0.0;
+    double eg = __shfl_up_sync(FULL, vg, 1, G), en = __shfl_up_sync(FULL, vn, 1, G);
+    if (gl == 0) eg = en = 0.0;
     eg += run_g;
     en += run_n;
-    run_g += __shfl_sync(0xffffffffu, vg, 31);
-    run_n += __shfl_sync(0xffffffffu, vn, 31);
+    run_g += __shfl_sync(FULL, vg, G - 1, G);
+    run_n += __shfl_sync(FULL, vn, G - 1, G);
     // start position js = j + 1 (js % 3 == 0) uses score[j]
     int wv[3], nrec[3], lane_total = 0;
 #pragma unroll
@@ -1156,9 +1298,9 @@ __device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, cons
     }
     int incl = lane_total;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+    for (int d = 1; d < G; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, d, G);
+      if (gl >= d) incl += t;
     }
     int below = emitted_below + incl - lane_total;  // records at start positions below this lane's run
 #pragma unroll
@@ -1181,29 +1323,24 @@ __device__ bool g3_accumulate_fast(const DevIcm& gene, const DevIcm& indep, cons
         }
       }
     }
-    emitted_below += __shfl_sync(0xffffffffu, incl, 31);
+    emitted_below += __shfl_sync(FULL, incl, G - 1, G);
   }
-  for (int d = 16; d > 0; d >>= 1) {
-    emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
-    asum += __shfl_xor_sync(0xffffffffu, asum, d);
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) {
+    emin = min(emin, __shfl_xor_sync(FULL, emin, d, G));
+    asum += __shfl_xor_sync(FULL, asum, d, G);
   }
   const int gexp = (int)(emin >> 23) - 150;
   return emin != 0u && asum < ldexp(1.0, gexp + 52);
 }
 
-template <bool kWrite>
-__global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
-                                                    const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
-                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                    const float* __restrict__ planes, CodonSets cs, DevParams P,
-                                                    int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
-                                                    gmg_start* __restrict__ starts,
-                                                    unsigned long long* __restrict__ n_ordered) {
-  __shared__ float s_lut[384];
-  if (kWrite) {
-    if (indep.W == 3) fill_indep_lut(indep, s_lut);
-    __syncthreads();
-  }
+// Count pass: one warp per ORF finds the emitting positions with ballots over 32 codons at a time.
+// A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and (codon is a start ||
+// (nothing emitted yet && truncated)).  counts[oi] = records, first_js[oi] = j of the first (largest-j) one.
+__global__ void __launch_bounds__(256) k3_g3_count(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                   const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                   int64_t n_orfs, CodonSets cs, DevParams P,
+                                                   int64_t* __restrict__ counts, int32_t* __restrict__ first_js) {
   const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (oi >= n_orfs) return;
@@ -1214,55 +1351,69 @@ __global__ void __launch_bounds__(128) k3_g3_starts(DevIcm gene, DevIcm indep, c
   const G3Geom g = g3_geom(o, L, P);
   const int m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
-
-  // pass A: positions that emit (descending j), needs only codons.  first_j = largest qualifying j.
-  // A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and
-  // (codon is a start || (nothing emitted yet && truncated)).
-  int n_emit = 0;        // total records
-  int first_j = -1;      // j of the first (largest-j) emitting position
-  {
-    // largest j % 3 == 0 that is <= m-1
-    int jtop = (m - 1) - ((m - 1) % 3);
-    int found_first = -1, cnt = 0;
-    for (int jb = jtop; jb >= lowest_j; jb -= 96) {
-      int j = jb - 3 * lane;
-      bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
-      int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
-      bool is_codon = ok && w >= 0;
-      // truncated rule can only apply to the very first candidate position examined (first_pos == 0)
-      unsigned cm = __ballot_sync(0xffffffffu, is_codon);
-      unsigned okm = __ballot_sync(0xffffffffu, ok);
-      if (found_first < 0) {
-        if (g.trunc && okm) {
-          int l0 = __ffs(okm) - 1;  // first ok lane = largest j
-          found_first = jb - 3 * l0;
-          cnt += 1 + ((cm >> l0) & 1);
-          cm &= ~(1u << l0);
-          cnt += __popc(cm);
-        } else if (!g.trunc && cm) {
-          int l0 = __ffs(cm) - 1;
-          found_first = jb - 3 * l0;
-          cnt += __popc(cm);
-        }
-      } else {
+  const int jtop = (m - 1) - ((m - 1) % 3);  // largest j % 3 == 0 that is <= m-1
+  int found_first = -1, cnt = 0;
+  for (int jb = jtop; jb >= lowest_j; jb -= 96) {
+    const int j = jb - 3 * lane;
+    const bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
+    const int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
+    const bool is_codon = ok && w >= 0;
+    // the truncated rule can only apply to the very first candidate position examined (first_pos == 0)
+    unsigned cm = __ballot_sync(0xffffffffu, is_codon);
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    if (found_first < 0) {
+      if (g.trunc && okm) {
+        const int l0 = __ffs(okm) - 1;  // first ok lane = largest j
+        found_first = jb - 3 * l0;
+        cnt += 1 + ((cm >> l0) & 1);
+        cm &= ~(1u << l0);
+        cnt += __popc(cm);
+      } else if (!g.trunc && cm) {
+        const int l0 = __ffs(cm) - 1;
+        found_first = jb - 3 * l0;
         cnt += __popc(cm);
       }
+    } else {
+      cnt += __popc(cm);
     }
-    n_emit = cnt;
-    first_j = found_first;
   }
-  if (!kWrite) {
-    if (lane == 0) counts[oi] = n_emit;
-    return;
+  if (lane == 0) {
+    counts[oi] = cnt;
+    first_js[oi] = found_first;
   }
-  if (n_emit == 0) return;
-  gmg_start* out = starts + start_off[oi];
+}
 
-  // pass B: FP64 sums of gene / indep along j, emitting score[j-1] for start position j
-  const int cls = (g.frame > 0) ? (g.hi % 3) : (g.lo % 3);
-  const float* plane = planes + (size_t)((g.frame > 0 ? 0 : 3) + cls) * total;
-  if (!g3_accumulate_fast(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out)) {
-    g3_accumulate<true>(gene, indep, s_lut, words, a, g, plane, cs, P, first_j, n_emit, out);
+// Write pass: one warp per ORF forms the FP64 sums of gene / indep along j and emits score[j-1] for every start
+// position j found by the count pass.  (Measured alternatives, all slower on the 5 Mbp benchmark contig because they
+// trade occupancy for fewer instructions and this kernel is latency-bound: persistent CTAs with the gene model's
+// branch table in shared memory, 8-lane groups with four ORFs per warp, and one thread per ORF over a
+// length-sorted ORF list -- see profiles/README.md.)
+__global__ void __launch_bounds__(128, 7) k3_g3_write(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                   const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                   const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                   const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                   const int64_t* __restrict__ start_off,
+                                                   const int32_t* __restrict__ first_js, gmg_start* __restrict__ starts,
+                                                   unsigned long long* __restrict__ n_ordered) {
+  __shared__ float s_lut[384];
+  if (indep.lut3)
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
+  __syncthreads();
+  const float* lut = indep.lut3 ? s_lut : NULL;
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (oi >= n_orfs) return;
+  const int64_t so = start_off[oi];
+  const int n_emit = (int)(start_off[oi + 1] - so);
+  if (n_emit == 0) return;
+  const int first_j = first_js[oi];
+  const int32_t s = orf_seq[oi];
+  const int64_t a = off[s];
+  const G3Geom g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
+  const float* plane = planes + (size_t)(g.frame > 0 ? 0 : 3) * total;  // the strand's three period planes
+  const bool fast = lut != NULL && gene.W - 1 <= 32;
+  if (!fast || !g3_accumulate_group<32>(true, gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, starts + so)) {
+    g3_accumulate<true>(gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, starts + so);
     if (lane == 0) atomicAdd(n_ordered, 1ull);
   }
 }
@@ -1311,7 +1462,7 @@ __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* _
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const int f = mod3(1 + q - c);
-          const float gval = planes[(size_t)(3 + c) * total + a + q];
+          const float gval = planes[(size_t)(3 + f) * total + a + q];
           const float nval = icm_rev(indep, words, a + q, q, 0, f);
           x[c] = (double)gval - (double)nval;
           if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
@@ -1386,7 +1537,7 @@ __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* _
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const int f = mod3(c - q);
-          const float gval = planes[(size_t)c * total + a + q];
+          const float gval = planes[(size_t)f * total + a + q];
           const float nval = icm_fwd(indep, words, a + q, q, L, f);
           x[c] = (double)gval - (double)nval;
           if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
@@ -1702,14 +1853,14 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
   GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
-  void* d_counts;
+  void *d_counts, *d_first;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 1) * sizeof(int64_t), &d_counts)) return 1;
+  if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
   int64_t* counts = (int64_t*)d_counts;
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, sizeof(int64_t), ctx->stream));
-  unsigned grid = (unsigned)((s->n_orfs * 32 + 127) / 128);
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_g3_starts<false><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs,
-                                                     s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp, counts, NULL, NULL, NULL);
+  k3_g3_count<<<(unsigned)((s->n_orfs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+      s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, cs, dp, counts, (int32_t*)d_first);
   gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -1718,13 +1869,15 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_start_capacity(s, total_starts)) return 1;
-  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_g3_starts<true><<<grid, 128, 0, ctx->stream>>>(gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq,
-                                                    s->n_orfs, s->total, planes, cs, dp, NULL, s->d_start_off, s->d_starts,
-                                                    s->d_gc + 1);
-  gmg_prof_end(ctx, GMG_PROF_K3);
-  ctx->launches++;
-  GMG_CUDA(cudaGetLastError());
+  if (total_starts > 0) {
+    if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+    k3_g3_write<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp,
+        s->d_start_off, (const int32_t*)d_first, s->d_starts, s->d_gc + 1);
+    gmg_prof_end(ctx, GMG_PROF_K3);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
   s->n_starts = total_starts;
   if (n_starts) *n_starts = total_starts;
   return 0;

@@ -63,7 +63,7 @@ __global__ void k_unpack(const uint64_t* __restrict__ words, int64_t total, char
   if (i < total) out[i] = "acgt"[gmg_base_at(words, i)];
 }
 
-// sequence that holds base 32*b (binary search over the offsets; run once per batch)
+// sequence that holds base 32*b (binary search over the offsets; run once per batch), plus the interior flag
 __global__ void k_blk2seq(const int64_t* __restrict__ off, int64_t n, int64_t nblk, int32_t* __restrict__ blk2seq) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblk) return;
@@ -74,7 +74,10 @@ __global__ void k_blk2seq(const int64_t* __restrict__ off, int64_t n, int64_t nb
     if (off[mid] <= p) lo = mid;
     else hi = mid;
   }
-  blk2seq[b] = (int32_t)lo;
+  // bit 31: "interior" block -- all 32 bases lie in one sequence, at least 32 bases from either end, so no
+  // window of up to GMG_MAX_W bases around them is partial (K1's fast path needs no sequence lookup at all)
+  const bool interior = (p - off[lo] >= 32) && (p + 64 <= off[lo + 1]);
+  blk2seq[b] = (int32_t)lo | (interior ? (int32_t)0x80000000 : 0);
 }
 
 int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc) {

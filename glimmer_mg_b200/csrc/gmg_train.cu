@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(512) k4_count(const uint64_t* __restrict__ wor
   int* mine = kSmem ? s_cnt + ((threadIdx.x >> 5) % copies) * slab : counts;
   const int wp = W % P;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    int32_t s = __ldg(blk2seq + (p >> 5));
+    int32_t s = __ldg(blk2seq + (p >> 5)) & 0x7FFFFFFF;
     while (p >= __ldg(off + s + 1)) s++;
     const int64_t a = __ldg(off + s);
     const int len = (int)(__ldg(off + s + 1) - a);
