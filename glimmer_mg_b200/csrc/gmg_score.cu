@@ -1076,25 +1076,18 @@ __device__ __forceinline__ int g3_codon_which(const uint64_t* __restrict__ words
   return ((cs.start_mask >> c) & 1) ? (int)cs.which[c] : -1;
 }
 
-// Pass B of k3_g3_starts: gene / indep running sums along j and emission of the start records.
-//   kOrdered = true : lane-ordered serial accumulation, the reference's association (icm.cc:390-402).
-//   kOrdered = false: warp-parallel inclusive scans.  Returns (to every lane) whether the sums are CERTIFIED to
-//                     be bit-identical to the serial ones: every term is a float, i.e. an integer multiple of
-//                     2^(e_min - 150) (e_min = smallest biased exponent among the non-zero terms), so when
-//                     sum |term| < 2^(e_min - 150 + 52) every partial sum of ANY association is exactly
-//                     representable in FP64 and no addition rounds.  The caller re-runs uncertified ORFs ordered.
-template <bool kOrdered>
-__device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
-                              const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
-                              const float* __restrict__ plane, int64_t total, const CodonSets& cs, const DevParams& P,
-                              int first_j,
-                              int n_emit, gmg_start* __restrict__ out) {
+// Ordered pass (the fallback of k3_g3_emit): gene / indep running sums along j in the reference's association
+// (icm.cc:390-402) and emission of the start records.  Lanes evaluate 32 consecutive j; the running sums are
+// formed by a lane-ordered accumulation, so every prefix has exactly the reference's serial rounding.
+__device__ void g3_accumulate_ordered(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
+                                      const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
+                                      const float* __restrict__ plane, int64_t total, const CodonSets& cs,
+                                      const DevParams& P, int first_j, int n_emit, gmg_start* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int W = gene.W, m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
   const bool use_lut = (lut != NULL);
-  double run_g = 0.0, run_n = 0.0, asum = 0.0;
-  unsigned emin = 0x7F800000u;
+  double run_g = 0.0, run_n = 0.0;
   int emitted_below = 0;           // records of start positions below the current chunk (ascending j)
   const int j_last = first_j - 1;  // scores are needed up to index first_j - 1
   for (int base = 0; base <= j_last; base += 32) {
@@ -1114,37 +1107,16 @@ __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const flo
         else xn = icm_rev(indep, words, a + q, q, g.lo, f);
       }
     }
-    double my_g, my_n;
-    if (kOrdered) {
-      // position base+0, base+1, ... exactly like the serial loop
-      my_g = my_n = 0.0;
-      const int cnt = min(32, j_last + 1 - base);
-      for (int l = 0; l < cnt; l++) {
-        run_g += (double)__shfl_sync(0xffffffffu, xg, l);
-        run_n += (double)__shfl_sync(0xffffffffu, xn, l);
-        if (l == lane) {
-          my_g = run_g;
-          my_n = run_n;
-        }
+    // position base+0, base+1, ... exactly like the serial loop
+    double my_g = 0.0, my_n = 0.0;
+    const int cnt = min(32, j_last + 1 - base);
+    for (int l = 0; l < cnt; l++) {
+      run_g += (double)__shfl_sync(0xffffffffu, xg, l);
+      run_n += (double)__shfl_sync(0xffffffffu, xn, l);
+      if (l == lane) {
+        my_g = run_g;
+        my_n = run_n;
       }
-    } else {
-      const unsigned eg = __float_as_uint(xg) & 0x7F800000u, en = __float_as_uint(xn) & 0x7F800000u;
-      if (xg != 0.f) emin = min(emin, eg);
-      if (xn != 0.f) emin = min(emin, en);
-      asum += fmax(fabs((double)xg), fabs((double)xn));
-      double vg = (double)xg, vn = (double)xn;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double tg = __shfl_up_sync(0xffffffffu, vg, d), tn = __shfl_up_sync(0xffffffffu, vn, d);
-        if (lane >= d) {
-          vg += tg;
-          vn += tn;
-        }
-      }
-      my_g = run_g + vg;
-      my_n = run_n + vn;
-      run_g = __shfl_sync(0xffffffffu, my_g, 31);
-      run_n = __shfl_sync(0xffffffffu, my_n, 31);
     }
     // start position js = j + 1 uses score[j]
     const int js = j + 1;
@@ -1167,171 +1139,14 @@ __device__ bool g3_accumulate(const DevIcm& gene, const DevIcm& indep, const flo
       e.out = out;
       e.n = slot;
       if (is_first && g.trunc) {
-        if (w >= 0) {
-          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
-          emit_start(e, js + 2, kpos, sc, w, 0, 0, 0, NULL, NULL, P.ignore_score_len);
-        } else {
-          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
-        }
+        emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+        if (w >= 0) emit_start(e, js + 2, kpos, sc, w, 0, 0, 0, NULL, NULL, P.ignore_score_len);
       } else {
         emit_start(e, js + 2, kpos, sc, w, 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
       }
     }
     emitted_below += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (kOrdered) return true;
-  for (int d = 16; d > 0; d >>= 1) {
-    emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
-    asum += __shfl_xor_sync(0xffffffffu, asum, d);
-  }
-  // asum over-counts by at most its own rounding (< 2^-40 relative); one binade of margin (52, not 53)
-  const int gexp = (int)(emin >> 23) - 150;
-  return emin != 0u && asum < ldexp(1.0, gexp + 52);
-}
-
-// Pass B, fast form.  A group of G lanes owns one ORF (32 / G ORFs per warp: most ORFs are a few hundred bases, so
-// a whole warp per ORF would mostly idle).  Every lane sums a run of 8 consecutive j serially, one G-wide scan
-// joins the runs (8 G positions per step).  Any association gives the reference's bits when the certificate of
-// g3_accumulate holds; the group's result is false (caller re-runs the ORF in the reference's order) when it
-// does not.  Must be called by all 32 lanes; `active` = this lane's group has an ORF to do.
-template <int G>
-__device__ bool g3_accumulate_group(bool active, const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
-                                    const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
-                                    const float* __restrict__ plane, int64_t total, const CodonSets& cs,
-                                    const DevParams& P, int first_j, int n_emit, gmg_start* __restrict__ out) {
-  constexpr unsigned FULL = 0xffffffffu;
-  const int gl = (threadIdx.x & 31) % G;  // lane within the group
-  const int W = gene.W, m = g.len;
-  const int lowest_j = min(3, P.min_gene_len - 3);
-  const bool fwd = g.frame > 0;
-  const int bound = fwd ? g.hi : g.lo;
-  const int j_last = active ? first_j - 1 : -1;
-  // partial-window head of the ORF string (positions j < W-1 <= 2 G): group lane gl evaluates j = gl and G + gl
-  float h0 = 0.f, h1 = 0.f, hn = 0.f;
-  {
-    const int j1 = G + gl;
-    if (gl < W - 1 && gl <= j_last) {
-      const int q = fwd ? g.hi - 1 - gl : g.lo + gl;
-      const int f = (1 + gl) % 3;
-      h0 = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
-      if (gl < 2) hn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
-    }
-    if (j1 < W - 1 && j1 <= j_last) {
-      const int q = fwd ? g.hi - 1 - j1 : g.lo + j1;
-      const int f = (1 + j1) % 3;
-      h1 = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
-    }
-  }
-  double run_g = 0.0, run_n = 0.0, asum = 0.0;
-  unsigned emin = 0x7F800000u;
-  int emitted_below = 0;
-  for (int base = 0; __any_sync(FULL, base <= j_last); base += 8 * G) {
-    const int j0 = base + 8 * gl;
-    const int r0 = j0 % 3;
-    const int k0 = r0 == 0 ? 2 : (r0 == 1 ? 1 : 0);  // j % 3 == 2 at k = k0, k0 + 3, k0 + 6
-    double lg = 0.0, ln = 0.0;
-    double sg[3] = {0.0, 0.0, 0.0}, sn[3] = {0.0, 0.0, 0.0};
-    {
-      const bool in0 = j0 <= j_last;
-      const int q0 = fwd ? g.hi - 1 - j0 : g.lo + j0;
-      // forward: bases q0-7 .. q0+2 (position q0-k needs q0-k .. q0-k+2); reverse: q0-2 .. q0+7
-      const uint32_t win = in0 ? (uint32_t)gmg_extract32(words, a + (fwd ? q0 - 7 : q0 - 2)) : 0u;
-      const float* pl = plane + a + q0;  // + f * total selects the period's plane
-      const float* lt = lut + (fwd ? 0 : 192);
-      int f = (1 + j0) % 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int j = j0 + k;
-        float xg = 0.f, xn = 0.f;
-        if (base == 0) {  // warp-uniform: head value of position j is held by group lane j % G, round j / G
-          const int hl = j % G;
-          const float t0 = __shfl_sync(FULL, h0, hl, G), t1 = __shfl_sync(FULL, h1, hl, G), tn = __shfl_sync(FULL, hn, hl, G);
-          xg = j < G ? t0 : t1;
-          xn = j < 2 ? tn : 0.f;
-        }
-        if (j <= j_last) {
-          if (j >= W - 1) xg = __ldg((fwd ? pl - k : pl + k) + (size_t)f * total);
-          if (j >= 2) xn = lt[f * 64 + (int)((win >> (fwd ? 2 * (7 - k) : 2 * k)) & 63u)];
-        } else {
-          xg = xn = 0.f;
-        }
-        if (xg != 0.f) emin = min(emin, __float_as_uint(xg) & 0x7F800000u);
-        if (xn != 0.f) emin = min(emin, __float_as_uint(xn) & 0x7F800000u);
-        asum += (double)fmaxf(fabsf(xg), fabsf(xn));
-        lg += (double)xg;
-        ln += (double)xn;
-        if (k % 3 == k0) {
-          sg[k / 3] = lg;
-          sn[k / 3] = ln;
-        }
-        f = (f == 2) ? 0 : f + 1;
-      }
-    }
-    // join the runs: exclusive prefix of the run totals over the group's lanes
-    double vg = lg, vn = ln;
-#pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const double tg = __shfl_up_sync(FULL, vg, d, G), tn = __shfl_up_sync(FULL, vn, d, G);
-      if (gl >= d) {
-        vg += tg;
-        vn += tn;
-      }
-    }
-    double eg = __shfl_up_sync(FULL, vg, 1, G), en = __shfl_up_sync(FULL, vn, 1, G);
-    if (gl == 0) eg = en = 0.0;
-    eg += run_g;
-    en += run_n;
-    run_g += __shfl_sync(FULL, vg, G - 1, G);
-    run_n += __shfl_sync(FULL, vn, G - 1, G);
-    // start position js = j + 1 (js % 3 == 0) uses score[j]
-    int wv[3], nrec[3], lane_total = 0;
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int k = k0 + 3 * t, js = j0 + k + 1;
-      const bool cand = (k < 8) && (js - 1 <= j_last) && (js >= lowest_j) && (js <= m - 1) && (js + 3 >= P.min_gene_len);
-      const int w = cand ? g3_codon_which(words, a, g, js, cs) : -2;
-      const bool is_first = cand && (js == first_j);
-      const bool emits = cand && (w >= 0 || (is_first && g.trunc));
-      wv[t] = w;
-      nrec[t] = emits ? ((is_first && g.trunc && w >= 0) ? 2 : 1) : 0;
-      lane_total += nrec[t];
-    }
-    int incl = lane_total;
-#pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, d, G);
-      if (gl >= d) incl += t;
-    }
-    int below = emitted_below + incl - lane_total;  // records at start positions below this lane's run
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      if (nrec[t]) {
-        const int js = j0 + k0 + 3 * t + 1;
-        below += nrec[t];
-        // records are stored in DESCENDING j order: slot = n_emit - (records at positions <= js)
-        Emit e;
-        e.out = out;
-        e.n = n_emit - below;
-        const double sc = (eg + sg[t]) - (en + sn[t]);
-        const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
-        const bool is_first = (js == first_j);
-        if (is_first && g.trunc) {
-          emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
-          if (wv[t] >= 0) emit_start(e, js + 2, kpos, sc, wv[t], 0, 0, 0, NULL, NULL, P.ignore_score_len);
-        } else {
-          emit_start(e, js + 2, kpos, sc, wv[t], 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
-        }
-      }
-    }
-    emitted_below += __shfl_sync(FULL, incl, G - 1, G);
-  }
-#pragma unroll
-  for (int d = G / 2; d > 0; d >>= 1) {
-    emin = min(emin, __shfl_xor_sync(FULL, emin, d, G));
-    asum += __shfl_xor_sync(FULL, asum, d, G);
-  }
-  const int gexp = (int)(emin >> 23) - 150;
-  return emin != 0u && asum < ldexp(1.0, gexp + 52);
 }
 
 // Count pass: one warp per ORF finds the emitting positions with ballots over 32 codons at a time.
@@ -1383,18 +1198,161 @@ __global__ void __launch_bounds__(256) k3_g3_count(const uint64_t* __restrict__ 
   }
 }
 
-// Write pass: one warp per ORF forms the FP64 sums of gene / indep along j and emits score[j-1] for every start
-// position j found by the count pass.  (Measured alternatives, all slower on the 5 Mbp benchmark contig because they
-// trade occupancy for fewer instructions and this kernel is latency-bound: persistent CTAs with the gene model's
-// branch table in shared memory, 8-lane groups with four ORFs per warp, and one thread per ORF over a
-// length-sorted ORF list -- see profiles/README.md.)
-__global__ void __launch_bounds__(128, 7) k3_g3_write(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
-                                                   const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
-                                                   const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                   const float* __restrict__ planes, CodonSets cs, DevParams P,
-                                                   const int64_t* __restrict__ start_off,
-                                                   const int32_t* __restrict__ first_js, gmg_start* __restrict__ starts,
-                                                   unsigned long long* __restrict__ n_ordered) {
+// K2 (glimmer3 path): codon-boundary cumulative log-odds.
+//
+// Every start position js of every ORF needs score[js-1] = sum_{j < js} (gene_j - indep_j) along the ORF string
+// (glimmer3.cc:1346-1371).  Past the first W-1 positions the terms are plain full-window values, i.e. K1 plane
+// entries, and position p contributes to a forward ORF with the period (r - p) mod 3, r = (hi + a) mod 3 -- so
+// there are only three forward and three reverse "streams" over the whole batch, and a start only ever asks
+// for a stream's running sum at a position where the period is 0 (j mod 3 == 2): p mod 3 == r.  Hence every
+// position is the boundary of exactly ONE forward and ONE reverse stream and 16 B/base hold all the sums:
+//   CF[p] = sum of the forward stream p%3 over codon slots p, p+3, ... to the end of p's tile  (suffix sums)
+//   CR[p] = sum of the reverse stream with boundary residue p%3 from the start of p's tile     (prefix sums)
+// where the slot of boundary p is the three terms at p, p+1, p+2 (periods 0, 2, 1) forward and p, p-1, p-2
+// (periods 0, 2, 1) reverse.  Sums restart at every tile of G3_TS codon slots, so tiles are independent CTAs;
+// per tile and stream the kernel also keeps the total T, the sum A of |gene| + |indep| and (per tile) the smallest
+// biased float exponent E among the non-zero terms: an ORF's sums are differences / sums of these values, and
+// they carry the reference's bits whenever no addition can round (k3_g3_emit checks A and E over the tiles an
+// ORF touches; see DESIGN.md "exactness").
+#define G3_TS 512  // codon slots (3 bases each) per tile = threads per CTA
+
+__global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict__ lut3,
+                                                         const uint64_t* __restrict__ words, int64_t total,
+                                                         const float* __restrict__ planes,
+                                                         double* __restrict__ cumc, int64_t tot3,
+                                                         double* __restrict__ tileT, float* __restrict__ tileA,
+                                                         unsigned* __restrict__ tileE) {
+  constexpr int NW = G3_TS / 32;
+  __shared__ float s_lut[384];
+  __shared__ double s_wtot[6][NW];
+  __shared__ float s_wa[6][NW];
+  __shared__ unsigned s_we[NW];
+  __shared__ double s_out[2][3 * G3_TS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 384; i += G3_TS) s_lut[i] = lut3[i];
+  __syncthreads();
+  const int64_t p0 = 3 * ((int64_t)blockIdx.x * G3_TS + tid);
+  double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
+  float au[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f};
+  unsigned emin = 0x7F800000u;
+  if (p0 - 2 < total) {
+    const uint64_t win = gmg_extract32(words, p0 - 4);  // base b at bits 2 (b - p0 + 4)
+#pragma unroll
+    for (int rho = 0; rho < 3; rho++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
+        const int64_t pf = p0 + rho + k, pr = p0 + rho - k;
+        if (pf < total) {  // forward term: window = bases pf, pf+1, pf+2
+          const float g = __ldg(planes + (size_t)f * total + pf);
+          const float n = s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
+          u[rho] += (double)g - (double)n;
+          au[rho] += fabsf(g) + fabsf(n);
+          if (g != 0.f) emin = min(emin, __float_as_uint(g) & 0x7F800000u);
+          if (n != 0.f) emin = min(emin, __float_as_uint(n) & 0x7F800000u);
+        }
+        if (pr >= 0 && pr < total) {  // reverse term: window = complement of bases pr-2, pr-1, pr
+          const float g = __ldg(planes + (size_t)(3 + f) * total + pr);
+          const float n = s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
+          v[rho] += (double)g - (double)n;
+          av[rho] += fabsf(g) + fabsf(n);
+          if (g != 0.f) emin = min(emin, __float_as_uint(g) & 0x7F800000u);
+          if (n != 0.f) emin = min(emin, __float_as_uint(n) & 0x7F800000u);
+        }
+      }
+    }
+  }
+  // warp level: suffix scans (forward streams), prefix scans (reverse streams), |term| sums, exponent minimum
+#pragma unroll
+  for (int rho = 0; rho < 3; rho++) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double tu = __shfl_down_sync(0xffffffffu, u[rho], d), tv = __shfl_up_sync(0xffffffffu, v[rho], d);
+      if (lane + d < 32) u[rho] += tu;
+      if (lane >= d) v[rho] += tv;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      au[rho] += __shfl_xor_sync(0xffffffffu, au[rho], d);
+      av[rho] += __shfl_xor_sync(0xffffffffu, av[rho], d);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
+  if (lane == 0) {
+#pragma unroll
+    for (int rho = 0; rho < 3; rho++) {
+      s_wtot[rho][wid] = u[rho];
+      s_wa[rho][wid] = au[rho];
+      s_wa[3 + rho][wid] = av[rho];
+    }
+    s_we[wid] = emin;
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int rho = 0; rho < 3; rho++) s_wtot[3 + rho][wid] = v[rho];
+  }
+  __syncthreads();
+  // warp k < 6 turns the warp totals of stream k into exclusive offsets and writes the tile's T / A (/ E)
+  if (wid < 6) {
+    const bool fw = wid < 3;
+    double x = lane < NW ? s_wtot[wid][lane] : 0.0;
+    float a = lane < NW ? s_wa[wid][lane] : 0.f;
+    unsigned e = lane < NW ? s_we[lane] : 0x7F800000u;
+    double incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double td = __shfl_down_sync(0xffffffffu, incl, d), tu = __shfl_up_sync(0xffffffffu, incl, d);
+      if (fw && lane + d < 32) incl += td;
+      if (!fw && lane >= d) incl += tu;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, d);
+      e = min(e, __shfl_xor_sync(0xffffffffu, e, d));
+    }
+    if (lane < NW) s_wtot[wid][lane] = incl - x;  // exclusive: warps after (forward) / before (reverse) this one
+    const double tot = __shfl_sync(0xffffffffu, incl, fw ? 0 : 31);
+    if (lane == 0) {
+      tileT[(size_t)blockIdx.x * 6 + wid] = tot;
+      tileA[(size_t)blockIdx.x * 6 + wid] = a * 1.001f;  // upper bound: the float sum itself rounds
+      if (wid == 0) tileE[blockIdx.x] = e;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rho = 0; rho < 3; rho++) {
+    s_out[0][3 * tid + rho] = u[rho] + s_wtot[rho][wid];
+    s_out[1][3 * tid + rho] = v[rho] + s_wtot[3 + rho][wid];
+  }
+  __syncthreads();
+  const size_t o0 = (size_t)blockIdx.x * (3 * G3_TS);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    cumc[o0 + i * G3_TS + tid] = s_out[0][i * G3_TS + tid];
+    cumc[(size_t)tot3 + o0 + i * G3_TS + tid] = s_out[1][i * G3_TS + tid];
+  }
+}
+
+// K3 (glimmer3) emit pass: one warp per ORF writes the start records the count pass found.  score[js-1] of a
+// start is  H + (stream sum between the anchor position j = ja and j = js-1)  where H sums the first ja+1
+// positions of the ORF string explicitly (the W-1 partial windows only see the ORF string, icm.cc:376-388;
+// ja = first j >= W-2 with j mod 3 == 2) and the stream sum is read off k2_g3_codon_cum's tables: two loads
+// when both ends share a tile, plus the totals of the tiles in between otherwise.  All of it is exact -- and
+// therefore bit-identical to the reference's serial FP64 sums -- when no addition of float-granular terms can
+// round: every term is an integer multiple of 2^(E-150) (E = smallest biased exponent among the non-zero
+// terms) and every partial sum of any association is bounded by A = sum |gene| + |indep| < 2^(E-150+52).
+// ORFs whose certificate fails (or that span more than 32 tiles) are re-done in the reference's order.
+__global__ void __launch_bounds__(128) k3_g3_emit(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                  const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                  const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                  const float* __restrict__ planes, const double* __restrict__ cumc,
+                                                  int64_t tot3, const double* __restrict__ tileT,
+                                                  const float* __restrict__ tileA, const unsigned* __restrict__ tileE,
+                                                  CodonSets cs, DevParams P, const int64_t* __restrict__ start_off,
+                                                  const int32_t* __restrict__ first_js, gmg_start* __restrict__ starts,
+                                                  unsigned long long* __restrict__ n_ordered) {
+  constexpr unsigned FULL = 0xffffffffu;
   __shared__ float s_lut[384];
   if (indep.lut3)
     for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
@@ -1410,11 +1368,126 @@ __global__ void __launch_bounds__(128, 7) k3_g3_write(DevIcm gene, DevIcm indep,
   const int32_t s = orf_seq[oi];
   const int64_t a = off[s];
   const G3Geom g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
-  const float* plane = planes + (size_t)(g.frame > 0 ? 0 : 3) * total;  // the strand's three period planes
-  const bool fast = lut != NULL && gene.W - 1 <= 32;
-  if (!fast || !g3_accumulate_group<32>(true, gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, starts + so)) {
-    g3_accumulate<true>(gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, starts + so);
+  const bool fwd = g.frame > 0;
+  const float* plane = planes + (size_t)(fwd ? 0 : 3) * total;  // the strand's three period planes
+  gmg_start* out = starts + so;
+  const int W = gene.W, m = g.len;
+  const int j_last = first_j - 1;
+  const int ja = (W - 2) + (5 - (W - 2) % 3) % 3;  // first j >= W-2 with j % 3 == 2
+  bool fast = cumc != NULL && lut != NULL && ja < 32 && W >= 2;
+  // ---- head: positions 0 .. min(ja, j_last) of the ORF string, one lane each ----
+  const int bound = fwd ? g.hi : g.lo;
+  double hs = 0.0;
+  float asum = 0.f;
+  unsigned emin = 0x7F800000u;
+  if (fast && lane <= min(ja, j_last)) {
+    const int f = (1 + lane) % 3;
+    const int q = fwd ? g.hi - 1 - lane : g.lo + lane;
+    const float xg = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
+    float xn;
+    if (lane >= 2) xn = fwd ? lut[f * 64 + (int)(gmg_extract32(words, a + q) & 63)]
+                            : lut[(3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63)];
+    else xn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
+    hs = (double)xg - (double)xn;
+    asum = fabsf(xg) + fabsf(xn);
+    if (xg != 0.f) emin = min(emin, __float_as_uint(xg) & 0x7F800000u);
+    if (xn != 0.f) emin = min(emin, __float_as_uint(xn) & 0x7F800000u);
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double t = __shfl_up_sync(FULL, hs, d);
+    if (lane >= d) hs += t;
+  }
+  // ---- the tiles between the anchor (j = ja) and the farthest start (j = j_last) ----
+  const int strand = fwd ? 0 : 1;
+  const bool span = j_last > ja;
+  int64_t pa = 0, ta = 0;
+  int rho = 0, nt = 0;
+  double q_tiles = 0.0, c_a = 0.0, t_a = 0.0;
+  if (fast && span) {
+    pa = a + (fwd ? g.hi - 1 - ja : g.lo + ja);
+    const int64_t pl = a + (fwd ? g.hi - 1 - j_last : g.lo + j_last);
+    rho = (int)(pa % 3);
+    ta = pa / (3 * G3_TS);
+    const int64_t tl = pl / (3 * G3_TS);
+    nt = (int)(fwd ? ta - tl : tl - ta);
+    if (nt >= 32) fast = false;
+  }
+  if (fast && span) {
+    if (lane <= nt) {
+      const int64_t tk = fwd ? ta - lane : ta + lane;
+      const double tt = tileT[(size_t)tk * 6 + strand * 3 + rho];
+      asum += tileA[(size_t)tk * 6 + strand * 3 + rho];
+      emin = min(emin, tileE[tk]);
+      if (lane == 0) t_a = tt;
+      else q_tiles = tt;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {  // q_tiles of lane k = total of the k tiles after the anchor's
+      const double t = __shfl_up_sync(FULL, q_tiles, d);
+      if (lane >= d) q_tiles += t;
+    }
+    t_a = __shfl_sync(FULL, t_a, 0);
+    c_a = cumc[(size_t)strand * tot3 + pa];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    asum += __shfl_xor_sync(FULL, asum, d);
+    emin = min(emin, __shfl_xor_sync(FULL, emin, d));
+  }
+  if (fast) fast = emin != 0u && (double)asum * 1.001 < ldexp(1.0, (int)(emin >> 23) - 150 + 52);
+  if (!fast) {
+    g3_accumulate_ordered(gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, out);
     if (lane == 0) atomicAdd(n_ordered, 1ull);
+    return;
+  }
+  const double h_ja = __shfl_sync(FULL, hs, min(ja, 31));
+  // ---- the start positions, 32 codons per step in descending j (= generation order) ----
+  const int lowest_j = min(3, P.min_gene_len - 3);
+  const int jtop = (m - 1) - ((m - 1) % 3);
+  int emitted = 0;
+  for (int jb = min(jtop, first_j); jb >= lowest_j; jb -= 96) {
+    const int js = jb - 3 * lane;
+    const bool ok = (js >= lowest_j) && (js + 3 >= P.min_gene_len);
+    const int w = ok ? g3_codon_which(words, a, g, js, cs) : -2;
+    const bool is_first = ok && js == first_j;
+    const bool emits = ok && (w >= 0 || (is_first && g.trunc));
+    const int nrec = emits ? ((is_first && g.trunc && w >= 0) ? 2 : 1) : 0;
+    int incl = nrec;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int j = js - 1;  // the start at js uses score[js - 1]
+    // stream part for j > ja
+    int dt = 0;
+    double c_j = 0.0;
+    if (emits && j > ja) {
+      const int64_t pj = a + (fwd ? g.hi - 1 - j : g.lo + j);
+      const int64_t tj = pj / (3 * G3_TS);
+      dt = (int)(fwd ? ta - tj : tj - ta);
+      c_j = cumc[(size_t)strand * tot3 + pj];
+    }
+    const double qd = __shfl_sync(FULL, q_tiles, dt > 0 ? dt - 1 : 0);
+    const double hj = __shfl_sync(FULL, hs, (j >= 0 && j < 32) ? j : 0);
+    if (emits) {
+      double sc;
+      if (j <= ja) sc = hj;
+      else if (dt == 0) sc = h_ja + (c_j - c_a);
+      else sc = h_ja + ((c_j + qd) + (t_a - c_a));
+      const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
+      Emit e;
+      e.out = out;
+      e.n = emitted + incl - nrec;
+      if (is_first && g.trunc) {
+        emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+        if (w >= 0) emit_start(e, js + 2, kpos, sc, w, 0, 0, 0, NULL, NULL, P.ignore_score_len);
+      } else {
+        emit_start(e, js + 2, kpos, sc, w, 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
+      }
+    }
+    emitted += __shfl_sync(FULL, incl, 31);
   }
 }
 
@@ -1853,6 +1926,28 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
   GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
+  // K2 (glimmer3 path): codon-boundary cumulative sums, tile by tile
+  double *cumc = NULL, *tileT = NULL;
+  float* tileA = NULL;
+  unsigned* tileE = NULL;
+  const int64_t ntiles = s->total / (3 * G3_TS) + 1, tot3 = ntiles * 3 * G3_TS;
+  static const bool no_cum = getenv("GMG_G3_ORDERED") && atoi(getenv("GMG_G3_ORDERED"));
+  if (indep->dev.lut3 && gene->W >= 2 && gene->W <= 30 && !no_cum) {
+    void *d_cum, *d_tiles;
+    if (gmg_scratch(ctx, SCR_CUM, (size_t)2 * tot3 * sizeof(double), &d_cum)) return 1;
+    if (gmg_scratch(ctx, SCR_QUAL, (size_t)ntiles * (6 * sizeof(double) + 6 * sizeof(float) + sizeof(unsigned)), &d_tiles))
+      return 1;
+    cumc = (double*)d_cum;
+    tileT = (double*)d_tiles;
+    tileA = (float*)(tileT + 6 * ntiles);
+    tileE = (unsigned*)(tileA + 6 * ntiles);
+    if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
+    k2_g3_codon_cum<<<(unsigned)ntiles, G3_TS, 0, ctx->stream>>>(indep->dev.lut3, s->d_words, s->total, planes, cumc, tot3,
+                                                                tileT, tileA, tileE);
+    gmg_prof_end(ctx, GMG_PROF_K2);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
   void *d_counts, *d_first;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 1) * sizeof(int64_t), &d_counts)) return 1;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
@@ -1871,9 +1966,9 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (total_starts > 0) {
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-    k3_g3_write<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-        gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp,
-        s->d_start_off, (const int32_t*)d_first, s->d_starts, s->d_gc + 1);
+    k3_g3_emit<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cumc, tot3,
+        tileT, tileA, tileE, cs, dp, s->d_start_off, (const int32_t*)d_first, s->d_starts, s->d_gc + 1);
     gmg_prof_end(ctx, GMG_PROF_K3);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
