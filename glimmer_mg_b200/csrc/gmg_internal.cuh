@@ -96,12 +96,20 @@ struct gmg_icm {
   float* d_mprob;
   float* d_lut3;
   DevIcmFast fast;
+  // value statistics of `prob` (lazily computed, see gmg_icm_value_stats)
+  int stat_valid, stat_ulp_exp;
+  float stat_max_abs;
 };
+
+// smallest ulp exponent (every entry is an integer multiple of 2^ulp_exp) and largest magnitude of the model's
+// log-probabilities: the inputs of the static FP64 exactness certificates
+void gmg_icm_value_stats(const gmg_icm* m, int* ulp_exp, float* max_abs);
 
 struct gmg_seqset {
   gmg_ctx* ctx;
   int64_t n;                 // sequences
   int64_t total;             // bases
+  int64_t max_len;           // longest sequence
   std::vector<int64_t> off;  // host copy, n+1
   int64_t* d_off;            // n+1
   uint64_t* d_words_base;    // allocation incl. padding
@@ -109,6 +117,11 @@ struct gmg_seqset {
   int32_t* d_blk2seq;        // sequence holding base 32*b; bit 31 = interior block (see k_blk2seq)
   uint8_t* d_qual;           // per-base quality (input file values) or NULL
   unsigned long long* d_gc;  // {gc count, ORFs of the last g3 scoring call that took the ordered-sum fallback}
+  // codon bitmaps (k_codon_bits): uint2 {start bits, stop bits} [strand][stream r][nwc]; bit i of word w <-> the
+  // codon whose three bases start at global index 3 (32 w + i) + r
+  uint2* d_cbits;
+  int64_t nwc;
+  unsigned long long cbits_key[4];  // the raw codon masks the bitmaps were built for
   // ORFs
   int64_t n_orfs;
   gmg_orf* d_orfs;

@@ -11,6 +11,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <float.h>
+#include <math.h>
+
 #include "gmg_internal.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -228,6 +231,11 @@ static int base_code(char ch) {
   }
 }
 
+void gmg_icm_value_stats(const gmg_icm* m, int* ulp_exp, float* max_abs) {
+  *ulp_exp = m->stat_ulp_exp;
+  *max_abs = m->stat_max_abs;
+}
+
 static int num_nodes_for(int d) {
   long n = 1, pw = 1;
   for (int i = 0; i < d; i++) {
@@ -260,6 +268,26 @@ static int icm_upload(gmg_icm* m) {
   GMG_CUDA(cudaMemcpyAsync(m->d_mip, mip8.data(), mip8.size(), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(m->d_prob, eff.data(), eff.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  // value statistics for the static exactness certificates
+  {
+    int ue = 1024;
+    float mx = 0.f;
+    for (float v : m->prob) {
+      if (v == 0.f) continue;
+      if (!(fabsf(v) <= FLT_MAX)) {  // inf / nan: nothing can be certified
+        ue = -100000;
+        continue;
+      }
+      int e;
+      frexpf(v, &e);  // |v| in [2^(e-1), 2^e)
+      e = (e - 1 < -126 ? -126 : e - 1) - 23;
+      if (e < ue) ue = e;
+      if (fabsf(v) > mx) mx = fabsf(v);
+    }
+    m->stat_valid = 1;
+    m->stat_ulp_exp = ue;
+    m->stat_max_abs = mx;
+  }
   // marker-indexed tables of the K1 fast path
   m->fast.valid = 0;
   if (m->W <= 16 && D >= 1 && D <= 8) {

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "gmg_internal.cuh"
@@ -105,6 +106,9 @@ __device__ __forceinline__ int codon_rev_starting_at(const uint64_t* __restrict_
 struct CodonSets {
   unsigned long long start_mask;  // bit c set: 6-bit codon c is a start codon
   unsigned long long stop_mask;
+  // the same sets over the RAW packed code  b(c) | b(c+1) << 2 | b(c+2) << 4  of the bases at c, c+1, c+2:
+  // [0] forward start, [1] forward stop, [2] reverse-strand start, [3] reverse-strand stop (k_codon_bits)
+  unsigned long long raw_mask[4];
   unsigned char which[64];        // index of the first matching start codon (Can_Be order)
 };
 
@@ -139,6 +143,14 @@ static int make_codon_sets(const gmg_params* p, CodonSets* cs, DevParams* dp) {
     int a = code_of(p->stop_codon[i][0]), b = code_of(p->stop_codon[i][1]), c = code_of(p->stop_codon[i][2]);
     GMG_CHECK(a >= 0 && b >= 0 && c >= 0, "stop codon '%s': only a/c/g/t codons are supported", p->stop_codon[i]);
     cs->stop_mask |= 1ull << (a * 16 + b * 4 + c);
+  }
+  for (int raw = 0; raw < 64; raw++) {
+    const int b0 = raw & 3, b1 = (raw >> 2) & 3, b2 = raw >> 4;
+    const int fc = b0 * 16 + b1 * 4 + b2, rc = (3 - b2) * 16 + (3 - b1) * 4 + (3 - b0);
+    if (cs->start_mask >> fc & 1) cs->raw_mask[0] |= 1ull << raw;
+    if (cs->stop_mask >> fc & 1) cs->raw_mask[1] |= 1ull << raw;
+    if (cs->start_mask >> rc & 1) cs->raw_mask[2] |= 1ull << raw;
+    if (cs->stop_mask >> rc & 1) cs->raw_mask[3] |= 1ull << raw;
   }
   GMG_CHECK(p->indel_max >= 0 && p->indel_max <= 2, "indel_max %d unsupported (0..2)", p->indel_max);
   dp->min_gene_len = p->min_gene_len;
@@ -654,40 +666,106 @@ extern "C" int gmg_icm_partial_window_prob(gmg_ctx* ctx, const gmg_icm* m, int p
 }
 
 // ------------------------------------------------------------------------------------------------
+// Codon bitmaps.  For every strand and reading-frame stream r = (codon's first base) mod 3 one bit per codon
+// says "start codon" and one "stop codon":  uint2 {start, stop} [strand][r][nwc],  bit i of word w <-> the codon
+// at global bases 3 (32 w + i) + r .. + 2 (reverse strand: the same three bases read as their reverse
+// complement).  The ORF finder and the glimmer3 start enumeration then work on 32 codons per word with
+// clz / ffs / popc instead of per-codon extraction.  One thread builds the 12 words of one word index.
+__global__ void __launch_bounds__(128) k_codon_bits(const uint64_t* __restrict__ words, int64_t nwc, CodonSets cs,
+                                                    uint2* __restrict__ cb) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwc) return;
+  // bases 96 w .. 96 w + 127 (zero padding past the end of the batch)
+  uint64_t x[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) x[k] = __ldg(words + 3 * w + k);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    unsigned fs = 0, fp = 0, rs = 0, rp = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const int o = 3 * i + r, k = o >> 5, sh = 2 * (o & 31);
+      uint64_t v = x[k] >> sh;
+      if (sh > 58) v |= x[k + 1] << (64 - sh);
+      const int raw = (int)(v & 63);
+      fs |= (unsigned)((cs.raw_mask[0] >> raw) & 1) << i;
+      fp |= (unsigned)((cs.raw_mask[1] >> raw) & 1) << i;
+      rs |= (unsigned)((cs.raw_mask[2] >> raw) & 1) << i;
+      rp |= (unsigned)((cs.raw_mask[3] >> raw) & 1) << i;
+    }
+    cb[(size_t)r * nwc + w] = make_uint2(fs, fp);
+    cb[(size_t)(3 + r) * nwc + w] = make_uint2(rs, rp);
+  }
+}
+
+static int ensure_codon_bits(gmg_ctx* ctx, gmg_seqset* s, const CodonSets& cs) {
+  if (s->d_cbits && memcmp(s->cbits_key, cs.raw_mask, sizeof s->cbits_key) == 0) return 0;
+  const int64_t nwc = s->total / 96 + 2;
+  if (!s->d_cbits) {
+    // the last word index reads packed words up to 3 (nwc - 1) + 3 <= total / 32 + 6: inside the zero padding
+    static_assert(GMG_PAD_WORDS >= 4, "k_codon_bits reads up to three words past the last base");
+    GMG_CUDA(cudaMallocAsync(&s->d_cbits, (size_t)6 * nwc * sizeof(uint2), ctx->stream));
+    s->nwc = nwc;
+  }
+  k_codon_bits<<<(unsigned)((nwc + 127) / 128), 128, 0, ctx->stream>>>(s->d_words, nwc, cs, s->d_cbits);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  memcpy(s->cbits_key, cs.raw_mask, sizeof s->cbits_key);
+  return 0;
+}
+
+// Scan one stream's codon bits downwards over the slots [s_lo, s_hi]: the highest slot with a stop bit
+// (-1 = none) and, among the slots above it, the lowest (`far`) and highest (`near`) one with a start bit.
+struct BackScan {
+  int64_t stop, far, near;
+};
+__device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int64_t s_hi, int64_t s_lo) {
+  BackScan r;
+  r.stop = r.far = r.near = -1;
+  if (s_hi < s_lo) return r;
+  const int64_t w_hi = s_hi >> 5, w_lo = s_lo >> 5;
+  const unsigned m_hi = (2u << (int)(s_hi & 31)) - 1u, m_lo = ~0u << (int)(s_lo & 31);
+  for (int64_t w = w_hi; w >= w_lo; --w) {
+    const uint2 x = __ldg(cb + w);
+    const unsigned m = (w == w_hi ? m_hi : ~0u) & (w == w_lo ? m_lo : ~0u);
+    unsigned st = x.x & m;
+    const unsigned sp = x.y & m;
+    int b = -1;
+    if (sp) {
+      b = 31 - __clz(sp);
+      st &= ~((2u << b) - 1u);  // only starts above the stop count
+    }
+    if (st) {
+      if (r.near < 0) r.near = (w << 5) + 31 - __clz(st);
+      r.far = (w << 5) + __ffs(st) - 1;
+    }
+    if (sp) {
+      r.stop = (w << 5) + b;
+      break;
+    }
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Device ORF finder (Find_Orfs, glimmer_base.cc:638-817; linear sequences, no ignore regions).
 //
-// Every ORF is created by the stop codon that closes it.  A warp owns 32 consecutive bases; for every base
-// that closes an ORF (at most one forward and one reverse stop, plus the Finish_Orfs reverse ORFs and the
-// three virtual forward stops at a sequence's last base) the WHOLE warp searches backwards for the previous
-// in-frame stop, 32 codons per step (ballot + find-first), so the cost of a long ORF is shared by 32 lanes
-// instead of serialising one.  Two passes (count, block scan, write) give the reference's output order
-// deterministically: by closing base; forward before reverse; then the end-of-sequence extras.
+// Every ORF is created by the stop codon that closes it.  One thread per base: a base that closes an ORF (at
+// most one forward and one reverse stop, plus the Finish_Orfs reverse ORFs and the three virtual forward stops
+// at a sequence's last base) looks up the previous in-frame stop and the relevant start codon in the codon
+// bitmaps (32 codons per word).  Two passes (count, device scan of the CTA totals, write) give the
+// reference's output order deterministically: by closing base; forward before reverse; then the
+// end-of-sequence extras.
 
-// forward ORF closed by the (possibly virtual) stop codon whose last base is i.  Warp-uniform arguments and
-// result; all 32 lanes must call.
-__device__ bool orf_fwd_closed_warp(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool virt,
-                                    const CodonSets& cs, const DevParams& P, gmg_orf* o) {
-  const int lane = threadIdx.x & 31;
-  int first_start = INT_MAX;
-  int prev = 0;  // 1-based first base of the previous stop, 0 = none
-  for (int tb = i - 3; tb >= 2; tb -= 96) {
-    const int t = tb - 3 * lane;
-    bool is_stop = false, is_start = false;
-    if (t >= 2 && t < L) {  // virtual closing stop: codons hanging past the end do not exist
-      const int c = codon6_at(words, a + t - 2);
-      is_stop = (cs.stop_mask >> c) & 1;
-      is_start = (cs.start_mask >> c) & 1;
-    }
-    const unsigned stopm = __ballot_sync(0xffffffffu, is_stop);
-    unsigned startm = __ballot_sync(0xffffffffu, is_start);
-    if (stopm) {
-      const int sl = __ffs(stopm) - 1;
-      prev = tb - 3 * sl - 1;
-      startm &= (1u << sl) - 1u;
-    }
-    if (startm) first_start = tb - 3 * (31 - __clz(startm)) - 1;  // farthest from i = nearest to the previous stop
-    if (stopm) break;
-  }
+// forward ORF closed by the (possibly virtual) stop codon whose last base is i (sequence coordinates).
+__device__ bool orf_fwd_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i,
+                               const DevParams& P, gmg_orf* o) {
+  // candidate codons end at t = i-3, i-6, ... >= 2, i.e. start at i-5, i-8, ... >= 0
+  const int r = (int)((a + i + 1) % 3);
+  const int64_t s_hi = i >= 5 ? (a + i - 5) / 3 : -1, s_lo = (a - r + 2) / 3;
+  const BackScan f = scan_back(cb + (size_t)r * nwc, s_hi, s_lo);
+  const int prev = f.stop >= 0 ? (int)(3 * f.stop + r - a) + 1 : 0;  // 1-based first base of the previous stop
+  const int first_start = f.far >= 0 ? (int)(3 * f.far + r - a) + 1 : INT_MAX;
   int gene_len, orf_len;
   if (prev == 0) {
     int pos = i - 1;
@@ -710,30 +788,14 @@ __device__ bool orf_fwd_closed_warp(const uint64_t* __restrict__ words, int64_t 
 
 // reverse ORF closed at i (real reverse stop whose highest base is i), or with finish = true the
 // Finish_Orfs ORF of frame class fr = i % 3 where i is the last position of that class (< L).
-__device__ bool orf_rev_closed_warp(const uint64_t* __restrict__ words, int64_t a, int L, int i, bool finish,
-                                    const CodonSets& cs, const DevParams& P, gmg_orf* o) {
-  const int lane = threadIdx.x & 31;
-  const int t0 = finish ? i : i - 3;
-  int last_start = 0, prev = 0;
-  for (int tb = t0; tb >= 2; tb -= 96) {
-    const int t = tb - 3 * lane;
-    bool is_stop = false, is_start = false;
-    if (t >= 2) {
-      const int c = 63 - codon6_at(words, a + t - 2);  // complement ...
-      const int rc = ((c & 3) << 4) | (c & 12) | (c >> 4);  // ... read in the other direction
-      is_stop = (cs.stop_mask >> rc) & 1;
-      is_start = (cs.start_mask >> rc) & 1;
-    }
-    const unsigned stopm = __ballot_sync(0xffffffffu, is_stop);
-    unsigned startm = __ballot_sync(0xffffffffu, is_start);
-    if (stopm) {
-      const int sl = __ffs(stopm) - 1;
-      prev = tb - 3 * sl - 1;
-      startm &= (1u << sl) - 1u;
-    }
-    if (last_start == 0 && startm) last_start = tb - 3 * (__ffs(startm) - 1) - 1;  // nearest to i
-    if (stopm) break;
-  }
+__device__ bool orf_rev_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i, bool finish,
+                               const DevParams& P, gmg_orf* o) {
+  const int t0 = finish ? i : i - 3;  // candidate codons end at t0, t0-3, ... >= 2
+  const int r = (int)((a + t0 + 1) % 3);
+  const int64_t s_hi = t0 >= 2 ? (a + t0 - 2) / 3 : -1, s_lo = (a - r + 2) / 3;
+  const BackScan f = scan_back(cb + (size_t)(3 + r) * nwc, s_hi, s_lo);
+  const int prev = f.stop >= 0 ? (int)(3 * f.stop + r - a) + 1 : 0;
+  const int last_start = f.near >= 0 ? (int)(3 * f.near + r - a) + 1 : 0;  // nearest to i
   int gene_len, orf_len, orf_stop;
   if (!finish) {
     if (prev == 0) {
@@ -769,106 +831,54 @@ __device__ bool orf_rev_closed_warp(const uint64_t* __restrict__ words, int64_t 
 
 // kWrite = false: per-CTA ORF counts.  kWrite = true: ORF records at block_base[blockIdx] + in-block rank.
 template <bool kWrite>
-__global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                              const int32_t* __restrict__ blk2seq, int64_t total, CodonSets cs,
-                                              DevParams P, int64_t* __restrict__ block_counts,
-                                              int64_t* __restrict__ warp_pack, const int64_t* __restrict__ block_base,
+__global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words, const uint2* __restrict__ cb,
+                                              int64_t nwc, const int64_t* __restrict__ off,
+                                              const int32_t* __restrict__ blk2seq, int64_t total, DevParams P,
+                                              int64_t* __restrict__ block_counts, const int64_t* __restrict__ block_base,
                                               gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
-  __shared__ int wsum[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  typedef cub::BlockScan<int, 256> Scan;
+  __shared__ typename Scan::TempStorage tmp;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // what this lane's base closes
-  int64_t a = 0;
-  int L = 0, q = 0;
+  gmg_orf rec[8];
+  int n = 0;
   int32_t sq = 0;
-  bool cf = false, cr = false, last = false;
   if (p < total) {
     SeqView sv = locate(off, blk2seq, p, &sq);
-    a = sv.a;
-    L = sv.len;
-    q = (int)(p - a);
+    const int64_t a = sv.a;
+    const int L = sv.len, q = (int)(p - a);
     if (L >= P.min_gene_len) {
-      if (q >= 2) {
-        const int c = codon6_at(words, p - 2);
-        cf = (cs.stop_mask >> c) & 1;
-        const int cc = 63 - c;
-        cr = (cs.stop_mask >> (((cc & 3) << 4) | (cc & 12) | (cc >> 4))) & 1;
+      if (q >= 2) {  // the codon q-2 .. q: forward stop / reverse stop?
+        const int64_t c = p - 2;
+        const int r = (int)(c % 3);
+        const int64_t sl = c / 3;
+        const unsigned bit = 1u << (int)(sl & 31);
+        if (__ldg(cb + (size_t)r * nwc + (sl >> 5)).y & bit) n += orf_fwd_closed(cb, nwc, a, L, q, P, &rec[n]);
+        if (__ldg(cb + (size_t)(3 + r) * nwc + (sl >> 5)).y & bit) n += orf_rev_closed(cb, nwc, a, L, q, false, P, &rec[n]);
       }
-      last = (q == L - 1);
-    }
-  }
-  const unsigned mf = __ballot_sync(0xffffffffu, cf), mr = __ballot_sync(0xffffffffu, cr),
-                 ml = __ballot_sync(0xffffffffu, last);
-  // write pass: this warp's first slot = block base + the ORFs of the block's earlier warps (packed, 8 bits each)
-  int64_t base = 0;
-  if (kWrite) {
-    base = block_base[blockIdx.x];
-    const unsigned long long pack = (unsigned long long)warp_pack[blockIdx.x];
-    for (int w = 0; w < wid; w++) base += (int)((pack >> (8 * w)) & 0xFF);
-  }
-  int n = 0;  // warp-uniform count of ORFs found so far
-  unsigned any = mf | mr | ml;
-  while (any) {
-    const int l = __ffs(any) - 1;
-    any &= any - 1;
-    const int64_t al = __shfl_sync(0xffffffffu, a, l);
-    const int Ll = __shfl_sync(0xffffffffu, L, l), ql = __shfl_sync(0xffffffffu, q, l);
-    const int32_t sl = __shfl_sync(0xffffffffu, sq, l);
-    gmg_orf o;
-    if ((mf >> l) & 1)
-      if (orf_fwd_closed_warp(words, al, Ll, ql, false, cs, P, &o)) {
-        if (kWrite && lane == 0) {
-          orfs[base + n] = o;
-          orf_seq[base + n] = sl;
-        }
-        n++;
-      }
-    if ((mr >> l) & 1)
-      if (orf_rev_closed_warp(words, al, Ll, ql, false, cs, P, &o)) {
-        if (kWrite && lane == 0) {
-          orfs[base + n] = o;
-          orf_seq[base + n] = sl;
-        }
-        n++;
-      }
-    if ((ml >> l) & 1) {
-      for (int fr = 0; fr < 3; fr++) {
-        int i = Ll - 1 - mod3(Ll - 1 - fr);  // last index of class fr that is < L
-        if (i < 0) i = fr;                   // degenerate; the search loop is empty
-        if (orf_rev_closed_warp(words, al, Ll, i, true, cs, P, &o)) {
-          o.frame = -1 - (fr + 1) % 3;  // only depends on fr (= i % 3 when i >= 0)
-          if (kWrite && lane == 0) {
-            orfs[base + n] = o;
-            orf_seq[base + n] = sl;
-          }
-          n++;
-        }
-      }
-      if (P.allow_truncated)
-        for (int i = Ll; i < Ll + 3; i++)
-          if (orf_fwd_closed_warp(words, al, Ll, i, true, cs, P, &o)) {
-            if (kWrite && lane == 0) {
-              orfs[base + n] = o;
-              orf_seq[base + n] = sl;
-            }
+      if (q == L - 1) {
+        for (int fr = 0; fr < 3; fr++) {
+          int i = L - 1 - mod3(L - 1 - fr);  // last index of class fr that is < L
+          if (i < 0) i = fr;                 // degenerate; the search range is empty
+          if (orf_rev_closed(cb, nwc, a, L, i, true, P, &rec[n])) {
+            rec[n].frame = -1 - (fr + 1) % 3;  // only depends on fr (= i % 3 when i >= 0)
             n++;
           }
+        }
+        if (P.allow_truncated)
+          for (int i = L; i < L + 3; i++) n += orf_fwd_closed(cb, nwc, a, L, i, P, &rec[n]);
+      }
     }
   }
-  if (!kWrite) {
-    // a warp closes at most 2 * 32 + 6 ORFs, so eight warp counts pack into one 64-bit word
-    if (lane == 0) wsum[wid] = n;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = 0;
-      unsigned long long pack = 0;
-      for (int w = 0; w < 8; w++) {
-        t += wsum[w];
-        pack |= (unsigned long long)wsum[w] << (8 * w);
-      }
-      block_counts[blockIdx.x] = t;
-      warp_pack[blockIdx.x] = (int64_t)pack;
+  int rank, block_total;
+  Scan(tmp).ExclusiveSum(n, rank, block_total);
+  if (kWrite) {
+    const int64_t base = block_base[blockIdx.x] + rank;
+    for (int k = 0; k < n; k++) {
+      orfs[base + k] = rec[k];
+      orf_seq[base + k] = sq;
     }
+  } else if (threadIdx.x == 0) {
+    block_counts[blockIdx.x] = block_total;
   }
 }
 
@@ -939,16 +949,16 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
     if (n_orfs) *n_orfs = 0;
     return 0;
   }
+  if (ensure_codon_bits(ctx, s, cs)) return 1;
   int64_t nblk = (s->total + 255) / 256;
   void* d_counts;
-  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(3 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(2 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
   int64_t* counts = (int64_t*)d_counts;
   int64_t* bases = counts + nblk + 1;
-  int64_t* packs = bases + nblk + 1;
   GMG_CUDA(cudaMemsetAsync(counts + nblk, 0, sizeof(int64_t), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orfs<false><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, counts,
-                                                         packs, NULL, NULL, NULL);
+  k_orfs<false><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq,
+                                                         s->total, dp, counts, NULL, NULL, NULL);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -958,8 +968,8 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_orf_capacity(s, total_orfs)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orfs<true><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total, cs, dp, NULL,
-                                                        packs, bases, s->d_orfs, s->d_orf_seq);
+  k_orfs<true><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq,
+                                                        s->total, dp, NULL, bases, s->d_orfs, s->d_orf_seq);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
@@ -1149,53 +1159,121 @@ __device__ void g3_accumulate_ordered(const DevIcm& gene, const DevIcm& indep, c
   }
 }
 
-// Count pass: one warp per ORF finds the emitting positions with ballots over 32 codons at a time.
-// A start at j qualifies iff j % 3 == 0, lowest_j <= j <= m-1, j + 3 >= min_gene_len and (codon is a start ||
-// (nothing emitted yet && truncated)).  counts[oi] = records, first_js[oi] = j of the first (largest-j) one.
-__global__ void __launch_bounds__(256) k3_g3_count(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                   const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
-                                                   int64_t n_orfs, CodonSets cs, DevParams P,
-                                                   int64_t* __restrict__ counts, int32_t* __restrict__ first_js) {
-  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (oi >= n_orfs) return;
-  const gmg_orf o = orfs[oi];
-  const int32_t s = orf_seq[oi];
-  const int64_t a = off[s];
-  const int L = (int)(off[s + 1] - a);
-  const G3Geom g = g3_geom(o, L, P);
-  const int m = g.len;
+// The candidate start positions of an ORF string are js = jmin, jmin+3, ..., jmax (js % 3 == 0,
+// lowest_j <= js, js + 3 >= min_gene_len, codon complete: js <= m - 3); their codons are consecutive slots of ONE
+// codon-bitmap stream: forward  slot(js) = s0 - js / 3,  reverse  slot(js) = s0 + js / 3.
+struct G3Range {
+  int jmin, jmax;  // empty iff jmax < jmin
+  int r;           // stream
+  int64_t s0;      // slot of js = 0
+};
+__device__ __forceinline__ G3Range g3_range(const G3Geom& g, int64_t a, const DevParams& P) {
+  G3Range R;
   const int lowest_j = min(3, P.min_gene_len - 3);
-  const int jtop = (m - 1) - ((m - 1) % 3);  // largest j % 3 == 0 that is <= m-1
-  int found_first = -1, cnt = 0;
-  for (int jb = jtop; jb >= lowest_j; jb -= 96) {
-    const int j = jb - 3 * lane;
-    const bool ok = (j >= lowest_j) && (j + 3 >= P.min_gene_len);
-    const int w = ok ? g3_codon_which(words, a, g, j, cs) : -2;
-    const bool is_codon = ok && w >= 0;
-    // the truncated rule can only apply to the very first candidate position examined (first_pos == 0)
-    unsigned cm = __ballot_sync(0xffffffffu, is_codon);
-    const unsigned okm = __ballot_sync(0xffffffffu, ok);
-    if (found_first < 0) {
-      if (g.trunc && okm) {
-        const int l0 = __ffs(okm) - 1;  // first ok lane = largest j
-        found_first = jb - 3 * l0;
-        cnt += 1 + ((cm >> l0) & 1);
-        cm &= ~(1u << l0);
-        cnt += __popc(cm);
-      } else if (!g.trunc && cm) {
-        const int l0 = __ffs(cm) - 1;
-        found_first = jb - 3 * l0;
-        cnt += __popc(cm);
+  int jmin = max(max(lowest_j, P.min_gene_len - 3), 0);
+  jmin += (3 - jmin % 3) % 3;
+  int jmax = g.len - 3;
+  jmax -= mod3(jmax);
+  R.jmin = jmin;
+  R.jmax = jmax;
+  const int64_t c0 = g.frame > 0 ? a + g.hi - 3 : a + g.lo;  // first base of the codon of js = 0
+  R.r = (int)(c0 % 3);
+  R.s0 = c0 / 3;
+  return R;
+}
+
+// Count pass, one thread per ORF: popcount of the start bits over the ORF's slot range.
+// counts[oi] = records, first_js[oi] = js of the first (largest-js) one; with the truncated rule the first
+// candidate position emits a (which = -1) record whatever its codon (glimmer3.cc:1423-1432).
+__global__ void __launch_bounds__(128) k3_g3_count(const uint2* __restrict__ cb, int64_t nwc,
+                                                   const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                   const int32_t* __restrict__ orf_seq, int64_t n_orfs, DevParams P,
+                                                   int64_t* __restrict__ counts, int32_t* __restrict__ first_js,
+                                                   int* __restrict__ max_len) {
+  const int64_t oi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = oi < n_orfs;
+  G3Geom g;
+  g.len = 0;
+  int64_t a = 0;
+  if (live) {
+    const int32_t s = orf_seq[oi];
+    a = off[s];
+    g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
+  }
+  {  // longest ORF string of the batch (the emit pass's exactness bound)
+    const int wmax = __reduce_max_sync(0xffffffffu, g.len);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(max_len, wmax);
+  }
+  if (!live) return;
+  const G3Range R = g3_range(g, a, P);
+  int cnt = 0, first = -1;
+  if (R.jmax >= R.jmin) {
+    const bool fwd = g.frame > 0;
+    const int64_t s_lo = fwd ? R.s0 - R.jmax / 3 : R.s0 + R.jmin / 3;
+    const int64_t s_hi = fwd ? R.s0 - R.jmin / 3 : R.s0 + R.jmax / 3;
+    const uint2* st = cb + (size_t)(fwd ? R.r : 3 + R.r) * nwc;
+    const int64_t w_lo = s_lo >> 5, w_hi = s_hi >> 5;
+    const unsigned m_lo = ~0u << (int)(s_lo & 31), m_hi = (2u << (int)(s_hi & 31)) - 1u;
+    int64_t ext = -1;  // forward: lowest set slot (largest js); reverse: highest set slot
+    for (int64_t w = w_lo; w <= w_hi; w++) {
+      const unsigned x = __ldg(st + w).x & (w == w_lo ? m_lo : ~0u) & (w == w_hi ? m_hi : ~0u);
+      if (x) {
+        cnt += __popc(x);
+        if (fwd) {
+          if (ext < 0) ext = (w << 5) + __ffs(x) - 1;
+        } else {
+          ext = (w << 5) + 31 - __clz(x);
+        }
       }
-    } else {
-      cnt += __popc(cm);
+    }
+    if (ext >= 0) first = (int)(fwd ? 3 * (R.s0 - ext) : 3 * (ext - R.s0));
+  }
+  if (g.trunc) {  // the largest candidate position, complete codon or not
+    const int jtop = (g.len - 1) - mod3(g.len - 1);
+    if (jtop >= R.jmin) {
+      first = jtop;
+      cnt += 1;
     }
   }
-  if (lane == 0) {
-    counts[oi] = cnt;
-    first_js[oi] = found_first;
+  counts[oi] = cnt;
+  first_js[oi] = first;
+}
+
+// Heads, kHG lanes per ORF: positions 0 .. ja of the ORF string evaluated explicitly -- the W-1 partial windows
+// only see the ORF string (icm.cc:376-388) -- and prefix-summed; heads[oi][k] = sum over j <= 3k+2 of
+// (gene_j - indep_j), k < nh = (ja+1)/3, ja = first j >= W-2 with j % 3 == 2 (the anchor of k3_g3_emit).
+template <int kHG>
+__global__ void __launch_bounds__(128) k3_g3_heads(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                   const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                   const int32_t* __restrict__ orf_seq, int64_t n_orfs, DevParams P,
+                                                   const int64_t* __restrict__ counts, int ja, double* __restrict__ heads) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kHG;
+  const int gl = threadIdx.x % kHG;
+  const bool live = oi < n_orfs && counts[oi] > 0;
+  double hs = 0.0;
+  if (live) {
+    const int32_t s = orf_seq[oi];
+    const int64_t a = off[s];
+    const G3Geom g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
+    if (gl <= ja && gl < g.len) {
+      const bool fwd = g.frame > 0;
+      const int f = (1 + gl) % 3, bound = fwd ? g.hi : g.lo;
+      const int q = fwd ? g.hi - 1 - gl : g.lo + gl;
+      const float xg = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
+      float xn;
+      if (gl >= 2) xn = fwd ? __ldg(indep.lut3 + f * 64 + (int)(gmg_extract32(words, a + q) & 63))
+                            : __ldg(indep.lut3 + (3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63));
+      else xn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
+      hs = (double)xg - (double)xn;
+    }
   }
+#pragma unroll
+  for (int d = 1; d < kHG; d <<= 1) {
+    const double t = __shfl_up_sync(FULL, hs, d, kHG);
+    if (gl >= d) hs += t;
+  }
+  if (live && gl <= ja && gl % 3 == 2) heads[(size_t)oi * ((ja + 1) / 3) + gl / 3] = hs;
 }
 
 // K2 (glimmer3 path): codon-boundary cumulative log-odds.
@@ -1210,59 +1288,56 @@ __global__ void __launch_bounds__(256) k3_g3_count(const uint64_t* __restrict__ 
 //   CR[p] = sum of the reverse stream with boundary residue p%3 from the start of p's tile     (prefix sums)
 // where the slot of boundary p is the three terms at p, p+1, p+2 (periods 0, 2, 1) forward and p, p-1, p-2
 // (periods 0, 2, 1) reverse.  Sums restart at every tile of G3_TS codon slots, so tiles are independent CTAs;
-// per tile and stream the kernel also keeps the total T, the sum A of |gene| + |indep| and (per tile) the smallest
-// biased float exponent E among the non-zero terms: an ORF's sums are differences / sums of these values, and
-// they carry the reference's bits whenever no addition can round (k3_g3_emit checks A and E over the tiles an
-// ORF touches; see DESIGN.md "exactness").
+// tileT[tile][6] keeps each stream's tile total.  An ORF's sums are differences / sums of these values; they
+// carry the reference's bits because no addition can round (the static certificate of gmg_score_orfs_g3).
 #define G3_TS 512  // codon slots (3 bases each) per tile = threads per CTA
 
 __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict__ lut3,
                                                          const uint64_t* __restrict__ words, int64_t total,
                                                          const float* __restrict__ planes,
                                                          double* __restrict__ cumc, int64_t tot3,
-                                                         double* __restrict__ tileT, float* __restrict__ tileA,
-                                                         unsigned* __restrict__ tileE) {
+                                                         double* __restrict__ tileT) {
   constexpr int NW = G3_TS / 32;
   __shared__ float s_lut[384];
   __shared__ double s_wtot[6][NW];
-  __shared__ float s_wa[6][NW];
-  __shared__ unsigned s_we[NW];
   __shared__ double s_out[2][3 * G3_TS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < 384; i += G3_TS) s_lut[i] = lut3[i];
   __syncthreads();
   const int64_t p0 = 3 * ((int64_t)blockIdx.x * G3_TS + tid);
   double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
-  float au[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f};
-  unsigned emin = 0x7F800000u;
   if (p0 - 2 < total) {
     const uint64_t win = gmg_extract32(words, p0 - 4);  // base b at bits 2 (b - p0 + 4)
+    const float* pl = planes + p0;
+    const size_t T = (size_t)total;
+    if (p0 >= 2 && p0 + 4 < total) {  // interior slot: every term exists
 #pragma unroll
-    for (int rho = 0; rho < 3; rho++) {
+      for (int rho = 0; rho < 3; rho++) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
-        const int64_t pf = p0 + rho + k, pr = p0 + rho - k;
-        if (pf < total) {  // forward term: window = bases pf, pf+1, pf+2
-          const float g = __ldg(planes + (size_t)f * total + pf);
-          const float n = s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
-          u[rho] += (double)g - (double)n;
-          au[rho] += fabsf(g) + fabsf(n);
-          if (g != 0.f) emin = min(emin, __float_as_uint(g) & 0x7F800000u);
-          if (n != 0.f) emin = min(emin, __float_as_uint(n) & 0x7F800000u);
+        for (int k = 0; k < 3; k++) {
+          const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
+          u[rho] += (double)__ldg(pl + f * T + (rho + k)) - (double)s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
+          v[rho] += (double)__ldg(pl + (3 + f) * T + (rho - k)) -
+                    (double)s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
         }
-        if (pr >= 0 && pr < total) {  // reverse term: window = complement of bases pr-2, pr-1, pr
-          const float g = __ldg(planes + (size_t)(3 + f) * total + pr);
-          const float n = s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
-          v[rho] += (double)g - (double)n;
-          av[rho] += fabsf(g) + fabsf(n);
-          if (g != 0.f) emin = min(emin, __float_as_uint(g) & 0x7F800000u);
-          if (n != 0.f) emin = min(emin, __float_as_uint(n) & 0x7F800000u);
+      }
+    } else {
+#pragma unroll
+      for (int rho = 0; rho < 3; rho++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
+          const int64_t pf = p0 + rho + k, pr = p0 + rho - k;
+          if (pf < total)  // forward term: window = bases pf, pf+1, pf+2
+            u[rho] += (double)__ldg(pl + f * T + (rho + k)) - (double)s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
+          if (pr >= 0 && pr < total)  // reverse term: window = complement of bases pr-2, pr-1, pr
+            v[rho] += (double)__ldg(pl + (3 + f) * T + (rho - k)) -
+                      (double)s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
         }
       }
     }
   }
-  // warp level: suffix scans (forward streams), prefix scans (reverse streams), |term| sums, exponent minimum
+  // warp level: suffix scans (forward streams), prefix scans (reverse streams)
 #pragma unroll
   for (int rho = 0; rho < 3; rho++) {
 #pragma unroll
@@ -1271,34 +1346,20 @@ __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict
       if (lane + d < 32) u[rho] += tu;
       if (lane >= d) v[rho] += tv;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      au[rho] += __shfl_xor_sync(0xffffffffu, au[rho], d);
-      av[rho] += __shfl_xor_sync(0xffffffffu, av[rho], d);
-    }
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
   if (lane == 0) {
 #pragma unroll
-    for (int rho = 0; rho < 3; rho++) {
-      s_wtot[rho][wid] = u[rho];
-      s_wa[rho][wid] = au[rho];
-      s_wa[3 + rho][wid] = av[rho];
-    }
-    s_we[wid] = emin;
+    for (int rho = 0; rho < 3; rho++) s_wtot[rho][wid] = u[rho];
   }
   if (lane == 31) {
 #pragma unroll
     for (int rho = 0; rho < 3; rho++) s_wtot[3 + rho][wid] = v[rho];
   }
   __syncthreads();
-  // warp k < 6 turns the warp totals of stream k into exclusive offsets and writes the tile's T / A (/ E)
+  // warp k < 6 turns the warp totals of stream k into exclusive offsets and writes the tile total
   if (wid < 6) {
     const bool fw = wid < 3;
-    double x = lane < NW ? s_wtot[wid][lane] : 0.0;
-    float a = lane < NW ? s_wa[wid][lane] : 0.f;
-    unsigned e = lane < NW ? s_we[lane] : 0x7F800000u;
+    const double x = lane < NW ? s_wtot[wid][lane] : 0.0;
     double incl = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1306,18 +1367,9 @@ __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict
       if (fw && lane + d < 32) incl += td;
       if (!fw && lane >= d) incl += tu;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, d);
-      e = min(e, __shfl_xor_sync(0xffffffffu, e, d));
-    }
     if (lane < NW) s_wtot[wid][lane] = incl - x;  // exclusive: warps after (forward) / before (reverse) this one
     const double tot = __shfl_sync(0xffffffffu, incl, fw ? 0 : 31);
-    if (lane == 0) {
-      tileT[(size_t)blockIdx.x * 6 + wid] = tot;
-      tileA[(size_t)blockIdx.x * 6 + wid] = a * 1.001f;  // upper bound: the float sum itself rounds
-      if (wid == 0) tileE[blockIdx.x] = e;
-    }
+    if (lane == 0) tileT[(size_t)blockIdx.x * 6 + wid] = tot;
   }
   __syncthreads();
 #pragma unroll
@@ -1334,161 +1386,175 @@ __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict
   }
 }
 
-// K3 (glimmer3) emit pass: one warp per ORF writes the start records the count pass found.  score[js-1] of a
-// start is  H + (stream sum between the anchor position j = ja and j = js-1)  where H sums the first ja+1
-// positions of the ORF string explicitly (the W-1 partial windows only see the ORF string, icm.cc:376-388;
-// ja = first j >= W-2 with j mod 3 == 2) and the stream sum is read off k2_g3_codon_cum's tables: two loads
-// when both ends share a tile, plus the totals of the tiles in between otherwise.  All of it is exact -- and
-// therefore bit-identical to the reference's serial FP64 sums -- when no addition of float-granular terms can
-// round: every term is an integer multiple of 2^(E-150) (E = smallest biased exponent among the non-zero
-// terms) and every partial sum of any association is bounded by A = sum |gene| + |indep| < 2^(E-150+52).
-// ORFs whose certificate fails (or that span more than 32 tiles) are re-done in the reference's order.
-__global__ void __launch_bounds__(128) k3_g3_emit(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
-                                                  const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
-                                                  const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                  const float* __restrict__ planes, const double* __restrict__ cumc,
-                                                  int64_t tot3, const double* __restrict__ tileT,
-                                                  const float* __restrict__ tileA, const unsigned* __restrict__ tileE,
-                                                  CodonSets cs, DevParams P, const int64_t* __restrict__ start_off,
-                                                  const int32_t* __restrict__ first_js, gmg_start* __restrict__ starts,
-                                                  unsigned long long* __restrict__ n_ordered) {
+// K3 (glimmer3) emit pass, kG lanes per ORF: every lane takes one 32-codon word of the ORF's start-bit range per
+// step and writes the records of its set bits.  score[js-1] of a start is  H + (stream sum between the anchor
+// position j = ja and j = js-1): H from k3_g3_heads, the stream sum read off k2_g3_codon_cum's tables -- two
+// loads when both ends share a tile, plus the totals of the tiles in between otherwise.  Records are stored in
+// generation order (descending js): forward ORFs walk their slots upwards, reverse ORFs downwards.
+template <int kG>
+__global__ void __launch_bounds__(128) k3_g3_emit(const uint64_t* __restrict__ words, const uint2* __restrict__ cb,
+                                                  int64_t nwc, const int64_t* __restrict__ off,
+                                                  const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                  int64_t n_orfs, const double* __restrict__ cumc, int64_t tot3,
+                                                  const double* __restrict__ tileT, const double* __restrict__ heads,
+                                                  int ja, CodonSets cs, DevParams P,
+                                                  const int64_t* __restrict__ start_off,
+                                                  const int32_t* __restrict__ first_js, int exact_len,
+                                                  gmg_start* __restrict__ starts) {
   constexpr unsigned FULL = 0xffffffffu;
+  __shared__ unsigned char s_which[64];
+  if (threadIdx.x < 64) s_which[threadIdx.x] = cs.which[threadIdx.x];
+  __syncthreads();
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kG;
+  const int gl = threadIdx.x % kG;
+  int n_emit = 0;
+  int64_t so = 0;
+  if (oi < n_orfs && orfs[oi].orf_len <= exact_len) {  // longer ORFs: k3_g3_ordered
+    so = start_off[oi];
+    n_emit = (int)(start_off[oi + 1] - so);
+  }
+  const bool live = n_emit > 0;
+  // per-ORF state (identical in the kG lanes of a group)
+  G3Geom g;
+  G3Range R;
+  int64_t a = 0, s_first = 0, pa = 0, ta = 0;
+  int first_j = 0, nwords = 0, strand = 0, rho = 0;
+  bool fwd = true;
+  double c_a = 0.0, t_a = 0.0, h_ja = 0.0;
+  const double* hd = NULL;
+  if (live) {
+    first_j = first_js[oi];
+    const int32_t s = orf_seq[oi];
+    a = off[s];
+    g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
+    R = g3_range(g, a, P);
+    fwd = g.frame > 0;
+    strand = fwd ? 0 : 1;
+    // slots in generation order: from js = min(first_j, jmax) down to jmin
+    const int jhi = min(first_j, R.jmax);
+    s_first = fwd ? R.s0 - jhi / 3 : R.s0 + jhi / 3;
+    const int64_t s_last = fwd ? R.s0 - R.jmin / 3 : R.s0 + R.jmin / 3;
+    nwords = jhi >= R.jmin ? (int)(fwd ? (s_last >> 5) - (s_first >> 5) : (s_first >> 5) - (s_last >> 5)) + 1 : 0;
+    hd = heads + (size_t)oi * ((ja + 1) / 3);
+    if (first_j - 1 > ja) {
+      pa = a + (fwd ? g.hi - 1 - ja : g.lo + ja);
+      rho = (int)(pa % 3);
+      ta = pa / (3 * G3_TS);
+      c_a = __ldg(cumc + (size_t)strand * tot3 + pa);
+      t_a = __ldg(tileT + (size_t)ta * 6 + strand * 3 + rho);
+      h_ja = __ldg(hd + ja / 3);
+    }
+  }
+  gmg_start* out = starts + so;
+  int emitted = 0;
+  // truncated rule: the first candidate position emits a which = -1 record whatever its codon
+  const bool trunc_first = live && g.trunc;
+  if (trunc_first) emitted = 1;
+  const int64_t s_lo = live ? (fwd ? s_first : R.s0 + R.jmin / 3) : 0;
+  const int64_t s_hi = live ? (fwd ? R.s0 - R.jmin / 3 : s_first) : 0;
+  for (int wb = 0; __any_sync(FULL, wb < nwords); wb += kG) {
+    const int wi = wb + gl;
+    unsigned x = 0;
+    int64_t w = 0;
+    if (wi < nwords) {
+      w = fwd ? (s_lo >> 5) + wi : (s_hi >> 5) - wi;
+      x = __ldg(cb + (size_t)(fwd ? R.r : 3 + R.r) * nwc + w).x;
+      if (w == (s_lo >> 5)) x &= ~0u << (int)(s_lo & 31);
+      if (w == (s_hi >> 5)) x &= (2u << (int)(s_hi & 31)) - 1u;
+    }
+    const int cnt = __popc(x);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < kG; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, d, kG);
+      if (gl >= d) incl += t;
+    }
+    int slot = emitted + incl - cnt;
+    while (x) {
+      const int b = fwd ? __ffs(x) - 1 : 31 - __clz(x);
+      x &= ~(1u << b);
+      const int64_t sl = (w << 5) + b;
+      const int js = (int)(fwd ? 3 * (R.s0 - sl) : 3 * (sl - R.s0));
+      const int j = js - 1;
+      double sc;
+      if (j <= ja) {
+        sc = __ldg(hd + j / 3);
+      } else {
+        const int64_t pj = a + (fwd ? g.hi - 1 - j : g.lo + j);
+        const int64_t tj = pj / (3 * G3_TS);
+        const double c_j = __ldg(cumc + (size_t)strand * tot3 + pj);
+        if (tj == ta) {
+          sc = h_ja + (c_j - c_a);
+        } else {
+          double qd = 0.0;  // totals of the tiles strictly between the anchor's and this start's
+          if (fwd) for (int64_t t = ta - 1; t > tj; t--) qd += __ldg(tileT + (size_t)t * 6 + rho);
+          else for (int64_t t = ta + 1; t < tj; t++) qd += __ldg(tileT + (size_t)t * 6 + 3 + rho);
+          sc = h_ja + ((c_j + qd) + (t_a - c_a));
+        }
+      }
+      // the start codon: S[c], S[c+1], S[c+2] forward / complement of S[c+2], S[c+1], S[c] reverse, c = 3 sl + r
+      const int raw = (int)(gmg_extract32(words, 3 * sl + R.r) & 63);
+      const int b0 = raw & 3, b1 = (raw >> 2) & 3, b2 = raw >> 4;
+      const int code = fwd ? b0 * 16 + b1 * 4 + b2 : (3 - b2) * 16 + (3 - b1) * 4 + (3 - b0);
+      const int which = s_which[code];
+      const int m = g.len;
+      const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
+      Emit e;
+      e.out = out;
+      e.n = slot++;
+      emit_start(e, js + 2, kpos, sc, which, 0, (js == first_j && !g.trunc) ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
+    }
+    emitted += __shfl_sync(FULL, incl, kG - 1, kG);
+  }
+  if (trunc_first && gl == 0) {
+    const int js = first_j, j = js - 1;
+    double sc;
+    if (j <= ja) {
+      sc = __ldg(hd + j / 3);
+    } else {
+      const int64_t pj = a + (fwd ? g.hi - 1 - j : g.lo + j);
+      const int64_t tj = pj / (3 * G3_TS);
+      const double c_j = __ldg(cumc + (size_t)strand * tot3 + pj);
+      double qd = 0.0;
+      if (fwd) for (int64_t t = ta - 1; t > tj; t--) qd += __ldg(tileT + (size_t)t * 6 + rho);
+      else for (int64_t t = ta + 1; t < tj; t++) qd += __ldg(tileT + (size_t)t * 6 + 3 + rho);
+      sc = tj == ta ? h_ja + (c_j - c_a) : h_ja + ((c_j + qd) + (t_a - c_a));
+    }
+    const int m = g.len;
+    const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
+    Emit e;
+    e.out = out;
+    e.n = 0;
+    emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
+  }
+}
+
+// The reference's own association for every ORF (one warp each): used when the static exactness certificate
+// of gmg_score_orfs_g3 does not hold for the model pair / sequence lengths at hand.
+__global__ void __launch_bounds__(128) k3_g3_ordered(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
+                                                     const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
+                                                     const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                     const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                     const int64_t* __restrict__ start_off,
+                                                     const int32_t* __restrict__ first_js, int exact_len,
+                                                     gmg_start* __restrict__ starts,
+                                                     unsigned long long* __restrict__ n_ordered) {
   __shared__ float s_lut[384];
   if (indep.lut3)
     for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
   __syncthreads();
   const float* lut = indep.lut3 ? s_lut : NULL;
   const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (oi >= n_orfs) return;
+  if (oi >= n_orfs || orfs[oi].orf_len <= exact_len) return;
+  if ((threadIdx.x & 31) == 0) atomicAdd(n_ordered, 1ull);
   const int64_t so = start_off[oi];
   const int n_emit = (int)(start_off[oi + 1] - so);
   if (n_emit == 0) return;
-  const int first_j = first_js[oi];
   const int32_t s = orf_seq[oi];
   const int64_t a = off[s];
   const G3Geom g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
-  const bool fwd = g.frame > 0;
-  const float* plane = planes + (size_t)(fwd ? 0 : 3) * total;  // the strand's three period planes
-  gmg_start* out = starts + so;
-  const int W = gene.W, m = g.len;
-  const int j_last = first_j - 1;
-  const int ja = (W - 2) + (5 - (W - 2) % 3) % 3;  // first j >= W-2 with j % 3 == 2
-  bool fast = cumc != NULL && lut != NULL && ja < 32 && W >= 2;
-  // ---- head: positions 0 .. min(ja, j_last) of the ORF string, one lane each ----
-  const int bound = fwd ? g.hi : g.lo;
-  double hs = 0.0;
-  float asum = 0.f;
-  unsigned emin = 0x7F800000u;
-  if (fast && lane <= min(ja, j_last)) {
-    const int f = (1 + lane) % 3;
-    const int q = fwd ? g.hi - 1 - lane : g.lo + lane;
-    const float xg = fwd ? icm_fwd(gene, words, a + q, q, bound, f) : icm_rev(gene, words, a + q, q, bound, f);
-    float xn;
-    if (lane >= 2) xn = fwd ? lut[f * 64 + (int)(gmg_extract32(words, a + q) & 63)]
-                            : lut[(3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63)];
-    else xn = fwd ? icm_fwd(indep, words, a + q, q, bound, f) : icm_rev(indep, words, a + q, q, bound, f);
-    hs = (double)xg - (double)xn;
-    asum = fabsf(xg) + fabsf(xn);
-    if (xg != 0.f) emin = min(emin, __float_as_uint(xg) & 0x7F800000u);
-    if (xn != 0.f) emin = min(emin, __float_as_uint(xn) & 0x7F800000u);
-  }
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const double t = __shfl_up_sync(FULL, hs, d);
-    if (lane >= d) hs += t;
-  }
-  // ---- the tiles between the anchor (j = ja) and the farthest start (j = j_last) ----
-  const int strand = fwd ? 0 : 1;
-  const bool span = j_last > ja;
-  int64_t pa = 0, ta = 0;
-  int rho = 0, nt = 0;
-  double q_tiles = 0.0, c_a = 0.0, t_a = 0.0;
-  if (fast && span) {
-    pa = a + (fwd ? g.hi - 1 - ja : g.lo + ja);
-    const int64_t pl = a + (fwd ? g.hi - 1 - j_last : g.lo + j_last);
-    rho = (int)(pa % 3);
-    ta = pa / (3 * G3_TS);
-    const int64_t tl = pl / (3 * G3_TS);
-    nt = (int)(fwd ? ta - tl : tl - ta);
-    if (nt >= 32) fast = false;
-  }
-  if (fast && span) {
-    if (lane <= nt) {
-      const int64_t tk = fwd ? ta - lane : ta + lane;
-      const double tt = tileT[(size_t)tk * 6 + strand * 3 + rho];
-      asum += tileA[(size_t)tk * 6 + strand * 3 + rho];
-      emin = min(emin, tileE[tk]);
-      if (lane == 0) t_a = tt;
-      else q_tiles = tt;
-    }
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {  // q_tiles of lane k = total of the k tiles after the anchor's
-      const double t = __shfl_up_sync(FULL, q_tiles, d);
-      if (lane >= d) q_tiles += t;
-    }
-    t_a = __shfl_sync(FULL, t_a, 0);
-    c_a = cumc[(size_t)strand * tot3 + pa];
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    asum += __shfl_xor_sync(FULL, asum, d);
-    emin = min(emin, __shfl_xor_sync(FULL, emin, d));
-  }
-  if (fast) fast = emin != 0u && (double)asum * 1.001 < ldexp(1.0, (int)(emin >> 23) - 150 + 52);
-  if (!fast) {
-    g3_accumulate_ordered(gene, indep, lut, words, a, g, plane, total, cs, P, first_j, n_emit, out);
-    if (lane == 0) atomicAdd(n_ordered, 1ull);
-    return;
-  }
-  const double h_ja = __shfl_sync(FULL, hs, min(ja, 31));
-  // ---- the start positions, 32 codons per step in descending j (= generation order) ----
-  const int lowest_j = min(3, P.min_gene_len - 3);
-  const int jtop = (m - 1) - ((m - 1) % 3);
-  int emitted = 0;
-  for (int jb = min(jtop, first_j); jb >= lowest_j; jb -= 96) {
-    const int js = jb - 3 * lane;
-    const bool ok = (js >= lowest_j) && (js + 3 >= P.min_gene_len);
-    const int w = ok ? g3_codon_which(words, a, g, js, cs) : -2;
-    const bool is_first = ok && js == first_j;
-    const bool emits = ok && (w >= 0 || (is_first && g.trunc));
-    const int nrec = emits ? ((is_first && g.trunc && w >= 0) ? 2 : 1) : 0;
-    int incl = nrec;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const int j = js - 1;  // the start at js uses score[js - 1]
-    // stream part for j > ja
-    int dt = 0;
-    double c_j = 0.0;
-    if (emits && j > ja) {
-      const int64_t pj = a + (fwd ? g.hi - 1 - j : g.lo + j);
-      const int64_t tj = pj / (3 * G3_TS);
-      dt = (int)(fwd ? ta - tj : tj - ta);
-      c_j = cumc[(size_t)strand * tot3 + pj];
-    }
-    const double qd = __shfl_sync(FULL, q_tiles, dt > 0 ? dt - 1 : 0);
-    const double hj = __shfl_sync(FULL, hs, (j >= 0 && j < 32) ? j : 0);
-    if (emits) {
-      double sc;
-      if (j <= ja) sc = hj;
-      else if (dt == 0) sc = h_ja + (c_j - c_a);
-      else sc = h_ja + ((c_j + qd) + (t_a - c_a));
-      const int kpos = fwd ? g.k0 + (m - 1 - js) : g.k0 - (m - 1 - js);
-      Emit e;
-      e.out = out;
-      e.n = emitted + incl - nrec;
-      if (is_first && g.trunc) {
-        emit_start(e, js + 2, kpos, sc, -1, 1, 1, 0, NULL, NULL, P.ignore_score_len);
-        if (w >= 0) emit_start(e, js + 2, kpos, sc, w, 0, 0, 0, NULL, NULL, P.ignore_score_len);
-      } else {
-        emit_start(e, js + 2, kpos, sc, w, 0, is_first ? 1 : 0, 0, NULL, NULL, P.ignore_score_len);
-      }
-    }
-    emitted += __shfl_sync(FULL, incl, 31);
-  }
+  const float* plane = planes + (size_t)(g.frame > 0 ? 0 : 3) * total;  // the strand's three period planes
+  g3_accumulate_ordered(gene, indep, lut, words, a, g, plane, total, cs, P, first_js[oi], n_emit, starts + so);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1923,54 +1989,90 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   s->uncertified = 0;
   if (n_starts) *n_starts = 0;
   if (s->n_orfs == 0) return 0;
+  if (ensure_codon_bits(ctx, s, cs)) return 1;
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
+  // Static exactness certificate: every term is a float of the two models, i.e. an integer multiple of
+  // 2^gexp (gexp = smallest ulp exponent over both tables); every sum formed for an ORF -- and every partial sum of
+  // the reference's serial accumulation -- has at most orf_len + 4 tiles of terms, each bounded by max|gene| +
+  // max|indep|.  While that bound stays below 2^(gexp+52) no addition can round, so any association gives the
+  // reference's bits: ORFs up to exact_len bases take the scan-based path, longer ones (and every ORF when the
+  // independent model is not the usual 3-base one) are accumulated in the reference's own order.
+  const int ja = (gene->W - 2) + (5 - (gene->W - 2) % 3) % 3;  // first j >= W-2 with j % 3 == 2
+  int exact_len = -1;
+  const bool force_ordered = getenv("GMG_G3_ORDERED") && atoi(getenv("GMG_G3_ORDERED"));  // test hook
+  if (indep->dev.lut3 != NULL && gene->W >= 2 && ja < 32 && !force_ordered) {
+    int eg, en;
+    float mg, mn;
+    gmg_icm_value_stats(gene, &eg, &mg);
+    gmg_icm_value_stats(indep, &en, &mn);
+    const double lim = ldexp(1.0, (eg < en ? eg : en) + 52) / (((double)mg + (double)mn) * 1.01 + 1e-300) - 12.0 * G3_TS;
+    exact_len = lim >= 2e9 ? INT_MAX : (lim < 0 ? -1 : (int)lim);
+  }
+  const bool exact = exact_len >= 0;
   GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
-  // K2 (glimmer3 path): codon-boundary cumulative sums, tile by tile
-  double *cumc = NULL, *tileT = NULL;
-  float* tileA = NULL;
-  unsigned* tileE = NULL;
+  double *cumc = NULL, *tileT = NULL, *heads = NULL;
   const int64_t ntiles = s->total / (3 * G3_TS) + 1, tot3 = ntiles * 3 * G3_TS;
-  static const bool no_cum = getenv("GMG_G3_ORDERED") && atoi(getenv("GMG_G3_ORDERED"));
-  if (indep->dev.lut3 && gene->W >= 2 && gene->W <= 30 && !no_cum) {
-    void *d_cum, *d_tiles;
+  const int nh = (ja + 1) / 3;
+  if (exact) {  // K2 (glimmer3 path): codon-boundary cumulative sums, tile by tile
+    void *d_cum, *d_tiles, *d_heads;
     if (gmg_scratch(ctx, SCR_CUM, (size_t)2 * tot3 * sizeof(double), &d_cum)) return 1;
-    if (gmg_scratch(ctx, SCR_QUAL, (size_t)ntiles * (6 * sizeof(double) + 6 * sizeof(float) + sizeof(unsigned)), &d_tiles))
-      return 1;
+    if (gmg_scratch(ctx, SCR_QUAL, (size_t)ntiles * 6 * sizeof(double), &d_tiles)) return 1;
+    if (gmg_scratch(ctx, SCR_TMP2, (size_t)s->n_orfs * nh * sizeof(double), &d_heads)) return 1;
     cumc = (double*)d_cum;
     tileT = (double*)d_tiles;
-    tileA = (float*)(tileT + 6 * ntiles);
-    tileE = (unsigned*)(tileA + 6 * ntiles);
+    heads = (double*)d_heads;
     if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
     k2_g3_codon_cum<<<(unsigned)ntiles, G3_TS, 0, ctx->stream>>>(indep->dev.lut3, s->d_words, s->total, planes, cumc, tot3,
-                                                                tileT, tileA, tileE);
+                                                                tileT);
     gmg_prof_end(ctx, GMG_PROF_K2);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
   }
   void *d_counts, *d_first;
-  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 1) * sizeof(int64_t), &d_counts)) return 1;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
   int64_t* counts = (int64_t*)d_counts;
-  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, sizeof(int64_t), ctx->stream));
+  int* d_maxlen = (int*)(counts + s->n_orfs + 1);
+  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_g3_count<<<(unsigned)((s->n_orfs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-      s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, cs, dp, counts, (int32_t*)d_first);
-  gmg_prof_end(ctx, GMG_PROF_K3);
+  k3_g3_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_orfs,
+                                                                            s->d_orf_seq, s->n_orfs, dp, counts,
+                                                                            (int32_t*)d_first, d_maxlen);
   ctx->launches++;
+  if (exact) {
+    if (ja < 16)
+      k3_g3_heads<16><<<(unsigned)((s->n_orfs * 16 + 127) / 128), 128, 0, ctx->stream>>>(
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
+    else
+      k3_g3_heads<32><<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
+    ctx->launches++;
+  }
+  gmg_prof_end(ctx, GMG_PROF_K3);
   GMG_CUDA(cudaGetLastError());
   if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
   int64_t total_starts = 0;
+  int max_orf_len = 0;
   GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(&max_orf_len, d_maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (total_starts > 0) {
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-    k3_g3_emit<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-        gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cumc, tot3,
-        tileT, tileA, tileE, cs, dp, s->d_start_off, (const int32_t*)d_first, s->d_starts, s->d_gc + 1);
+    if (exact) {
+      k3_g3_emit<8><<<(unsigned)((s->n_orfs * 8 + 127) / 128), 128, 0, ctx->stream>>>(
+          s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, cumc, tot3, tileT, heads, ja, cs,
+          dp, s->d_start_off, (const int32_t*)d_first, exact_len, s->d_starts);
+      ctx->launches++;
+    }
+    if (max_orf_len > exact_len) {
+      k3_g3_ordered<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp,
+          s->d_start_off, (const int32_t*)d_first, exact_len, s->d_starts, s->d_gc + 1);
+      ctx->launches++;
+    }
     gmg_prof_end(ctx, GMG_PROF_K3);
-    ctx->launches++;
     GMG_CUDA(cudaGetLastError());
   }
   s->n_starts = total_starts;

@@ -94,16 +94,21 @@ int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_
 static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off, int64_t n, const void* d_qual,
                         gmg_seqset** out) {
   GMG_CHECK(n >= 0 && n < (1ll << 31), "gmg_seqset_create: %lld sequences unsupported", (long long)n);
-  for (int64_t i = 0; i < n; i++)
+  int64_t max_len = 0;
+  for (int64_t i = 0; i < n; i++) {
     GMG_CHECK(h_off[i + 1] >= h_off[i], "gmg_seqset_create: offsets not monotone at %lld", (long long)i);
+    if (h_off[i + 1] - h_off[i] > max_len) max_len = h_off[i + 1] - h_off[i];
+  }
   GMG_CHECK(n == 0 || h_off[0] == 0, "gmg_seqset_create: offsets must start at 0");
   gmg_seqset* s = new gmg_seqset();
   s->ctx = ctx;
   s->n = n;
   s->total = n ? h_off[n] : 0;
+  s->max_len = max_len;
   s->off.assign(h_off, h_off + n + 1);
   if (n == 0) s->off.assign(1, 0);
   s->d_off = NULL; s->d_words_base = NULL; s->d_words = NULL; s->d_blk2seq = NULL; s->d_qual = NULL; s->d_gc = NULL;
+  s->d_cbits = NULL; s->nwc = 0; memset(s->cbits_key, 0, sizeof s->cbits_key);
   s->n_orfs = 0; s->d_orfs = NULL; s->d_orf_off = NULL; s->d_orf_seq = NULL;
   s->n_starts = 0; s->d_starts = NULL; s->d_start_off = NULL; s->uncertified = 0;
   s->cap_orfs = s->cap_starts = 0;
@@ -165,7 +170,7 @@ extern "C" void gmg_seqset_free(gmg_seqset* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   void* ptrs[] = {s->d_off, s->d_words_base, s->d_blk2seq, s->d_qual, s->d_gc, s->d_orfs, s->d_orf_off,
-                  s->d_orf_seq, s->d_starts, s->d_start_off};
+                  s->d_orf_seq, s->d_starts, s->d_start_off, s->d_cbits};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s->ctx->stream);
   delete s;

@@ -306,6 +306,63 @@ def test_g3_full_genome_matches_oracle(gm, ctx, genome, truncated):
     assert ss.ordered_fallbacks <= len(orfs) // 20
 
 
+def _g3_check(gm, ctx, seqs, gene, og, **pkw):
+    """glimmer3 scoring half of a batch of sequences against the oracle, sequence by sequence."""
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    gc = ss.gc_fraction()
+    p = gm.Params(False, **pkw)
+    p.set_ignore_score_len(gc)
+    op = O.params(False, **pkw)
+    op.ignore_score_len = p.ignore_score_len
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    oi = O.build_indep(gc)
+    ss.find_orfs(p)
+    ss.score_orfs_g3(gene, indep, p)
+    orfs, ooff = ss.get_orfs()
+    starts, soff = ss.get_starts()
+    n_starts = 0
+    for i, s0 in enumerate(seqs):
+        s = O.filter_lower(s0)
+        want_orfs = O.find_orfs(s, op)
+        assert orfs[ooff[i]:ooff[i + 1]].tolist() == want_orfs.tolist(), i
+        woff, wst = O.g3_score_orfs(og, oi, s, op, want_orfs)
+        lo, hi = soff[ooff[i]], soff[ooff[i + 1]]
+        assert ((soff[ooff[i]:ooff[i + 1] + 1] - lo) == woff).all(), i
+        got = starts[lo:hi]
+        for f in ("j", "pos", "which", "truncated", "first"):
+            assert (got[f] == wst[f]).all(), (i, f)
+        assert (_bits(got["score"]) == _bits(wst["score"])).all(), i
+        n_starts += len(wst)
+    return ss, n_starts
+
+
+def test_g3_ordered_path_gives_the_same_bits(gm, ctx, genome, monkeypatch):
+    """The reference-order accumulation (taken when the exactness bound fails) and the scan-based path agree."""
+    path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, path)
+    og = O.lib().orc_icm_read(path.encode())
+    seqs = [genome[:200000]]
+    ss, n = _g3_check(gm, ctx, seqs, gene, og)
+    assert n > 1000 and ss.ordered_fallbacks == 0
+    monkeypatch.setenv("GMG_G3_ORDERED", "1")
+    ss, n2 = _g3_check(gm, ctx, seqs, gene, og)
+    assert n2 == n and ss.ordered_fallbacks == ss.n_orfs > 0
+
+
+@pytest.mark.parametrize("pkw", [dict(), dict(allow_truncated=1), dict(min_gene_len=9), dict(min_gene_len=30, allow_truncated=1)])
+def test_g3_many_contigs_ragged(gm, ctx, genome, pkw):
+    """Several contigs in one batch (offsets not multiples of 3 or of the scan tiles, very short and empty
+    sequences, ORFs that cross tile boundaries) and small Min_Gene_Len values (starts inside the partial-window
+    head of the ORF string)."""
+    path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, path)
+    og = O.lib().orc_icm_read(path.encode())
+    cuts = [0, 1537, 1537, 1600, 4673, 4680, 30001, 30013, 90000, 90100, 150001]
+    seqs = [genome[a:b] for a, b in zip(cuts[:-1], cuts[1:])] + [b"", b"atg", genome[200000:200011]]
+    ss, n = _g3_check(gm, ctx, seqs, gene, og, **pkw)
+    assert n > 300
+
+
 def _train_strings(name):
     return [s.lower() for _, s in O.read_fasta(os.path.join(G, name))]
 
