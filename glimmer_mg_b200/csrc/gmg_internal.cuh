@@ -56,10 +56,13 @@ struct DevIcm {
 //  msh    uint8 [P][2 * 4^(D-1)]  30 - 2 * mut_info_pos of the descendable nodes (left shift that brings the
 //                                 branch base to the top two bits of the 32-bit window register); 255 = stop
 //  mprob  float [P][2 * 4^D][4]   log-probabilities, cut nodes pre-resolved to their parent's row
+//  bleaf  float [P][4][N]         log-probabilities by predicted base in the reference's dense node order
+//                                 (node n's children are 4n+1 .. 4n+4): the table a K1 role keeps in shared memory
 struct DevIcmFast {
-  int valid, W, D, P, inner_m, leaves_m;
+  int valid, W, D, P, N, inner_m, leaves_m;
   const uint8_t* msh;
   const float* mprob;
+  const float* bleaf;
 };
 
 struct gmg_ctx {
@@ -94,6 +97,7 @@ struct gmg_icm {
   DevIcm dev;
   uint8_t* d_msh;
   float* d_mprob;
+  float* d_bleaf;
   float* d_lut3;
   DevIcmFast fast;
   // value statistics of `prob` (lazily computed, see gmg_icm_value_stats)
@@ -117,6 +121,14 @@ struct gmg_seqset {
   int32_t* d_blk2seq;        // sequence holding base 32*b; bit 31 = interior block (see k_blk2seq)
   uint8_t* d_qual;           // per-base quality (input file values) or NULL
   unsigned long long* d_gc;  // {gc count, ORFs of the last g3 scoring call that took the ordered-sum fallback}
+  // base buckets (k_bucket_*): the K1 planes are stored bucketed by the base at each position (see gmg_plane_index)
+  uint32_t* d_bktidx;        // [nblk][4] plane index of the first base-b position at or after 32-base block blk
+  // walk-ready contexts in plane-index order (model independent; K1 shifts them down by 32 - 2 W):
+  uint32_t* d_ctxf;          // [total] forward strand: base p+j at bits 30-2j, j = 0..15
+  uint32_t* d_ctxr;          // [total] reverse strand: complement of base p-15+i at bits 2i, i = 0..15
+  uint8_t* d_cdist;          // [total] min(q, 15) | min(len-1-q, 15) << 4, q = position in its sequence
+  int64_t n_base[4];         // positions with base a / c / g / t (host copy valid iff n_base_valid)
+  int n_base_valid;
   // codon bitmaps (k_codon_bits): uint2 {start bits, stop bits} [strand][stream r][nwc]; bit i of word w <-> the
   // codon whose three bases start at global index 3 (32 w + i) + r
   uint2* d_cbits;
@@ -170,6 +182,23 @@ __device__ __forceinline__ float gmg_walk(const int8_t* __restrict__ mipf, const
     node = 4 * node + (int)((ctx >> (2 * pos)) & 3) + 1;
   }
   return __ldg(probf + 4 * (size_t)node + (int)((ctx >> (2 * (W - 1))) & 3));
+}
+
+// The six K1 planes (float [6][total]) are not stored in position order but bucketed by the base at each
+// position: all 'a' positions first (ascending), then 'c', 'g', 't'.  K1's role-persistent CTAs each keep ONE
+// (period, predicted base) leaf table in shared memory and stream through one bucket, reading and writing
+// densely; every consumer maps a position to its plane index with one 16-byte load and a popcount:
+//   index(p) = bktidx[p / 32][b] + #{ q in the same 32-base block, q < p, base(q) == b },  b = base(p).
+// Consecutive positions of one base have consecutive indices, so a warp reading 32 consecutive positions touches
+// four dense runs (the same number of 32-byte sectors as a position-ordered plane).
+__device__ __forceinline__ uint32_t gmg_plane_index(const uint64_t* __restrict__ words,
+                                                    const uint32_t* __restrict__ bktidx, int64_t p) {
+  const uint64_t w = __ldg(words + (p >> 5));
+  const int i = (int)(p & 31);
+  const unsigned b = (unsigned)(w >> (2 * i)) & 3u;
+  const uint64_t x = w ^ (0x5555555555555555ull * b);
+  const uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull & ((1ull << (2 * i)) - 1ull);
+  return __ldg(bktidx + ((p >> 5) << 2) + b) + (uint32_t)__popcll(eq);
 }
 
 // reverse the order of the low W bases of v (base i <-> base W-1-i)

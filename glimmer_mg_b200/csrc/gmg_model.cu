@@ -316,6 +316,16 @@ static int icm_upload(gmg_icm* m) {
     GMG_CUDA(cudaMemcpyAsync(m->d_msh, msh.data(), msh.size(), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(m->d_mprob, mprob.data(), mprob.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t np = ((size_t)N + 3) & ~(size_t)3;  // row stride: 16-byte aligned rows
+    std::vector<float> bleaf((size_t)P * 4 * np, 0.0f);
+    for (int f = 0; f < P; f++)
+      for (int b = 0; b < 4; b++)
+        for (int n = 0; n < N; n++) bleaf[((size_t)f * 4 + b) * np + n] = eff[((size_t)f * N + n) * 4 + b];
+    GMG_CUDA(cudaMalloc(&m->d_bleaf, bleaf.size() * sizeof(float) + 64));
+    GMG_CUDA(cudaMemcpyAsync(m->d_bleaf, bleaf.data(), bleaf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->fast.N = N;
+    m->fast.bleaf = m->d_bleaf;
     m->fast.valid = 1;
     m->fast.W = m->W;
     m->fast.D = D;
@@ -379,6 +389,8 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->d_prob = NULL;
   m->d_msh = NULL;
   m->d_mprob = NULL;
+  m->d_bleaf = NULL;
+  m->d_bleaf = NULL;
   m->d_lut3 = NULL;
   for (size_t i = 0; i < m->mip.size(); i++)
     if (m->mip[i] >= w - 1 && w > 1) {
@@ -504,6 +516,7 @@ extern "C" void gmg_icm_free(gmg_icm* m) {
   if (m->d_prob) cudaFree(m->d_prob);
   if (m->d_msh) cudaFree(m->d_msh);
   if (m->d_mprob) cudaFree(m->d_mprob);
+  if (m->d_bleaf) cudaFree(m->d_bleaf);
   if (m->d_lut3) cudaFree(m->d_lut3);
   delete m;
 }

@@ -202,7 +202,8 @@ __device__ __forceinline__ void walk_many(const int8_t* const* mipf, const float
 
 __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __restrict__ words,
                                                  const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
-                                                 int64_t total, float* __restrict__ planes) {
+                                                 const uint32_t* __restrict__ bktidx, int64_t total,
+                                                 float* __restrict__ planes) {
   extern __shared__ int8_t s_mip[];
   const int nmip = gene.P * gene.inner;
   for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip[i] = gene.mip[i];
@@ -233,217 +234,103 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
       lim[3 + f] = lr;
     }
     walk_many<6>(mipf, probf, ctx, lim, W, D, v);
+    const size_t pi = gmg_plane_index(words, bktidx, p);
 #pragma unroll
-    for (int f = 0; f < 6; f++) planes[(size_t)f * total + p] = v[f];
+    for (int f = 0; f < 6; f++) planes[(size_t)f * total + pi] = v[f];
   }
 }
 
-// K1 fast path (W <= 16, D <= 8; the build-icm defaults are 12 / 7): marker-indexed tables (DevIcmFast), 32-bit
-// window registers, one LDS + one compare + two funnel/shift instructions per tree level and walk.
-//   window register: window position k at bits 2k for BOTH strands (the forward strand's bases are
-//   order-reversed once per thread with BREV + a pair swap), so both strands share one shift table.
-// One CTA of 1024 threads, two per SM (48 KB of shift tables per SM leaves ~180 KB of L1 for the leaf gathers).
-template <int kD>  // kD > 0: depth known at compile time (table offsets fold into the LDS immediates); 0: runtime depth
-__global__ void __launch_bounds__(1024, 2) k1_planes_fast(DevIcmFast gm, const uint32_t* __restrict__ w32,
-                                                          const int64_t* __restrict__ off,
-                                                          const int32_t* __restrict__ blk2seq, int64_t total,
-                                                          float* __restrict__ planes) {
-  extern __shared__ uint8_t s_sh[];
-  {
-    const int n16 = (3 * gm.inner_m) >> 4;  // inner_m is a multiple of 16 for D >= 3; tail handled below
-    const uint4* src = reinterpret_cast<const uint4*>(gm.msh);
-    uint4* dst = reinterpret_cast<uint4*>(s_sh);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = (n16 << 4) + threadIdx.x; i < 3 * gm.inner_m; i += blockDim.x) s_sh[i] = gm.msh[i];
-  }
-  __syncthreads();
-  const int W = gm.W, D = kD > 0 ? kD : gm.D;
-  const int inner_m = kD > 0 ? (2 << (2 * (kD > 0 ? kD - 1 : 0))) : gm.inner_m;
-  const int wsh = 32 - 2 * W, psh = 2 * (W - 1);
-  const uint8_t* sh0 = s_sh;
-  const uint8_t* sh1 = s_sh + inner_m;
-  const uint8_t* sh2 = s_sh + 2 * inner_m;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    int32_t s;
-    SeqView sv = locate(off, blk2seq, p, &s);
-    const int q = (int)(p - sv.a);
-    // forward: bases p .. p+15; reverse: bases p-(W-1) .. p+16-W (16 bases starting W-1 to the left)
-    const int64_t pr = p - (W - 1);
-    const uint32_t* wf = w32 + (p >> 4);
-    const uint32_t* wr = w32 + (pr >> 4);
-    const uint32_t rawf = __funnelshift_r(__ldg(wf), __ldg(wf + 1), 2 * (int)(p & 15));
-    const uint32_t rawr = __funnelshift_r(__ldg(wr), __ldg(wr + 1), 2 * (int)(pr & 15));
-    uint32_t cf = __brev(rawf);
-    cf = ((cf >> 1) & 0x55555555u) | ((cf & 0x55555555u) << 1);
-    cf >>= wsh;                  // window position k <-> base p + W-1-k
-    const uint32_t cr = ~rawr;   // window position k <-> complement of base p - (W-1) + k
-    int lf = q + W - sv.len;     // first available window position (0 = full window)
-    lf = lf > 0 ? lf : 0;
-    int lr = W - 1 - q;
-    lr = lr > 0 ? lr : 0;
-    const unsigned lshf = 30 - 2 * lf, lshr = 30 - 2 * lr;  // a node may be descended iff its shift <= this
-    uint32_t m0 = 1, m1 = 1, m2 = 1, m3 = 1, m4 = 1, m5 = 1;
-    bool a0 = true, a1 = true, a2 = true, a3 = true, a4 = true, a5 = true;
-#pragma unroll
-    for (int l = 0; l < D; l++) {
-      const unsigned s0 = sh0[m0], s1 = sh1[m1], s2 = sh2[m2], s3 = sh0[m3], s4 = sh1[m4], s5 = sh2[m5];
-      a0 = a0 && (s0 <= lshf);
-      a1 = a1 && (s1 <= lshf);
-      a2 = a2 && (s2 <= lshf);
-      a3 = a3 && (s3 <= lshr);
-      a4 = a4 && (s4 <= lshr);
-      a5 = a5 && (s5 <= lshr);
-      const uint32_t n0 = __funnelshift_l(cf << (s0 & 31), m0, 2), n1 = __funnelshift_l(cf << (s1 & 31), m1, 2),
-                     n2 = __funnelshift_l(cf << (s2 & 31), m2, 2), n3 = __funnelshift_l(cr << (s3 & 31), m3, 2),
-                     n4 = __funnelshift_l(cr << (s4 & 31), m4, 2), n5 = __funnelshift_l(cr << (s5 & 31), m5, 2);
-      m0 = a0 ? n0 : m0;
-      m1 = a1 ? n1 : m1;
-      m2 = a2 ? n2 : m2;
-      m3 = a3 ? n3 : m3;
-      m4 = a4 ? n4 : m4;
-      m5 = a5 ? n5 : m5;
-    }
-    const uint32_t bf = (cf >> psh) & 3u, br = (cr >> psh) & 3u;
-    const float* pb0 = gm.mprob;
-    const float* pb1 = gm.mprob + (size_t)gm.leaves_m * 4;
-    const float* pb2 = gm.mprob + (size_t)gm.leaves_m * 8;
-    const float v0 = __ldg(pb0 + (m0 * 4 + bf)), v1 = __ldg(pb1 + (m1 * 4 + bf)), v2 = __ldg(pb2 + (m2 * 4 + bf));
-    const float v3 = __ldg(pb0 + (m3 * 4 + br)), v4 = __ldg(pb1 + (m4 * 4 + br)), v5 = __ldg(pb2 + (m5 * 4 + br));
-    float* o = planes + p;
-    const size_t T = (size_t)total;
-    o[0] = v0;
-    o[T] = v1;
-    o[2 * T] = v2;
-    o[3 * T] = v3;
-    o[4 * T] = v4;
-    o[5 * T] = v5;
-  }
-}
+// K1, bucketed form (the default for W <= 16, D <= 7): role-persistent CTAs.  The planes are stored bucketed by
+// the base at each position (gmg_plane_index), so all positions whose PREDICTED base is pb -- the base itself on the
+// forward strand, its complement on the reverse strand -- are one dense run of plane indices.  A CTA keeps the
+// leaf probabilities of ONE (period f, predicted base pb) pair (N floats, 87 KB at depth 7) and the period's shift
+// table (8 KB) in shared memory and streams through its share of that role's run: position list in (dense), window
+// from the packed bases, D shared-memory byte lookups, one shared-memory float lookup, result out (dense).  No
+// global gathers are left on the walk (measured, tools/gpu/ubench_leaf.cu: a warp-wide random 4-byte read costs
+// 4 SM cycles from shared memory against 11 from an L1-resident and 28 from an L2-resident table).
+// The 24 (f, pb, strand) segments are linearised; CTA c takes the c-th equal share of the 6 * total walks, which
+// spans at most two roles unless the batch is tiny.
+struct K1Segs {
+  long long lo[25];        // linearised start of segment (f * 4 + pb) * 2 + strand; lo[24] = 6 * total
+  unsigned bucket_lo[4];   // plane index of the first position of each base bucket
+};
 
-// K1, period-phased form (the default): the CTA walks its contiguous chunk of bases three times, once per
-// model period, so that only ONE period's leaf table (256 KB of `mprob` for the default depth 7) is live in
-// the SM's L1 at a time -- measured (tools/gpu/ubench_gather.cu): random 4-byte gathers cost 11 cycles per
-// warp and SM from an L1-resident 256 KB table against 28 from the L2-resident 1.5 MB one.  Per phase a thread
-// keeps six walks in flight (three bases x two strands).  One 1024-thread CTA per SM, 8 KB of shift table.
-// one phase-step of k1_planes_phased for kU bases per thread (2 kU walks in flight).  kInterior: every base is
-// at least 32 bases from both ends of its sequence (warp-uniform), so all windows are full and the stop test
-// degenerates to "is this node descendable".
-template <int kD, int kU, bool kInterior>
-__device__ __forceinline__ void k1_phase_step(const DevIcmFast& gm, const uint8_t* s_sh, const uint32_t* __restrict__ w32,
-                                              const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
-                                              const float* __restrict__ pb, float* __restrict__ of,
-                                              float* __restrict__ orv, int64_t p0, int64_t c0, int64_t c1, int nt) {
-  const int W = gm.W, D = kD > 0 ? kD : gm.D;
-  const int wsh = 32 - 2 * W, psh = 2 * (W - 1);
-  uint32_t cf[kU], cr[kU], mf[kU], mr[kU];
-  unsigned lshf[kU], lshr[kU];
-  bool af[kU], ar[kU], ok[kU];
-#pragma unroll
-  for (int u = 0; u < kU; u++) {
-    const int64_t p = p0 + (int64_t)nt * u;
-    ok[u] = p < c1;
-    const int64_t pp = ok[u] ? p : c0;  // harmless in-range stand-in
-    const int64_t pr = pp - (W - 1);
-    const uint32_t* wf = w32 + (pp >> 4);
-    const uint32_t* wr = w32 + (pr >> 4);
-    const uint32_t rawf = __funnelshift_r(__ldg(wf), __ldg(wf + 1), 2 * (int)(pp & 15));
-    const uint32_t rawr = __funnelshift_r(__ldg(wr), __ldg(wr + 1), 2 * (int)(pr & 15));
-    uint32_t c = __brev(rawf);
-    c = ((c >> 1) & 0x55555555u) | ((c & 0x55555555u) << 1);
-    cf[u] = c >> wsh;   // window position k <-> base p + W-1-k
-    cr[u] = ~rawr;      // window position k <-> complement of base p - (W-1) + k
-    if (kInterior) {
-      lshf[u] = lshr[u] = 30;
-    } else {
-      int32_t s;
-      SeqView sv = locate(off, blk2seq, pp, &s);
-      const int q = (int)(pp - sv.a);
-      int lf = q + W - sv.len;  // first available window position (0 = full window)
-      lf = lf > 0 ? lf : 0;
-      int lr = W - 1 - q;
-      lr = lr > 0 ? lr : 0;
-      lshf[u] = 30 - 2 * lf;  // a node may be descended iff its shift <= this
-      lshr[u] = 30 - 2 * lr;
-    }
-    mf[u] = mr[u] = 1;
-    af[u] = ar[u] = true;
-  }
-#pragma unroll
-  for (int l = 0; l < D; l++) {
-    unsigned sf[kU], sr[kU];
-#pragma unroll
-    for (int u = 0; u < kU; u++) {
-      sf[u] = s_sh[mf[u]];
-      sr[u] = s_sh[mr[u]];
-    }
-#pragma unroll
-    for (int u = 0; u < kU; u++) {
-      af[u] = af[u] && (sf[u] <= (kInterior ? 30u : lshf[u]));
-      ar[u] = ar[u] && (sr[u] <= (kInterior ? 30u : lshr[u]));
-      const uint32_t nf = __funnelshift_l(cf[u] << (sf[u] & 31), mf[u], 2);
-      const uint32_t nr = __funnelshift_l(cr[u] << (sr[u] & 31), mr[u], 2);
-      mf[u] = af[u] ? nf : mf[u];
-      mr[u] = ar[u] ? nr : mr[u];
-    }
-  }
-  float vf[kU], vr[kU];
-#pragma unroll
-  for (int u = 0; u < kU; u++) {
-    vf[u] = __ldg(pb + (mf[u] * 4 + ((cf[u] >> psh) & 3u)));
-    vr[u] = __ldg(pb + (mr[u] * 4 + ((cr[u] >> psh) & 3u)));
-  }
-#pragma unroll
-  for (int u = 0; u < kU; u++)
-    if (ok[u]) {
-      of[p0 + (int64_t)nt * u] = vf[u];
-      orv[p0 + (int64_t)nt * u] = vr[u];
-    }
-}
-
-// K1, period-phased form (the default): the CTA walks its contiguous chunk of bases three times, once per
-// model period, so that only ONE period's leaf table (256 KB of `mprob` for the default depth 7) is live in
-// the SM's L1 at a time -- measured (tools/gpu/ubench_gather.cu): random 4-byte gathers cost 11 cycles per
-// warp and SM from an L1-resident 256 KB table against 28 from the L2-resident 1.5 MB one.  Per phase a thread
-// keeps 2 kU walks in flight (kU bases x two strands); 8 KB of shift table per CTA.
 template <int kD, int kU>
-__global__ void __launch_bounds__(1024, 2) k1_planes_phased(DevIcmFast gm, const uint32_t* __restrict__ w32,
-                                                            const int64_t* __restrict__ off,
-                                                            const int32_t* __restrict__ blk2seq, int64_t total,
-                                                            float* __restrict__ planes) {
-  extern __shared__ uint8_t s_sh[];
-  const int inner_m = gm.inner_m;
-  // contiguous chunk of this CTA (a multiple of 32 bases: warps are aligned with the blocks of blk2seq)
-  const int nt = blockDim.x;
-  int64_t per = (total + gridDim.x - 1) / gridDim.x;
-  per = (per + 31) / 32 * 32;
-  const int64_t c0 = (int64_t)blockIdx.x * per;
-  const int64_t c1 = c0 + per < total ? c0 + per : total;
-  for (int f = 0; f < 3; f++) {
-    __syncthreads();
-    {
-      const uint8_t* src8 = gm.msh + (size_t)f * inner_m;
-      if ((inner_m & 15) == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(src8);
+__global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
+                                                              const uint32_t* __restrict__ ctxr,
+                                                              const uint8_t* __restrict__ cdist, unsigned total,
+                                                              K1Segs segs, int np, float* __restrict__ planes) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  constexpr int inner_m = 2 << (2 * (kD - 1));
+  uint8_t* s_sh = s_raw;
+  float* s_leaf = reinterpret_cast<float*>(s_raw + inner_m);
+  const int W = gm.W, nt = blockDim.x;
+  const int wsh = 32 - 2 * W;
+  const long long all = segs.lo[24];
+  const long long w0 = all * blockIdx.x / gridDim.x, w1 = all * (blockIdx.x + 1) / gridDim.x;
+  int seg = 0;
+  while (segs.lo[seg + 1] <= w0 && seg < 23) seg++;
+  int have_f = -1, have_role = -1;
+  for (; seg < 24 && segs.lo[seg] < w1; seg++) {
+    const long long a0 = max(w0, segs.lo[seg]), a1 = min(w1, segs.lo[seg + 1]);
+    if (a1 <= a0) continue;
+    const int role = seg >> 1, f = role >> 2, pb = role & 3, rev = seg & 1;
+    if (role != have_role) {  // CTA-uniform
+      __syncthreads();
+      if (f != have_f) {
+        const uint4* src = reinterpret_cast<const uint4*>(gm.msh + (size_t)f * inner_m);
         uint4* dst = reinterpret_cast<uint4*>(s_sh);
-        for (int i = threadIdx.x; i < (inner_m >> 4); i += blockDim.x) dst[i] = __ldg(src + i);
-      } else {
-        for (int i = threadIdx.x; i < inner_m; i += blockDim.x) s_sh[i] = src8[i];
+        for (int i = threadIdx.x; i < (inner_m >> 4); i += nt) dst[i] = __ldg(src + i);
       }
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(gm.bleaf + (size_t)role * np);
+        uint4* dst = reinterpret_cast<uint4*>(s_leaf);
+        for (int i = threadIdx.x; i < (np >> 2); i += nt) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+      have_f = f;
+      have_role = role;
     }
-    __syncthreads();
-    const float* pb = gm.mprob + (size_t)f * gm.leaves_m * 4;
-    float* of = planes + (size_t)f * total;
-    float* orv = planes + (size_t)(3 + f) * total;
-    for (int64_t p0 = c0 + threadIdx.x; p0 < c1; p0 += (int64_t)kU * nt) {
-      // the warp's kU 32-base blocks (c0 and nt are multiples of 32): all interior?
-      bool interior = true;
+    const unsigned own = rev ? 3 - pb : pb;
+    // plane indices [g0, g1) of this share; the strand's contexts and its period-f plane
+    const unsigned g0 = segs.bucket_lo[own] + (unsigned)(a0 - segs.lo[seg]);
+    const unsigned g1 = segs.bucket_lo[own] + (unsigned)(a1 - segs.lo[seg]);
+    const uint32_t* __restrict__ cx = rev ? ctxr : ctxf;
+    const int dsh = rev ? 0 : 4;  // which nibble of cdist limits the window: distance to the start / to the end
+    float* __restrict__ out = planes + (size_t)(rev ? 3 + f : f) * total;
+    for (unsigned i0 = g0 + threadIdx.x; i0 < g1; i0 += kU * nt) {
+      uint32_t c[kU], m[kU];
+      unsigned lsh[kU];
+      bool act[kU];
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        const int64_t p = p0 + (int64_t)nt * u;
-        interior = interior && (p < c1) && (__ldg(blk2seq + (p >> 5)) < 0);
+        const unsigned gi = min(i0 + nt * u, g1 - 1);
+        c[u] = __ldg(cx + gi) >> wsh;  // window position k at bits 2k
+        const int d = (__ldg(cdist + gi) >> dsh) & 15;
+        const int lim = max(W - 1 - d, 0);  // first available window position (0 = full window)
+        lsh[u] = 30 - 2 * lim;              // a node may be descended iff its shift <= this
+        m[u] = 1;
+        act[u] = true;
       }
-      if (interior) k1_phase_step<kD, kU, true>(gm, s_sh, w32, off, blk2seq, pb, of, orv, p0, c0, c1, nt);
-      else k1_phase_step<kD, kU, false>(gm, s_sh, w32, off, blk2seq, pb, of, orv, p0, c0, c1, nt);
+#pragma unroll
+      for (int l = 0; l < kD; l++) {
+        unsigned sv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) sv[u] = s_sh[m[u]];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+          act[u] = act[u] && (sv[u] <= lsh[u]);
+          const uint32_t nx = __funnelshift_l(c[u] << (sv[u] & 31), m[u], 2);
+          m[u] = act[u] ? nx : m[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        // marker index m = 4^l + i  ->  dense node number (4^l - 1) / 3 + i
+        const uint32_t hb = 0x80000000u >> __clz(m[u]);
+        const float v = s_leaf[m[u] - hb + (0x55555555u & (hb - 1u))];
+        if (i0 + nt * u < g1) out[i0 + nt * u] = v;
+      }
     }
   }
 }
@@ -454,48 +341,44 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
   *planes_out = (float*)planes;
   if (s->total == 0) return 0;
-  static const bool phased = !(getenv("GMG_K1_UNPHASED") && atoi(getenv("GMG_K1_UNPHASED")));
-  if (gene->fast.valid && phased) {
-    size_t smem = (size_t)gene->fast.inner_m;
-    if (smem > 48 * 1024)  // only depth 8
-      GMG_CUDA(cudaFuncSetAttribute(k1_planes_phased<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const int nt = getenv("GMG_K1_THREADS") ? atoi(getenv("GMG_K1_THREADS")) : 1024;
-    static const int per_sm = getenv("GMG_K1_CTAS") ? atoi(getenv("GMG_K1_CTAS")) : 2;
-    static const int ku = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 1;
-    int64_t need = (s->total + ku * nt - 1) / (ku * nt);
-    int64_t cap = (int64_t)ctx->sm_count * per_sm;
-    int grid = (int)(need < cap ? need : cap);
-    if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
-    const uint32_t* w32 = (const uint32_t*)s->d_words;
-#define GMG_K1_LAUNCH(KD, KU) \
-  k1_planes_phased<KD, KU><<<grid, nt, smem, ctx->stream>>>(gene->fast, w32, s->d_off, s->d_blk2seq, s->total, (float*)planes)
-    if (gene->fast.D == 7) {
-      if (ku == 1) GMG_K1_LAUNCH(7, 1);
-      else if (ku == 3) GMG_K1_LAUNCH(7, 3);
-      else GMG_K1_LAUNCH(7, 2);
-    } else {
-      GMG_K1_LAUNCH(0, 2);
+  static const int k1_mode = getenv("GMG_K1_MODE") ? atoi(getenv("GMG_K1_MODE")) : 0;  // 0 bucketed, 1 generic
+  if (gene->fast.valid && gene->fast.D == 7 && k1_mode == 0) {
+    if (!s->n_base_valid) {
+      unsigned long long nb[4];
+      GMG_CUDA(cudaMemcpyAsync(nb, s->d_gc + 2, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
+      GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int b = 0; b < 4; b++) s->n_base[b] = (int64_t)nb[b];
+      s->n_base_valid = 1;
     }
-#undef GMG_K1_LAUNCH
-    gmg_prof_end(ctx, GMG_PROF_K1);
-    ctx->launches++;
-    GMG_CUDA(cudaGetLastError());
-    return 0;
-  }
-  if (gene->fast.valid) {
-    size_t smem = (size_t)3 * gene->fast.inner_m;
-    if (smem > 48 * 1024)
-      GMG_CUDA(cudaFuncSetAttribute(k1_planes_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t need = (s->total + 1023) / 1024;
-    int64_t cap = (int64_t)ctx->sm_count * 2;
+    K1Segs segs;
+    long long acc = 0;
+    for (int f = 0; f < 3; f++)
+      for (int pb = 0; pb < 4; pb++)
+        for (int rev = 0; rev < 2; rev++) {
+          segs.lo[(f * 4 + pb) * 2 + rev] = acc;
+          acc += s->n_base[rev ? 3 - pb : pb];
+        }
+    segs.lo[24] = acc;
+    unsigned bl = 0;
+    for (int b = 0; b < 4; b++) {
+      segs.bucket_lo[b] = bl;
+      bl += (unsigned)s->n_base[b];
+    }
+    const int np = (gene->fast.N + 3) & ~3;
+    const size_t smem = (size_t)gene->fast.inner_m + (size_t)np * sizeof(float);
+    static const int ku = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 2;
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long need = (acc + 4095) / 4096;
+    long long cap = (long long)ctx->sm_count * 2;
     int grid = (int)(need < cap ? need : cap);
     if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
-    if (gene->fast.D == 7)
-      k1_planes_fast<7><<<grid, 1024, smem, ctx->stream>>>(gene->fast, (const uint32_t*)s->d_words, s->d_off,
-                                                           s->d_blk2seq, s->total, (float*)planes);
+    if (ku == 1)
+      k1_planes_bucketed<7, 1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
+                                                                 (unsigned)s->total, segs, np, (float*)planes);
     else
-      k1_planes_fast<0><<<grid, 1024, smem, ctx->stream>>>(gene->fast, (const uint32_t*)s->d_words, s->d_off,
-                                                           s->d_blk2seq, s->total, (float*)planes);
+      k1_planes_bucketed<7, 2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
+                                                                 (unsigned)s->total, segs, np, (float*)planes);
     gmg_prof_end(ctx, GMG_PROF_K1);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
@@ -509,7 +392,8 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   int64_t cap = (int64_t)ctx->sm_count * 8;
   int grid = (int)(need < cap ? need : cap);
   if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
-  k1_planes<<<grid, 256, smem, ctx->stream>>>(gene->dev, s->d_words, s->d_off, s->d_blk2seq, s->total, (float*)planes);
+  k1_planes<<<grid, 256, smem, ctx->stream>>>(gene->dev, s->d_words, s->d_off, s->d_blk2seq, s->d_bktidx, s->total,
+                                              (float*)planes);
   gmg_prof_end(ctx, GMG_PROF_K1);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -527,19 +411,21 @@ extern "C" int gmg_k1_score_planes(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset
 
 __global__ void __launch_bounds__(256) k_frame_scores(DevIcm indep, const uint64_t* __restrict__ words,
                                                       const int64_t* __restrict__ off,
-                                                      const int32_t* __restrict__ blk2seq, int64_t total,
+                                                      const int32_t* __restrict__ blk2seq,
+                                                      const uint32_t* __restrict__ bktidx, int64_t total,
                                                       const float* __restrict__ planes, double* __restrict__ fs) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
+  const size_t pi = gmg_plane_index(words, bktidx, p);
   int32_t s;
   SeqView sv = locate(off, blk2seq, p, &s);
   const int q = (int)(p - sv.a);
   double* row = fs + 6 * sv.a;
   for (int f = 0; f < 3; f++) {
-    float g = planes[(size_t)f * total + p];
+    float g = planes[(size_t)f * total + pi];
     float n = icm_fwd(indep, words, p, q, sv.len, f);
     row[(size_t)f * sv.len + q] = (double)g - (double)n;
-    g = planes[(size_t)(3 + f) * total + p];
+    g = planes[(size_t)(3 + f) * total + pi];
     n = icm_rev(indep, words, p, q, 0, f);
     row[(size_t)(3 + f) * sv.len + q] = (double)g - (double)n;
   }
@@ -560,7 +446,8 @@ extern "C" int gmg_score_all_frames(gmg_ctx* ctx, const gmg_icm* gene, const gmg
   }
   if (gmg_prof_begin(ctx, GMG_PROF_FS)) return 1;
   k_frame_scores<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off,
-                                                                             s->d_blk2seq, s->total, planes, d_fs);
+                                                                             s->d_blk2seq, s->d_bktidx, s->total, planes,
+                                                                             d_fs);
   gmg_prof_end(ctx, GMG_PROF_FS);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -1091,8 +978,9 @@ __device__ __forceinline__ int g3_codon_which(const uint64_t* __restrict__ words
 // formed by a lane-ordered accumulation, so every prefix has exactly the reference's serial rounding.
 __device__ void g3_accumulate_ordered(const DevIcm& gene, const DevIcm& indep, const float* __restrict__ lut,
                                       const uint64_t* __restrict__ words, int64_t a, const G3Geom& g,
-                                      const float* __restrict__ plane, int64_t total, const CodonSets& cs,
-                                      const DevParams& P, int first_j, int n_emit, gmg_start* __restrict__ out) {
+                                      const float* __restrict__ plane, const uint32_t* __restrict__ bktidx,
+                                      int64_t total, const CodonSets& cs, const DevParams& P, int first_j, int n_emit,
+                                      gmg_start* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int W = gene.W, m = g.len;
   const int lowest_j = min(3, P.min_gene_len - 3);
@@ -1107,12 +995,14 @@ __device__ void g3_accumulate_ordered(const DevIcm& gene, const DevIcm& indep, c
       const int f = (1 + j) % 3;
       if (g.frame > 0) {
         const int q = g.hi - 1 - j;
-        xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f) : __ldg(plane + (size_t)f * total + a + q);
+        xg = (j < W - 1) ? icm_fwd(gene, words, a + q, q, g.hi, f)
+                         : __ldg(plane + (size_t)f * total + gmg_plane_index(words, bktidx, a + q));
         if (use_lut && j >= 2) xn = lut[f * 64 + (int)(gmg_extract32(words, a + q) & 63)];
         else xn = icm_fwd(indep, words, a + q, q, g.hi, f);
       } else {
         const int q = g.lo + j;
-        xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f) : __ldg(plane + (size_t)f * total + a + q);
+        xg = (j < W - 1) ? icm_rev(gene, words, a + q, q, g.lo, f)
+                         : __ldg(plane + (size_t)f * total + gmg_plane_index(words, bktidx, a + q));
         if (use_lut && j >= 2) xn = lut[(3 + f) * 64 + (int)(gmg_extract32(words, a + q - 2) & 63)];
         else xn = icm_rev(indep, words, a + q, q, g.lo, f);
       }
@@ -1295,6 +1185,7 @@ __global__ void __launch_bounds__(128) k3_g3_heads(DevIcm gene, DevIcm indep, co
 __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict__ lut3,
                                                          const uint64_t* __restrict__ words, int64_t total,
                                                          const float* __restrict__ planes,
+                                                         const uint32_t* __restrict__ bktidx,
                                                          double* __restrict__ cumc, int64_t tot3,
                                                          double* __restrict__ tileT) {
   constexpr int NW = G3_TS / 32;
@@ -1308,32 +1199,44 @@ __global__ void __launch_bounds__(G3_TS) k2_g3_codon_cum(const float* __restrict
   double u[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
   if (p0 - 2 < total) {
     const uint64_t win = gmg_extract32(words, p0 - 4);  // base b at bits 2 (b - p0 + 4)
-    const float* pl = planes + p0;
     const size_t T = (size_t)total;
-    if (p0 >= 2 && p0 + 4 < total) {  // interior slot: every term exists
+    // plane indices of the seven positions p0-2 .. p0+4 (they lie in at most two 32-base blocks)
+    uint32_t pi[7];
+    bool pv[7];
+    {
+      const int64_t nblk = (total + 31) >> 5;
+      const int64_t P0 = p0 - 2;
+      int64_t ba = P0 >> 5;
+      ba = ba < 0 ? 0 : ba;
+      int64_t bb = (P0 + 6) >> 5;
+      bb = bb >= nblk ? nblk - 1 : bb;
+      const uint64_t wa = __ldg(words + ba), wb = __ldg(words + bb);
+      const uint4 ra = __ldg(reinterpret_cast<const uint4*>(bktidx) + ba), rb = __ldg(reinterpret_cast<const uint4*>(bktidx) + bb);
 #pragma unroll
-      for (int rho = 0; rho < 3; rho++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
-          u[rho] += (double)__ldg(pl + f * T + (rho + k)) - (double)s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
-          v[rho] += (double)__ldg(pl + (3 + f) * T + (rho - k)) -
-                    (double)s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
-        }
+      for (int k = 0; k < 7; k++) {
+        const int64_t p = P0 + k;
+        pv[k] = p >= 0 && p < total;
+        const bool ina = (p >> 5) <= ba;
+        const uint64_t w = ina ? wa : wb;
+        const uint4 r = ina ? ra : rb;
+        const int i = (int)(p & 31);
+        const unsigned bs = (unsigned)(w >> (2 * i)) & 3u;
+        const uint64_t x = w ^ (0x5555555555555555ull * bs);
+        const uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull & ((1ull << (2 * i)) - 1ull);
+        pi[k] = (bs == 0 ? r.x : (bs == 1 ? r.y : (bs == 2 ? r.z : r.w))) + (uint32_t)__popcll(eq);
       }
-    } else {
+    }
 #pragma unroll
-      for (int rho = 0; rho < 3; rho++) {
+    for (int rho = 0; rho < 3; rho++) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
-          const int64_t pf = p0 + rho + k, pr = p0 + rho - k;
-          if (pf < total)  // forward term: window = bases pf, pf+1, pf+2
-            u[rho] += (double)__ldg(pl + f * T + (rho + k)) - (double)s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
-          if (pr >= 0 && pr < total)  // reverse term: window = complement of bases pr-2, pr-1, pr
-            v[rho] += (double)__ldg(pl + (3 + f) * T + (rho - k)) -
-                      (double)s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
-        }
+      for (int k = 0; k < 3; k++) {
+        const int f = k == 0 ? 0 : (k == 1 ? 2 : 1);
+        const int kf = rho + k + 2, kr = rho - k + 2;  // slots of pi[] of the forward / reverse term's position
+        if (pv[kf])  // forward term at p0 + rho + k: window = bases pf, pf+1, pf+2
+          u[rho] += (double)__ldg(planes + f * T + pi[kf]) - (double)s_lut[f * 64 + (int)((win >> (2 * (rho + k + 4))) & 63)];
+        if (pv[kr])  // reverse term at p0 + rho - k: window = complement of bases pr-2, pr-1, pr
+          v[rho] += (double)__ldg(planes + (3 + f) * T + pi[kr]) -
+                    (double)s_lut[(3 + f) * 64 + (int)((win >> (2 * (rho - k + 2))) & 63)];
       }
     }
   }
@@ -1534,7 +1437,8 @@ __global__ void __launch_bounds__(128) k3_g3_emit(const uint64_t* __restrict__ w
 __global__ void __launch_bounds__(128) k3_g3_ordered(DevIcm gene, DevIcm indep, const uint64_t* __restrict__ words,
                                                      const int64_t* __restrict__ off, const gmg_orf* __restrict__ orfs,
                                                      const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                     const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                     const float* __restrict__ planes,
+                                                     const uint32_t* __restrict__ bktidx, CodonSets cs, DevParams P,
                                                      const int64_t* __restrict__ start_off,
                                                      const int32_t* __restrict__ first_js, int exact_len,
                                                      gmg_start* __restrict__ starts,
@@ -1554,7 +1458,7 @@ __global__ void __launch_bounds__(128) k3_g3_ordered(DevIcm gene, DevIcm indep, 
   const int64_t a = off[s];
   const G3Geom g = g3_geom(orfs[oi], (int)(off[s + 1] - a), P);
   const float* plane = planes + (size_t)(g.frame > 0 ? 0 : 3) * total;  // the strand's three period planes
-  g3_accumulate_ordered(gene, indep, lut, words, a, g, plane, total, cs, P, first_js[oi], n_emit, starts + so);
+  g3_accumulate_ordered(gene, indep, lut, words, a, g, plane, bktidx, total, cs, P, first_js[oi], n_emit, starts + so);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1573,7 +1477,8 @@ __device__ __forceinline__ int low_bit_exp(double x) {
 
 __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* __restrict__ words,
                                                  const int64_t* __restrict__ off, int64_t n_seq, int64_t total,
-                                                 const float* __restrict__ planes, CodonSets cs, DevParams P,
+                                                 const float* __restrict__ planes, const uint32_t* __restrict__ bktidx,
+                                                 CodonSets cs, DevParams P,
                                                  const uint8_t* __restrict__ qual_in, double* __restrict__ cum,
                                                  int32_t* __restrict__ fwd_prev, int32_t* __restrict__ rev_next,
                                                  uint8_t* __restrict__ qual, uint8_t* __restrict__ cert) {
@@ -1598,10 +1503,11 @@ __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* _
       const bool in = q < L;
       double x[3] = {0.0, 0.0, 0.0};
       if (in) {
+        const size_t pi = gmg_plane_index(words, bktidx, a + q);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const int f = mod3(1 + q - c);
-          const float gval = planes[(size_t)(3 + f) * total + a + q];
+          const float gval = planes[(size_t)(3 + f) * total + pi];
           const float nval = icm_rev(indep, words, a + q, q, 0, f);
           x[c] = (double)gval - (double)nval;
           if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
@@ -1673,10 +1579,11 @@ __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* _
       const bool in = q >= 0;
       double x[3] = {0.0, 0.0, 0.0};
       if (in) {
+        const size_t pi = gmg_plane_index(words, bktidx, a + q);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const int f = mod3(c - q);
-          const float gval = planes[(size_t)f * total + a + q];
+          const float gval = planes[(size_t)f * total + pi];
           const float nval = icm_fwd(indep, words, a + q, q, L, f);
           x[c] = (double)gval - (double)nval;
           if (x[c] != 0.0) gmin = min(gmin, low_bit_exp(x[c]));
@@ -2023,8 +1930,8 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     tileT = (double*)d_tiles;
     heads = (double*)d_heads;
     if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
-    k2_g3_codon_cum<<<(unsigned)ntiles, G3_TS, 0, ctx->stream>>>(indep->dev.lut3, s->d_words, s->total, planes, cumc, tot3,
-                                                                tileT);
+    k2_g3_codon_cum<<<(unsigned)ntiles, G3_TS, 0, ctx->stream>>>(indep->dev.lut3, s->d_words, s->total, planes,
+                                                                s->d_bktidx, cumc, tot3, tileT);
     gmg_prof_end(ctx, GMG_PROF_K2);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
@@ -2068,8 +1975,8 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     }
     if (max_orf_len > exact_len) {
       k3_g3_ordered<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, cs, dp,
-          s->d_start_off, (const int32_t*)d_first, exact_len, s->d_starts, s->d_gc + 1);
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total, planes, s->d_bktidx,
+          cs, dp, s->d_start_off, (const int32_t*)d_first, exact_len, s->d_starts, s->d_gc + 1);
       ctx->launches++;
     }
     gmg_prof_end(ctx, GMG_PROF_K3);
@@ -2122,7 +2029,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   const bool need_qual = p->allow_indels || p->have_quality_file;
   unsigned g2 = (unsigned)((s->n * 32 + 127) / 128);
   if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
-  k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, cs, dp,
+  k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, s->d_bktidx, cs, dp,
                                          p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
                                          need_qual ? (uint8_t*)d_qual : NULL, cert);
   gmg_prof_end(ctx, GMG_PROF_K2);

@@ -7,6 +7,8 @@
 //   Set_GC_Fraction        Glimmer/glimmer_base.cc:2564-2595
 #include <string.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "gmg_internal.cuh"
 
 // 2-bit code of tolower(Filter(ch)): a=0 c=1 g=2 t=3 (ALPHA_STRING "acgt", icm.hh:30)
@@ -80,6 +82,94 @@ __global__ void k_blk2seq(const int64_t* __restrict__ off, int64_t n, int64_t nb
   blk2seq[b] = (int32_t)lo | (interior ? (int32_t)0x80000000 : 0);
 }
 
+// ---- base buckets (see gmg_plane_index) ---------------------------------------------------------------
+// per 32-base block: how many a / c / g / t (positions at or past `total` are not counted)
+__global__ void __launch_bounds__(256) k_bucket_count(const uint64_t* __restrict__ words, int64_t total, int64_t nblk,
+                                                      uint4* __restrict__ cnt) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  const uint64_t w = __ldg(words + b);
+  const int n = (int)(total - (b << 5) < 32 ? total - (b << 5) : 32);
+  const uint64_t valid = n >= 32 ? 0x5555555555555555ull : (0x5555555555555555ull & ((1ull << (2 * n)) - 1ull));
+  const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+  uint4 c;
+  c.x = (unsigned)__popcll(~lo & ~hi & valid);
+  c.y = (unsigned)__popcll(lo & ~hi & valid);
+  c.z = (unsigned)__popcll(~lo & hi & valid);
+  c.w = (unsigned)__popcll(lo & hi & valid);
+  cnt[b] = c;
+}
+
+struct Uint4Add {
+  __device__ __forceinline__ uint4 operator()(const uint4& a, const uint4& b) const {
+    return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+};
+
+// exclusive per-base prefix -> absolute plane index of each block's first a / c / g / t, and the walk-ready
+// contexts of every position stored at its plane index
+__global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restrict__ words, int64_t total, int64_t nblk,
+                                                       const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
+                                                       const uint4* __restrict__ prefix, const uint4* __restrict__ cnt,
+                                                       uint4* __restrict__ bktidx, uint32_t* __restrict__ ctxf,
+                                                       uint32_t* __restrict__ ctxr, uint8_t* __restrict__ cdist,
+                                                       unsigned long long* __restrict__ n_base) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4 lp = prefix[nblk - 1], lc = cnt[nblk - 1];
+  const unsigned na = lp.x + lc.x, nc = lp.y + lc.y, ng = lp.z + lc.z, nt = lp.w + lc.w;
+  if (p == 0) {
+    n_base[0] = na; n_base[1] = nc; n_base[2] = ng; n_base[3] = nt;
+  }
+  if (p >= total) return;
+  const int64_t blk = p >> 5;
+  uint4 pre = prefix[blk];
+  pre.y += na;
+  pre.z += na + nc;
+  pre.w += na + nc + ng;
+  if ((p & 31) == 0) bktidx[blk] = pre;
+  const uint64_t w = __ldg(words + blk);
+  const int i = (int)(p & 31);
+  const unsigned b = (unsigned)(w >> (2 * i)) & 3u;
+  const uint64_t x = w ^ (0x5555555555555555ull * b);
+  const uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull & ((1ull << (2 * i)) - 1ull);
+  const unsigned first = b == 0 ? pre.x : (b == 1 ? pre.y : (b == 2 ? pre.z : pre.w));
+  const unsigned idx = first + (unsigned)__popcll(eq);
+  // forward: bases p .. p+15, order reversed (base p in the top pair)
+  uint32_t f = (uint32_t)gmg_extract32(words, p);
+  f = __brev(f);
+  f = ((f >> 1) & 0x55555555u) | ((f & 0x55555555u) << 1);
+  ctxf[idx] = f;
+  ctxr[idx] = ~(uint32_t)gmg_extract32(words, p - 15);
+  int32_t sq = __ldg(blk2seq + blk) & 0x7FFFFFFF;
+  while (p >= __ldg(off + sq + 1)) sq++;
+  const int64_t q = p - __ldg(off + sq), e = __ldg(off + sq + 1) - 1 - p;
+  cdist[idx] = (uint8_t)((q < 15 ? q : 15) | ((e < 15 ? e : 15) << 4));
+}
+
+static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
+  const int64_t nblk = (s->total + 31) >> 5;
+  GMG_CHECK(s->total < (1ll << 32), "batches of 2^32 bases or more are not supported (got %lld)", (long long)s->total);
+  GMG_CUDA(cudaMallocAsync(&s->d_bktidx, (size_t)(nblk + 1) * sizeof(uint4), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_ctxf, (size_t)(s->total + 64) * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_ctxr, (size_t)(s->total + 64) * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_cdist, (size_t)s->total + 64, ctx->stream));
+  void *d_cnt, *d_tmp;
+  if (gmg_scratch(ctx, SCR_TMP3, (size_t)2 * nblk * sizeof(uint4), &d_cnt)) return 1;
+  uint4* cnt = (uint4*)d_cnt;
+  uint4* prefix = cnt + nblk;
+  k_bucket_count<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d_words, s->total, nblk, cnt);
+  size_t tmp_bytes = 0;
+  GMG_CUDA(cub::DeviceScan::ExclusiveScan(NULL, tmp_bytes, cnt, prefix, Uint4Add(), make_uint4(0, 0, 0, 0), nblk, ctx->stream));
+  if (gmg_scratch(ctx, SCR_TMP4, tmp_bytes, &d_tmp)) return 1;
+  GMG_CUDA(cub::DeviceScan::ExclusiveScan(d_tmp, tmp_bytes, cnt, prefix, Uint4Add(), make_uint4(0, 0, 0, 0), nblk, ctx->stream));
+  k_bucket_finish<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(
+      s->d_words, s->total, nblk, s->d_off, s->d_blk2seq, prefix, cnt, (uint4*)s->d_bktidx, s->d_ctxf, s->d_ctxr,
+      s->d_cdist, s->d_gc + 2);
+  ctx->launches += 4;
+  GMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc) {
   int64_t nwords = (total + 31) >> 5;
   if (nwords == 0) return 0;
@@ -108,7 +198,7 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
   s->off.assign(h_off, h_off + n + 1);
   if (n == 0) s->off.assign(1, 0);
   s->d_off = NULL; s->d_words_base = NULL; s->d_words = NULL; s->d_blk2seq = NULL; s->d_qual = NULL; s->d_gc = NULL;
-  s->d_cbits = NULL; s->nwc = 0; memset(s->cbits_key, 0, sizeof s->cbits_key);
+  s->d_cbits = NULL; s->nwc = 0; s->d_bktidx = NULL; s->d_ctxf = NULL; s->d_ctxr = NULL; s->d_cdist = NULL; memset(s->n_base, 0, sizeof s->n_base); s->n_base_valid = 0; memset(s->cbits_key, 0, sizeof s->cbits_key);
   s->n_orfs = 0; s->d_orfs = NULL; s->d_orf_off = NULL; s->d_orf_seq = NULL;
   s->n_starts = 0; s->d_starts = NULL; s->d_start_off = NULL; s->uncertified = 0;
   s->cap_orfs = s->cap_starts = 0;
@@ -123,13 +213,14 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
   GMG_CUDA(cudaMemcpyAsync(s->d_off, s->off.data(), (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            ctx->stream));
   GMG_CUDA(cudaMallocAsync(&s->d_blk2seq, (size_t)nblk * sizeof(int32_t), s->ctx->stream));
-  GMG_CUDA(cudaMallocAsync(&s->d_gc, 2 * sizeof(unsigned long long), s->ctx->stream));
-  GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_gc, 6 * sizeof(unsigned long long), s->ctx->stream));
+  GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, 6 * sizeof(unsigned long long), ctx->stream));
   if (s->total > 0) {
     if (gmg_launch_pack(ctx, (const uint8_t*)d_ascii, s->total, s->d_words, s->d_gc)) return 1;
     k_blk2seq<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d_off, s->n, nblk, s->d_blk2seq);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
+    if (build_buckets(ctx, s)) return 1;
     if (d_qual) {
       GMG_CUDA(cudaMallocAsync(&s->d_qual, (size_t)s->total, s->ctx->stream));
       GMG_CUDA(cudaMemcpyAsync(s->d_qual, d_qual, (size_t)s->total, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -170,7 +261,7 @@ extern "C" void gmg_seqset_free(gmg_seqset* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   void* ptrs[] = {s->d_off, s->d_words_base, s->d_blk2seq, s->d_qual, s->d_gc, s->d_orfs, s->d_orf_off,
-                  s->d_orf_seq, s->d_starts, s->d_start_off, s->d_cbits};
+                  s->d_orf_seq, s->d_starts, s->d_start_off, s->d_cbits, s->d_bktidx, s->d_ctxf, s->d_ctxr, s->d_cdist};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s->ctx->stream);
   delete s;
