@@ -50,18 +50,19 @@ struct DevIcm {
   const float* lut3;
 };
 
-// "marker-indexed" view of the same ICM for the K1 fast path (W <= 16, D <= 8): node on level l with
-// in-level index i is addressed by m = 4^l + i (a leading 1 marks the level), so a child is
-// m' = 4 m + base with no "+1" and no per-level offsets, and one funnel shift descends one level.
-//  msh    uint8 [P][2 * 4^(D-1)]  30 - 2 * mut_info_pos of the descendable nodes (left shift that brings the
-//                                 branch base to the top two bits of the 32-bit window register); 255 = stop
-//  mprob  float [P][2 * 4^D][4]   log-probabilities, cut nodes pre-resolved to their parent's row
-//  bleaf  float [P][4][N]         log-probabilities by predicted base in the reference's dense node order
-//                                 (node n's children are 4n+1 .. 4n+4): the table a K1 role keeps in shared memory
+// Tables of the bucketed K1 kernel (W <= 16, D == 7, P == 3), see icm_upload:
+//  mw     uint32 [P][4 + 64 + 1024]  one word per node of levels 1, 3, 5: bits 0-4 the node's shift, bits 5+5k..9+5k
+//                                    the shift of child k, bit 25 / bits 26+k their stop flags.  shift = 30 - 2 *
+//                                    mut_info_pos (the left shift that brings the branch base to the top two bits of
+//                                    the 32-bit window register), 0 where the walk stops
+//  bleaf  float [P][4][np]           log-probabilities by predicted base in the reference's dense node order (node
+//                                    n's children are 4n+1 .. 4n+4) over the COMPLETED tree: descendants of a node
+//                                    where walks stop carry that node's value
+//  s0 / stop0                        shift / stop flag of the three roots
 struct DevIcmFast {
-  int valid, W, D, P, N, inner_m, leaves_m;
-  const uint8_t* msh;
-  const float* mprob;
+  int valid, W, D, P, N, np;
+  int s0[3], stop0[3];
+  const uint32_t* mw;
   const float* bleaf;
 };
 
@@ -96,7 +97,6 @@ struct gmg_icm {
   float* d_prob;
   DevIcm dev;
   uint8_t* d_msh;
-  float* d_mprob;
   float* d_bleaf;
   float* d_lut3;
   DevIcmFast fast;

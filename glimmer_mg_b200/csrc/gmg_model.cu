@@ -288,52 +288,60 @@ static int icm_upload(gmg_icm* m) {
     m->stat_ulp_exp = ue;
     m->stat_max_abs = mx;
   }
-  // marker-indexed tables of the K1 fast path
+  // tables of the bucketed K1 kernel (the build-icm defaults: window <= 16, depth 7, period 3)
   m->fast.valid = 0;
-  if (m->W <= 16 && D >= 1 && D <= 8) {
-    size_t inner_m = 2, leaves_m = 8;  // 2 * 4^(D-1), 2 * 4^D
-    for (int i = 1; i < D; i++) inner_m *= 4;
-    leaves_m = inner_m * 4;
-    std::vector<uint8_t> msh((size_t)P * inner_m, 255);
-    std::vector<float> mprob((size_t)P * leaves_m * 4, 0.0f);
+  if (m->W <= 16 && D == 7 && P == 3) {
+    // Completed tree: a walk that stops at node n (leaf, cut node, or depth reached) is continued through
+    // VIRTUAL descendants that all carry n's value, so the full-window fast path needs no stop test and always
+    // reads a level-D entry.  stop[n] = "a real walk stops here or has stopped above".
+    const size_t np = ((size_t)N + 3) & ~(size_t)3;  // row stride: 16-byte aligned rows
+    const int NW = 4 + 64 + 1024;                    // merged words: nodes of levels 1, 3, 5
+    std::vector<float> bleaf((size_t)P * 4 * np, 0.0f);
+    std::vector<uint32_t> mw((size_t)P * NW, 0u);
+    const int inner = num_nodes_for(D - 1);
     for (int f = 0; f < P; f++) {
-      size_t first = 0, width = 1;  // dense index of the level's first node, nodes on the level
-      for (int l = 0; l <= D; l++) {
-        for (size_t i = 0; i < width; i++) {
-          const size_t n = first + i, mk = width + i;
-          if (l < D) {
-            int v = m->mip[(size_t)f * N + n];
-            msh[(size_t)f * inner_m + mk] = (uint8_t)(v >= 0 ? 30 - 2 * v : 255);
+      std::vector<int> src(N);
+      std::vector<uint8_t> stop(N), sh(N, 0);
+      for (int n = 0; n < N; n++) {
+        const int par = n ? (n - 1) / 4 : -1;
+        const bool virt = n && stop[par];
+        src[n] = virt ? src[par] : n;
+        const int v = n < inner ? (int)m->mip[(size_t)f * N + n] : -1;
+        stop[n] = virt || v < 0;
+        sh[n] = (uint8_t)(stop[n] ? 0 : 30 - 2 * v);
+        for (int b = 0; b < 4; b++) bleaf[((size_t)f * 4 + b) * np + n] = eff[((size_t)f * N + src[n]) * 4 + b];
+      }
+      m->fast.s0[f] = sh[0];
+      m->fast.stop0[f] = stop[0];
+      int wbase = 0;
+      for (int l = 1; l <= 5; l += 2) {
+        const int first = num_nodes_for(l - 1), width = 1 << (2 * l);  // dense index of the level's first node
+        for (int i = 0; i < width; i++) {
+          const int n = first + i;
+          uint32_t w = sh[n] | ((uint32_t)stop[n] << 25);
+          for (int k = 0; k < 4; k++) {
+            const int c = 4 * n + 1 + k;
+            w |= (uint32_t)sh[c] << (5 + 5 * k);
+            w |= (uint32_t)stop[c] << (26 + k);
           }
-          memcpy(&mprob[((size_t)f * leaves_m + mk) * 4], &eff[((size_t)f * N + n) * 4], 4 * sizeof(float));
+          mw[(size_t)f * NW + wbase + i] = w;
         }
-        first += width;
-        width *= 4;
+        wbase += width;
       }
     }
-    GMG_CUDA(cudaMalloc(&m->d_msh, msh.size() + 16));
-    GMG_CUDA(cudaMalloc(&m->d_mprob, mprob.size() * sizeof(float) + 16));
-    GMG_CUDA(cudaMemcpyAsync(m->d_msh, msh.data(), msh.size(), cudaMemcpyHostToDevice, ctx->stream));
-    GMG_CUDA(cudaMemcpyAsync(m->d_mprob, mprob.data(), mprob.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t np = ((size_t)N + 3) & ~(size_t)3;  // row stride: 16-byte aligned rows
-    std::vector<float> bleaf((size_t)P * 4 * np, 0.0f);
-    for (int f = 0; f < P; f++)
-      for (int b = 0; b < 4; b++)
-        for (int n = 0; n < N; n++) bleaf[((size_t)f * 4 + b) * np + n] = eff[((size_t)f * N + n) * 4 + b];
+    GMG_CUDA(cudaMalloc(&m->d_msh, mw.size() * sizeof(uint32_t) + 64));
+    GMG_CUDA(cudaMemcpyAsync(m->d_msh, mw.data(), mw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaMalloc(&m->d_bleaf, bleaf.size() * sizeof(float) + 64));
     GMG_CUDA(cudaMemcpyAsync(m->d_bleaf, bleaf.data(), bleaf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     m->fast.N = N;
+    m->fast.np = (int)np;
     m->fast.bleaf = m->d_bleaf;
+    m->fast.mw = reinterpret_cast<const uint32_t*>(m->d_msh);
     m->fast.valid = 1;
     m->fast.W = m->W;
     m->fast.D = D;
     m->fast.P = P;
-    m->fast.inner_m = (int)inner_m;
-    m->fast.leaves_m = (int)leaves_m;
-    m->fast.msh = m->d_msh;
-    m->fast.mprob = m->d_mprob;
   }
   // full-window lookup table of W == 3 models (Build_Indep_WO_Stops makes an ICM_t(3,2,3))
   m->dev.lut3 = NULL;
@@ -388,8 +396,6 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->d_mip = NULL;
   m->d_prob = NULL;
   m->d_msh = NULL;
-  m->d_mprob = NULL;
-  m->d_bleaf = NULL;
   m->d_bleaf = NULL;
   m->d_lut3 = NULL;
   for (size_t i = 0; i < m->mip.size(); i++)
@@ -515,7 +521,6 @@ extern "C" void gmg_icm_free(gmg_icm* m) {
   if (m->d_mip) cudaFree(m->d_mip);
   if (m->d_prob) cudaFree(m->d_prob);
   if (m->d_msh) cudaFree(m->d_msh);
-  if (m->d_mprob) cudaFree(m->d_mprob);
   if (m->d_bleaf) cudaFree(m->d_bleaf);
   if (m->d_lut3) cudaFree(m->d_lut3);
   delete m;

@@ -255,16 +255,47 @@ struct K1Segs {
   unsigned bucket_lo[4];   // plane index of the first position of each base bucket
 };
 
-template <int kD, int kU>
+// two tree levels from one merged word (DevIcmFast::mw): i = index of the node within its (odd) level on entry, of
+// its grandchild on exit.  No stop test: the tables describe the completed tree.
+__device__ __forceinline__ uint32_t k1_step2(uint32_t w, uint32_t c, uint32_t i) {
+  const uint32_t y1 = c << (w & 31);
+  const uint32_t t = w >> (5 * (y1 >> 30) + 5);
+  const uint32_t y2 = c << (t & 31);
+  return __funnelshift_l(y2, __funnelshift_l(y1, i, 2), 2);
+}
+
+// the same two levels for a window whose positions below `lim` are not available (lsh = 30 - 2 lim): stops at the
+// first node that is a real stop or branches on an unavailable position and returns true with *res = that node's
+// dense number (off = dense number of the first node of the entry level, 4 off + 1 of the next).
+__device__ __forceinline__ bool k1_step2_tested(uint32_t w, uint32_t c, unsigned lsh, uint32_t off, uint32_t* i,
+                                                uint32_t* res) {
+  const uint32_t s1 = w & 31;
+  if (((w >> 25) & 1u) || s1 > lsh) {
+    *res = off + *i;
+    return true;
+  }
+  const uint32_t y1 = c << s1, b1 = y1 >> 30;
+  const uint32_t i2 = __funnelshift_l(y1, *i, 2);
+  const uint32_t s2 = (w >> (5 * b1 + 5)) & 31;
+  if (((w >> (26 + b1)) & 1u) || s2 > lsh) {
+    *res = 4 * off + 1 + i2;
+    return true;
+  }
+  *i = __funnelshift_l(c << s2, i2, 2);
+  return false;
+}
+
+template <int kU>
 __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
                                                               const uint32_t* __restrict__ ctxr,
                                                               const uint8_t* __restrict__ cdist, unsigned total,
-                                                              K1Segs segs, int np, float* __restrict__ planes) {
+                                                              K1Segs segs, float* __restrict__ planes) {
   extern __shared__ __align__(16) uint8_t s_raw[];
-  constexpr int inner_m = 2 << (2 * (kD - 1));
-  uint8_t* s_sh = s_raw;
-  float* s_leaf = reinterpret_cast<float*>(s_raw + inner_m);
-  const int W = gm.W, nt = blockDim.x;
+  constexpr int NWORDS = 4 + 64 + 1024;      // merged words of one period (levels 1, 3, 5)
+  constexpr uint32_t OFF7 = (16384 - 1) / 3;  // dense number of the first level-7 node
+  uint32_t* s_mw = reinterpret_cast<uint32_t*>(s_raw);
+  float* s_leaf = reinterpret_cast<float*>(s_raw + NWORDS * 4);
+  const int W = gm.W, nt = blockDim.x, np = gm.np;
   const int wsh = 32 - 2 * W;
   const long long all = segs.lo[24];
   const long long w0 = all * blockIdx.x / gridDim.x, w1 = all * (blockIdx.x + 1) / gridDim.x;
@@ -278,9 +309,9 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
     if (role != have_role) {  // CTA-uniform
       __syncthreads();
       if (f != have_f) {
-        const uint4* src = reinterpret_cast<const uint4*>(gm.msh + (size_t)f * inner_m);
-        uint4* dst = reinterpret_cast<uint4*>(s_sh);
-        for (int i = threadIdx.x; i < (inner_m >> 4); i += nt) dst[i] = __ldg(src + i);
+        const uint4* src = reinterpret_cast<const uint4*>(gm.mw + (size_t)f * NWORDS);
+        uint4* dst = reinterpret_cast<uint4*>(s_mw);
+        for (int i = threadIdx.x; i < NWORDS / 4; i += nt) dst[i] = __ldg(src + i);
       }
       {
         const uint4* src = reinterpret_cast<const uint4*>(gm.bleaf + (size_t)role * np);
@@ -291,6 +322,8 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
       have_f = f;
       have_role = role;
     }
+    const unsigned s0 = f == 0 ? gm.s0[0] : (f == 1 ? gm.s0[1] : gm.s0[2]);
+    const bool stop0 = (f == 0 ? gm.stop0[0] : (f == 1 ? gm.stop0[1] : gm.stop0[2])) != 0;
     const unsigned own = rev ? 3 - pb : pb;
     // plane indices [g0, g1) of this share; the strand's contexts and its period-f plane
     const unsigned g0 = segs.bucket_lo[own] + (unsigned)(a0 - segs.lo[seg]);
@@ -298,37 +331,63 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
     const uint32_t* __restrict__ cx = rev ? ctxr : ctxf;
     const int dsh = rev ? 0 : 4;  // which nibble of cdist limits the window: distance to the start / to the end
     float* __restrict__ out = planes + (size_t)(rev ? 3 + f : f) * total;
-    for (unsigned i0 = g0 + threadIdx.x; i0 < g1; i0 += kU * nt) {
-      uint32_t c[kU], m[kU];
+    // software pipeline: the contexts of the next iteration are in flight while this one walks
+    uint32_t nc[kU];
+    unsigned nd[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const unsigned gi = min(g0 + threadIdx.x + nt * u, g1 - 1);
+      nc[u] = __ldg(cx + gi);
+      nd[u] = __ldg(cdist + gi);
+    }
+    // (the trip count is warp-uniform -- the loop body votes -- so the test uses the warp's first index)
+    for (unsigned i0 = g0 + threadIdx.x; i0 - (threadIdx.x & 31) < g1; i0 += kU * nt) {
+      uint32_t c[kU];
       unsigned lsh[kU];
-      bool act[kU];
+      bool partial = false;
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        const unsigned gi = min(i0 + nt * u, g1 - 1);
-        c[u] = __ldg(cx + gi) >> wsh;  // window position k at bits 2k
-        const int d = (__ldg(cdist + gi) >> dsh) & 15;
-        const int lim = max(W - 1 - d, 0);  // first available window position (0 = full window)
-        lsh[u] = 30 - 2 * lim;              // a node may be descended iff its shift <= this
-        m[u] = 1;
-        act[u] = true;
+        c[u] = nc[u] >> wsh;  // window position k at bits 2k
+        const int lim = max(W - 1 - (int)((nd[u] >> dsh) & 15), 0);  // first available window position
+        lsh[u] = 30 - 2 * lim;  // a node may be descended iff its shift <= this
+        partial |= lim > 0;
+        const unsigned gi = min(i0 + kU * nt + nt * u, g1 - 1);
+        nc[u] = __ldg(cx + gi);
+        nd[u] = __ldg(cdist + gi);
       }
+      uint32_t idx[kU];
+      if (!__any_sync(0xffffffffu, partial || stop0)) {
+        uint32_t i[kU], w[kU];
 #pragma unroll
-      for (int l = 0; l < kD; l++) {
-        unsigned sv[kU];
+        for (int u = 0; u < kU; u++) i[u] = (c[u] << s0) >> 30;
 #pragma unroll
-        for (int u = 0; u < kU; u++) sv[u] = s_sh[m[u]];
+        for (int u = 0; u < kU; u++) w[u] = s_mw[i[u]];
+#pragma unroll
+        for (int u = 0; u < kU; u++) i[u] = k1_step2(w[u], c[u], i[u]);
+#pragma unroll
+        for (int u = 0; u < kU; u++) w[u] = s_mw[4 + i[u]];
+#pragma unroll
+        for (int u = 0; u < kU; u++) i[u] = k1_step2(w[u], c[u], i[u]);
+#pragma unroll
+        for (int u = 0; u < kU; u++) w[u] = s_mw[68 + i[u]];
+#pragma unroll
+        for (int u = 0; u < kU; u++) idx[u] = OFF7 + k1_step2(w[u], c[u], i[u]);
+      } else {
 #pragma unroll
         for (int u = 0; u < kU; u++) {
-          act[u] = act[u] && (sv[u] <= lsh[u]);
-          const uint32_t nx = __funnelshift_l(c[u] << (sv[u] & 31), m[u], 2);
-          m[u] = act[u] ? nx : m[u];
+          uint32_t res = 0;
+          if (!(stop0 || s0 > lsh[u])) {
+            uint32_t i = (c[u] << s0) >> 30;
+            if (!k1_step2_tested(s_mw[i], c[u], lsh[u], 1, &i, &res))
+              if (!k1_step2_tested(s_mw[4 + i], c[u], lsh[u], 21, &i, &res))
+                if (!k1_step2_tested(s_mw[68 + i], c[u], lsh[u], 341, &i, &res)) res = OFF7 + i;
+          }
+          idx[u] = res;
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        // marker index m = 4^l + i  ->  dense node number (4^l - 1) / 3 + i
-        const uint32_t hb = 0x80000000u >> __clz(m[u]);
-        const float v = s_leaf[m[u] - hb + (0x55555555u & (hb - 1u))];
+        const float v = s_leaf[idx[u]];
         if (i0 + nt * u < g1) out[i0 + nt * u] = v;
       }
     }
@@ -342,7 +401,7 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   *planes_out = (float*)planes;
   if (s->total == 0) return 0;
   static const int k1_mode = getenv("GMG_K1_MODE") ? atoi(getenv("GMG_K1_MODE")) : 0;  // 0 bucketed, 1 generic
-  if (gene->fast.valid && gene->fast.D == 7 && k1_mode == 0) {
+  if (gene->fast.valid && k1_mode == 0) {
     if (!s->n_base_valid) {
       unsigned long long nb[4];
       GMG_CUDA(cudaMemcpyAsync(nb, s->d_gc + 2, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -364,21 +423,20 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
       segs.bucket_lo[b] = bl;
       bl += (unsigned)s->n_base[b];
     }
-    const int np = (gene->fast.N + 3) & ~3;
-    const size_t smem = (size_t)gene->fast.inner_m + (size_t)np * sizeof(float);
+    const size_t smem = (size_t)(4 + 64 + 1024) * 4 + (size_t)gene->fast.np * sizeof(float);
     static const int ku = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 2;
-    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long need = (acc + 4095) / 4096;
     long long cap = (long long)ctx->sm_count * 2;
     int grid = (int)(need < cap ? need : cap);
     if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
     if (ku == 1)
-      k1_planes_bucketed<7, 1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
-                                                                 (unsigned)s->total, segs, np, (float*)planes);
+      k1_planes_bucketed<1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
+                                                              (unsigned)s->total, segs, (float*)planes);
     else
-      k1_planes_bucketed<7, 2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
-                                                                 (unsigned)s->total, segs, np, (float*)planes);
+      k1_planes_bucketed<2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
+                                                              (unsigned)s->total, segs, (float*)planes);
     gmg_prof_end(ctx, GMG_PROF_K1);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
