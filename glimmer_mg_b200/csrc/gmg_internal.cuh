@@ -11,7 +11,7 @@
 
 #define GMG_MAX_W 32      // window bases held in one 64-bit register
 #define GMG_MAX_DEPTH 12
-#define GMG_PAD_WORDS 4   // 64-bit words of zero padding before/after the packed bases
+#define GMG_PAD_WORDS 8   // 64-bit words of zero padding before/after the packed bases
 #define GMG_NPROF 8
 #define GMG_PROF_RING 64
 
@@ -123,10 +123,9 @@ struct gmg_seqset {
   unsigned long long* d_gc;  // {gc count, ORFs of the last g3 scoring call that took the ordered-sum fallback}
   // base buckets (k_bucket_*): the K1 planes are stored bucketed by the base at each position (see gmg_plane_index)
   uint32_t* d_bktidx;        // [nblk][4] plane index of the first base-b position at or after 32-base block blk
-  // walk-ready contexts in plane-index order (model independent; K1 shifts them down by 32 - 2 W):
-  uint32_t* d_ctxf;          // [total] forward strand: base p+j at bits 30-2j, j = 0..15
-  uint32_t* d_ctxr;          // [total] reverse strand: complement of base p-15+i at bits 2i, i = 0..15
-  uint8_t* d_cdist;          // [total] min(q, 15) | min(len-1-q, 15) << 4, q = position in its sequence
+  // walk-ready contexts in plane-index order (model independent; K1 shifts them down by 32 - 2 W, W <= 14):
+  uint32_t* d_ctxf;          // [total] forward strand: base p+j at bits 30-2j, j = 0..13; bits 0-3 min(len-1-q, 15)
+  uint32_t* d_ctxr;          // [total] reverse strand: complement of base p-15+i at bits 2i, i = 2..15; bits 0-3 min(q, 15)
   int64_t n_base[4];         // positions with base a / c / g / t (host copy valid iff n_base_valid)
   int n_base_valid;
   // codon bitmaps (k_codon_bits): uint2 {start bits, stop bits} [strand][stream r][nwc]; bit i of word w <-> the

@@ -287,8 +287,7 @@ __device__ __forceinline__ bool k1_step2_tested(uint32_t w, uint32_t c, unsigned
 
 template <int kU>
 __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
-                                                              const uint32_t* __restrict__ ctxr,
-                                                              const uint8_t* __restrict__ cdist, unsigned total,
+                                                              const uint32_t* __restrict__ ctxr, unsigned total,
                                                               K1Segs segs, float* __restrict__ planes) {
   extern __shared__ __align__(16) uint8_t s_raw[];
   constexpr int NWORDS = 4 + 64 + 1024;      // merged words of one period (levels 1, 3, 5)
@@ -325,41 +324,35 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
     const unsigned s0 = f == 0 ? gm.s0[0] : (f == 1 ? gm.s0[1] : gm.s0[2]);
     const bool stop0 = (f == 0 ? gm.stop0[0] : (f == 1 ? gm.stop0[1] : gm.stop0[2])) != 0;
     const unsigned own = rev ? 3 - pb : pb;
-    // plane indices [g0, g1) of this share; the strand's contexts and its period-f plane
+    // plane indices [g0, g0 + n) of this share; the strand's contexts and its period-f plane, both offset to g0
     const unsigned g0 = segs.bucket_lo[own] + (unsigned)(a0 - segs.lo[seg]);
-    const unsigned g1 = segs.bucket_lo[own] + (unsigned)(a1 - segs.lo[seg]);
-    const uint32_t* __restrict__ cx = rev ? ctxr : ctxf;
-    const int dsh = rev ? 0 : 4;  // which nibble of cdist limits the window: distance to the start / to the end
-    float* __restrict__ out = planes + (size_t)(rev ? 3 + f : f) * total;
-    // software pipeline: the contexts of the next iteration are in flight while this one walks
-    uint32_t nc[kU];
-    unsigned nd[kU];
+    const unsigned n = (unsigned)(a1 - a0), last = n - 1;
+    const uint32_t* __restrict__ cx = (rev ? ctxr : ctxf) + g0;
+    float* __restrict__ out = planes + (size_t)(rev ? 3 + f : f) * total + g0;
+    // every thread runs the same number of trips (the body votes); indices past the end are clamped to the last
+    // entry, whose value is then simply stored more than once
+    const unsigned trips = (n + kU * nt - 1) / (kU * nt);
+    unsigned i0 = threadIdx.x;
+    uint32_t nc[kU];  // software pipeline: the contexts of the next trip are in flight while this one walks
 #pragma unroll
-    for (int u = 0; u < kU; u++) {
-      const unsigned gi = min(g0 + threadIdx.x + nt * u, g1 - 1);
-      nc[u] = __ldg(cx + gi);
-      nd[u] = __ldg(cdist + gi);
-    }
-    // (the trip count is warp-uniform -- the loop body votes -- so the test uses the warp's first index)
-    for (unsigned i0 = g0 + threadIdx.x; i0 - (threadIdx.x & 31) < g1; i0 += kU * nt) {
+    for (int u = 0; u < kU; u++) nc[u] = __ldg(cx + min(i0 + nt * u, last));
+    for (unsigned t = 0; t < trips; t++, i0 += kU * nt) {
       uint32_t c[kU];
-      unsigned lsh[kU];
       bool partial = false;
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        c[u] = nc[u] >> wsh;  // window position k at bits 2k
-        const int lim = max(W - 1 - (int)((nd[u] >> dsh) & 15), 0);  // first available window position
-        lsh[u] = 30 - 2 * lim;  // a node may be descended iff its shift <= this
-        partial |= lim > 0;
-        const unsigned gi = min(i0 + kU * nt + nt * u, g1 - 1);
-        nc[u] = __ldg(cx + gi);
-        nd[u] = __ldg(cdist + gi);
+        c[u] = nc[u];
+        partial |= (int)(c[u] & 15u) < W - 1;  // some window position does not exist
+        nc[u] = __ldg(cx + min(i0 + kU * nt + nt * u, last));
       }
       uint32_t idx[kU];
       if (!__any_sync(0xffffffffu, partial || stop0)) {
         uint32_t i[kU], w[kU];
 #pragma unroll
-        for (int u = 0; u < kU; u++) i[u] = (c[u] << s0) >> 30;
+        for (int u = 0; u < kU; u++) {
+          c[u] >>= wsh;  // window position k at bits 2k
+          i[u] = (c[u] << s0) >> 30;
+        }
 #pragma unroll
         for (int u = 0; u < kU; u++) w[u] = s_mw[i[u]];
 #pragma unroll
@@ -375,21 +368,21 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
       } else {
 #pragma unroll
         for (int u = 0; u < kU; u++) {
+          const int lim = max(W - 1 - (int)(c[u] & 15u), 0);  // first available window position
+          const unsigned lsh = 30 - 2 * lim;                   // a node may be descended iff its shift <= this
+          const uint32_t cw = c[u] >> wsh;
           uint32_t res = 0;
-          if (!(stop0 || s0 > lsh[u])) {
-            uint32_t i = (c[u] << s0) >> 30;
-            if (!k1_step2_tested(s_mw[i], c[u], lsh[u], 1, &i, &res))
-              if (!k1_step2_tested(s_mw[4 + i], c[u], lsh[u], 21, &i, &res))
-                if (!k1_step2_tested(s_mw[68 + i], c[u], lsh[u], 341, &i, &res)) res = OFF7 + i;
+          if (!(stop0 || s0 > lsh)) {
+            uint32_t i = (cw << s0) >> 30;
+            if (!k1_step2_tested(s_mw[i], cw, lsh, 1, &i, &res))
+              if (!k1_step2_tested(s_mw[4 + i], cw, lsh, 21, &i, &res))
+                if (!k1_step2_tested(s_mw[68 + i], cw, lsh, 341, &i, &res)) res = OFF7 + i;
           }
           idx[u] = res;
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; u++) {
-        const float v = s_leaf[idx[u]];
-        if (i0 + nt * u < g1) out[i0 + nt * u] = v;
-      }
+      for (int u = 0; u < kU; u++) out[min(i0 + nt * u, last)] = s_leaf[idx[u]];
     }
   }
 }
@@ -401,7 +394,7 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
   *planes_out = (float*)planes;
   if (s->total == 0) return 0;
   static const int k1_mode = getenv("GMG_K1_MODE") ? atoi(getenv("GMG_K1_MODE")) : 0;  // 0 bucketed, 1 generic
-  if (gene->fast.valid && k1_mode == 0) {
+  if (gene->fast.valid && gene->W <= 14 && k1_mode == 0) {
     if (!s->n_base_valid) {
       unsigned long long nb[4];
       GMG_CUDA(cudaMemcpyAsync(nb, s->d_gc + 2, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -432,11 +425,11 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     int grid = (int)(need < cap ? need : cap);
     if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
     if (ku == 1)
-      k1_planes_bucketed<1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
-                                                              (unsigned)s->total, segs, (float*)planes);
+      k1_planes_bucketed<1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,
+                                                              (float*)planes);
     else
-      k1_planes_bucketed<2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, s->d_cdist,
-                                                              (unsigned)s->total, segs, (float*)planes);
+      k1_planes_bucketed<2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,
+                                                              (float*)planes);
     gmg_prof_end(ctx, GMG_PROF_K1);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
@@ -647,8 +640,8 @@ static int ensure_codon_bits(gmg_ctx* ctx, gmg_seqset* s, const CodonSets& cs) {
   if (s->d_cbits && memcmp(s->cbits_key, cs.raw_mask, sizeof s->cbits_key) == 0) return 0;
   const int64_t nwc = s->total / 96 + 2;
   if (!s->d_cbits) {
-    // the last word index reads packed words up to 3 (nwc - 1) + 3 <= total / 32 + 6: inside the zero padding
-    static_assert(GMG_PAD_WORDS >= 4, "k_codon_bits reads up to three words past the last base");
+    // the last word index reads packed words up to 3 (nwc - 1) + 3 <= total / 32 + 6: inside the zero padding (8 words)
+    static_assert(GMG_PAD_WORDS >= 7, "k_codon_bits reads up to seven words past the last base");
     GMG_CUDA(cudaMallocAsync(&s->d_cbits, (size_t)6 * nwc * sizeof(uint2), ctx->stream));
     s->nwc = nwc;
   }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
                                                        const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
                                                        const uint4* __restrict__ prefix, const uint4* __restrict__ cnt,
                                                        uint4* __restrict__ bktidx, uint32_t* __restrict__ ctxf,
-                                                       uint32_t* __restrict__ ctxr, uint8_t* __restrict__ cdist,
+                                                       uint32_t* __restrict__ ctxr,
                                                        unsigned long long* __restrict__ n_base) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint4 lp = prefix[nblk - 1], lc = cnt[nblk - 1];
@@ -138,12 +138,14 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
   uint32_t f = (uint32_t)gmg_extract32(words, p);
   f = __brev(f);
   f = ((f >> 1) & 0x55555555u) | ((f & 0x55555555u) << 1);
-  ctxf[idx] = f;
-  ctxr[idx] = ~(uint32_t)gmg_extract32(words, p - 15);
+  const uint32_t r = ~(uint32_t)gmg_extract32(words, p - 15);
+  // the low four bits (the two bases farthest from p; windows of up to 14 bases never see them) hold the distance
+  // to the end / start of the sequence, clipped to 15: which window positions exist
   int32_t sq = __ldg(blk2seq + blk) & 0x7FFFFFFF;
   while (p >= __ldg(off + sq + 1)) sq++;
   const int64_t q = p - __ldg(off + sq), e = __ldg(off + sq + 1) - 1 - p;
-  cdist[idx] = (uint8_t)((q < 15 ? q : 15) | ((e < 15 ? e : 15) << 4));
+  ctxf[idx] = (f & ~15u) | (uint32_t)(e < 15 ? e : 15);
+  ctxr[idx] = (r & ~15u) | (uint32_t)(q < 15 ? q : 15);
 }
 
 static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
@@ -152,7 +154,6 @@ static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
   GMG_CUDA(cudaMallocAsync(&s->d_bktidx, (size_t)(nblk + 1) * sizeof(uint4), ctx->stream));
   GMG_CUDA(cudaMallocAsync(&s->d_ctxf, (size_t)(s->total + 64) * sizeof(uint32_t), ctx->stream));
   GMG_CUDA(cudaMallocAsync(&s->d_ctxr, (size_t)(s->total + 64) * sizeof(uint32_t), ctx->stream));
-  GMG_CUDA(cudaMallocAsync(&s->d_cdist, (size_t)s->total + 64, ctx->stream));
   void *d_cnt, *d_tmp;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)2 * nblk * sizeof(uint4), &d_cnt)) return 1;
   uint4* cnt = (uint4*)d_cnt;
@@ -164,7 +165,7 @@ static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
   GMG_CUDA(cub::DeviceScan::ExclusiveScan(d_tmp, tmp_bytes, cnt, prefix, Uint4Add(), make_uint4(0, 0, 0, 0), nblk, ctx->stream));
   k_bucket_finish<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(
       s->d_words, s->total, nblk, s->d_off, s->d_blk2seq, prefix, cnt, (uint4*)s->d_bktidx, s->d_ctxf, s->d_ctxr,
-      s->d_cdist, s->d_gc + 2);
+      s->d_gc + 2);
   ctx->launches += 4;
   GMG_CUDA(cudaGetLastError());
   return 0;
@@ -198,7 +199,7 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
   s->off.assign(h_off, h_off + n + 1);
   if (n == 0) s->off.assign(1, 0);
   s->d_off = NULL; s->d_words_base = NULL; s->d_words = NULL; s->d_blk2seq = NULL; s->d_qual = NULL; s->d_gc = NULL;
-  s->d_cbits = NULL; s->nwc = 0; s->d_bktidx = NULL; s->d_ctxf = NULL; s->d_ctxr = NULL; s->d_cdist = NULL; memset(s->n_base, 0, sizeof s->n_base); s->n_base_valid = 0; memset(s->cbits_key, 0, sizeof s->cbits_key);
+  s->d_cbits = NULL; s->nwc = 0; s->d_bktidx = NULL; s->d_ctxf = NULL; s->d_ctxr = NULL; memset(s->n_base, 0, sizeof s->n_base); s->n_base_valid = 0; memset(s->cbits_key, 0, sizeof s->cbits_key);
   s->n_orfs = 0; s->d_orfs = NULL; s->d_orf_off = NULL; s->d_orf_seq = NULL;
   s->n_starts = 0; s->d_starts = NULL; s->d_start_off = NULL; s->uncertified = 0;
   s->cap_orfs = s->cap_starts = 0;
@@ -261,7 +262,7 @@ extern "C" void gmg_seqset_free(gmg_seqset* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   void* ptrs[] = {s->d_off, s->d_words_base, s->d_blk2seq, s->d_qual, s->d_gc, s->d_orfs, s->d_orf_off,
-                  s->d_orf_seq, s->d_starts, s->d_start_off, s->d_cbits, s->d_bktidx, s->d_ctxf, s->d_ctxr, s->d_cdist};
+                  s->d_orf_seq, s->d_starts, s->d_start_off, s->d_cbits, s->d_bktidx, s->d_ctxf, s->d_ctxr};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s->ctx->stream);
   delete s;
