@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
 // 4 SM cycles from shared memory against 11 from an L1-resident and 28 from an L2-resident table).
 // The 24 (f, pb, strand) segments are linearised; CTA c takes the c-th equal share of the 6 * total walks, which
 // spans at most two roles unless the batch is tiny.
+#define K1_PAD 8192  // entries of padding after the context arrays: two trips of two entries per thread
 struct K1Segs {
   long long lo[25];        // linearised start of segment (f * 4 + pb) * 2 + strand; lo[24] = 6 * total
   unsigned bucket_lo[4];   // plane index of the first position of each base bucket
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
   constexpr uint32_t OFF7 = (16384 - 1) / 3;  // dense number of the first level-7 node
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(s_raw);
   float* s_leaf = reinterpret_cast<float*>(s_raw + NWORDS * 4);
-  const int W = gm.W, nt = blockDim.x, np = gm.np;
+  constexpr int NT = 1024;  // threads per CTA (launch_k1)
+  const int W = gm.W, nt = NT, np = gm.np;
   const int wsh = 32 - 2 * W;
   const long long all = segs.lo[24];
   const long long w0 = all * blockIdx.x / gridDim.x, w1 = all * (blockIdx.x + 1) / gridDim.x;
@@ -326,24 +328,27 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
     const unsigned own = rev ? 3 - pb : pb;
     // plane indices [g0, g0 + n) of this share; the strand's contexts and its period-f plane, both offset to g0
     const unsigned g0 = segs.bucket_lo[own] + (unsigned)(a0 - segs.lo[seg]);
-    const unsigned n = (unsigned)(a1 - a0), last = n - 1;
+    const unsigned n = (unsigned)(a1 - a0);
     const uint32_t* __restrict__ cx = (rev ? ctxr : ctxf) + g0;
     float* __restrict__ out = planes + (size_t)(rev ? 3 + f : f) * total + g0;
-    // every thread runs the same number of trips (the body votes); indices past the end are clamped to the last
-    // entry, whose value is then simply stored more than once
-    const unsigned trips = (n + kU * nt - 1) / (kU * nt);
+    // every thread runs the same number of trips (the body votes).  Lanes past the end of the share walk whatever
+    // context lies there (the arrays are padded by K1_PAD entries) and simply do not store.
+    const unsigned trips = (n + kU * NT - 1) / (kU * NT);
     unsigned i0 = threadIdx.x;
+    const uint32_t* __restrict__ pc = cx + i0;
+    float* __restrict__ po = out + i0;
     uint32_t nc[kU];  // software pipeline: the contexts of the next trip are in flight while this one walks
 #pragma unroll
-    for (int u = 0; u < kU; u++) nc[u] = __ldg(cx + min(i0 + nt * u, last));
-    for (unsigned t = 0; t < trips; t++, i0 += kU * nt) {
+    for (int u = 0; u < kU; u++) nc[u] = __ldg(pc + NT * u);
+    for (unsigned t = 0; t < trips; t++, i0 += kU * NT, po += kU * NT) {
       uint32_t c[kU];
       bool partial = false;
+      pc += kU * NT;
 #pragma unroll
       for (int u = 0; u < kU; u++) {
         c[u] = nc[u];
         partial |= (int)(c[u] & 15u) < W - 1;  // some window position does not exist
-        nc[u] = __ldg(cx + min(i0 + kU * nt + nt * u, last));
+        nc[u] = __ldg(pc + NT * u);
       }
       uint32_t idx[kU];
       if (!__any_sync(0xffffffffu, partial || stop0)) {
@@ -382,7 +387,13 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; u++) out[min(i0 + nt * u, last)] = s_leaf[idx[u]];
+      for (int u = 0; u < kU; u++) {
+        const float v = s_leaf[idx[u]];
+        // predicated store (no branch): only entries of this share
+        asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p st.global.f32 [%2], %3; }" ::"r"(i0 + NT * u), "r"(n),
+                     "l"(po + NT * u), "f"(v)
+                     : "memory");
+      }
     }
   }
 }
