@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="contig5m", choices=["contig5m"])
+    ap.add_argument("--workload", default="contig5m", choices=["contig5m", "reads400", "reads100", "train500m"])
+    ap.add_argument("--scale", type=float, default=1.0,
+                    help="shrink a non-default workload (fraction of its reads / training strings); 1.0 = BASELINE size")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
 
@@ -364,9 +366,523 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ===================================================================================================
+# The other BASELINE.json configs (parity-test cases at N=1 per the bench contract; selectable with
+# --workload so that every SURVEY.md section 8(d) config has a measured line under profiles/).
+#   reads400   configs[2]: 1M x 400 bp 454-like reads (seed 42), glimmer-mg -i scoring half; step = one batch
+#              of 25 000 reads (10 Mbp); rank r takes batches r, r+N, ...
+#   reads100   configs[4]: 16 synthetic genomes (GC 0.30..0.70) with their own device-trained ICMs, 625 000
+#              error-free 100 bp reads each (seed 5); step = one half-cluster batch of 312 500 reads
+#              (31.25 Mbp) scored with its cluster's ICM; rank r takes batches r, r+N, ...
+#   train500m  configs[3]: build-icm -r on 500 500 x 999 bp stop-free coding strings (seed 7), strings dealt
+#              round-robin to ranks, every level's count slab all-reduced (NCCL) -- "strong" scaling;
+#              step = one full Train_Model.
+K2_BYTES_PER_BASE = 24 + 48 + 8 + 1   # planes read; cum doubles, stop tables, quality written
+READS400_BATCH, READS400_TOTAL, READS400_LEN = 25_000, 1_000_000, 400
+READS100_BATCH, READS100_PER_CLUSTER, READS100_LEN, READS100_CLUSTERS = 312_500, 625_000, 100, 16
+TRAIN_SEQS, TRAIN_CODONS = 500_500, 333
+MAX_RESIDENT_BATCHES = 6
+
+
+def reads_batches(kind, rank, world, scale, n_wanted):
+    """Host data of the batches this rank processes -> list of (ascii, off, model id), plus a description."""
+    import numpy as np
+    import workloads as W
+    out = []
+    if kind == "reads400":
+        contig = W.contig(W.CONTIG_SEED, CONTIG_LEN)
+        per = max(64, int(READS400_BATCH * scale))
+        n_batches = READS400_TOTAL // READS400_BATCH
+        for i in range(min(n_wanted, MAX_RESIDENT_BATCHES)):
+            b = (rank + world * i) % n_batches
+            a, off = W.reads(contig, per, READS400_LEN, W.READS400_SEED + 7919 * b, indel=True)
+            out.append((a, off, 0))
+        desc = (f"reads400: {per} reads x {READS400_LEN} bp per step, 454-like homopolymer indels, drawn from the config-2 "
+                f"contig (seed 42 + batch), glimmer-mg -i scoring half: K1 + K2 prefix/stops/quality + K3 indel "
+                f"start recursion (BASELINE.json configs[2])")
+        return out, desc
+    freq = W.codon_freq()
+    per = max(64, int(READS100_BATCH * scale))
+    n_batches = READS100_CLUSTERS * (READS100_PER_CLUSTER // READS100_BATCH)
+    genomes = {}
+    for i in range(min(n_wanted, MAX_RESIDENT_BATCHES)):
+        b = (rank + world * i) % n_batches
+        k = b % READS100_CLUSTERS
+        if k not in genomes:
+            gc = float(np.linspace(0.30, 0.70, READS100_CLUSTERS)[k])
+            genomes[k] = W.contig(W.READS100_SEED * 1000 + k, 2_000_000, freq=W.reweight_gc(freq, gc), gc=gc)
+        a, off = W.reads(genomes[k], per, READS100_LEN, W.READS100_SEED + 7919 * b, indel=False)
+        out.append((a, off, k))
+    desc = (f"reads100: {per} error-free reads x {READS100_LEN} bp per step from one of {READS100_CLUSTERS} synthetic genomes "
+            f"(GC 0.30..0.70), each scored with its own cluster ICM trained on the device, glimmer-mg scoring half "
+            f"(BASELINE.json configs[4])")
+    return out, desc
+
+
+def cluster_training_strings(k):
+    """Training genes of cluster k: stop-free coding strings from the genome's re-weighted codon table."""
+    import numpy as np
+    import workloads as W
+    gc = float(np.linspace(0.30, 0.70, READS100_CLUSTERS)[k])
+    return W.coding(1500, 333, seed=W.READS100_SEED * 1000 + 500 + k, freq=W.reweight_gc(W.codon_freq(), gc))
+
+
+def ref_glimmer_mg_seconds(fastas, workdir, flags, models):
+    """One reference glimmer-mg per FASTA concurrently; wall seconds of the slowest."""
+    exe = ref_bin("glimmer-mg")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([exe, "-u", "1.0", *flags, "-m", models[i], fa, os.path.join(workdir, f"out{i}")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=workdir)
+             for i, fa in enumerate(fastas)]
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("reference glimmer-mg failed")
+    return time.perf_counter() - t0
+
+
+def port_mg_seconds(ascii_arr, off, indels):
+    """Oracle port of the glimmer-mg scoring half on a few reads, 1 thread (used when oracle/_ref is absent)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import workloads as W
+    og = O.lib().orc_icm_read(W.gene_model_path().encode())
+    s_all = ascii_arr.tobytes()
+    gc = (s_all.count(b"c") + s_all.count(b"g")) / max(1, len(s_all))
+    oi = O.build_indep(gc)
+    op = O.params(True, allow_indels=1 if indels else 0)
+    t0 = time.perf_counter()
+    for i in range(len(off) - 1):
+        s = s_all[off[i]:off[i + 1]]
+        O.mg_score_orfs(og, oi, s, op, O.find_orfs(s, op))
+    return time.perf_counter() - t0
+
+
+def reads_cpu_sample(kind, ascii_arr, off, n_reads, tmp, model_path, tag=0):
+    import workloads as W
+    fa = os.path.join(tmp, f"sample{tag}.fa")
+    W.write_fasta(fa, ascii_arr[:off[n_reads]], off[:n_reads + 1], prefix="r")
+    return fa
+
+
+def run_reference_reads(args, kind):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    import workloads as W
+    cores = host_cores()
+    n_sample = 1500 if kind == "reads400" else 15000
+    flags = ["-i"] if kind == "reads400" else []
+    tmp = tempfile.mkdtemp(prefix="gmg_ref_")
+    try:
+        batches, desc = reads_batches(kind, 0, 1, max(args.scale, 1e-9), 1)
+        a, off, _ = batches[0]
+        have = ref_bin("glimmer-mg") is not None
+        fastas, bases = [], 0
+        n_avail = len(off) - 1
+        for i in range(cores if have else 1):
+            lo = (i * n_sample) % max(1, n_avail - n_sample)
+            sa, so = a[off[lo]:off[lo + n_sample]], off[lo:lo + n_sample + 1] - off[lo]
+            bases += int(so[-1])
+            if have:
+                fa = os.path.join(tmp, f"s{i}.fa")
+                W.write_fasta(fa, sa, so, prefix="r")
+                fastas.append(fa)
+            else:
+                port_in = (sa, so)
+        times = []
+        for k in range(args.warmup + args.steps):
+            sec = (ref_glimmer_mg_seconds(fastas, tmp, flags, [W.gene_model_path()] * len(fastas)) if have
+                   else port_mg_seconds(port_in[0], port_in[1], kind == "reads400"))
+            if k >= args.warmup:
+                times.append(sec)
+        value = bases * len(times) / sum(times) / 1e9
+        used = cores if have else 1
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": desc, "model": "tests/golden/NC_000915.icm"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference" if have else "port",
+                                 "sample": f"each step: {used} concurrent glimmer-mg {' '.join(flags)} processes, each on its own "
+                                           f"{n_sample} reads of the workload (FASTA read + scoring + event DP + .predict)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_b200_reads(args, kind):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import glimmer_mg_b200 as g
+    import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    K, Wu = args.steps, max(args.warmup, 3)
+    indels = kind == "reads400"
+    with torch.cuda.stream(stream):
+        ctx = g.Context(local, stream.cuda_stream)
+        batches, desc = reads_batches(kind, rank, world, args.scale, K + Wu)
+        nb = len(batches)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        # models: the sample genome's ICM (reads400) or one device-trained ICM per cluster (reads100)
+        genes = {}
+        for _, _, k in batches:
+            if k in genes:
+                continue
+            if kind == "reads400":
+                genes[k] = g.ICM.Read(ctx, W.gene_model_path())
+            else:
+                ts, toff = cluster_training_strings(k)
+                genes[k] = g.ICMTraining(ctx, 12, 7, 3).Train_Model(g.SeqSet(ctx, ascii=ts, offsets=toff), reverse=True)
+        pinned, sets, indeps, params = [], [], [], []
+        for a, off, k in batches:
+            h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
+            h.numpy()[:] = a
+            pinned.append(h)
+            ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
+            gc = ss.gc_fraction()
+            p = g.Params(True, allow_indels=1 if indels else 0)
+            p.set_ignore_score_len(gc)
+            indeps.append(g.ICM.Build_Indep_WO_Stops(ctx, gc, p.stop_codons))
+            params.append(p)
+            ss.find_orfs(p)
+            sets.append(ss)
+        bases = [int(b[1][-1]) for b in batches]
+        n_starts = 0
+        for i in range(Wu):
+            j = i % nb
+            n_starts = sets[j].score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
+        ctx.sync()
+        ctx.profile(True)
+        for k in ("k1", "k2", "k3", "orf", "pack"):
+            ctx.profile_read(k)
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        clocks = ClockSampler(local) if rank == 0 else None
+        barrier()
+        launches0 = ctx.launches
+        t_wall0 = time.time()
+        done_bases = 0
+        for k in range(K):
+            j = (Wu + k) % nb
+            flush.zero_()
+            e0[k].record(stream)
+            n_starts = sets[j].score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
+            e1[k].record(stream)
+            done_bases += bases[j]
+        barrier()
+        t_wall1 = time.time()
+        launches = ctx.launches - launches0
+        ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        kms = {k: ctx.profile_read(k) for k in ("k1", "k2", "k3")}
+        clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+        n_orfs_last, uncert = sets[(Wu + K - 1) % nb].n_orfs, sets[(Wu + K - 1) % nb].uncertified
+
+        # ---- end to end: pinned host ASCII in, ORF table + start lists out (pinned) ----
+        for s in sets:
+            s.close()
+        e2e_ms, d2h, h2d, e2e_bases = 0.0, 0, 0, 0
+        for k in range(Wu + K):
+            j = k % nb
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            s2 = g.SeqSet(ctx, ascii=pinned[j].numpy(), offsets=batches[j][1])
+            s2.find_orfs(params[j])
+            s2.score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
+            orfs, ooff = s2.get_orfs(pinned=True)
+            starts, soff = s2.get_starts(pinned=True)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if k >= Wu:
+                e2e_ms += a.elapsed_time(b)
+                e2e_bases += bases[j]
+                d2h = orfs.nbytes + ooff.nbytes + starts.nbytes + soff.nbytes
+                h2d = len(batches[j][0]) + batches[j][1].nbytes
+            s2.close()
+        ctx.profile(False)
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    tb = torch.tensor([done_bases, e2e_bases], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+    ms_max, e2e_max = t.tolist()
+    all_bases, all_e2e_bases = tb.tolist()
+    if rank == 0:
+        value = all_bases / (ms_max / 1e3) / 1e9
+        e2e = all_e2e_bases / (e2e_max / 1e3) / 1e9
+        peak, peak_src = measured_peak()
+        per_base = {"k1": K1_BYTES_PER_BASE, "k2": K2_BYTES_PER_BASE}
+        dom = max(("k1", "k2"), key=lambda k: kms[k][0])
+        nb_avg = done_bases / K
+        dom_ms = kms[dom][0] / max(kms[dom][1], 1)
+        achieved = nb_avg * per_base[dom] / (dom_ms / 1e3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "model": "tests/golden/NC_000915.icm (12/7/3)" if indels else
+                           "one 12/7/3 ICM per cluster, trained on the device (build-icm -r) from 1500 x 999 bp genes",
+                           "bases_per_step_per_gpu": int(nb_avg), "orfs_last_step": int(n_orfs_last),
+                           "starts_last_step": int(n_starts), "uncertified_reads": int(uncert),
+                           "l2": "256 MB flush write before every timed step",
+                           "sharding": "batches dealt to ranks, no collective"},
+                "roofline": {"bound": "hbm", "kernel": {"k1": "k1_planes", "k2": "k2_prefix"}[dom], "achieved": achieved,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": nb_avg * per_base[dom],
+                             "kernel_ms": dom_ms, "kernel_share_of_step": kms[dom][0] / ms,
+                             "ms_per_step_by_kernel": {k: v[0] / K for k, v in kms.items()},
+                             "note": "k3_mg_starts (per-ORF indel recursion) is latency/divergence-bound and has no "
+                                     "HBM roofline; its time is listed beside the two streaming kernels"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_max / K},
+                "gpu_launches": int(launches), "clocks": clk}
+        if world == 1 and not args.no_cpu_baseline:
+            tmp = tempfile.mkdtemp(prefix="gmg_bench_")
+            try:
+                a, off, _ = batches[0]
+                n_s = min(len(off) - 1, 4000 if indels else 40000)
+                if ref_bin("glimmer-mg"):
+                    fa = reads_cpu_sample(kind, a, off, n_s, tmp, W.gene_model_path())
+                    sec = ref_glimmer_mg_seconds([fa], tmp, ["-i"] if indels else [], [W.gene_model_path()])
+                    kindname = "reference"
+                else:
+                    sec = port_mg_seconds(a[:off[n_s]], off[:n_s + 1], indels)
+                    kindname = "port"
+                line["cpu_baseline"] = {"value": int(off[n_s]) / sec / 1e9, "unit": UNIT, "cores": 1, "kind": kindname,
+                                        "sample": f"first {n_s} reads of the first batch through glimmer-mg -u 1.0"
+                                                  f"{' -i' if indels else ''} on one core (single-threaded binary; "
+                                                  f"sample-genome ICM), {sec:.2f} s"}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+TRAIN_METRIC = "counted Gbp/s"
+
+
+def ref_build_icm_seconds(ascii_arr, off, tmp):
+    import workloads as W
+    fa = os.path.join(tmp, "train.fa")
+    W.write_fasta(fa, ascii_arr, off, prefix="g")
+    exe = ref_bin("build-icm")
+    t0 = time.perf_counter()
+    with open(fa, "rb") as fin:
+        rc = subprocess.run([exe, "-r", os.path.join(tmp, "m.icm")], stdin=fin, stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL).returncode
+    if rc != 0:
+        raise RuntimeError("reference build-icm failed")
+    return time.perf_counter() - t0
+
+
+def port_train_seconds(ascii_arr, off):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    s_all = ascii_arr.tobytes()
+    rev = [s_all[off[i]:off[i + 1]][::-1] for i in range(len(off) - 1)]
+    arr = O.cstr_array(rev)
+    t0 = time.perf_counter()
+    O.lib().orc_icm_train(arr, len(rev), 12, 7, 3)
+    return time.perf_counter() - t0
+
+
+def train_cpu(n_seqs):
+    import workloads as W
+    a, off = W.coding(n_seqs, TRAIN_CODONS, W.TRAIN_SEED)
+    tmp = tempfile.mkdtemp(prefix="gmg_bench_")
+    try:
+        if ref_bin("build-icm"):
+            return int(off[-1]), ref_build_icm_seconds(a, off, tmp), "reference"
+        return int(off[-1]), port_train_seconds(a, off), "port"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def train_desc(n_seqs):
+    return (f"train500m: build-icm -r (Train_Model, 12/7/3) on {n_seqs} stop-free coding strings x {3 * TRAIN_CODONS} bp "
+            f"(seed 7), strings dealt round-robin to ranks, one int32 count-slab all-reduce per tree level "
+            f"(BASELINE.json configs[3])")
+
+
+def run_reference_train(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_seqs = max(16, int(TRAIN_SEQS * args.scale))
+    n_sample = min(n_seqs, 2500)
+    times = []
+    for k in range(args.warmup + args.steps):
+        bases, sec, kind = train_cpu(n_sample)
+        if k >= args.warmup:
+            times.append(sec)
+    value = bases * len(times) / sum(times) / 1e9
+    line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": train_desc(n_seqs)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": f"each step: build-icm -r on the first {n_sample} training strings ({bases} bp), one "
+                                       f"core -- one model cannot be split over processes (SURVEY.md 8(d))"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_train(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import glimmer_mg_b200 as g
+    from glimmer_mg_b200 import shard
+    import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    K, Wu = args.steps, max(args.warmup, 3)
+    n_seqs = max(16, int(TRAIN_SEQS * args.scale))
+    with torch.cuda.stream(stream):
+        ctx = g.Context(local, stream.cuda_stream)
+        a_all, off_all = W.coding(n_seqs, TRAIN_CODONS, W.TRAIN_SEED)
+        if world > 1:
+            a, off = shard.take_sequences(a_all, off_all, shard.round_robin(n_seqs, rank, world))
+        else:
+            a, off = a_all, off_all
+        total_bases = int(off_all[-1])
+        del a_all
+        h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
+        h.numpy()[:] = a
+        ar = shard.torch_allreduce(local) if world > 1 else None
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
+        trainer = g.ICMTraining(ctx, 12, 7, 3)
+        model = None
+        for _ in range(Wu):
+            model = trainer.Train_Model(ss, reverse=True, allreduce=ar)
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_read("k4")
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        clocks = ClockSampler(local) if rank == 0 else None
+        barrier()
+        launches0 = ctx.launches
+        t_wall0 = time.time()
+        for k in range(K):
+            flush.zero_()
+            e0[k].record(stream)
+            model = trainer.Train_Model(ss, reverse=True, allreduce=ar)
+            e1[k].record(stream)
+        barrier()
+        t_wall1 = time.time()
+        launches = ctx.launches - launches0
+        ms = sum(x.elapsed_time(y) for x, y in zip(e0, e1))
+        k4_ms, k4_n = ctx.profile_read("k4")
+        clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+        ss.close()
+        # ---- end to end: pinned host strings in, model tables out ----
+        e2e_ms, d2h = 0.0, 0
+        for k in range(Wu + K):
+            flush.zero_()
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            x.record(stream)
+            s2 = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
+            m2 = trainer.Train_Model(s2, reverse=True, allreduce=ar)
+            mip, prob = m2.tables()
+            y.record(stream)
+            torch.cuda.synchronize()
+            if k >= Wu:
+                e2e_ms += x.elapsed_time(y)
+                d2h = mip.nbytes + prob.nbytes
+            s2.close()
+            m2.close()
+        ctx.profile(False)
+        import hashlib
+        digest = hashlib.sha256(mip.tobytes() + prob.tobytes()).hexdigest()[:16]
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = t.tolist()
+    if rank == 0:
+        value = total_bases * K / (ms_max / 1e3) / 1e9
+        e2e = total_bases * K / (e2e_max / 1e3) / 1e9
+        peak, peak_src = measured_peak()
+        my_bases = int(off[-1])
+        alg = my_bases * 8 * 0.25  # eight level passes over the packed strings
+        k4_step_ms = k4_ms / K
+        achieved = alg / (k4_step_ms / 1e3) / 1e9
+        line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": train_desc(n_seqs), "training_bases": total_bases, "bases_per_gpu": my_bases,
+                           "model_sha256_16": digest, "l2": "256 MB flush write before every timed step",
+                           "sharding": "round-robin strings; NCCL all-reduce of each level's count slab" if world > 1
+                           else "single GPU, no exchange"},
+                "roofline": {"bound": "hbm", "kernel": "k4_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg / 8, "kernel_ms": k4_ms / max(k4_n, 1),
+                             "kernel_share_of_step": k4_ms / ms,
+                             "atomic_payload_gbs": my_bases * 352 / (k4_step_ms / 1e3) / 1e9,
+                             "note": "K4 is bound by the shared/L2 atomic rate (88 int32 increments per base per model, "
+                                     "352 B/base of RMW payload), not by HBM: the HBM figure is the packed-string "
+                                     "re-read (8 x 0.25 B/base) and is expected to be a small fraction of peak"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(len(a) + off.nbytes),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max / K},
+                "gpu_launches": int(launches), "clocks": clk}
+        if world == 1 and not args.no_cpu_baseline:
+            bases, sec, kind = train_cpu(min(n_seqs, 5000))
+            line["cpu_baseline"] = {"value": bases / sec / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"build-icm -r on the first {min(n_seqs, 5000)} training strings ({bases} bp) on "
+                                              f"one core (one model cannot be split over processes), {sec:.2f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload in ("reads400", "reads100"):
+        (run_reference_reads if args.impl == "reference" else run_b200_reads)(args, args.workload)
+    elif args.workload == "train500m":
+        (run_reference_train if args.impl == "reference" else run_b200_train)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
