@@ -806,8 +806,11 @@ def run_b200_train(args):
         for k in range(K):
             flush.zero_()
             e0[k].record(stream)
+            tw = time.perf_counter()
             model = trainer.Train_Model(ss, reverse=True, allreduce=ar)
             e1[k].record(stream)
+            if os.environ.get("GMG_BENCH_DEBUG"):
+                print(f"train step {k}: host wall {1e3 * (time.perf_counter() - tw):.1f} ms", file=sys.stderr)
         barrier()
         t_wall1 = time.time()
         launches = ctx.launches - launches0

@@ -93,6 +93,7 @@ struct gmg_icm {
   int W, D, P, N;
   std::vector<int16_t> mip;  // [P][N]   host mirror, exactly as ICM_t::score[][].mut_info_pos
   std::vector<float> prob;   // [P][N][4] exactly as ICM_t::score[][].prob
+  std::vector<float> mut_info;  // [P][N] ICM_Score_Node_t::mut_info: set by training, 0 for models read from a file
   int8_t* d_mip;
   float* d_prob;
   DevIcm dev;

@@ -393,6 +393,7 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->W = w; m->D = d; m->P = p; m->N = n;
   m->mip.assign(h_mip, h_mip + (size_t)p * n);
   m->prob.assign(h_prob, h_prob + (size_t)p * n * 4);
+  m->mut_info.assign((size_t)p * n, 0.0f);
   m->d_mip = NULL;
   m->d_prob = NULL;
   m->d_msh = NULL;
@@ -512,6 +513,12 @@ extern "C" int gmg_icm_tables(const gmg_icm* m, int16_t* h_mip, float* h_prob) {
   GMG_CHECK(m, "gmg_icm_tables: NULL model");
   if (h_mip) memcpy(h_mip, m->mip.data(), m->mip.size() * sizeof(int16_t));
   if (h_prob) memcpy(h_prob, m->prob.data(), m->prob.size() * sizeof(float));
+  return 0;
+}
+
+extern "C" int gmg_icm_mut_info(const gmg_icm* m, float* h_out) {
+  GMG_CHECK(m && h_out, "gmg_icm_mut_info: NULL argument");
+  memcpy(h_out, m->mut_info.data(), m->mut_info.size() * sizeof(float));
   return 0;
 }
 

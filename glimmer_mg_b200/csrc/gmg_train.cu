@@ -31,6 +31,7 @@ struct gmg_trainer {
   int W, D, P, N, reverse;
   std::vector<int16_t> mip;  // [P][N]
   std::vector<float> prob;   // [P][N][4] probabilities (logs only after finish)
+  std::vector<float> mut_info;  // [P][N] mutual information of the chosen position (icm.cc:1156, 1438)
   int8_t* d_mip;             // [P][N] current tree (levels not built yet are -1)
   int32_t* d_counts;         // slab of the level being counted
   size_t counts_cap;
@@ -119,6 +120,7 @@ extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int
   t->N = (int)((level_nodes(d + 1) - 1) / 3);
   t->mip.assign((size_t)p * t->N, 0);
   t->prob.assign((size_t)p * t->N * 4, 0.0f);
+  t->mut_info.assign((size_t)p * t->N, 0.0f);
   t->d_mip = NULL;
   t->d_counts = NULL;
   t->counts_cap = 0;
@@ -209,18 +211,21 @@ static const float kChi2Val[7] = {2.37f, 4.11f, 6.25f, 7.81f, 9.35f, 11.3f, 12.8
 static const float kChi2Sig[7] = {0.50f, 0.75f, 0.90f, 0.95f, 0.975f, 0.99f, 0.995f};         // icm.hh:39-40
 
 // position choice for one node; returns max_pos (no pruning applied) and best_info
-static int choose_position(const int32_t* node_counts, int W, int sum, double* best_out) {
+static int choose_position(const int32_t* node_counts, int W, int sum, double* best_out, double* used_out) {
   int max_pos = 0;
-  double best = mutual_info16(node_counts, sum);
+  double best = mutual_info16(node_counts, sum), used = best;
   for (int i = 1; i < W - 1; i++) {
     double next = mutual_info16(node_counts + 16 * i, sum);
     if (next >= best) {
-      best = next;
+      used = best = next;
       max_pos = i;
-    } else if (next >= best / (1.0 + 0.03))  // MUT_INFO_BIAS: prefer positions to the right
+    } else if (next >= best / (1.0 + 0.03)) {  // MUT_INFO_BIAS: prefer positions to the right
       max_pos = i;
+      used = next;
+    }
   }
   *best_out = best;
+  *used_out = used;  // information of the position actually chosen (what the node stores, icm.cc:1156)
   return max_pos;
 }
 
@@ -282,8 +287,9 @@ extern "C" int gmg_trainer_finish_level(gmg_trainer* t, int level) {
           sum += nc[k];
           final_ct[j] += nc[k];
         }
-      double best;
-      int max_pos = choose_position(nc, W, sum, &best);
+      double best, used;
+      int max_pos = choose_position(nc, W, sum, &best, &used);
+      t->mut_info[(size_t)f * N + sub] = (float)(level == 0 ? best : used);  // root keeps the maximum (icm.cc:1438)
       if (level == 0) {
         // float arithmetic (icm.cc:1411-1413)
         for (int j = 0; j < 4; j++) pr[j] = ((float)final_ct[j] + float(0.001 / 4)) / float(sum + 0.001);
@@ -329,7 +335,9 @@ extern "C" int gmg_trainer_finish(gmg_trainer* t, gmg_icm** out) {
   GMG_CHECK(t->next_level == t->D + 1, "gmg_trainer_finish: only %d of %d levels built", t->next_level, t->D + 1);
   std::vector<float> logs(t->prob.size());
   for (size_t i = 0; i < logs.size(); i++) logs[i] = (t->prob[i] > 0.0f) ? logf(t->prob[i]) : -FLT_MAX;
-  return gmg_icm_from_tables(t->ctx, t->W, t->D, t->P, t->mip.data(), logs.data(), out);
+  if (gmg_icm_from_tables(t->ctx, t->W, t->D, t->P, t->mip.data(), logs.data(), out)) return 1;
+  (*out)->mut_info = t->mut_info;
+  return 0;
 }
 
 extern "C" int gmg_icm_train(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_allreduce_fn ar,

@@ -78,6 +78,7 @@ def lib():
         "gmg_icm_write": (i32, [vp, C.c_char_p]),
         "gmg_icm_dims": (i32, [vp, vp]),
         "gmg_icm_tables": (i32, [vp, vp, vp]),
+        "gmg_icm_mut_info": (i32, [vp, vp]),
         "gmg_icm_free": (None, [vp]),
         "gmg_seqset_create": (i32, [vp, vp, vp, i64, vp, P(vp)]),
         "gmg_seqset_create_device": (i32, [vp, vp, vp, i64, vp, P(vp)]),

@@ -118,6 +118,10 @@ int gmg_icm_write(const gmg_icm* m, const char* path);
 /* {model_len, model_depth, periodicity, num_nodes}  (Get_Model_Len / Get_Periodicity) */
 int gmg_icm_dims(const gmg_icm* m, int32_t dims[4]);
 int gmg_icm_tables(const gmg_icm* m, int16_t* h_mip, float* h_prob);
+/* ICM_Score_Node_t::mut_info (icm.hh:106-113, STORE_MUT_INFO): [P][N] floats, the mutual information of each
+ * node's branch position as stored by Train_Model (icm.cc:1156,1438); 0 for models read from a file (the
+ * binary format does not carry it, icm.cc:614-727).  Only the text form of ICM_t::Output prints it. */
+int gmg_icm_mut_info(const gmg_icm* m, float* h_out);
 void gmg_icm_free(gmg_icm* m);
 
 /* ---- sequence batches -------------------------------------------------------------- */

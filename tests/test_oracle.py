@@ -199,3 +199,22 @@ def test_training_bit_identical_to_reference_library(tmp_path):
             g = L.orc_icm_read(os.path.join(G, "NC_000915.icm").encode())
             assert (O.icm_tables(m)[0] == O.icm_tables(g)[0]).all()
         R.ref_icm_train_free(r)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_reference_build_reproduces_golden_predict(tmp_path):
+    """The unmodified reference compiled by oracle/Makefile reproduces the repository's own golden .predict
+    (sample-run/glimmer3, 1 549 gene lines) -- this is what makes oracle/_ref a valid parity anchor."""
+    import gzip
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "bin", "glimmer3")
+    if not os.path.exists(exe):
+        pytest.skip("reference glimmer3 not built")
+    g = os.path.join(root, "tests", "golden")
+    fna = tmp_path / "g.fna"
+    fna.write_bytes(gzip.open(os.path.join(g, "NC_000915.fna.gz"), "rb").read())
+    r = subprocess.run([exe, "-u", "-12", "-m", os.path.join(g, "NC_000915.icm"), str(fna), str(tmp_path / "out")],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0
+    assert open(tmp_path / "out.predict", "rb").read() == gzip.open(os.path.join(g, "NC_000915.run1.predict.gz"), "rb").read()
