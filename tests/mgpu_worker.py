@@ -29,7 +29,7 @@ def main():
     with torch.cuda.stream(stream):
         ctx = g.Context(local, stream.cuda_stream)
         # ---- (1) training ----
-        strs = [s.lower().encode() for _, s in O.read_fasta(os.path.join(G, "NC_000915.train.gz"))]
+        strs = [s.lower() for _, s in O.read_fasta(os.path.join(G, "NC_000915.train.gz"))]
         mine = [strs[i] for i in shard.round_robin(len(strs), rank, world)]
         m = g.ICMTraining(ctx, 12, 7, 3).Train_Model(mine, reverse=True, allreduce=shard.torch_allreduce(local))
         mip, prob = m.tables()
@@ -41,11 +41,11 @@ def main():
             alone = g.ICMTraining(ctx, 12, 7, 3).Train_Model(strs, reverse=True)
             amip, aprob = alone.tables()
             assert amip.tobytes() + aprob.tobytes() == blob, "sharded training differs from single-GPU training"
-            rev = [s.decode()[::-1] for s in strs]
+            rev = [s[::-1] for s in strs]
             omip, oprob = O.icm_tables(O.lib().orc_icm_train(O.cstr_array(rev), len(rev), 12, 7, 3))
             assert (omip == mip).all() and (oprob.view(np.uint32) == prob.view(np.uint32)).all(), "differs from the oracle"
         # ---- (2) scoring ----
-        reads = [s.encode() for _, s in O.read_fasta(os.path.join(G, "seqs.fa.gz"))[:200]]
+        reads = [s for _, s in O.read_fasta(os.path.join(G, "seqs.fa.gz"))[:200]]
         off = np.zeros(len(reads) + 1, np.int64)
         off[1:] = np.cumsum([len(r) for r in reads])
         cut = shard.balanced_ranges(off, world)
