@@ -76,6 +76,8 @@ struct gmg_ctx {
   void* scratch[8];
   size_t scratch_bytes[8];
   double* h_penalty;  // pinned staging
+  int64_t* h_scalars;  // pinned: small device -> host results (totals) that must not serialise the stream
+  cudaEvent_t ev_scalars;
   // per-kernel device timing (gmg_ctx_profile): event pairs around the launches of each kernel class
   int prof_on;
   int prof_n[GMG_NPROF];

@@ -61,6 +61,8 @@ extern "C" int gmg_ctx_create(int device, void* stream, gmg_ctx** out) {
     unsigned long long keep = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
+  GMG_CUDA(cudaMallocHost(&c->h_scalars, 16 * sizeof(int64_t)));
+  GMG_CUDA(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -81,6 +83,8 @@ extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
   for (int i = 0; i < 8; i++)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->h_penalty) cudaFreeHost(c->h_penalty);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->ev_scalars) cudaEventDestroy(c->ev_scalars);
   for (int k = 0; k < GMG_NPROF; k++)
     for (int i = 0; i < GMG_PROF_RING; i++)
       for (int e = 0; e < 2; e++)

@@ -778,13 +778,18 @@ __device__ bool orf_rev_closed(const uint2* __restrict__ cb, int64_t nwc, int64_
   return true;
 }
 
-// kWrite = false: per-CTA ORF counts.  kWrite = true: ORF records at block_base[blockIdx] + in-block rank.
-template <bool kWrite>
+// kMode 0: per-CTA ORF counts only.  kMode 1: ORF records at block_base[blockIdx] + in-block rank (second pass).
+// kMode 2: single pass -- per-CTA counts AND the records staged at slot blockIdx * ORF_STAGE_CAP + rank (a CTA with
+// more than ORF_STAGE_CAP ORFs raises *overflow and the caller re-runs the batch as two passes); k_orfs_compact
+// then moves the staged records to their final, scan-ordered places.
+#define ORF_STAGE_CAP 64
+template <int kMode>
 __global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words, const uint2* __restrict__ cb,
                                               int64_t nwc, const int64_t* __restrict__ off,
                                               const int32_t* __restrict__ blk2seq, int64_t total, DevParams P,
                                               int64_t* __restrict__ block_counts, const int64_t* __restrict__ block_base,
-                                              gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
+                                              gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq,
+                                              int* __restrict__ overflow) {
   typedef cub::BlockScan<int, 256> Scan;
   __shared__ typename Scan::TempStorage tmp;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -820,15 +825,40 @@ __global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words
   }
   int rank, block_total;
   Scan(tmp).ExclusiveSum(n, rank, block_total);
-  if (kWrite) {
+  if (kMode == 1) {
     const int64_t base = block_base[blockIdx.x] + rank;
     for (int k = 0; k < n; k++) {
       orfs[base + k] = rec[k];
       orf_seq[base + k] = sq;
     }
-  } else if (threadIdx.x == 0) {
-    block_counts[blockIdx.x] = block_total;
+  } else {
+    if (kMode == 2 && block_total <= ORF_STAGE_CAP) {
+      const int64_t base = (int64_t)blockIdx.x * ORF_STAGE_CAP + rank;
+      for (int k = 0; k < n; k++) {
+        orfs[base + k] = rec[k];
+        orf_seq[base + k] = sq;
+      }
+    }
+    if (threadIdx.x == 0) {
+      block_counts[blockIdx.x] = block_total;
+      if (kMode == 2 && block_total > ORF_STAGE_CAP) *overflow = 1;
+    }
   }
+}
+
+// staged records of CTA b -> orfs[block_base[b] ..): ORF_STAGE_CAP threads per CTA of k_orfs<2>
+__global__ void __launch_bounds__(256) k_orfs_compact(const gmg_orf* __restrict__ st_orfs,
+                                                      const int32_t* __restrict__ st_seq,
+                                                      const int64_t* __restrict__ block_base, int64_t nblk,
+                                                      gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = g / ORF_STAGE_CAP;
+  const int t = (int)(g % ORF_STAGE_CAP);
+  if (b >= nblk) return;
+  const int64_t lo = block_base[b];
+  if (t >= block_base[b + 1] - lo) return;
+  orfs[lo + t] = st_orfs[g];
+  orf_seq[lo + t] = st_seq[g];
 }
 
 // first ORF of every sequence (orf_seq is sorted): lower bound
@@ -905,20 +935,37 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   int64_t* counts = (int64_t*)d_counts;
   int64_t* bases = counts + nblk + 1;
   GMG_CUDA(cudaMemsetAsync(counts + nblk, 0, sizeof(int64_t), ctx->stream));
+  // single pass: records staged per CTA (ORF_STAGE_CAP slots each), counted, scanned, compacted
+  void *d_stage;
+  const size_t stage_slots = (size_t)nblk * ORF_STAGE_CAP;
+  if (gmg_scratch(ctx, SCR_TMP2, stage_slots * (sizeof(gmg_orf) + sizeof(int32_t)) + 16, &d_stage)) return 1;
+  gmg_orf* st_orfs = (gmg_orf*)d_stage;
+  int32_t* st_seq = (int32_t*)(st_orfs + stage_slots);
+  int* d_overflow = (int*)(st_seq + stage_slots);
+  GMG_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orfs<false><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq,
-                                                         s->total, dp, counts, NULL, NULL, NULL);
+  k_orfs<2><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total, dp,
+                                                     counts, NULL, st_orfs, st_seq, d_overflow);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   if (exclusive_sum_i64(ctx, counts, bases, nblk + 1)) return 1;
-  int64_t total_orfs = 0;
-  GMG_CUDA(cudaMemcpyAsync(&total_orfs, bases + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_scalars[2] = 0;
+  ctx->h_scalars[3] = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[2], bases + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[3], d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t total_orfs = ctx->h_scalars[2];
+  const char* two_pass = getenv("GMG_ORF_TWO_PASS");  // test hook: take the overflow path
+  const bool overflow = (ctx->h_scalars[3] & 0xffffffff) != 0 || (two_pass && atoi(two_pass));
   if (ensure_orf_capacity(s, total_orfs)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orfs<true><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq,
-                                                        s->total, dp, NULL, bases, s->d_orfs, s->d_orf_seq);
+  if (!overflow)
+    k_orfs_compact<<<(unsigned)((stage_slots + 255) / 256), 256, 0, ctx->stream>>>(st_orfs, st_seq, bases, nblk, s->d_orfs,
+                                                                                 s->d_orf_seq);
+  else  // some CTA found more ORFs than it could stage: write pass over the whole batch
+    k_orfs<1><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total,
+                                                       dp, NULL, bases, s->d_orfs, s->d_orf_seq, NULL);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
@@ -1959,8 +2006,6 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   if (n_starts) *n_starts = 0;
   if (s->n_orfs == 0) return 0;
   if (ensure_codon_bits(ctx, s, cs)) return 1;
-  float* planes;
-  if (launch_k1(ctx, gene, s, &planes)) return 1;
   // Static exactness certificate: every term is a float of the two models, i.e. an integer multiple of
   // 2^gexp (gexp = smallest ulp exponent over both tables); every sum formed for an ORF -- and every partial sum of
   // the reference's serial accumulation -- has at most orf_len + 4 tiles of terms, each bounded by max|gene| +
@@ -1980,6 +2025,31 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   }
   const bool exact = exact_len >= 0;
   GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
+  // Start counts first: they only need the codon bitmaps, and the host has to learn the total before it can size
+  // the output.  The total travels to pinned memory behind an event, so the walks and sums below are already
+  // queued -- the stream never drains -- by the time the host reads it.
+  void *d_counts, *d_first;
+  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
+  if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
+  int64_t* counts = (int64_t*)d_counts;
+  int* d_maxlen = (int*)(counts + s->n_orfs + 1);
+  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+  k3_g3_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_orfs,
+                                                                            s->d_orf_seq, s->n_orfs, dp, counts,
+                                                                            (int32_t*)d_first, d_maxlen);
+  ctx->launches++;
+  gmg_prof_end(ctx, GMG_PROF_K3);
+  GMG_CUDA(cudaGetLastError());
+  if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
+  ctx->h_scalars[0] = 0;
+  ctx->h_scalars[1] = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[0], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[1], d_maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaEventRecord(ctx->ev_scalars, ctx->stream));
+
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
   double *cumc = NULL, *tileT = NULL, *heads = NULL;
   const int64_t ntiles = s->total / (3 * G3_TS) + 1, tot3 = ntiles * 3 * G3_TS;
   const int nh = (ja + 1) / 3;
@@ -1997,19 +2067,7 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     gmg_prof_end(ctx, GMG_PROF_K2);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
-  }
-  void *d_counts, *d_first;
-  if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
-  if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
-  int64_t* counts = (int64_t*)d_counts;
-  int* d_maxlen = (int*)(counts + s->n_orfs + 1);
-  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
-  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_g3_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_orfs,
-                                                                            s->d_orf_seq, s->n_orfs, dp, counts,
-                                                                            (int32_t*)d_first, d_maxlen);
-  ctx->launches++;
-  if (exact) {
+    if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
     if (ja < 16)
       k3_g3_heads<16><<<(unsigned)((s->n_orfs * 16 + 127) / 128), 128, 0, ctx->stream>>>(
           gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
@@ -2017,15 +2075,12 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
       k3_g3_heads<32><<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
           gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
     ctx->launches++;
+    gmg_prof_end(ctx, GMG_PROF_K3);
+    GMG_CUDA(cudaGetLastError());
   }
-  gmg_prof_end(ctx, GMG_PROF_K3);
-  GMG_CUDA(cudaGetLastError());
-  if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
-  int64_t total_starts = 0;
-  int max_orf_len = 0;
-  GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  GMG_CUDA(cudaMemcpyAsync(&max_orf_len, d_maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  GMG_CUDA(cudaEventSynchronize(ctx->ev_scalars));
+  const int64_t total_starts = ctx->h_scalars[0];
+  const int max_orf_len = (int)(ctx->h_scalars[1] & 0xffffffff);
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (total_starts > 0) {
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;

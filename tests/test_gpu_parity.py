@@ -277,6 +277,21 @@ def test_g3_start_lists_match_reference_dump(gm, ctx, genome):
         assert mine[o["o"]] == o["starts"], o["o"]
 
 
+def test_find_orfs_two_pass_path_gives_the_same_table(gm, ctx, reads, monkeypatch):
+    """The single-pass finder stages at most 64 ORFs per 256-base CTA; the overflow path (two passes) must give the
+    identical table."""
+    p = gm.Params(True, allow_indels=1)
+    rs = [s for _, s in reads[:300]]
+    ss = gm.SeqSet(ctx, seqs=rs)
+    ss.find_orfs(p)
+    a, aoff = ss.get_orfs()
+    monkeypatch.setenv("GMG_ORF_TWO_PASS", "1")
+    ss2 = gm.SeqSet(ctx, seqs=rs)
+    ss2.find_orfs(p)
+    b, boff = ss2.get_orfs()
+    assert len(a) > 5000 and a.tobytes() == b.tobytes() and aoff.tolist() == boff.tolist()
+
+
 @pytest.mark.parametrize("truncated", [0, 1])
 def test_g3_full_genome_matches_oracle(gm, ctx, genome, truncated):
     path = os.path.join(G, "NC_000915.icm")
