@@ -1974,6 +1974,478 @@ __global__ void __launch_bounds__(128) k3_mg_starts(const uint64_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3 (glimmer-mg), warp-cooperative form (the default): one WARP per ORF runs the same recursion with
+// warp-uniform control flow.  The frame on top of the stack is walked 32 positions (j values) at a time: every
+// lane evaluates its position -- quality gate and the two indel branch scores, start codon / truncation test --
+// and ballots turn that into three event masks (deletion branch, insertion branch, own start) which are
+// consumed in the reference's order (position descending; deletion, insertion, then the position's own start,
+// glimmer-mg.cc:1809-1856).  Runs of starts with no branch in between are written by their lanes in parallel;
+// a taken branch pushes a child frame (parameters broadcast from the branching lane) and the parent chunk is
+// re-evaluated when the child returns.  Frames live in shared memory (5 per warp); everything a lane needs is
+// a coalesced load (qualities, prefix sums) or a broadcast (stop tables).
+struct MgFrame {
+  int lo, hi, m, trunc;
+  int jtop;        // highest j of the chunk being walked
+  int cur;         // events with key (lane * 4 + phase) < cur are done; phase 0 deletion, 1 insertion, 2 own start
+  int suffix_j, n_err;
+  int first_zero;  // first_pos == 0 at the start of the chunk
+  int fresh;       // substitution pre-step not run yet
+  int err_pos[2], err_type[2];
+  double suffix_score, cbase;
+};
+
+__device__ __forceinline__ void mg_open_frame(const MgSeq& S, const DevParams& P, int frame, int end_point, MgFrame& c) {
+  const int L = S.L;
+  if (frame > 0) {
+    c.hi = end_point;
+    const int e = end_point - 1;
+    c.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
+    c.m = c.hi - c.lo;
+    c.trunc = (c.lo < 3 && P.allow_truncated);
+    c.cbase = mg_cum_f(S, mod3(c.hi), c.hi);
+  } else {
+    c.lo = end_point;
+    const int e = end_point - 1;
+    c.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
+    c.m = c.hi - c.lo;
+    c.trunc = (L - (c.hi - 1) < 3 && P.allow_truncated);
+    c.cbase = mg_cum_r(S, mod3(c.lo - 1), c.lo - 2);
+  }
+  if (c.m < 0) c.m = 0;
+  c.jtop = c.m - 1;
+  c.cur = 0;
+  c.first_zero = 1;
+  c.fresh = 1;
+}
+
+__device__ __forceinline__ double mg_frame_score(const MgSeq& S, int frame, const MgFrame& c, int j) {
+  if (frame > 0) return mg_cum_f(S, mod3(c.hi), c.hi - 1 - j) - c.cbase;
+  return mg_cum_r(S, mod3(c.lo - 1), c.lo - 1 + j) - c.cbase;
+}
+
+// A LEAF call: a call that can neither branch nor substitute any further (n_err == indel_max, or a substitution
+// child) only enumerates its own starts, so one lane handles it alone: the candidate start codons are a contiguous
+// slot range of one codon-bitmap stream (k_codon_bits), counted with popcounts; only emitted positions touch
+// the prefix sums.  Most calls of an -i run are leaves (the call tree fans out ~0.1 x positions per level).
+struct MgLeaf {
+  int lo, hi, m, trunc;
+  int j_lo, j_hi, j_hs;  // eligible j (multiples of 3): j_lo..j_hi; start-codon test only for j <= j_hs
+  const uint2* st;       // bitmap stream
+  int64_t cpos;          // forward: slot(j) = (cpos - j) / 3; reverse: slot(j) = (cpos + j) / 3  (both exact)
+};
+
+__device__ __forceinline__ void mg_leaf_open(const MgSeq& S, const DevParams& P, int frame, int end_point, int suffix_j,
+                                             int lowest_j, const uint2* __restrict__ cb, int64_t nwc, MgLeaf& f) {
+  const int L = S.L;
+  const int e = end_point - 1;
+  if (frame > 0) {
+    f.hi = end_point;
+    f.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
+    f.trunc = (f.lo < 3 && P.allow_truncated);
+  } else {
+    f.lo = end_point;
+    f.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
+    f.trunc = (L - (f.hi - 1) < 3 && P.allow_truncated);
+  }
+  f.m = f.hi - f.lo;
+  if (f.m < 0) f.m = 0;
+  int jl = max(lowest_j, P.min_gene_len - 3 - suffix_j);
+  if (jl < 0) jl = 0;
+  f.j_lo = jl + (3 - jl % 3) % 3;
+  f.j_hi = (f.m - 1) >= 0 ? (f.m - 1) - (f.m - 1) % 3 : -3;
+  f.j_hs = (f.m - 3) >= 0 ? (f.m - 3) - (f.m - 3) % 3 : -3;
+  if (frame > 0) {
+    f.cpos = S.a + f.hi - 3;  // first base of the codon ending at bidx = hi-1-j is cpos - j
+    const int r = (int)(f.cpos % 3);
+    f.st = cb + (size_t)r * nwc;
+  } else {
+    f.cpos = S.a + f.lo - 1;  // first base of the reverse codon starting at bidx = lo-1+j is cpos + j
+    const int r = (int)(f.cpos % 3);
+    f.st = cb + (size_t)(3 + r) * nwc;
+  }
+}
+
+__device__ __forceinline__ bool mg_leaf_bit(const MgLeaf& f, bool fwd, int j) {
+  const int64_t sl = (fwd ? f.cpos - j : f.cpos + j) / 3;
+  return (__ldg(f.st + (sl >> 5)).x >> (int)(sl & 31)) & 1u;
+}
+
+// number of start bits at eligible j in [ja, jb] (multiples of 3, ja <= jb)
+__device__ __forceinline__ int mg_leaf_popc(const MgLeaf& f, bool fwd, int ja, int jb) {
+  const int64_t s1 = (fwd ? f.cpos - jb : f.cpos + ja) / 3, s2 = (fwd ? f.cpos - ja : f.cpos + jb) / 3;
+  const int64_t w1 = s1 >> 5, w2 = s2 >> 5;
+  const unsigned m1 = ~0u << (int)(s1 & 31), m2 = (2u << (int)(s2 & 31)) - 1u;
+  int cnt = 0;
+  for (int64_t w = w1; w <= w2; w++)
+    cnt += __popc(__ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u));
+  return cnt;
+}
+
+// Records of a leaf call in the reference's order (j descending).  out == NULL: count only.
+__device__ int mg_leaf_run(const MgSeq& S, const DevParams& P, const CodonSets& cs, int frame, const MgLeaf& f,
+                           double suffix_score, int suffix_j, int n_err, const int* err_pos, const int* err_type,
+                           gmg_start* __restrict__ out) {
+  const bool fwd = frame > 0;
+  if (f.j_hi < f.j_lo) return 0;
+  int cnt = 0;
+  int jt = f.j_hi;
+  bool state = true;  // first_pos == 0
+  double cbase = 0.0;
+  if (out) cbase = fwd ? mg_cum_f(S, mod3(f.hi), f.hi) : mg_cum_r(S, mod3(f.lo - 1), f.lo - 2);
+  auto put = [&](int j, int which, int truncated, int first) {
+    if (out) {
+      const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
+      const double raw = fwd ? mg_cum_f(S, mod3(f.hi), f.hi - j) : mg_cum_r(S, mod3(f.lo - 1), f.lo - 2 + j);  // score[j-1]
+      const double sc = ((raw - cbase) - 0.0) + suffix_score;
+      const int jj = j + 2 + suffix_j;
+      gmg_start st;
+      st.j = jj;
+      st.pos = k;
+      st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
+      st.which = which;
+      st.truncated = truncated;
+      st.first = first;
+      st.n_err = n_err;
+      st.err_pos[0] = n_err > 0 ? err_pos[0] : 0;
+      st.err_pos[1] = n_err > 1 ? err_pos[1] : 0;
+      st.err_type[0] = n_err > 0 ? err_type[0] : 0;
+      st.err_type[1] = n_err > 1 ? err_type[1] : 0;
+      out[cnt] = st;
+    }
+    cnt++;
+  };
+  auto which_at = [&](int j) -> int {
+    const int bidx = fwd ? f.hi - 1 - j : f.lo - 1 + j;
+    const int cd = fwd ? codon_fwd_ending_at(S.words, S.a, bidx) : codon_rev_starting_at(S.words, S.a, bidx);
+    return (int)cs.which[cd];
+  };
+  if (f.trunc) {  // every eligible position emits while first_pos is still 0 (glimmer-mg.cc:1836-1853)
+    while (state && jt >= f.j_lo) {
+      const bool is_start = jt <= f.j_hs && mg_leaf_bit(f, fwd, jt);
+      if (is_start) {
+        put(jt, -1, 1, 1);
+        put(jt, out ? which_at(jt) : 0, 0, 0);
+      } else {
+        put(jt, -1, 1, 1);
+      }
+      const int k = fwd ? f.lo + f.m - 2 - jt : f.lo + jt + 2;
+      if (k != 0) state = false;
+      jt -= 3;
+    }
+  }
+  const int jb = min(jt, f.j_hs);
+  if (jb < f.j_lo) return cnt;
+  if (!out) return cnt + mg_leaf_popc(f, fwd, f.j_lo, jb);
+  // write: walk the set bits in descending j
+  const int64_t s1 = (fwd ? f.cpos - jb : f.cpos + f.j_lo) / 3, s2 = (fwd ? f.cpos - f.j_lo : f.cpos + jb) / 3;
+  const int64_t w1 = s1 >> 5, w2 = s2 >> 5;
+  const unsigned m1 = ~0u << (int)(s1 & 31), m2 = (2u << (int)(s2 & 31)) - 1u;
+  for (int64_t wi = 0; wi <= w2 - w1; wi++) {
+    const int64_t w = fwd ? w1 + wi : w2 - wi;
+    unsigned x = __ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u);
+    while (x) {
+      const int b = fwd ? __ffs(x) - 1 : 31 - __clz(x);
+      x &= ~(1u << b);
+      const int64_t sl = (w << 5) + b;
+      const int64_t rr = f.cpos % 3;  // (cpos -/+ j) = 3 sl + rr
+      const int j = (int)(fwd ? f.cpos - rr - 3 * sl : 3 * sl + rr - f.cpos);
+      const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
+      put(j, which_at(j), 0, state ? 1 : 0);
+      if (k != 0) state = false;
+    }
+  }
+  return cnt;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128) k3_mg_starts_warp(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                         const gmg_orf* __restrict__ orfs,
+                                                         const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
+                                                         const double* __restrict__ cum, const int32_t* __restrict__ fwd_prev,
+                                                         const int32_t* __restrict__ rev_next, const uint8_t* __restrict__ qual,
+                                                         const double* __restrict__ tables, CodonSets cs, DevParams P,
+                                                         int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
+                                                         gmg_start* __restrict__ starts, const uint2* __restrict__ cb,
+                                                         int64_t nwc) {
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ MgFrame s_stack[4][5];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (oi >= n_orfs) return;  // warp-uniform
+  const int32_t sq = orf_seq[oi];
+  MgSeq S;
+  S.words = words;
+  S.a = off[sq];
+  S.L = (int)(off[sq + 1] - S.a);
+  S.total = total;
+  S.cum = cum;
+  S.fwd_prev = fwd_prev;
+  S.rev_next = rev_next;
+  S.qual = qual;
+  S.penalty = tables;
+  S.stop_pen = tables + 256;
+  S.codon_p = tables + 260;
+  const gmg_orf o = orfs[oi];
+  const int frame = o.frame;
+  const bool fwd = frame > 0;
+  const int lowest_j = min(3, P.min_gene_len - 3);
+  gmg_start* out = kWrite ? starts + start_off[oi] : NULL;
+  int64_t n = 0;  // records so far (warp-uniform)
+  MgFrame* stk = s_stack[wid];
+  int sp = 0;
+  MgFrame c;
+  mg_open_frame(S, P, frame, fwd ? o.stop_position - 1 : o.stop_position + 3, c);
+  c.suffix_score = 0.0;
+  c.suffix_j = 0;
+  c.n_err = 0;
+  c.err_pos[0] = c.err_pos[1] = c.err_type[0] = c.err_type[1] = 0;
+  for (;;) {
+    if (c.fresh) {
+      c.fresh = 0;
+      // substitution through the previous stop (glimmer-mg.cc:1771-1806)
+      if (P.allow_subs && c.n_err < 1) {
+        int eep, epos;
+        if (fwd) { eep = c.lo - 3; epos = c.lo - 2; }
+        else { eep = c.hi + 3; epos = c.hi + 2; }
+        if (eep >= 0 && eep - 2 < S.L) {
+          double ess = c.suffix_score + mg_pass_stop_penalty(S, P, frame, c.lo, c.hi);
+          if (c.m > 0) ess += mg_frame_score(S, frame, c, c.m - 1) - 0.0;
+          __syncwarp();
+          if (lane == 0) stk[sp] = c;
+          __syncwarp();
+          MgFrame nc;
+          mg_open_frame(S, P, frame, eep, nc);
+          nc.suffix_score = ess;
+          nc.suffix_j = c.suffix_j + c.m;
+          nc.n_err = c.n_err + 1;
+          nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
+          nc.err_pos[1] = c.err_pos[1]; nc.err_type[1] = c.err_type[1];
+          if (c.n_err == 0) { nc.err_pos[0] = epos; nc.err_type[0] = 2; }
+          else { nc.err_pos[1] = epos; nc.err_type[1] = 2; }
+          c = nc;
+          sp++;
+          continue;
+        }
+      }
+    }
+    if (c.jtop < lowest_j) {  // this call is finished
+      if (sp == 0) break;
+      sp--;
+      __syncwarp();
+      c = stk[sp];
+      continue;
+    }
+    // ---- evaluate the chunk: lane l looks at j = jtop - l ----
+    const int j = c.jtop - lane;
+    const bool valid = j >= lowest_j;
+    const int k = fwd ? c.lo + c.m - 2 - j : c.lo + j + 2;
+    const int bidx = fwd ? c.hi - 1 - j : c.lo - 1 + j;
+    const int jm3 = valid ? j % 3 : 0;
+    bool del_ok = false, ins_ok = false;
+    double ess_del = 0.0, ess_ins = 0.0;
+    double sc_prev = 0.0;  // score[j - 1] of this call
+    const bool can_branch = P.allow_indels && c.n_err < P.indel_max;
+    if (valid) {
+      const bool need_emit_score = (jm3 == 0);
+      int qv = 255;
+      if (can_branch) qv = S.qual[S.a + bidx];
+      const bool gate = can_branch && qv <= P.indel_q_thresh;
+      if (gate || need_emit_score) sc_prev = mg_frame_score(S, frame, c, j - 1);
+      if (gate) {
+        const double pen = S.penalty[qv];
+        ess_del = c.suffix_score + mg_frame_score(S, frame, c, j) - 0.0 + pen;
+        ess_ins = c.suffix_score + sc_prev - 0.0 + pen;
+        del_ok = ess_del > P.indel_suffix_thresh;
+        ins_ok = ess_ins > P.indel_suffix_thresh;
+      }
+    }
+    int which = -1;
+    bool len_ok = false;
+    if (valid && jm3 == 0) {
+      if (j <= c.m - 3) {
+        const int cd = fwd ? codon_fwd_ending_at(S.words, S.a, bidx) : codon_rev_starting_at(S.words, S.a, bidx);
+        if ((cs.start_mask >> cd) & 1) which = cs.which[cd];
+      }
+      len_ok = j + 3 + c.suffix_j >= P.min_gene_len;
+    }
+    const unsigned D = __ballot_sync(FULL, del_ok), I = __ballot_sync(FULL, ins_ok);
+    const unsigned A = __ballot_sync(FULL, len_ok && which >= 0);         // start codon that may be emitted
+    const unsigned T = __ballot_sync(FULL, len_ok && c.trunc);            // emitted while first_pos == 0
+    const unsigned Z = __ballot_sync(FULL, valid && k == 0);              // an emit here leaves first_pos == 0
+    // own starts of the chunk and their `first` flags, from the chunk-start state (glimmer-mg.cc:1836-1853)
+    unsigned EM = A, FI = 0;
+    int state = c.first_zero;
+    {
+      unsigned rem = A | T;
+      while (state && rem) {
+        const int l = __ffs(rem) - 1;
+        rem &= rem - 1;
+        EM |= 1u << l;
+        FI |= 1u << l;
+        if (!((Z >> l) & 1u)) state = 0;
+      }
+    }
+    const unsigned DB = EM & FI & A & T;  // truncated copy + real start at the same position: two records
+    // ---- children that are leaves: every lane runs its own (up to two) children, no push ----
+    {
+      const int cn = c.n_err + 1;
+      const bool child_is_leaf = !(P.allow_indels && cn < P.indel_max) && !(P.allow_subs && cn < 1);
+      if (child_is_leaf) {
+        if (D | I | EM) {
+          int eperr[2] = {c.err_pos[0], c.err_pos[1]}, etype[2] = {c.err_type[0], c.err_type[1]};
+          MgLeaf fd, fi;
+          int cnt_d = 0, cnt_i = 0;
+          const int esj = c.suffix_j + j + 2 - jm3;
+          if (del_ok) {
+            mg_leaf_open(S, P, frame, fwd ? k + jm3 : k - jm3, esj, lowest_j, cb, nwc, fd);
+            cnt_d = mg_leaf_run(S, P, cs, frame, fd, ess_del, esj, cn, eperr, etype, NULL);
+          }
+          if (ins_ok) {
+            mg_leaf_open(S, P, frame, fwd ? k - (2 - jm3) : k + 2 - jm3, esj, lowest_j, cb, nwc, fi);
+            cnt_i = mg_leaf_run(S, P, cs, frame, fi, ess_ins, esj, cn, eperr, etype, NULL);
+          }
+          const int own = ((EM >> lane) & 1u) ? (((DB >> lane) & 1u) ? 2 : 1) : 0;
+          const int tot = cnt_d + cnt_i + own;
+          int incl = tot;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+          }
+          const int all = __shfl_sync(FULL, incl, 31);
+          if (kWrite && tot) {
+            gmg_start* o = out + n + (incl - tot);
+            if (cnt_d) {
+              eperr[c.n_err] = fwd ? k + 3 : k - 1;
+              etype[c.n_err] = 1;
+              mg_leaf_run(S, P, cs, frame, fd, ess_del, esj, cn, eperr, etype, o);
+              o += cnt_d;
+            }
+            if (cnt_i) {
+              eperr[c.n_err] = fwd ? k + 2 : k - 2;
+              etype[c.n_err] = 0;
+              mg_leaf_run(S, P, cs, frame, fi, ess_ins, esj, cn, eperr, etype, o);
+              o += cnt_i;
+            }
+            if (own) {
+              const double sc = (sc_prev - 0.0) + c.suffix_score;
+              const int jj = j + 2 + c.suffix_j;
+              const int first = (FI >> lane) & 1u;
+              gmg_start st;
+              st.j = jj;
+              st.pos = k;
+              st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
+              st.n_err = c.n_err;
+              st.err_pos[0] = c.n_err > 0 ? c.err_pos[0] : 0;
+              st.err_pos[1] = c.n_err > 1 ? c.err_pos[1] : 0;
+              st.err_type[0] = c.n_err > 0 ? c.err_type[0] : 0;
+              st.err_type[1] = c.n_err > 1 ? c.err_type[1] : 0;
+              if (own == 2) {
+                st.which = -1; st.truncated = 1; st.first = first;
+                o[0] = st;
+                st.which = which; st.truncated = 0; st.first = 0;
+                o[1] = st;
+              } else {
+                st.which = which; st.truncated = which < 0; st.first = first;
+                o[0] = st;
+              }
+            }
+          }
+          n += all;
+        }
+        c.jtop -= 32;
+        c.cur = 0;
+        c.first_zero = state;
+        continue;
+      }
+    }
+    // ---- consume events from the cursor on ----
+    bool pushed = false;
+    for (;;) {
+      const int cl = c.cur >> 2, cp = c.cur & 3;
+      const unsigned ge = cl >= 32 ? 0u : (FULL << cl);          // lanes >= cursor lane
+      const unsigned gt = cl >= 31 ? 0u : (FULL << (cl + 1));    // lanes > cursor lane
+      const unsigned Dr = D & (cp <= 0 ? ge : gt), Ir = I & (cp <= 1 ? ge : gt), Er = EM & (cp <= 2 ? ge : gt);
+      const unsigned Br = Dr | Ir;
+      if (!(Br | Er)) break;
+      const int lb = Br ? __ffs(Br) - 1 : 32, le = Er ? __ffs(Er) - 1 : 32;
+      if (le < lb) {
+        // run of own starts before the next branch: lanes le .. lb-1 of Er write their records in parallel
+        const unsigned run = Er & (lb >= 32 ? FULL : ((1u << lb) - 1u));
+        const unsigned below = (1u << lane) - 1u;
+        if ((run >> lane) & 1u) {
+          const int64_t at = n + __popc(run & below) + __popc(run & DB & below);
+          if (kWrite) {
+            const double sc = (sc_prev - 0.0) + c.suffix_score;
+            const int jj = j + 2 + c.suffix_j;
+            const int first = (FI >> lane) & 1u;
+            gmg_start st;
+            st.j = jj;
+            st.pos = k;
+            st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
+            st.n_err = c.n_err;
+            st.err_pos[0] = c.n_err > 0 ? c.err_pos[0] : 0;
+            st.err_pos[1] = c.n_err > 1 ? c.err_pos[1] : 0;
+            st.err_type[0] = c.n_err > 0 ? c.err_type[0] : 0;
+            st.err_type[1] = c.n_err > 1 ? c.err_type[1] : 0;
+            if ((DB >> lane) & 1u) {
+              st.which = -1; st.truncated = 1; st.first = first;
+              out[at] = st;
+              st.which = which; st.truncated = 0; st.first = 0;
+              out[at + 1] = st;
+            } else {
+              st.which = which; st.truncated = which < 0; st.first = first;
+              out[at] = st;
+            }
+          }
+        }
+        n += __popc(run) + __popc(run & DB);
+        c.cur = (31 - __clz(run)) * 4 + 3;
+        continue;
+      }
+      // branch at lane lb: deletion first, then insertion
+      const bool is_del = (Dr >> lb) & 1u;
+      const int ph = is_del ? 0 : 1;
+      const int bj = c.jtop - lb;
+      const int bk = fwd ? c.lo + c.m - 2 - bj : c.lo + bj + 2;
+      const int b3 = bj % 3;
+      const double ess = __shfl_sync(FULL, is_del ? ess_del : ess_ins, lb);
+      int eep, epos;
+      if (ph == 0) {  // deletion
+        eep = fwd ? bk + b3 : bk - b3;
+        epos = fwd ? bk + 3 : bk - 1;
+      } else {        // insertion
+        eep = fwd ? bk - (2 - b3) : bk + 2 - b3;
+        epos = fwd ? bk + 2 : bk - 2;
+      }
+      c.cur = lb * 4 + ph + 1;
+      __syncwarp();
+      if (lane == 0) stk[sp] = c;
+      __syncwarp();
+      MgFrame nc;
+      mg_open_frame(S, P, frame, eep, nc);
+      nc.suffix_score = ess;
+      nc.suffix_j = c.suffix_j + bj + 2 - b3;
+      nc.n_err = c.n_err + 1;
+      nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
+      nc.err_pos[1] = c.err_pos[1]; nc.err_type[1] = c.err_type[1];
+      if (c.n_err == 0) { nc.err_pos[0] = epos; nc.err_type[0] = (ph == 0) ? 1 : 0; }
+      else { nc.err_pos[1] = epos; nc.err_type[1] = (ph == 0) ? 1 : 0; }
+      c = nc;
+      sp++;
+      pushed = true;
+      break;
+    }
+    if (pushed) continue;
+    // chunk done: next 32 positions
+    c.jtop -= 32;
+    c.cur = 0;
+    c.first_zero = state;
+  }
+  if (!kWrite && lane == 0) counts[oi] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host drivers of the two scoring halves
 
 static int ensure_start_capacity(gmg_seqset* s, int64_t n) {
@@ -2116,6 +2588,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   s->uncertified = 0;
   if (n_starts) *n_starts = 0;
   if (s->n_orfs == 0) return 0;
+  if (ensure_codon_bits(ctx, s, cs)) return 1;  // start-codon bitmaps for the leaf calls of K3
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
   // K2
@@ -2159,6 +2632,13 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
   unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+  static const int k3mg_mode = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : 0;  // 0 warp per ORF, 1 thread per ORF
+  const unsigned g3w = (unsigned)((s->n_orfs * 32 + 127) / 128);
+  if (k3mg_mode == 0)
+    k3_mg_starts_warp<false><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                          (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs,
+                                                          dp, counts, NULL, NULL, s->d_cbits, s->nwc);
+  else
   k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
                                                    (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
                                                    counts, NULL, NULL);
@@ -2175,6 +2655,11 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   s->uncertified = bad;
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+  if (k3mg_mode == 0)
+    k3_mg_starts_warp<true><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                         (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs,
+                                                         dp, NULL, s->d_start_off, s->d_starts, s->d_cbits, s->nwc);
+  else
   k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
                                                   (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
                                                   NULL, s->d_start_off, s->d_starts);
