@@ -567,7 +567,7 @@ def run_b200_reads(args, kind):
             sets.append(ss)
         bases = [int(b[1][-1]) for b in batches]
         n_starts = 0
-        for i in range(Wu):
+        for i in range(max(Wu, nb)):  # every resident batch once: its start-list buffers exist before the timed steps
             j = i % nb
             n_starts = sets[j].score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
         ctx.sync()

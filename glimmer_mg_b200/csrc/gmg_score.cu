@@ -2158,7 +2158,7 @@ __device__ int mg_leaf_run(const MgSeq& S, const DevParams& P, const CodonSets& 
 }
 
 template <bool kWrite>
-__global__ void __launch_bounds__(128) k3_mg_starts_warp(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+__global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
                                                          const gmg_orf* __restrict__ orfs,
                                                          const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
                                                          const double* __restrict__ cum, const int32_t* __restrict__ fwd_prev,
@@ -2246,7 +2246,7 @@ __global__ void __launch_bounds__(128) k3_mg_starts_warp(const uint64_t* __restr
     double sc_prev = 0.0;  // score[j - 1] of this call
     const bool can_branch = P.allow_indels && c.n_err < P.indel_max;
     if (valid) {
-      const bool need_emit_score = (jm3 == 0);
+      const bool need_emit_score = kWrite && (jm3 == 0);  // the counting pass never needs a start's score
       int qv = 255;
       if (can_branch) qv = S.qual[S.a + bidx];
       const bool gate = can_branch && qv <= P.indel_q_thresh;
@@ -2293,17 +2293,18 @@ __global__ void __launch_bounds__(128) k3_mg_starts_warp(const uint64_t* __restr
       if (child_is_leaf) {
         if (D | I | EM) {
           int eperr[2] = {c.err_pos[0], c.err_pos[1]}, etype[2] = {c.err_type[0], c.err_type[1]};
-          MgLeaf fd, fi;
-          int cnt_d = 0, cnt_i = 0;
+          int cnt_b[2] = {0, 0};  // records of the deletion child, of the insertion child
           const int esj = c.suffix_j + j + 2 - jm3;
-          if (del_ok) {
-            mg_leaf_open(S, P, frame, fwd ? k + jm3 : k - jm3, esj, lowest_j, cb, nwc, fd);
-            cnt_d = mg_leaf_run(S, P, cs, frame, fd, ess_del, esj, cn, eperr, etype, NULL);
+#pragma unroll 1
+          for (int ph = 0; ph < 2; ph++) {
+            if (ph == 0 ? del_ok : ins_ok) {
+              MgLeaf lf;
+              const int eep = ph == 0 ? (fwd ? k + jm3 : k - jm3) : (fwd ? k - (2 - jm3) : k + 2 - jm3);
+              mg_leaf_open(S, P, frame, eep, esj, lowest_j, cb, nwc, lf);
+              cnt_b[ph] = mg_leaf_run(S, P, cs, frame, lf, 0.0, esj, cn, eperr, etype, NULL);
+            }
           }
-          if (ins_ok) {
-            mg_leaf_open(S, P, frame, fwd ? k - (2 - jm3) : k + 2 - jm3, esj, lowest_j, cb, nwc, fi);
-            cnt_i = mg_leaf_run(S, P, cs, frame, fi, ess_ins, esj, cn, eperr, etype, NULL);
-          }
+          const int cnt_d = cnt_b[0], cnt_i = cnt_b[1];
           const int own = ((EM >> lane) & 1u) ? (((DB >> lane) & 1u) ? 2 : 1) : 0;
           const int tot = cnt_d + cnt_i + own;
           int incl = tot;
@@ -2315,17 +2316,17 @@ __global__ void __launch_bounds__(128) k3_mg_starts_warp(const uint64_t* __restr
           const int all = __shfl_sync(FULL, incl, 31);
           if (kWrite && tot) {
             gmg_start* o = out + n + (incl - tot);
-            if (cnt_d) {
-              eperr[c.n_err] = fwd ? k + 3 : k - 1;
-              etype[c.n_err] = 1;
-              mg_leaf_run(S, P, cs, frame, fd, ess_del, esj, cn, eperr, etype, o);
-              o += cnt_d;
-            }
-            if (cnt_i) {
-              eperr[c.n_err] = fwd ? k + 2 : k - 2;
-              etype[c.n_err] = 0;
-              mg_leaf_run(S, P, cs, frame, fi, ess_ins, esj, cn, eperr, etype, o);
-              o += cnt_i;
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ph++) {
+              if (cnt_b[ph]) {
+                MgLeaf lf;
+                const int eep = ph == 0 ? (fwd ? k + jm3 : k - jm3) : (fwd ? k - (2 - jm3) : k + 2 - jm3);
+                mg_leaf_open(S, P, frame, eep, esj, lowest_j, cb, nwc, lf);
+                eperr[c.n_err] = ph == 0 ? (fwd ? k + 3 : k - 1) : (fwd ? k + 2 : k - 2);
+                etype[c.n_err] = ph == 0 ? 1 : 0;
+                mg_leaf_run(S, P, cs, frame, lf, ph == 0 ? ess_del : ess_ins, esj, cn, eperr, etype, o);
+                o += cnt_b[ph];
+              }
             }
             if (own) {
               const double sc = (sc_prev - 0.0) + c.suffix_score;
