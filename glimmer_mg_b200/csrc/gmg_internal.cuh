@@ -78,6 +78,8 @@ struct gmg_ctx {
   double* h_penalty;  // pinned staging
   int64_t* h_scalars;  // pinned: small device -> host results (totals) that must not serialise the stream
   cudaEvent_t ev_scalars;
+  void* h_stage;       // pinned staging for larger device -> host results (training count slabs), grown on demand
+  size_t h_stage_bytes;
   // per-kernel device timing (gmg_ctx_profile): event pairs around the launches of each kernel class
   int prof_on;
   int prof_n[GMG_NPROF];

@@ -84,6 +84,7 @@ extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->h_penalty) cudaFreeHost(c->h_penalty);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev_scalars) cudaEventDestroy(c->ev_scalars);
   for (int k = 0; k < GMG_NPROF; k++)
     for (int i = 0; i < GMG_PROF_RING; i++)

@@ -37,6 +37,8 @@ struct gmg_trainer {
   size_t counts_cap;
   std::vector<int32_t> h_counts;
   int next_level;
+  unsigned* d_hist;          // [P][4^W] windows by (frame, content): built once, walked by every level (large sets)
+  int hist_ready;
 };
 
 static inline int64_t level_nodes(int level) {
@@ -108,6 +110,97 @@ __global__ void __launch_bounds__(512) k4_count(const uint64_t* __restrict__ wor
   }
 }
 
+// ---- large training sets: one pass over the strings, then every level walks the DISTINCT windows -------------
+// hist[f][window content] = number of training windows of frame f with that content (W <= 12: 3 * 4^12 cells =
+// 201 MB).  A level pass then visits one cell per thread instead of one window per thread -- 10x fewer walks at
+// 500 Mbp -- and adds the cell's multiplicity.  Counts are sums of the same +1 events, so the slab is identical.
+__global__ void __launch_bounds__(512) k4_hist_build(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                     const int32_t* __restrict__ blk2seq, int64_t total, int W, int P,
+                                                     int reverse, unsigned* __restrict__ hist) {
+  const int wp = W % P;
+  const size_t cells = (size_t)1 << (2 * W);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s = __ldg(blk2seq + (p >> 5)) & 0x7FFFFFFF;
+    while (p >= __ldg(off + s + 1)) s++;
+    const int64_t a = __ldg(off + s);
+    const int len = (int)(__ldg(off + s + 1) - a);
+    const int q = (int)(p - a);
+    uint64_t ctx;
+    int t;
+    if (!reverse) {
+      if (q + W > len) continue;
+      t = q;
+      ctx = gmg_extract32(words, p);
+    } else {
+      if (q - (W - 1) < 0) continue;
+      t = len - 1 - q;
+      ctx = gmg_reverse_bases(gmg_extract32(words, p - (W - 1)), W);
+    }
+    const int f = (wp + t) % P;
+    atomicAdd(hist + (size_t)f * cells + (size_t)(ctx & (cells - 1)), 1u);
+  }
+}
+
+// One thread per histogram cell.  Consecutive cells differ only in window positions 0..2 (bits 0..5), so the 32
+// cells of a warp usually land in the same node and share the bases at positions >= 3 and the predicted base:
+// those W-1-3 counters get ONE atomic per warp (the warp's summed multiplicity); positions 0..2 add per lane.
+template <bool kSmem>
+__global__ void __launch_bounds__(512) k4_hist_level(const unsigned* __restrict__ hist, int W, int P, int N, int level,
+                                                     int first_node, int nodes_on_level, const int8_t* __restrict__ mip,
+                                                     int* __restrict__ counts, int slab, int copies) {
+  extern __shared__ int s_cnt[];
+  if (kSmem) {
+    for (int i = threadIdx.x; i < slab * copies; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+  }
+  int* mine = kSmem ? s_cnt + ((threadIdx.x >> 5) % copies) * slab : counts;
+  const int64_t cells = (int64_t)1 << (2 * W);
+  const int64_t all = cells * P;
+  const int lane = threadIdx.x & 31;
+  for (int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; g0 < all; g0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = g0 + lane;  // cells is a multiple of 32: a warp never straddles two frames
+    const unsigned cnt = __ldg(hist + g);
+    if (__ballot_sync(0xffffffffu, cnt != 0) == 0) continue;
+    const int f = (int)(g / cells);
+    const uint64_t ctx = (uint64_t)(g - (int64_t)f * cells);
+    int node = 0;
+    bool ok = true;
+    const int8_t* mf = mip + (size_t)f * N;
+    for (int i = 0; i < level; i++) {
+      const int j = mf[node];
+      if (j < 0) {
+        ok = false;
+        break;
+      }
+      node = 4 * node + (int)((ctx >> (2 * j)) & 3) + 1;
+    }
+    const int last = (int)((ctx >> (2 * (W - 1))) & 3);
+    const int c = ok ? (int)cnt : 0;
+    int* row = mine + ((size_t)f * nodes_on_level + (ok ? node - first_node : 0)) * (W - 1) * 16 + last;
+    const int node0 = __shfl_sync(0xffffffffu, ok ? node : -1, 0);
+    const bool uniform = __all_sync(0xffffffffu, (ok ? node : -1) == node0);
+    if (uniform) {
+      if (node0 < 0) continue;
+      const int sum = __reduce_add_sync(0xffffffffu, c);
+      const int lo = W - 1 < 3 ? W - 1 : 3;
+      if (c)
+        for (int i = 0; i < lo; i++) atomicAdd(row + i * 16 + 4 * (int)((ctx >> (2 * i)) & 3), c);
+      if (lane == 0 && sum)
+        for (int i = 3; i < W - 1; i++) atomicAdd(row + i * 16 + 4 * (int)((ctx >> (2 * i)) & 3), sum);
+    } else if (c) {
+      for (int i = 0; i < W - 1; i++) atomicAdd(row + i * 16 + 4 * (int)((ctx >> (2 * i)) & 3), c);
+    }
+  }
+  if (kSmem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < slab; i += blockDim.x) {
+      int v = 0;
+      for (int c = 0; c < copies; c++) v += s_cnt[c * slab + i];
+      if (v) atomicAdd(counts + i, v);
+    }
+  }
+}
+
 extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_trainer** out) {
   GMG_CHECK(ctx && s && out, "gmg_trainer_create: NULL argument");
   GMG_CHECK(w >= 2 && w <= GMG_MAX_W, "training: model_len %d unsupported (2..%d)", w, GMG_MAX_W);
@@ -125,11 +218,20 @@ extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int
   t->d_counts = NULL;
   t->counts_cap = 0;
   t->next_level = 0;
+  t->d_hist = NULL;
+  t->hist_ready = 0;
   GMG_CUDA(cudaSetDevice(ctx->device));
   GMG_CUDA(cudaMalloc(&t->d_mip, (size_t)p * t->N));
   GMG_CUDA(cudaMemsetAsync(t->d_mip, 0xFF, (size_t)p * t->N, ctx->stream));
+  // the count slab (and the window histogram) live in the context's scratch: no cudaMalloc / cudaFree per model
   size_t cap = (size_t)p * level_nodes(d) * (w - 1) * 16;
-  GMG_CUDA(cudaMalloc(&t->d_counts, cap * sizeof(int32_t)));
+  void* d_slab;
+  if (gmg_scratch(ctx, SCR_TMP, cap * sizeof(int32_t), &d_slab)) {
+    cudaFree(t->d_mip);
+    delete t;
+    return 1;
+  }
+  t->d_counts = (int32_t*)d_slab;
   t->counts_cap = cap;
   *out = t;
   return 0;
@@ -140,7 +242,6 @@ extern "C" void gmg_trainer_free(gmg_trainer* t) {
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->ctx->stream);
   if (t->d_mip) cudaFree(t->d_mip);
-  if (t->d_counts) cudaFree(t->d_counts);
   delete t;
 }
 
@@ -153,7 +254,49 @@ extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_count
   const int64_t nl = level_nodes(level);
   const int64_t slab = (int64_t)t->P * nl * (t->W - 1) * 16;
   GMG_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)slab * sizeof(int32_t), ctx->stream));
-  if (s->total > 0) {
+  // window histogram for large sets (W <= 12): GMG_K4_HIST=0/1 forces the direct / histogram path (tests)
+  const char* hist_env = getenv("GMG_K4_HIST");
+  const int hist_mode = hist_env ? atoi(hist_env) : -1;
+  const bool use_hist = t->W <= 12 && (hist_mode == 1 || (hist_mode < 0 && s->total >= ((int64_t)t->P << (2 * t->W)) * 2));
+  if (s->total > 0 && use_hist) {
+    const size_t cells = (size_t)t->P << (2 * t->W);
+    const int threads = 512;
+    if (gmg_prof_begin(ctx, GMG_PROF_K4)) return 1;
+    if (!t->hist_ready) {
+      if (!t->d_hist) {
+        void* d_h;
+        if (gmg_scratch(ctx, SCR_CUM, cells * sizeof(unsigned), &d_h)) return 1;
+        t->d_hist = (unsigned*)d_h;
+      }
+      GMG_CUDA(cudaMemsetAsync(t->d_hist, 0, cells * sizeof(unsigned), ctx->stream));
+      int64_t need = (s->total + threads - 1) / threads;
+      int64_t cap = (int64_t)ctx->sm_count * 4;
+      k4_hist_build<<<(int)(need < cap ? need : cap), threads, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_blk2seq, s->total,
+                                                                              t->W, t->P, t->reverse, t->d_hist);
+      ctx->launches++;
+      t->hist_ready = 1;
+    }
+    const size_t smem_budget = 200 * 1024;
+    const bool use_smem = (size_t)slab * sizeof(int) <= smem_budget;
+    int64_t need = ((int64_t)cells + threads - 1) / threads;
+    if (use_smem) {
+      int copies = (int)(smem_budget / ((size_t)slab * sizeof(int)));
+      if (copies > threads / 32) copies = threads / 32;
+      if (copies < 1) copies = 1;
+      size_t smem = (size_t)slab * copies * sizeof(int);
+      GMG_CUDA(cudaFuncSetAttribute(k4_hist_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);
+      k4_hist_level<true><<<grid, threads, smem, ctx->stream>>>(t->d_hist, t->W, t->P, t->N, level, (int)first_node_of(level),
+                                                               (int)nl, t->d_mip, t->d_counts, (int)slab, copies);
+    } else {
+      int64_t cap = (int64_t)ctx->sm_count * 4;
+      k4_hist_level<false><<<(int)(need < cap ? need : cap), threads, 0, ctx->stream>>>(
+          t->d_hist, t->W, t->P, t->N, level, (int)first_node_of(level), (int)nl, t->d_mip, t->d_counts, (int)slab, 1);
+    }
+    gmg_prof_end(ctx, GMG_PROF_K4);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  } else if (s->total > 0) {
     const size_t smem_budget = 200 * 1024;
     const bool use_smem = (size_t)slab * sizeof(int) <= smem_budget;
     const int threads = 512;
@@ -263,11 +406,20 @@ extern "C" int gmg_trainer_finish_level(gmg_trainer* t, int level) {
   const int W = t->W, P = t->P, N = t->N;
   const int64_t nl = level_nodes(level), first = first_node_of(level);
   const int64_t slab = (int64_t)P * nl * (W - 1) * 16;
-  t->h_counts.resize((size_t)slab);
-  GMG_CUDA(cudaMemcpyAsync(t->h_counts.data(), t->d_counts, (size_t)slab * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                           ctx->stream));
+  // the slab comes back through the context's page-locked staging buffer (46 MB at level 7: PCIe rate instead of a
+  // pageable copy)
+  const size_t slab_bytes = (size_t)slab * sizeof(int32_t);
+  if (ctx->h_stage_bytes < slab_bytes) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = NULL;
+    ctx->h_stage_bytes = 0;
+    const size_t want = (size_t)P * level_nodes(t->D) * (W - 1) * 16 * sizeof(int32_t);  // the deepest level of this model
+    GMG_CUDA(cudaMallocHost(&ctx->h_stage, want > slab_bytes ? want : slab_bytes));
+    ctx->h_stage_bytes = want > slab_bytes ? want : slab_bytes;
+  }
+  GMG_CUDA(cudaMemcpyAsync(ctx->h_stage, t->d_counts, slab_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
-  const int32_t* C = t->h_counts.data();
+  const int32_t* C = (const int32_t*)ctx->h_stage;
   const int64_t n_items = (int64_t)P * nl;
   auto work = [&](int64_t lo, int64_t hi) {
     for (int64_t it = lo; it < hi; it++) {

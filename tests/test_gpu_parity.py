@@ -403,6 +403,27 @@ def test_training_byte_identical_to_oracle(gm, ctx, tmp_path, fasta, depth, peri
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+@pytest.mark.parametrize("period,width", [(3, 12), (1, 10)])
+def test_training_histogram_path_gives_the_same_model(gm, ctx, tmp_path, monkeypatch, period, width):
+    """Large training sets count through the (frame, window) histogram; forced on here, it must give the byte-identical
+    model file (and the same count slabs) as the direct per-window path."""
+    strs = _train_strings("seqs.cluster-5.run1.filt.gene.fasta.gz")
+    a, b = str(tmp_path / "a.icm"), str(tmp_path / "b.icm")
+    monkeypatch.setenv("GMG_K4_HIST", "0")
+    gm.ICMTraining(ctx, width, 7, period).Train_Model(strs, reverse=True).Output(a)
+    tr = gm.ICMTraining(ctx, width, 7, period).levels(strs, reverse=True)
+    ptr, n = tr.count_level(0)
+    direct0 = ctx.d2h(ptr, n, np.int32).copy()
+    tr.close()
+    monkeypatch.setenv("GMG_K4_HIST", "1")
+    gm.ICMTraining(ctx, width, 7, period).Train_Model(strs, reverse=True).Output(b)
+    tr = gm.ICMTraining(ctx, width, 7, period).levels(strs, reverse=True)
+    ptr, n = tr.count_level(0)
+    assert (ctx.d2h(ptr, n, np.int32) == direct0).all() and direct0.sum() > 0
+    tr.close()
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 def test_count_level_matches_oracle(gm, ctx):
     """K4 in isolation: the count slab of every level equals Count_Char_Pairs(_Restricted) of the oracle."""
     strs = [s[::-1] for s in _train_strings("seqs.cluster-5.run1.filt.gene.fasta.gz")]
