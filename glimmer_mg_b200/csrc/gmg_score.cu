@@ -1744,6 +1744,390 @@ __global__ void __launch_bounds__(128) k2_prefix(DevIcm indep, const uint64_t* _
   }
 }
 
+// K2, lane-serial form (the default): one warp per sequence, every lane owns FOUR consecutive positions of a
+// 128-position tile whose start is aligned to 4 bases of the batch, so that a lane's four results of one array
+// are one aligned 32-byte run (two 16-byte stores for doubles, one for the int32 stop tables, one 4-byte store
+// for qualities) and its four plane indices share one block lookup.  Sums run serially inside the lane; one warp
+// scan per class joins the 32 lane totals -- 6 FP64 scans per 128 positions instead of 24 -- and the
+// independent model is the 384-entry full-window table (lut3) in shared memory except at the two end positions.
+// Any association gives the reference's bits under the read's certificate (same statement as above).
+#define K2_R 4
+// c + i for c in 0..2, i in 0..3, reduced mod 3 without a division
+__device__ __forceinline__ int k2_add3(int c, int i) {
+  int t = c + i;
+  t = t >= 3 ? t - 3 : t;
+  return t >= 3 ? t - 3 : t;
+}
+// certificate inputs of one float term: smallest magnitude bits of the non-zero terms (its exponent field bounds the
+// term's ulp: the value is an integer multiple of 2^(max(e,1) - 150)) and the running sum of magnitudes
+__device__ __forceinline__ void k2_cert_term(float v, unsigned& umin, float& asum) {
+  const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+  umin = min(umin, u ? u : 0x7fffffffu);
+  asum += fabsf(v);
+}
+
+__global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint64_t* __restrict__ words,
+                                                       const int64_t* __restrict__ off, int64_t n_seq, int64_t total,
+                                                       const float* __restrict__ planes, const uint32_t* __restrict__ bktidx,
+                                                       CodonSets cs, DevParams P, const uint8_t* __restrict__ qual_in,
+                                                       double* __restrict__ cum, int32_t* __restrict__ fwd_prev,
+                                                       int32_t* __restrict__ rev_next, uint8_t* __restrict__ qual,
+                                                       uint8_t* __restrict__ cert) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NONE_LO = -0x40000000, NONE_HI = 0x40000000;
+  __shared__ float s_lut[384];
+  const bool have_lut = indep.lut3 != NULL;
+  if (have_lut)
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
+  __syncthreads();
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_seq) return;
+  const int64_t a = off[s];
+  const int L = (int)(off[s + 1] - a);
+  if (L == 0) {
+    if (lane == 0) cert[s] = 1;
+    return;
+  }
+  unsigned umin = 0x7fffffffu;
+  float asum = 0.f;
+  const int shift = (int)(a & 3);  // tiles start at sequence position -shift: a + q0 is a multiple of 4
+  const int ntile = (L + shift + 127) >> 7;
+  const size_t T = (size_t)total;
+  const float* const pf0 = planes;
+  const float* const pf1 = planes + T;
+  const float* const pf2 = planes + 2 * T;
+  const float* const pr0 = planes + 3 * T;
+  const float* const pr1 = planes + 4 * T;
+  const float* const pr2 = planes + 5 * T;
+
+  // ---- left to right: reverse-strand prefix sums, previous forward stops, quality ----
+  {
+    double carry[3] = {0.0, 0.0, 0.0};
+    int last_stop[3] = {0, 1, -1};  // Save_Prev_Stops init (glimmer-mg.cc:684), by class q % 3
+    for (int t = 0; t < ntile; t++) {
+      const int q0 = t * 128 - shift + lane * K2_R;  // first of this lane's four positions
+      double v[3][K2_R];
+      int stp[K2_R];
+      uint32_t qv4 = 0;
+      uint64_t wblk = 0, win = 0;
+      uint4 rblk = make_uint4(0, 0, 0, 0);
+      const bool any_in = q0 + K2_R > 0 && q0 < L;
+      if (any_in) {
+        const int64_t blk = (a + q0) >> 5;
+        wblk = __ldg(words + blk);
+        rblk = __ldg(reinterpret_cast<const uint4*>(bktidx) + blk);
+        win = gmg_extract32(words, a + q0 - 4);  // base a+q0-4+k at bits 2k
+      }
+      const int c0 = mod3(q0);          // class of position q0 + i is c0 + i (mod 3)
+      const int rot0 = k2_add3(c0, 1);  // f of class c at q0 + i is rot0 + i - c (mod 3)
+      const int bi0 = (int)((a + q0) & 31);
+#pragma unroll
+      for (int i = 0; i < K2_R; i++) {
+        const int q = q0 + i;
+        const bool in = q >= 0 && q < L;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        stp[i] = NONE_LO;
+        if (in) {
+          const int bi = bi0 + i;
+          const unsigned bs = (unsigned)(wblk >> (2 * bi)) & 3u;
+          const uint64_t xx = wblk ^ (0x5555555555555555ull * bs);
+          const uint64_t eq = ~(xx | (xx >> 1)) & 0x5555555555555555ull & ((1ull << (2 * bi)) - 1ull);
+          const uint32_t pi = (bs == 0 ? rblk.x : (bs == 1 ? rblk.y : (bs == 2 ? rblk.z : rblk.w))) + (uint32_t)__popcll(eq);
+          const int raw_rev = (int)((win >> (2 * (i + 2))) & 63);  // bases q-2, q-1, q
+          const float g0 = __ldg(pr0 + pi), g1 = __ldg(pr1 + pi), g2 = __ldg(pr2 + pi);
+          float n0, n1, n2;
+          if (have_lut && q >= 2) {
+            n0 = s_lut[192 + raw_rev];
+            n1 = s_lut[256 + raw_rev];
+            n2 = s_lut[320 + raw_rev];
+          } else {
+            n0 = icm_rev(indep, words, a + q, q, 0, 0);
+            n1 = icm_rev(indep, words, a + q, q, 0, 1);
+            n2 = icm_rev(indep, words, a + q, q, 0, 2);
+          }
+          k2_cert_term(g0, umin, asum); k2_cert_term(g1, umin, asum); k2_cert_term(g2, umin, asum);
+          k2_cert_term(n0, umin, asum); k2_cert_term(n1, umin, asum); k2_cert_term(n2, umin, asum);
+          d0 = (double)g0 - (double)n0;
+          d1 = (double)g1 - (double)n1;
+          d2 = (double)g2 - (double)n2;
+          if (q >= 2) {  // forward stop whose last base is q
+            const int cd = ((raw_rev & 3) << 4) | (raw_rev & 12) | (raw_rev >> 4);
+            if ((cs.stop_mask >> cd) & 1) stp[i] = q;
+          }
+          if (qual) {
+            const int b = (int)bs;
+            const bool last_of_run = (q == L - 1) || ((int)((win >> (2 * (i + 5))) & 3) != b);
+            int qv;
+            if (qual_in) {
+              qv = qual_in[a + q];
+              if (qv <= 0) qv = 1;
+              if (!last_of_run && qv < P.indel_q_thresh + 1) qv = P.indel_q_thresh + 1;
+              qv = min(qv, 255);
+            } else if (!last_of_run) {
+              qv = 31;
+            } else {
+              int r = 1;
+              while (r < 5 && q - r >= 0 && (int)((win >> (2 * (i + 4 - r))) & 3) == b) r++;
+              qv = 31 - 5 * r;
+            }
+            qv4 |= (uint32_t)qv << (8 * i);
+          }
+        }
+        // class c takes the term of period f = rot - c (mod 3), rot = rot0 + i
+        const int rot = k2_add3(rot0, i);
+        const double x0 = rot == 0 ? d0 : (rot == 1 ? d1 : d2);
+        const double x1 = rot == 0 ? d2 : (rot == 1 ? d0 : d1);
+        const double x2 = rot == 0 ? d1 : (rot == 1 ? d2 : d0);
+        v[0][i] = (i ? v[0][i - 1] : 0.0) + x0;
+        v[1][i] = (i ? v[1][i - 1] : 0.0) + x1;
+        v[2][i] = (i ? v[2][i - 1] : 0.0) + x2;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double tot = v[c][K2_R - 1];
+        double inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double tt = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d) inc += tt;
+        }
+        const double base = carry[c] + (inc - tot);
+#pragma unroll
+        for (int i = 0; i < K2_R; i++) v[c][i] += base;
+        carry[c] += __shfl_sync(FULL, inc, 31);
+      }
+      // stop tables: running maximum per class inside the lane (classes relative to c0: position i has relative
+      // class i % 3), lane summaries joined per absolute class by three int max-scans
+      int rel[3] = {NONE_LO, NONE_LO, NONE_LO};
+      int outp[K2_R];
+#pragma unroll
+      for (int i = 0; i < K2_R; i++) {
+        rel[i % 3] = max(rel[i % 3], stp[i]);
+        outp[i] = rel[i % 3];
+      }
+      // absolute class c is relative class c - c0 (mod 3)
+      const int ab0 = c0 == 0 ? rel[0] : (c0 == 1 ? rel[2] : rel[1]);
+      const int ab1 = c0 == 0 ? rel[1] : (c0 == 1 ? rel[0] : rel[2]);
+      const int ab2 = c0 == 0 ? rel[2] : (c0 == 1 ? rel[1] : rel[0]);
+      int ex[3];
+      {
+        int inc[3] = {ab0, ab1, ab2};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int tt = __shfl_up_sync(FULL, inc[c], d);
+            if (lane >= d) inc[c] = max(inc[c], tt);
+          }
+          int e = __shfl_up_sync(FULL, inc[c], 1);
+          if (lane == 0) e = NONE_LO;
+          ex[c] = e > NONE_LO ? e : last_stop[c];
+          const int all = __shfl_sync(FULL, inc[c], 31);
+          if (all > NONE_LO) last_stop[c] = all;
+        }
+      }
+      // relative class r is absolute class c0 + r
+      const int er0 = c0 == 0 ? ex[0] : (c0 == 1 ? ex[1] : ex[2]);
+      const int er1 = c0 == 0 ? ex[1] : (c0 == 1 ? ex[2] : ex[0]);
+      const int er2 = c0 == 0 ? ex[2] : (c0 == 1 ? ex[0] : ex[1]);
+#pragma unroll
+      for (int i = 0; i < K2_R; i++)
+        if (outp[i] <= NONE_LO) outp[i] = (i % 3) == 0 ? er0 : ((i % 3) == 1 ? er1 : er2);
+      // stores: a lane's four positions are one aligned run
+      if (q0 >= 0 && q0 + K2_R <= L) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double* d1p = cum + (size_t)(3 + c) * T + a + q0;
+          if (((uintptr_t)d1p & 15) == 0) {
+            reinterpret_cast<double2*>(d1p)[0] = make_double2(v[c][0], v[c][1]);
+            reinterpret_cast<double2*>(d1p)[1] = make_double2(v[c][2], v[c][3]);
+          } else {
+            d1p[0] = v[c][0]; d1p[1] = v[c][1]; d1p[2] = v[c][2]; d1p[3] = v[c][3];
+          }
+        }
+        int32_t* p1 = fwd_prev + a + q0;
+        if (((uintptr_t)p1 & 15) == 0) *reinterpret_cast<int4*>(p1) = make_int4(outp[0], outp[1], outp[2], outp[3]);
+        else { p1[0] = outp[0]; p1[1] = outp[1]; p1[2] = outp[2]; p1[3] = outp[3]; }
+        if (qual) {
+          uint8_t* u1 = qual + a + q0;
+          if (((uintptr_t)u1 & 3) == 0) *reinterpret_cast<uint32_t*>(u1) = qv4;
+          else { u1[0] = (uint8_t)qv4; u1[1] = (uint8_t)(qv4 >> 8); u1[2] = (uint8_t)(qv4 >> 16); u1[3] = (uint8_t)(qv4 >> 24); }
+        }
+      } else if (any_in) {
+#pragma unroll
+        for (int i = 0; i < K2_R; i++) {
+          const int q = q0 + i;
+          if (q >= 0 && q < L) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) cum[(size_t)(3 + c) * T + a + q] = v[c][i];
+            fwd_prev[a + q] = outp[i];
+            if (qual) qual[a + q] = (uint8_t)(qv4 >> (8 * i));
+          }
+        }
+      }
+    }
+  }
+  // ---- right to left: forward-strand suffix sums, next reverse stops ----
+  {
+    double carry[3] = {0.0, 0.0, 0.0};
+    // Save_Prev_Stops reverse init (glimmer-mg.cc:706-708) by class r = (L-1-q) % 3: {L-1, L-2, L}
+    int next_stop[3] = {L - 1, L - 2, L};
+    for (int t = ntile - 1; t >= 0; t--) {
+      const int q0 = t * 128 - shift + (31 - lane) * K2_R;  // lane 0 owns the rightmost four positions
+      double v[3][K2_R];
+      int stp[K2_R];
+      uint64_t wblk = 0, win = 0;
+      uint4 rblk = make_uint4(0, 0, 0, 0);
+      const bool any_in = q0 + K2_R > 0 && q0 < L;
+      if (any_in) {
+        const int64_t blk = (a + q0) >> 5;
+        wblk = __ldg(words + blk);
+        rblk = __ldg(reinterpret_cast<const uint4*>(bktidx) + blk);
+        win = gmg_extract32(words, a + q0);  // base a+q0+k at bits 2k
+      }
+      // f of class c at position q is c - q (mod 3); at q0 + 3 (the lane's rightmost): rotr = -(q0 + 3) = -q0 (mod 3)
+      const int nq0 = mod3(-q0);
+      const int bi0 = (int)((a + q0) & 31);
+#pragma unroll
+      for (int ii = 0; ii < K2_R; ii++) {
+        const int i = K2_R - 1 - ii;  // right to left inside the lane
+        const int q = q0 + i;
+        const bool in = q >= 0 && q < L;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        stp[i] = NONE_HI;
+        if (in) {
+          const int bi = bi0 + i;
+          const unsigned bs = (unsigned)(wblk >> (2 * bi)) & 3u;
+          const uint64_t xx = wblk ^ (0x5555555555555555ull * bs);
+          const uint64_t eq = ~(xx | (xx >> 1)) & 0x5555555555555555ull & ((1ull << (2 * bi)) - 1ull);
+          const uint32_t pi = (bs == 0 ? rblk.x : (bs == 1 ? rblk.y : (bs == 2 ? rblk.z : rblk.w))) + (uint32_t)__popcll(eq);
+          const int raw_fwd = (int)((win >> (2 * i)) & 63);  // bases q, q+1, q+2
+          const float g0 = __ldg(pf0 + pi), g1 = __ldg(pf1 + pi), g2 = __ldg(pf2 + pi);
+          float n0, n1, n2;
+          if (have_lut && q <= L - 3) {
+            n0 = s_lut[raw_fwd];
+            n1 = s_lut[64 + raw_fwd];
+            n2 = s_lut[128 + raw_fwd];
+          } else {
+            n0 = icm_fwd(indep, words, a + q, q, L, 0);
+            n1 = icm_fwd(indep, words, a + q, q, L, 1);
+            n2 = icm_fwd(indep, words, a + q, q, L, 2);
+          }
+          k2_cert_term(g0, umin, asum); k2_cert_term(g1, umin, asum); k2_cert_term(g2, umin, asum);
+          k2_cert_term(n0, umin, asum); k2_cert_term(n1, umin, asum); k2_cert_term(n2, umin, asum);
+          d0 = (double)g0 - (double)n0;
+          d1 = (double)g1 - (double)n1;
+          d2 = (double)g2 - (double)n2;
+          if (q <= L - 3) {  // reverse-strand stop occupying q, q+1, q+2
+            const int cc = 63 - (((raw_fwd & 3) << 4) | (raw_fwd & 12) | (raw_fwd >> 4));
+            const int cd = ((cc & 3) << 4) | (cc & 12) | (cc >> 4);
+            if ((cs.stop_mask >> cd) & 1) stp[i] = q;
+          }
+        }
+        // class c takes f = c - q = c + nq0 - i (mod 3): with m = nq0 - i (mod 3), x_c = d[(c + m) % 3]
+        const int m = k2_add3(nq0, 3 - (i % 3));
+        const double x0 = m == 0 ? d0 : (m == 1 ? d1 : d2);
+        const double x1 = m == 0 ? d1 : (m == 1 ? d2 : d0);
+        const double x2 = m == 0 ? d2 : (m == 1 ? d0 : d1);
+        v[0][i] = (ii ? v[0][i + 1] : 0.0) + x0;
+        v[1][i] = (ii ? v[1][i + 1] : 0.0) + x1;
+        v[2][i] = (ii ? v[2][i + 1] : 0.0) + x2;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double tot = v[c][0];
+        double inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double tt = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d) inc += tt;
+        }
+        const double base = carry[c] + (inc - tot);
+#pragma unroll
+        for (int i = 0; i < K2_R; i++) v[c][i] += base;
+        carry[c] += __shfl_sync(FULL, inc, 31);
+      }
+      // next reverse stop per class r = (L-1-q) % 3: running minimum from the right.  Relative class of the
+      // ii-th position from the right is ii % 3; absolute class = r3 + ii, r3 = class of the rightmost position.
+      const int r3 = mod3(L - 1 - (q0 + K2_R - 1));
+      int rel[3] = {NONE_HI, NONE_HI, NONE_HI};
+      int outp[K2_R];
+#pragma unroll
+      for (int ii = 0; ii < K2_R; ii++) {
+        const int i = K2_R - 1 - ii;
+        rel[ii % 3] = min(rel[ii % 3], stp[i]);
+        outp[i] = rel[ii % 3];
+      }
+      const int ab0 = r3 == 0 ? rel[0] : (r3 == 1 ? rel[2] : rel[1]);
+      const int ab1 = r3 == 0 ? rel[1] : (r3 == 1 ? rel[0] : rel[2]);
+      const int ab2 = r3 == 0 ? rel[2] : (r3 == 1 ? rel[1] : rel[0]);
+      int ex[3];
+      {
+        int inc[3] = {ab0, ab1, ab2};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int tt = __shfl_up_sync(FULL, inc[c], d);
+            if (lane >= d) inc[c] = min(inc[c], tt);
+          }
+          int e = __shfl_up_sync(FULL, inc[c], 1);
+          if (lane == 0) e = NONE_HI;
+          ex[c] = e < NONE_HI ? e : next_stop[c];
+          const int all = __shfl_sync(FULL, inc[c], 31);
+          if (all < NONE_HI) next_stop[c] = all;
+        }
+      }
+      const int er0 = r3 == 0 ? ex[0] : (r3 == 1 ? ex[1] : ex[2]);
+      const int er1 = r3 == 0 ? ex[1] : (r3 == 1 ? ex[2] : ex[0]);
+      const int er2 = r3 == 0 ? ex[2] : (r3 == 1 ? ex[0] : ex[1]);
+#pragma unroll
+      for (int ii = 0; ii < K2_R; ii++) {
+        const int i = K2_R - 1 - ii;
+        if (outp[i] >= NONE_HI) outp[i] = (ii % 3) == 0 ? er0 : ((ii % 3) == 1 ? er1 : er2);
+      }
+      if (q0 >= 0 && q0 + K2_R <= L) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double* d1p = cum + (size_t)c * T + a + q0;
+          if (((uintptr_t)d1p & 15) == 0) {
+            reinterpret_cast<double2*>(d1p)[0] = make_double2(v[c][0], v[c][1]);
+            reinterpret_cast<double2*>(d1p)[1] = make_double2(v[c][2], v[c][3]);
+          } else {
+            d1p[0] = v[c][0]; d1p[1] = v[c][1]; d1p[2] = v[c][2]; d1p[3] = v[c][3];
+          }
+        }
+        int32_t* p1 = rev_next + a + q0;
+        if (((uintptr_t)p1 & 15) == 0) *reinterpret_cast<int4*>(p1) = make_int4(outp[0], outp[1], outp[2], outp[3]);
+        else { p1[0] = outp[0]; p1[1] = outp[1]; p1[2] = outp[2]; p1[3] = outp[3]; }
+      } else if (any_in) {
+#pragma unroll
+        for (int i = 0; i < K2_R; i++) {
+          const int q = q0 + i;
+          if (q >= 0 && q < L) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) cum[(size_t)c * T + a + q] = v[c][i];
+            rev_next[a + q] = outp[i];
+          }
+        }
+      }
+    }
+  }
+  // ---- certificate: every term is a multiple of 2^g, g from the smallest float exponent seen; every partial sum
+  // of any association is bounded by the sum of magnitudes (accumulated in FP32, 0.1 % margin for its rounding) ----
+  for (int d = 16; d > 0; d >>= 1) {
+    umin = min(umin, __shfl_xor_sync(FULL, umin, d));
+    asum += __shfl_xor_sync(FULL, asum, d);
+  }
+  if (lane == 0) {
+    const int e = (int)(umin >> 23);
+    const int g = (e > 0 ? e : 1) - 150;
+    bool ok = (umin == 0x7fffffffu) || ((double)asum * 1.001 < ldexp(1.0, g + 52));
+    cert[s] = ok ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3 (glimmer-mg): Score_Orf_Starts / Score_Indels / Pass_Stop_Penalty recursion, one thread per ORF,
 // explicit stack (depth <= 1 + indel_max + sub).  score[j] of any branch is a difference of two entries of
@@ -2620,6 +3004,12 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   const bool need_qual = p->allow_indels || p->have_quality_file;
   unsigned g2 = (unsigned)((s->n * 32 + 127) / 128);
   if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
+  static const int k2_mode = getenv("GMG_K2_MODE") ? atoi(getenv("GMG_K2_MODE")) : 0;  // 0 lane-serial tiles, 1 one position per lane
+  if (k2_mode == 0)
+    k2_prefix_lanes<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, s->d_bktidx, cs,
+                                                 dp, p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev,
+                                                 rev_next, need_qual ? (uint8_t*)d_qual : NULL, cert);
+  else
   k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, s->d_bktidx, cs, dp,
                                          p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
                                          need_qual ? (uint8_t*)d_qual : NULL, cert);
@@ -2633,7 +3023,10 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
   unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  static const int k3mg_mode = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : 0;  // 0 warp per ORF, 1 thread per ORF
+  // warp per ORF when calls can branch (-i / -s); without error branches an ORF is one short linear walk and one
+  // thread per ORF keeps 32x more ORFs in flight.  GMG_K3MG_MODE = 0 / 1 forces warp / thread per ORF (tests).
+  static const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
+  const int k3mg_mode = k3mg_env >= 0 ? k3mg_env : ((p->allow_indels || p->allow_subs) ? 0 : 1);
   const unsigned g3w = (unsigned)((s->n_orfs * 32 + 127) / 128);
   if (k3mg_mode == 0)
     k3_mg_starts_warp<false><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
