@@ -257,7 +257,7 @@ extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_count
   // window histogram for large sets (W <= 12): GMG_K4_HIST=0/1 forces the direct / histogram path (tests)
   const char* hist_env = getenv("GMG_K4_HIST");
   const int hist_mode = hist_env ? atoi(hist_env) : -1;
-  const bool use_hist = t->W <= 12 && (hist_mode == 1 || (hist_mode < 0 && s->total >= ((int64_t)t->P << (2 * t->W)) * 2));
+  const bool use_hist = t->W <= 12 && (hist_mode == 1 || (hist_mode < 0 && s->total >= ((int64_t)t->P << (2 * t->W)) / 2));  // >= 25 M windows at 12/7/3
   if (s->total > 0 && use_hist) {
     const size_t cells = (size_t)t->P << (2 * t->W);
     const int threads = 512;
