@@ -2376,6 +2376,7 @@ struct MgFrame {
   int fresh;       // substitution pre-step not run yet
   int err_pos[2], err_type[2];
   double suffix_score, cbase;
+  const double* row;  // this call's prefix-sum plane, offset to the sequence: score[j] = row[idx(j)] - cbase
 };
 
 __device__ __forceinline__ void mg_open_frame(const MgSeq& S, const DevParams& P, int frame, int end_point, MgFrame& c) {
@@ -2386,14 +2387,16 @@ __device__ __forceinline__ void mg_open_frame(const MgSeq& S, const DevParams& P
     c.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
     c.m = c.hi - c.lo;
     c.trunc = (c.lo < 3 && P.allow_truncated);
-    c.cbase = mg_cum_f(S, mod3(c.hi), c.hi);
+    c.row = S.cum + (size_t)mod3(c.hi) * S.total + S.a;
+    c.cbase = ((unsigned)c.hi < (unsigned)L) ? c.row[c.hi] : 0.0;
   } else {
     c.lo = end_point;
     const int e = end_point - 1;
     c.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
     c.m = c.hi - c.lo;
     c.trunc = (L - (c.hi - 1) < 3 && P.allow_truncated);
-    c.cbase = mg_cum_r(S, mod3(c.lo - 1), c.lo - 2);
+    c.row = S.cum + (size_t)(3 + mod3(c.lo - 1)) * S.total + S.a;
+    c.cbase = ((unsigned)(c.lo - 2) < (unsigned)L) ? c.row[c.lo - 2] : 0.0;
   }
   if (c.m < 0) c.m = 0;
   c.jtop = c.m - 1;
@@ -2403,8 +2406,8 @@ __device__ __forceinline__ void mg_open_frame(const MgSeq& S, const DevParams& P
 }
 
 __device__ __forceinline__ double mg_frame_score(const MgSeq& S, int frame, const MgFrame& c, int j) {
-  if (frame > 0) return mg_cum_f(S, mod3(c.hi), c.hi - 1 - j) - c.cbase;
-  return mg_cum_r(S, mod3(c.lo - 1), c.lo - 1 + j) - c.cbase;
+  const int q = frame > 0 ? c.hi - 1 - j : c.lo - 1 + j;
+  return (((unsigned)q < (unsigned)S.L) ? c.row[q] : 0.0) - c.cbase;
 }
 
 // A LEAF call: a call that can neither branch nor substitute any further (n_err == indel_max, or a substitution
@@ -2415,7 +2418,7 @@ struct MgLeaf {
   int lo, hi, m, trunc;
   int j_lo, j_hi, j_hs;  // eligible j (multiples of 3): j_lo..j_hi; start-codon test only for j <= j_hs
   const uint2* st;       // bitmap stream
-  int64_t cpos;          // forward: slot(j) = (cpos - j) / 3; reverse: slot(j) = (cpos + j) / 3  (both exact)
+  uint32_t cpos;         // forward: slot(j) = (cpos - j) / 3; reverse: slot(j) = (cpos + j) / 3 (batches < 2^32 bases)
 };
 
 __device__ __forceinline__ void mg_leaf_open(const MgSeq& S, const DevParams& P, int frame, int end_point, int suffix_j,
@@ -2439,28 +2442,29 @@ __device__ __forceinline__ void mg_leaf_open(const MgSeq& S, const DevParams& P,
   f.j_hi = (f.m - 1) >= 0 ? (f.m - 1) - (f.m - 1) % 3 : -3;
   f.j_hs = (f.m - 3) >= 0 ? (f.m - 3) - (f.m - 3) % 3 : -3;
   if (frame > 0) {
-    f.cpos = S.a + f.hi - 3;  // first base of the codon ending at bidx = hi-1-j is cpos - j
-    const int r = (int)(f.cpos % 3);
+    f.cpos = (uint32_t)(S.a + f.hi - 3);  // first base of the codon ending at bidx = hi-1-j is cpos - j
+    const int r = (int)(f.cpos % 3u);
     f.st = cb + (size_t)r * nwc;
   } else {
-    f.cpos = S.a + f.lo - 1;  // first base of the reverse codon starting at bidx = lo-1+j is cpos + j
-    const int r = (int)(f.cpos % 3);
+    f.cpos = (uint32_t)(S.a + f.lo - 1);  // first base of the reverse codon starting at bidx = lo-1+j is cpos + j
+    const int r = (int)(f.cpos % 3u);
     f.st = cb + (size_t)(3 + r) * nwc;
   }
 }
 
 __device__ __forceinline__ bool mg_leaf_bit(const MgLeaf& f, bool fwd, int j) {
-  const int64_t sl = (fwd ? f.cpos - j : f.cpos + j) / 3;
-  return (__ldg(f.st + (sl >> 5)).x >> (int)(sl & 31)) & 1u;
+  const uint32_t sl = (fwd ? f.cpos - (uint32_t)j : f.cpos + (uint32_t)j) / 3u;
+  return (__ldg(f.st + (sl >> 5)).x >> (sl & 31u)) & 1u;
 }
 
 // number of start bits at eligible j in [ja, jb] (multiples of 3, ja <= jb)
 __device__ __forceinline__ int mg_leaf_popc(const MgLeaf& f, bool fwd, int ja, int jb) {
-  const int64_t s1 = (fwd ? f.cpos - jb : f.cpos + ja) / 3, s2 = (fwd ? f.cpos - ja : f.cpos + jb) / 3;
-  const int64_t w1 = s1 >> 5, w2 = s2 >> 5;
-  const unsigned m1 = ~0u << (int)(s1 & 31), m2 = (2u << (int)(s2 & 31)) - 1u;
+  const uint32_t s1 = (fwd ? f.cpos - (uint32_t)jb : f.cpos + (uint32_t)ja) / 3u;
+  const uint32_t s2 = (fwd ? f.cpos - (uint32_t)ja : f.cpos + (uint32_t)jb) / 3u;
+  const uint32_t w1 = s1 >> 5, w2 = s2 >> 5;
+  const unsigned m1 = ~0u << (s1 & 31u), m2 = (2u << (s2 & 31u)) - 1u;
   int cnt = 0;
-  for (int64_t w = w1; w <= w2; w++)
+  for (uint32_t w = w1; w <= w2; w++)
     cnt += __popc(__ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u));
   return cnt;
 }
@@ -2521,18 +2525,19 @@ __device__ int mg_leaf_run(const MgSeq& S, const DevParams& P, const CodonSets& 
   if (jb < f.j_lo) return cnt;
   if (!out) return cnt + mg_leaf_popc(f, fwd, f.j_lo, jb);
   // write: walk the set bits in descending j
-  const int64_t s1 = (fwd ? f.cpos - jb : f.cpos + f.j_lo) / 3, s2 = (fwd ? f.cpos - f.j_lo : f.cpos + jb) / 3;
-  const int64_t w1 = s1 >> 5, w2 = s2 >> 5;
-  const unsigned m1 = ~0u << (int)(s1 & 31), m2 = (2u << (int)(s2 & 31)) - 1u;
-  for (int64_t wi = 0; wi <= w2 - w1; wi++) {
-    const int64_t w = fwd ? w1 + wi : w2 - wi;
+  const uint32_t s1 = (fwd ? f.cpos - (uint32_t)jb : f.cpos + (uint32_t)f.j_lo) / 3u;
+  const uint32_t s2 = (fwd ? f.cpos - (uint32_t)f.j_lo : f.cpos + (uint32_t)jb) / 3u;
+  const uint32_t w1 = s1 >> 5, w2 = s2 >> 5;
+  const unsigned m1 = ~0u << (s1 & 31u), m2 = (2u << (s2 & 31u)) - 1u;
+  const uint32_t rr = f.cpos % 3u;  // (cpos -/+ j) = 3 sl + rr
+  for (uint32_t wi = 0; wi <= w2 - w1; wi++) {
+    const uint32_t w = fwd ? w1 + wi : w2 - wi;
     unsigned x = __ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u);
     while (x) {
       const int b = fwd ? __ffs(x) - 1 : 31 - __clz(x);
       x &= ~(1u << b);
-      const int64_t sl = (w << 5) + b;
-      const int64_t rr = f.cpos % 3;  // (cpos -/+ j) = 3 sl + rr
-      const int j = (int)(fwd ? f.cpos - rr - 3 * sl : 3 * sl + rr - f.cpos);
+      const uint32_t sl = (w << 5) + (uint32_t)b;
+      const int j = (int)(fwd ? f.cpos - rr - 3u * sl : 3u * sl + rr - f.cpos);
       const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
       put(j, which_at(j), 0, state ? 1 : 0);
       if (k != 0) state = false;
