@@ -119,6 +119,7 @@ struct gmg_seqset {
   int64_t n;                 // sequences
   int64_t total;             // bases
   int64_t max_len;           // longest sequence
+  std::vector<int64_t> hdr_off, hdr_end;  // gmg_seqset_from_fasta: header text of record i = image[hdr_off[i], hdr_end[i])
   std::vector<int64_t> off;  // host copy, n+1
   int64_t* d_off;            // n+1
   uint64_t* d_words_base;    // allocation incl. padding

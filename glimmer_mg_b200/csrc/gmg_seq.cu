@@ -260,6 +260,159 @@ extern "C" int gmg_seqset_create(gmg_ctx* ctx, const char* h_ascii, const int64_
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// FASTA ingest on the device (Fasta_Read, Common/fasta.cc:236-283, and build-icm's
+// Read_String, ICM/build-icm.cc:262-315): everything before the first '>' is skipped; a '>' anywhere outside a
+// header line starts a record whose header runs to the end of that line; every other non-white-space byte up to
+// the next '>' is a sequence character.  "Inside a header line" is a property of the LAST '>' or '\n' at or before
+// a byte, i.e. an inclusive max-scan over (position, kind) keys; record numbers and compacted sequence indices are
+// a second (sum) scan.  Two cub scans and two elementwise kernels replace the reference's fgetc loop.
+
+struct FastaMaxOp {
+  __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+struct FastaSumOp {
+  __device__ __forceinline__ uint2 operator()(uint2 a, uint2 b) const { return make_uint2(a.x + b.x, a.y + b.y); }
+};
+__device__ __forceinline__ bool fasta_is_space(unsigned ch) { return ch == ' ' || (ch >= 9 && ch <= 13); }
+
+// key = (position + 1) * 2 + kind for '>' (kind 1) and '\n' (kind 0), 0 for every other byte
+__global__ void __launch_bounds__(256) k_fasta_keys(const uint8_t* __restrict__ in, int64_t n, uint32_t* __restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned ch = in[i];
+  key[i] = ch == '>' ? (uint32_t)((i + 1) * 2 + 1) : (ch == '\n' ? (uint32_t)((i + 1) * 2) : 0u);
+}
+
+// last[i] = inclusive max-scan of key.  flags.x = 1 for a kept sequence character, flags.y = 1 for a record start
+__global__ void __launch_bounds__(256) k_fasta_flags(const uint8_t* __restrict__ in, int64_t n,
+                                                     const uint32_t* __restrict__ last, uint2* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned ch = in[i];
+  const bool in_hdr = (last[i] & 1u) != 0;                 // the last '>' / '\n' at or before i is a '>'
+  const bool prev_hdr = i > 0 && (last[i - 1] & 1u) != 0;  // ... before i
+  const bool start = ch == '>' && !prev_hdr;
+  flags[i] = make_uint2((!in_hdr && !fasta_is_space(ch)) ? 1u : 0u, start ? 1u : 0u);
+}
+
+// incl[i] = inclusive sums of flags (.x characters outside header lines, .y records started).
+// Pass 1: per-record tables.  rec_chars[r] = characters counted before record r starts, hdr_off[r] = first byte of
+// its header text, hdr_end[r] = the '\n' ending the header line (pre-filled with n for a header cut off by the end).
+__global__ void __launch_bounds__(256) k_fasta_records(const uint8_t* __restrict__ in, int64_t n,
+                                                       const uint32_t* __restrict__ last, const uint2* __restrict__ incl,
+                                                       int64_t* __restrict__ rec_chars, int64_t* __restrict__ hdr_off,
+                                                       int64_t* __restrict__ hdr_end) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 me = incl[i];
+  const uint2 before = i > 0 ? incl[i - 1] : make_uint2(0u, 0u);
+  if (me.y != before.y) {  // record me.y - 1 starts at this '>'
+    rec_chars[me.y - 1] = before.x;
+    hdr_off[me.y - 1] = i + 1;
+  }
+  if (in[i] == '\n' && i > 0 && (last[i - 1] & 1u) != 0 && me.y > 0) hdr_end[me.y - 1] = i;
+}
+
+// Pass 2: the sequence characters of all records, compacted (characters before the first record are dropped)
+__global__ void __launch_bounds__(256) k_fasta_scatter(const uint8_t* __restrict__ in, int64_t n,
+                                                       const uint2* __restrict__ incl, const int64_t* __restrict__ rec_chars,
+                                                       uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 me = incl[i];
+  const uint32_t before = i > 0 ? incl[i - 1].x : 0u;
+  if (me.x != before && me.y > 0) out[(int64_t)before - rec_chars[0]] = in[i];
+}
+
+__global__ void k_fill_i64(int64_t* __restrict__ p, int64_t n, int64_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int gmg_seqset_from_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t n_bytes, gmg_seqset** out,
+                                     int64_t* n_records) {
+  GMG_CHECK(ctx && out && n_bytes >= 0 && (h_bytes || n_bytes == 0), "gmg_seqset_from_fasta: bad argument");
+  GMG_CHECK(n_bytes < (1ll << 30), "gmg_seqset_from_fasta: images of 1 GiB or more must be split at record boundaries "
+            "(got %lld bytes)", (long long)n_bytes);
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  if (n_records) *n_records = 0;
+  const int64_t n = n_bytes;
+  int64_t n_rec = 0, n_chars = 0;
+  std::vector<int64_t> h_tab;  // rec_chars | hdr_off | hdr_end
+  void* d_out = NULL;
+  if (n > 0) {
+    void *d_in, *d_work;
+    if (gmg_scratch(ctx, SCR_TMP, (size_t)n + 64, &d_in)) return 1;
+    GMG_CUDA(cudaMemcpyAsync(d_in, h_bytes, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    // keys / last (4 B per byte) and flags / sums (8 B per byte)
+    if (gmg_scratch(ctx, SCR_CUM, (size_t)n * 12 + 256, &d_work)) return 1;
+    uint2* d_flags = (uint2*)d_work;
+    uint32_t* d_key = (uint32_t*)(d_flags + n);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    k_fasta_keys<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key);
+    size_t tb1 = 0, tb2 = 0;
+    GMG_CUDA(cub::DeviceScan::InclusiveScan(NULL, tb1, d_key, d_key, FastaMaxOp(), n, ctx->stream));
+    GMG_CUDA(cub::DeviceScan::InclusiveScan(NULL, tb2, d_flags, d_flags, FastaSumOp(), n, ctx->stream));
+    void* d_tmp;
+    if (gmg_scratch(ctx, SCR_TMP4, tb1 > tb2 ? tb1 : tb2, &d_tmp)) return 1;
+    GMG_CUDA(cub::DeviceScan::InclusiveScan(d_tmp, tb1, d_key, d_key, FastaMaxOp(), n, ctx->stream));
+    k_fasta_flags<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key, d_flags);
+    GMG_CUDA(cub::DeviceScan::InclusiveScan(d_tmp, tb2, d_flags, d_flags, FastaSumOp(), n, ctx->stream));
+    ctx->launches += 4;
+    GMG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 4, d_flags + (n - 1), sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint2 tot;
+    memcpy(&tot, ctx->h_scalars + 4, sizeof tot);
+    n_rec = tot.y;
+    if (n_rec > 0) {
+      void* d_tab;
+      if (gmg_scratch(ctx, SCR_TMP3, (size_t)3 * n_rec * sizeof(int64_t), &d_tab)) return 1;
+      int64_t* rec_chars = (int64_t*)d_tab;
+      int64_t* hdr_off = rec_chars + n_rec;
+      int64_t* hdr_end = hdr_off + n_rec;
+      k_fill_i64<<<(unsigned)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(hdr_end, n_rec, n);
+      k_fasta_records<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key, d_flags, rec_chars, hdr_off, hdr_end);
+      if (gmg_scratch(ctx, SCR_TMP2, (size_t)tot.x + 64, &d_out)) return 1;
+      k_fasta_scatter<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_flags, rec_chars, (uint8_t*)d_out);
+      ctx->launches += 3;
+      GMG_CUDA(cudaGetLastError());
+      h_tab.resize((size_t)3 * n_rec);
+      GMG_CUDA(cudaMemcpyAsync(h_tab.data(), d_tab, h_tab.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+      n_chars = (int64_t)tot.x - h_tab[0];
+    }
+  }
+  // sequence offsets: characters counted before each record, relative to the first record
+  std::vector<int64_t> off((size_t)n_rec + 1, 0);
+  for (int64_t r = 0; r < n_rec; r++) off[(size_t)r] = h_tab[(size_t)r] - h_tab[0];
+  off[(size_t)n_rec] = n_chars;
+  gmg_seqset* s = NULL;
+  if (seqset_build(ctx, d_out, off.data(), n_rec, NULL, &s)) return 1;
+  s->hdr_off.assign(h_tab.begin() + (n_rec ? n_rec : 0), h_tab.begin() + (n_rec ? 2 * n_rec : 0));
+  s->hdr_end.assign(h_tab.begin() + (n_rec ? 2 * n_rec : 0), h_tab.end());
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // d_out (scratch) has been consumed by the pack kernel
+  *out = s;
+  if (n_records) *n_records = n_rec;
+  return 0;
+}
+
+extern "C" int64_t gmg_seqset_count(const gmg_seqset* s) { return s ? s->n : 0; }
+
+extern "C" int gmg_seqset_offsets(const gmg_seqset* s, int64_t* h_off) {
+  GMG_CHECK(s && h_off, "gmg_seqset_offsets: NULL argument");
+  memcpy(h_off, s->off.data(), s->off.size() * sizeof(int64_t));
+  return 0;
+}
+
+extern "C" int gmg_seqset_fasta_headers(const gmg_seqset* s, int64_t* h_hdr_off, int64_t* h_hdr_end) {
+  GMG_CHECK(s && h_hdr_off && h_hdr_end, "gmg_seqset_fasta_headers: NULL argument");
+  GMG_CHECK((int64_t)s->hdr_off.size() == s->n, "gmg_seqset_fasta_headers: the seqset was not built by gmg_seqset_from_fasta");
+  memcpy(h_hdr_off, s->hdr_off.data(), s->hdr_off.size() * sizeof(int64_t));
+  memcpy(h_hdr_end, s->hdr_end.data(), s->hdr_end.size() * sizeof(int64_t));
+  return 0;
+}
+
 extern "C" void gmg_seqset_free(gmg_seqset* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);

@@ -69,35 +69,21 @@ static bool Number(const char* arg, int* out, bool positive) {
   return true;
 }
 
-// multi-FASTA from fp: header lines start with '>', sequence lines are concatenated with white space removed
-// and letters lower-cased (build-icm.cc:262-343)
-static void Read_Training_Data(FILE* fp, std::vector<char*>& data) {
-  std::string cur;
-  bool have = false;
-  int ch;
-  auto flush = [&]() {
-    if (have) data.push_back(strdup(cur.c_str()));
-    cur.clear();
-  };
-  bool at_line_start = true;
-  while ((ch = fgetc(fp)) != EOF) {
-    if (ch == '>' ) {
-      flush();
-      have = true;
-      while ((ch = fgetc(fp)) != EOF && ch != '\n')
-        ;
-      at_line_start = true;
-      continue;
+// multi-FASTA image in memory -> training strings (host parser, used for -F and for images of 1 GiB or more):
+// header lines start with '>', sequence characters are concatenated with white space removed and letters
+// lower-cased (build-icm.cc:262-343)
+static void Read_Training_Data(const char* image, size_t n, std::vector<char*>& data) {
+  size_t i = 0;
+  while (i < n && image[i] != '>') i++;
+  while (i < n) {
+    while (i < n && image[i] != '\n') i++;  // header line
+    std::string cur;
+    while (i < n && image[i] != '>') {
+      const unsigned char ch = (unsigned char)image[i++];
+      if (!isspace(ch)) cur.push_back((char)tolower(ch));
     }
-    if (isspace(ch)) {
-      at_line_start = (ch == '\n');
-      continue;
-    }
-    if (have) cur.push_back((char)tolower(ch));
-    at_line_start = false;
+    data.push_back(strdup(cur.c_str()));
   }
-  (void)at_line_start;
-  flush();
 }
 
 int main(int argc, char** argv) {
@@ -156,8 +142,37 @@ int main(int argc, char** argv) {
   }
 
   ICM_Training_t model(Model_Len, Model_Depth, Model_Periodicity);
+  int64_t n_strings = 0;
+  // the whole standard input into page-locked memory
+  size_t cap = (size_t)64 << 20, used = 0;
+  char* image = NULL;
+  GMG_OR_DIE(gmg_host_alloc(cap, (void**)&image));
+  for (;;) {
+    if (used == cap) {
+      char* bigger = NULL;
+      GMG_OR_DIE(gmg_host_alloc(cap * 2, (void**)&bigger));
+      memcpy(bigger, image, used);
+      gmg_host_free(image);
+      image = bigger;
+      cap *= 2;
+    }
+    const size_t got = fread(image + used, 1, cap - used, stdin);
+    if (got == 0) break;
+    used += got;
+  }
+  if (!Skip_In_Frame_Stop_Strings && used < ((size_t)1 << 30)) {
+    // parsed, lower-cased and packed on the device (gmg_seqset_from_fasta)
+    n_strings = model.Train_Fasta(image, (int64_t)used, Reverse_Strings ? 1 : 0, NULL, NULL);
+    gmg_host_free(image);
+    if (n_strings == 0) {
+      fprintf(stderr, "ERROR:  Cannot create model--no input data\n");
+      fclose(out);
+      exit(EXIT_FAILURE);
+    }
+  } else {
   std::vector<char*> training;
-  Read_Training_Data(stdin, training);
+  Read_Training_Data(image, used, training);
+  gmg_host_free(image);
   if (training.empty()) {
     fprintf(stderr, "ERROR:  Cannot create model--no input data\n");
     fclose(out);
@@ -180,7 +195,9 @@ int main(int argc, char** argv) {
   }
   // -r: the device reads the packed strings back to front instead of reversing them on the host
   model.Train_Strings(training, Reverse_Strings ? 1 : 0, NULL, NULL);
-  if (Verbose > 0) fprintf(stderr, "trained on %d strings\n", (int)training.size());
+  n_strings = (int64_t)training.size();
+  }
+  if (Verbose > 0) fprintf(stderr, "trained on %lld strings\n", (long long)n_strings);
   model.Output(out, Print_Binary);
   if (out != stdout) fclose(out);
   return 0;

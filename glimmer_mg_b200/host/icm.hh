@@ -241,6 +241,21 @@ class ICM_Training_t : public ICM_t {
     gmg_host_free(cat);
     Adopt(h);
   }
+
+  // Train straight from a multi-FASTA image (parsed, lower-cased and packed on the device -- no per-character
+  // host loop): what build-icm does with its standard input.  Returns the number of training strings.
+  int64_t Train_Fasta(const char* image, int64_t n_bytes, int reverse, gmg_allreduce_fn allreduce, void* user) {
+    gmg_seqset* ss = NULL;
+    int64_t n_records = 0;
+    GMG_OR_DIE(gmg_seqset_from_fasta(Gmg_Context(), image, n_bytes, &ss, &n_records));
+    if (n_records > 0) {
+      gmg_icm* h = NULL;
+      GMG_OR_DIE(gmg_icm_train(Gmg_Context(), ss, model_len, model_depth, periodicity, reverse, allreduce, user, &h));
+      Adopt(h);
+    }
+    gmg_seqset_free(ss);
+    return n_records;
+  }
 };
 
 #endif  // GMG_HOST_ICM_HH

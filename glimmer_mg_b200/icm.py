@@ -83,6 +83,10 @@ def lib():
         "gmg_seqset_create": (i32, [vp, vp, vp, i64, vp, P(vp)]),
         "gmg_seqset_create_device": (i32, [vp, vp, vp, i64, vp, P(vp)]),
         "gmg_seqset_free": (None, [vp]),
+        "gmg_seqset_from_fasta": (i32, [vp, vp, i64, P(vp), P(i64)]),
+        "gmg_seqset_count": (i64, [vp]),
+        "gmg_seqset_offsets": (i32, [vp, vp]),
+        "gmg_seqset_fasta_headers": (i32, [vp, vp, vp]),
         "gmg_seqset_total_bases": (i64, [vp]),
         "gmg_seqset_gc_fraction": (i32, [vp, P(C.c_double)]),
         "gmg_seqset_unpack": (i32, [vp, vp]),
@@ -248,6 +252,31 @@ class SeqSet:
         self.total = int(self.off[-1])
         self.n_orfs = 0
         self.n_starts = 0
+
+    @classmethod
+    def from_fasta(cls, ctx, image):
+        """Parse a multi-FASTA image (bytes / uint8 array) on the device (Fasta_Read, Common/fasta.cc:236).
+        The returned set has ``headers``: the header text of every record."""
+        buf = np.frombuffer(image, np.uint8) if isinstance(image, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(image, np.uint8)
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        n = C.c_int64()
+        _check(lib().gmg_seqset_from_fasta(ctx.h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(self.h),
+                                           C.byref(n)))
+        self.n = n.value
+        self.off = np.zeros(self.n + 1, np.int64)
+        _check(lib().gmg_seqset_offsets(self.h, self.off.ctypes.data))
+        self.total = int(self.off[-1])
+        self.n_orfs = 0
+        self.n_starts = 0
+        ho, he = np.zeros(self.n, np.int64), np.zeros(self.n, np.int64)
+        if self.n:
+            _check(lib().gmg_seqset_fasta_headers(self.h, ho.ctypes.data, he.ctypes.data))
+        raw = buf.tobytes()
+        self.headers = [raw[a:b].decode(errors="replace") for a, b in zip(ho.tolist(), he.tolist())]
+        return self
 
     def close(self):
         if self.h:

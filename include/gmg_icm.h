@@ -134,6 +134,17 @@ int gmg_seqset_create(gmg_ctx* ctx, const char* h_ascii, const int64_t* h_off, i
 int gmg_seqset_create_device(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off, int64_t n,
                              const void* d_qual, gmg_seqset** out);
 void gmg_seqset_free(gmg_seqset* s);
+/* FASTA ingest on the device (Fasta_Read, Common/fasta.cc:236-283; build-icm's Read_String, ICM/build-icm.cc:262-315):
+ * `h_bytes` is a multi-FASTA image in host memory (page-locked memory from gmg_host_alloc makes the copy run at
+ * PCIe rate).  Bytes before the first '>' are skipped; a '>' outside a header line starts a record whose header
+ * runs to the end of the line; every other non-white-space byte up to the next '>' is a sequence character
+ * (Filter + lower-case applied as in gmg_seqset_create).  Images must be < 1 GiB (split larger files at record
+ * boundaries).  gmg_seqset_offsets returns the n+1 sequence offsets of any seqset; gmg_seqset_fasta_headers the
+ * header text of record i as image[hdr_off[i], hdr_end[i]) (after the '>', up to the line end). */
+int gmg_seqset_from_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t n_bytes, gmg_seqset** out, int64_t* n_records);
+int64_t gmg_seqset_count(const gmg_seqset* s);
+int gmg_seqset_offsets(const gmg_seqset* s, int64_t* h_off);
+int gmg_seqset_fasta_headers(const gmg_seqset* s, int64_t* h_hdr_off, int64_t* h_hdr_end);
 int64_t gmg_seqset_total_bases(const gmg_seqset* s);
 /* Set_GC_Fraction (glimmer_base.cc:2564-2595): (#c + #g after Filter) / total */
 int gmg_seqset_gc_fraction(gmg_seqset* s, double* gc);

@@ -85,6 +85,46 @@ def test_filter_pack_gc(gm, ctx):
     assert ss.gc_fraction() == _gc_oracle(seqs)
 
 
+def _py_fasta(image):
+    """Fasta_Read (Common/fasta.cc:236-283) restated: [(header text, sequence bytes)]."""
+    recs, i, n = [], image.find(b">"), len(image)
+    while i != -1:
+        e = image.find(b"\n", i)
+        e = n if e == -1 else e
+        nxt = image.find(b">", e)
+        body = image[e:(n if nxt == -1 else nxt)]
+        recs.append((image[i + 1:e], bytes(c for c in body if c not in b" \t\n\v\f\r")))
+        i = nxt
+    return recs
+
+
+@pytest.mark.parametrize("case", ["reads", "genome", "edge", "empty", "norecord"])
+def test_fasta_ingest_on_device(gm, ctx, case):
+    """gmg_seqset_from_fasta: records, headers, offsets and packed bases equal the reference reader's."""
+    import gzip
+    if case == "reads":
+        image = gzip.open(os.path.join(G, "seqs.fa.gz"), "rb").read()
+    elif case == "genome":
+        image = gzip.open(os.path.join(G, "NC_000915.fna.gz"), "rb").read()
+    elif case == "edge":
+        image = (b"junk before\nthe first record\n>r1 first  \r\nACGTNNacgt\r\n\r\nGG TT\tAA\n>empty\n>r3 > odd header\n"
+                 b"acgRYKM>r4 starts mid line\nttt\n\n>last header without newline")
+    elif case == "empty":
+        image = b""
+    else:
+        image = b"no records here\nacgt\n"
+    want = _py_fasta(image)
+    ss = gm.SeqSet.from_fasta(ctx, image)
+    assert ss.n == len(want)
+    assert [h.encode() for h in ss.headers] == [h for h, _ in want]
+    lens = [len(s) for _, s in want]
+    assert ss.off.tolist() == [0] + np.cumsum(lens).tolist() if lens else ss.off.tolist() == [0]
+    if ss.total:
+        assert ss.unpack() == b"".join(O.filter_lower(s) for _, s in want)
+        ref = gm.SeqSet(ctx, seqs=[s for _, s in want])
+        assert abs(ss.gc_fraction() - ref.gc_fraction()) == 0.0
+
+
 @pytest.mark.parametrize("k", [4, 5])
 def test_score_string_known_answers(gm, ctx, reads, k):
     m = gm.ICM.Read(ctx, os.path.join(G, f"cluster-{k}.icm"))
