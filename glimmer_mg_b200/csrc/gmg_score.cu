@@ -579,6 +579,101 @@ static int string_scores(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int fram
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Many-model read scoring (the `simple-score` step of the Phymm / Scimm
+// classification that precedes glimmer-mg, scripts/scoreReadsGlim.pl:450,482 -- Score_String of every read
+// against every ICM).  gridDim.y = model: a CTA stages its model's branch-position table (int8, levels
+// 0..D-1) in shared memory and gathers leaf probabilities from the L2-resident table; one warp per read, lanes
+// stride the positions and sum in FP64.  Summation order is free because gmg_icm_score_strings_many only routes a
+// model here when its static certificate holds for the longest read (every value an integer multiple of 2^g, and
+// len * max|value| < 2^(g+52): no addition can round); any other model goes through the ordered kernel.
+__global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ models, const int* __restrict__ slot,
+                                                    const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
+                                                    int64_t n, int frame0, double* __restrict__ out) {
+  extern __shared__ int8_t s_mipm[];
+  const DevIcm m = models[slot[blockIdx.y]];
+  const int nmip = m.P * m.inner;
+  for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mipm[i] = m.mip[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int fr0 = m.P == 1 ? 0 : frame0;
+  double* row = out + (size_t)slot[blockIdx.y] * n;
+  for (int64_t s = (int64_t)blockIdx.x * nw + wid; s < n; s += (int64_t)gridDim.x * nw) {
+    const int64_t a = off[s];
+    const int len = (int)(off[s + 1] - a);
+    double sum = 0.0;
+    for (int q = lane; q < len; q += 32) {
+      const int f = m.P == 1 ? 0 : (fr0 + q) % m.P;
+      const int lim = m.W - 1 - q;
+      sum += (double)gmg_walk(s_mipm + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_str(words, a + q, m.W), m.W,
+                              m.D, lim > 0 ? lim : 0);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) row[s] = sum;
+  }
+}
+
+extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* models, int n_models, gmg_seqset* s,
+                                          int frame, double* h_out) {
+  GMG_CHECK(ctx && models && s && h_out && n_models >= 0, "gmg_icm_score_strings_many: bad argument");
+  if (n_models == 0 || s->n == 0) return 0;
+  std::vector<DevIcm> dev((size_t)n_models);
+  std::vector<int> fast_slots, ordered_slots;
+  size_t smem = 0;
+  for (int k = 0; k < n_models; k++) {
+    const gmg_icm* m = models[k];
+    GMG_CHECK(m != NULL, "gmg_icm_score_strings_many: model %d is NULL", k);
+    GMG_CHECK(frame >= 0 && (frame < m->P || m->P == 1), "frame %d out of range for periodicity %d (model %d)", frame, m->P, k);
+    dev[(size_t)k] = m->dev;
+    int g;
+    float mx;
+    gmg_icm_value_stats(m, &g, &mx);
+    const size_t need = (size_t)m->dev.P * m->dev.inner;
+    const bool exact = (double)s->max_len * (double)mx * 1.01 < ldexp(1.0, g + 52);
+    if (exact && need <= 64 * 1024) {
+      fast_slots.push_back(k);
+      if (need > smem) smem = need;
+    } else {
+      ordered_slots.push_back(k);
+    }
+  }
+  void *d_out, *d_models;
+  if (gmg_scratch(ctx, SCR_CUM, (size_t)n_models * s->n * sizeof(double), &d_out)) return 1;
+  if (!fast_slots.empty()) {
+    const size_t mb = (size_t)n_models * sizeof(DevIcm), sb = fast_slots.size() * sizeof(int);
+    if (gmg_scratch(ctx, SCR_TMP3, mb + sb + 64, &d_models)) return 1;
+    int* d_slot = (int*)((char*)d_models + ((mb + 15) & ~(size_t)15));
+    GMG_CUDA(cudaMemcpyAsync(d_models, dev.data(), mb, cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaMemcpyAsync(d_slot, fast_slots.data(), sb, cudaMemcpyHostToDevice, ctx->stream));
+    if (smem > 48 * 1024)
+      GMG_CUDA(cudaFuncSetAttribute(k_score_many, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t need_ctas = (s->n + 7) / 8;
+    int64_t gx = (int64_t)ctx->sm_count * 8 / (int64_t)fast_slots.size() + 1;
+    if (gx > need_ctas) gx = need_ctas;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)fast_slots.size());
+    if (gmg_prof_begin(ctx, GMG_PROF_FS)) return 1;
+    k_score_many<<<grid, 256, smem, ctx->stream>>>((const DevIcm*)d_models, d_slot, s->d_words, s->d_off, s->n, frame,
+                                                  (double*)d_out);
+    gmg_prof_end(ctx, GMG_PROF_FS);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // dev / fast_slots are host temporaries
+  }
+  for (int k : ordered_slots) {  // serial FP64 order of the reference (icm.cc:886-900)
+    const gmg_icm* m = models[k];
+    int64_t threads = s->n * 32;
+    k_string_scores<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(m->dev, s->d_words, s->d_off, s->n, frame, 0,
+                                                                               (double*)d_out + (size_t)k * s->n);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
+  GMG_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)n_models * s->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int gmg_icm_score_strings(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out) {
   return string_scores(ctx, m, s, frame, 0, h_out);
 }

@@ -91,6 +91,7 @@ def lib():
         "gmg_seqset_gc_fraction": (i32, [vp, P(C.c_double)]),
         "gmg_seqset_unpack": (i32, [vp, vp]),
         "gmg_icm_score_strings": (i32, [vp, vp, vp, i32, vp]),
+        "gmg_icm_score_strings_many": (i32, [vp, P(vp), i32, vp, i32, vp]),
         "gmg_icm_cumulative_score": (i32, [vp, vp, vp, i32, vp]),
         "gmg_icm_frame_score": (i32, [vp, vp, vp, i32, vp]),
         "gmg_icm_full_window_prob": (i32, [vp, vp, C.c_char_p, i32, P(C.c_double)]),
@@ -479,6 +480,15 @@ class ICM:
         out = np.zeros(ss.total, np.float64)
         _check(lib().gmg_icm_frame_score(self.ctx.h, self.h, ss.h, frame, out.ctypes.data))
         return out
+
+
+def score_strings_many(ctx, models, strings, frame=0):
+    """Score_String of every string against every model (list of ICM) in one launch -> float64 [n_models, n_strings]."""
+    ss = strings if isinstance(strings, SeqSet) else SeqSet(ctx, seqs=strings)
+    arr = (C.c_void_p * len(models))(*[m.h for m in models])
+    out = np.zeros((len(models), ss.n), np.float64)
+    _check(lib().gmg_icm_score_strings_many(ctx.h, arr, len(models), ss.h, frame, out.ctypes.data))
+    return out
 
 
 def build_indep_wo_stops(ctx, gc, stops=("taa", "tag", "tga")):

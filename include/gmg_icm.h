@@ -155,6 +155,12 @@ int gmg_seqset_unpack(gmg_seqset* s, char* h_out);
 /* ICM_t::Score_String (icm.cc:864-903) for n strings of a seqset; frame = first base's period */
 int gmg_icm_score_strings(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out);
 /* ICM_t::Cumulative_Score (icm.cc:354-405): out[off[i]+t] for every string */
+/* Score_String of every sequence against every model in one launch (the many-model read scoring that precedes
+ * glimmer-mg: Phymm / Scimm `simple-score`, scripts/scoreReadsGlim.pl:450,482).  h_out[k * n_seqs + i] = score of
+ * sequence i under models[k]; models may differ in window, depth and periodicity.  Bit-identical to
+ * gmg_icm_score_strings model by model. */
+int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* models, int n_models, gmg_seqset* s, int frame,
+                               double* h_out);
 int gmg_icm_cumulative_score(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out);
 /* ICM_t::Frame_Score (icm.cc:485-509): per-position log-prob, fixed period */
 int gmg_icm_frame_score(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, double* h_out);

@@ -136,6 +136,31 @@ def test_score_string_known_answers(gm, ctx, reads, k):
         assert v == O.lib().orc_score_string(om, s, len(s), 0)
 
 
+def test_score_strings_many_models(gm, ctx, reads):
+    """Every read against every model in one launch (models of different periodicity mixed): the reference's golden
+    Score_String values (4 decimals), and bit-identical to the per-model call and to the oracle.  frame 1 exercises
+    the period cycling of the period-3 model."""
+    names = ["cluster-4.icm", "NC_000915.icm", "cluster-5.icm", "seqs.cluster-5.run1.filt.gicm"]
+    models = [gm.ICM.Read(ctx, os.path.join(G, nm)) for nm in names]
+    seqs = [s for _, s in reads] + [b"", b"acg", b"acgtacgtacgtac"]
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    for frame in (0, 1):
+        got = gm.score_strings_many(ctx, models, ss, frame)
+        assert got.shape == (len(models), len(seqs))
+        for k, (nm, m) in enumerate(zip(names, models)):
+            one = m.score_strings(ss, frame)
+            assert (got[k].view(np.uint64) == one.view(np.uint64)).all(), nm
+            om = O.lib().orc_icm_read(os.path.join(G, nm).encode())
+            P = m.Get_Periodicity()
+            for i in range(0, len(seqs), 7):
+                assert got[k, i] == O.lib().orc_score_string(om, seqs[i], len(seqs[i]), frame if P > 1 else 0), (nm, i)
+    for k, kk in ((0, 4), (2, 5)):
+        gold = [l.split() for l in open(os.path.join(G, f"icm-{kk}.scores.tmp"))]
+        got = gm.score_strings_many(ctx, models, ss, 0)
+        for (gh, gv), v in zip(gold, got[k]):
+            assert "%.4f" % v == "%.4f" % float(gv)
+
+
 def test_scalar_surface_matches_oracle(gm, ctx, reads):
     path = os.path.join(G, "NC_000915.icm")
     m = gm.ICM.Read(ctx, path)
