@@ -78,6 +78,7 @@ struct gmg_ctx {
   double* h_penalty;  // pinned staging
   int64_t* h_scalars;  // pinned: small device -> host results (totals) that must not serialise the stream
   cudaEvent_t ev_scalars;
+  double mg_rate[4];   // start records per base seen by the last gmg_score_orfs_mg call, by (indels, subs) mode
   void* h_stage;       // pinned staging for larger device -> host results (training count slabs), grown on demand
   size_t h_stage_bytes;
   // per-kernel device timing (gmg_ctx_profile): event pairs around the launches of each kernel class

@@ -2641,7 +2641,25 @@ __device__ int mg_leaf_run(const MgSeq& S, const DevParams& P, const CodonSets& 
   return cnt;
 }
 
-template <bool kWrite>
+// kMode 0: count only.  1: write into the CSR ranges given by start_off (second pass).  2: SINGLE PASS -- every run
+// of records reserves its exact size from a pool (one atomicAdd per run; consecutive reservations of a warp merge
+// into one extent), the per-ORF extent lists and counts are kept, and k3_mg_compact moves the records to their
+// CSR places after the scan: the recursion runs once instead of twice.  A pool or extent-table overflow only
+// drops writes (counts stay exact), and the caller then runs the write pass.
+struct MgExt {
+  long long start;
+  int len, next;
+};
+struct MgPool {
+  gmg_start* pool;
+  unsigned long long cap;
+  unsigned long long* cur;   // [0] pool cursor, [1] extent cursor, [2] overflow flag
+  MgExt* ext;
+  unsigned long long ext_cap;
+  int* orf_head;
+};
+
+template <int kMode>
 __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
                                                          const gmg_orf* __restrict__ orfs,
                                                          const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
@@ -2650,8 +2668,9 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
                                                          const double* __restrict__ tables, CodonSets cs, DevParams P,
                                                          int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
                                                          gmg_start* __restrict__ starts, const uint2* __restrict__ cb,
-                                                         int64_t nwc) {
+                                                         int64_t nwc, MgPool pool) {
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool kWrite = kMode != 0;
   __shared__ MgFrame s_stack[4][5];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -2673,8 +2692,52 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
   const int frame = o.frame;
   const bool fwd = frame > 0;
   const int lowest_j = min(3, P.min_gene_len - 3);
-  gmg_start* out = kWrite ? starts + start_off[oi] : NULL;
+  gmg_start* out = kMode == 1 ? starts + start_off[oi] : NULL;
   int64_t n = 0;  // records so far (warp-uniform)
+  // single pass: the warp's open extent and its list
+  long long ext_start = -1;
+  int ext_len = 0, ext_head = -1, ext_tail = -1;
+  auto flush_extent = [&]() {
+    if (ext_start < 0) return;
+    int e = 0;
+    if (lane == 0) {
+      e = (int)atomicAdd(pool.cur + 1, 1ull);
+      if ((unsigned long long)e < pool.ext_cap) {
+        MgExt x;
+        x.start = ext_start;
+        x.len = ext_len;
+        x.next = -1;
+        pool.ext[e] = x;
+        if (ext_tail >= 0 && (unsigned long long)ext_tail < pool.ext_cap) pool.ext[ext_tail].next = e;
+      } else {
+        pool.cur[2] = 1ull;
+      }
+    }
+    e = __shfl_sync(FULL, e, 0);
+    if (ext_head < 0) ext_head = e;
+    ext_tail = e;
+    ext_start = -1;
+  };
+  // where the next `cnt` records of this ORF go (NULL: nowhere -- counting, or the pool is full)
+  auto place = [&](int cnt) -> gmg_start* {
+    if (kMode == 1) return out + n;
+    if (kMode == 0 || cnt == 0) return NULL;
+    unsigned long long st = 0;
+    if (lane == 0) st = atomicAdd(pool.cur, (unsigned long long)cnt);
+    st = __shfl_sync(FULL, st, 0);
+    if (st + (unsigned long long)cnt > pool.cap) {
+      if (lane == 0) pool.cur[2] = 1ull;
+      return NULL;
+    }
+    if (ext_start >= 0 && (long long)st == ext_start + ext_len) {
+      ext_len += cnt;
+    } else {
+      flush_extent();
+      ext_start = (long long)st;
+      ext_len = cnt;
+    }
+    return pool.pool + st;
+  };
   MgFrame* stk = s_stack[wid];
   int sp = 0;
   MgFrame c;
@@ -2798,8 +2861,9 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
             if (lane >= d) incl += t;
           }
           const int all = __shfl_sync(FULL, incl, 31);
-          if (kWrite && tot) {
-            gmg_start* o = out + n + (incl - tot);
+          gmg_start* const dstb = place(all);
+          if (kWrite && tot && dstb) {
+            gmg_start* o = dstb + (incl - tot);
 #pragma unroll 1
             for (int ph = 0; ph < 2; ph++) {
               if (cnt_b[ph]) {
@@ -2858,9 +2922,10 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
         // run of own starts before the next branch: lanes le .. lb-1 of Er write their records in parallel
         const unsigned run = Er & (lb >= 32 ? FULL : ((1u << lb) - 1u));
         const unsigned below = (1u << lane) - 1u;
+        gmg_start* const dstb = place(__popc(run) + __popc(run & DB));
         if ((run >> lane) & 1u) {
-          const int64_t at = n + __popc(run & below) + __popc(run & DB & below);
-          if (kWrite) {
+          const int at = __popc(run & below) + __popc(run & DB & below);
+          if (kWrite && dstb) {
             const double sc = (sc_prev - 0.0) + c.suffix_score;
             const int jj = j + 2 + c.suffix_j;
             const int first = (FI >> lane) & 1u;
@@ -2875,12 +2940,12 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
             st.err_type[1] = c.n_err > 1 ? c.err_type[1] : 0;
             if ((DB >> lane) & 1u) {
               st.which = -1; st.truncated = 1; st.first = first;
-              out[at] = st;
+              dstb[at] = st;
               st.which = which; st.truncated = 0; st.first = 0;
-              out[at + 1] = st;
+              dstb[at + 1] = st;
             } else {
               st.which = which; st.truncated = which < 0; st.first = first;
-              out[at] = st;
+              dstb[at] = st;
             }
           }
         }
@@ -2927,7 +2992,28 @@ __global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __re
     c.cur = 0;
     c.first_zero = state;
   }
-  if (!kWrite && lane == 0) counts[oi] = n;
+  if (kMode == 2) {
+    flush_extent();
+    if (lane == 0) pool.orf_head[oi] = ext_head;
+  }
+  if (kMode != 1 && lane == 0) counts[oi] = n;
+}
+
+// single pass, step 2: the extents of ORF oi, in order, copied to its CSR range (48-byte records as 3 x 16 bytes)
+__global__ void __launch_bounds__(128) k3_mg_compact(MgPool pool, const int64_t* __restrict__ start_off, int64_t n_orfs,
+                                                     gmg_start* __restrict__ starts) {
+  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (oi >= n_orfs) return;
+  uint4* dst = reinterpret_cast<uint4*>(starts + start_off[oi]);
+  for (int e = pool.orf_head[oi]; e >= 0;) {
+    const MgExt x = pool.ext[e];
+    const uint4* src = reinterpret_cast<const uint4*>(pool.pool + x.start);
+    const int q = 3 * x.len;
+    for (int i = lane; i < q; i += 32) dst[i] = src[i];
+    dst += q;
+    e = x.next;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3128,35 +3214,76 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   static const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
   const int k3mg_mode = k3mg_env >= 0 ? k3mg_env : ((p->allow_indels || p->allow_subs) ? 0 : 1);
   const unsigned g3w = (unsigned)((s->n_orfs * 32 + 127) / 128);
-  if (k3mg_mode == 0)
-    k3_mg_starts_warp<false><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                          (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs,
-                                                          dp, counts, NULL, NULL, s->d_cbits, s->nwc);
+  // single pass (warp kernel only): pool sized from the rate of the previous call in the same error mode
+  const int rate_key = (p->allow_indels ? 1 : 0) | (p->allow_subs ? 2 : 0);
+  const char* env_two = getenv("GMG_K3MG_TWO_PASS");      // test hooks: force the two-pass form,
+  const char* env_scale = getenv("GMG_K3MG_POOL_SCALE");  // shrink the pool (overflow -> write pass)
+  const int k3mg_two_pass = env_two ? atoi(env_two) : 0;
+  const double pool_scale = env_scale ? atof(env_scale) : 1.25;
+  MgPool pool;
+  memset(&pool, 0, sizeof pool);
+  bool single = false;
+  if (k3mg_mode == 0 && !k3mg_two_pass && ctx->mg_rate[rate_key] > 0.0) {
+    const unsigned long long cap = (unsigned long long)(ctx->mg_rate[rate_key] * (double)s->total * pool_scale) + (env_scale ? 64ull : 65536ull);
+    // extent table, ORF heads and cursors live in the plane scratch (K3 does not read the planes)
+    const size_t avail = ctx->scratch_bytes[SCR_PLANES];
+    const size_t head_bytes = ((size_t)s->n_orfs * sizeof(int) + 64 + 15) & ~(size_t)15;
+    if (avail > head_bytes + (size_t)s->n_orfs * 2 * sizeof(MgExt)) {
+      void* d_pool;
+      if (gmg_scratch(ctx, SCR_TMP2, (size_t)cap * sizeof(gmg_start), &d_pool)) return 1;
+      char* base = (char*)ctx->scratch[SCR_PLANES];
+      pool.pool = (gmg_start*)d_pool;
+      pool.cap = cap;
+      pool.cur = (unsigned long long*)base;
+      pool.orf_head = (int*)(base + 64);
+      pool.ext = (MgExt*)(base + head_bytes);
+      pool.ext_cap = (avail - head_bytes) / sizeof(MgExt);
+      GMG_CUDA(cudaMemsetAsync(pool.cur, 0, 64, ctx->stream));
+      single = true;
+    }
+  }
+  if (single)
+    k3_mg_starts_warp<2><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                      counts, NULL, NULL, s->d_cbits, s->nwc, pool);
+  else if (k3mg_mode == 0)
+    k3_mg_starts_warp<0><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                      counts, NULL, NULL, s->d_cbits, s->nwc, pool);
   else
-  k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                   (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                   counts, NULL, NULL);
+    k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                     (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                     counts, NULL, NULL);
   gmg_prof_end(ctx, GMG_PROF_K3);
   k_count_zero_flags<<<(unsigned)((s->n + 255) / 256), 256, 0, ctx->stream>>>(cert, s->n,
                                                                              (unsigned long long*)(counts + s->n_orfs + 1));
   ctx->launches += 2;
   GMG_CUDA(cudaGetLastError());
   if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
-  int64_t total_starts = 0, bad = 0;
-  GMG_CUDA(cudaMemcpyAsync(&total_starts, s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  GMG_CUDA(cudaMemcpyAsync(&bad, counts + s->n_orfs + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_scalars[6] = ctx->h_scalars[7] = ctx->h_scalars[8] = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[6], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[7], counts + s->n_orfs + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (single)
+    GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[8], pool.cur + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t total_starts = ctx->h_scalars[6], bad = ctx->h_scalars[7];
+  const bool overflow = single && ctx->h_scalars[8] != 0;
   s->uncertified = bad;
+  ctx->mg_rate[rate_key] = s->total > 0 ? (double)total_starts / (double)s->total : 0.0;
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  if (k3mg_mode == 0)
-    k3_mg_starts_warp<true><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                         (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs,
-                                                         dp, NULL, s->d_start_off, s->d_starts, s->d_cbits, s->nwc);
-  else
-  k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                  (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                  NULL, s->d_start_off, s->d_starts);
+  if (single && !overflow) {
+    if (total_starts > 0)
+      k3_mg_compact<<<g3w, 128, 0, ctx->stream>>>(pool, s->d_start_off, s->n_orfs, s->d_starts);
+  } else if (k3mg_mode == 0) {
+    k3_mg_starts_warp<1><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                      NULL, s->d_start_off, s->d_starts, s->d_cbits, s->nwc, pool);
+  } else {
+    k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
+                                                    (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
+                                                    NULL, s->d_start_off, s->d_starts);
+  }
   gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());

@@ -323,6 +323,32 @@ def test_mg_start_lists_match_oracle_more_reads(gm, ctx, reads):
                 assert starts_as_tuples(starts[soff[o]:soff[o + 1]]) == starts_as_tuples(wst[woff[k]:woff[k + 1]])
 
 
+@pytest.mark.parametrize("flags", [dict(allow_indels=1), dict(allow_subs=1)])
+def test_mg_single_pass_two_pass_and_overflow_agree(gm, ctx, reads, monkeypatch, flags):
+    """-i / -s start lists come from one pass over a record pool (sized from the previous call's rate) plus a
+    compaction; the two-pass form and the pool-overflow fallback must give the identical CSR."""
+    rs = [s for _, s in reads[:150]]
+    gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, 0.39)
+    p = gm.Params(True, **flags)
+    p.set_ignore_score_len(0.39)
+
+    def run():
+        ss = gm.SeqSet(ctx, seqs=rs)
+        ss.find_orfs(p)
+        ss.score_orfs_mg(gene, indep, p)
+        st, off = ss.get_starts()
+        return st.tobytes(), off.tolist()
+
+    monkeypatch.setenv("GMG_K3MG_TWO_PASS", "1")
+    want = run()            # two passes (also primes the rate)
+    monkeypatch.delenv("GMG_K3MG_TWO_PASS")
+    assert run() == want    # single pass
+    monkeypatch.setenv("GMG_K3MG_POOL_SCALE", "0.05")
+    assert run() == want    # pool too small: counts from the single pass, records from the write pass
+    assert len(want[0]) > 48 * 5000
+
+
 def test_g3_start_lists_match_reference_dump(gm, ctx, genome):
     recs = parse_dump(os.path.join(G, "g3_300k.dump.gz"))
     s0 = genome[:(300000 // 70) * 70]
