@@ -761,15 +761,15 @@ static int ensure_codon_bits(gmg_ctx* ctx, gmg_seqset* s, const CodonSets& cs) {
 // Scan one stream's codon bits downwards over the slots [s_lo, s_hi]: the highest slot with a stop bit
 // (-1 = none) and, among the slots above it, the lowest (`far`) and highest (`near`) one with a start bit.
 struct BackScan {
-  int64_t stop, far, near;
+  int stop, far, near;  // slot numbers (< 2^32 / 3: batches hold fewer than 2^32 bases), -1 = none
 };
-__device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int64_t s_hi, int64_t s_lo) {
+__device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int s_hi, int s_lo) {
   BackScan r;
   r.stop = r.far = r.near = -1;
   if (s_hi < s_lo) return r;
-  const int64_t w_hi = s_hi >> 5, w_lo = s_lo >> 5;
-  const unsigned m_hi = (2u << (int)(s_hi & 31)) - 1u, m_lo = ~0u << (int)(s_lo & 31);
-  for (int64_t w = w_hi; w >= w_lo; --w) {
+  const int w_hi = s_hi >> 5, w_lo = s_lo >> 5;
+  const unsigned m_hi = (2u << (s_hi & 31)) - 1u, m_lo = ~0u << (s_lo & 31);
+  for (int w = w_hi; w >= w_lo; --w) {
     const uint2 x = __ldg(cb + w);
     const unsigned m = (w == w_hi ? m_hi : ~0u) & (w == w_lo ? m_lo : ~0u);
     unsigned st = x.x & m;
@@ -805,11 +805,13 @@ __device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int6
 __device__ bool orf_fwd_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i,
                                const DevParams& P, gmg_orf* o) {
   // candidate codons end at t = i-3, i-6, ... >= 2, i.e. start at i-5, i-8, ... >= 0
-  const int r = (int)((a + i + 1) % 3);
-  const int64_t s_hi = i >= 5 ? (a + i - 5) / 3 : -1, s_lo = (a - r + 2) / 3;
+  // 32-bit arithmetic: global base indices are below 2^32 (build_buckets checks the batch size)
+  const uint32_t a32 = (uint32_t)a;
+  const int r = (int)((a32 + (uint32_t)i + 1u) % 3u);
+  const int s_hi = i >= 5 ? (int)((a32 + (uint32_t)i - 5u) / 3u) : -1, s_lo = (int)((a32 - (uint32_t)r + 2u) / 3u);
   const BackScan f = scan_back(cb + (size_t)r * nwc, s_hi, s_lo);
-  const int prev = f.stop >= 0 ? (int)(3 * f.stop + r - a) + 1 : 0;  // 1-based first base of the previous stop
-  const int first_start = f.far >= 0 ? (int)(3 * f.far + r - a) + 1 : INT_MAX;
+  const int prev = f.stop >= 0 ? (int)(3u * (uint32_t)f.stop + (uint32_t)r - a32) + 1 : 0;  // 1-based first base of the previous stop
+  const int first_start = f.far >= 0 ? (int)(3u * (uint32_t)f.far + (uint32_t)r - a32) + 1 : INT_MAX;
   int gene_len, orf_len;
   if (prev == 0) {
     int pos = i - 1;
@@ -835,11 +837,12 @@ __device__ bool orf_fwd_closed(const uint2* __restrict__ cb, int64_t nwc, int64_
 __device__ bool orf_rev_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i, bool finish,
                                const DevParams& P, gmg_orf* o) {
   const int t0 = finish ? i : i - 3;  // candidate codons end at t0, t0-3, ... >= 2
-  const int r = (int)((a + t0 + 1) % 3);
-  const int64_t s_hi = t0 >= 2 ? (a + t0 - 2) / 3 : -1, s_lo = (a - r + 2) / 3;
+  const uint32_t a32 = (uint32_t)a;
+  const int r = (int)((a32 + (uint32_t)(t0 + 1)) % 3u);  // t0 >= -1 in every call
+  const int s_hi = t0 >= 2 ? (int)((a32 + (uint32_t)t0 - 2u) / 3u) : -1, s_lo = (int)((a32 - (uint32_t)r + 2u) / 3u);
   const BackScan f = scan_back(cb + (size_t)(3 + r) * nwc, s_hi, s_lo);
-  const int prev = f.stop >= 0 ? (int)(3 * f.stop + r - a) + 1 : 0;
-  const int last_start = f.near >= 0 ? (int)(3 * f.near + r - a) + 1 : 0;  // nearest to i
+  const int prev = f.stop >= 0 ? (int)(3u * (uint32_t)f.stop + (uint32_t)r - a32) + 1 : 0;
+  const int last_start = f.near >= 0 ? (int)(3u * (uint32_t)f.near + (uint32_t)r - a32) + 1 : 0;  // nearest to i
   int gene_len, orf_len, orf_stop;
   if (!finish) {
     if (prev == 0) {
@@ -897,10 +900,10 @@ __global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words
     const int L = sv.len, q = (int)(p - a);
     if (L >= P.min_gene_len) {
       if (q >= 2) {  // the codon q-2 .. q: forward stop / reverse stop?
-        const int64_t c = p - 2;
-        const int r = (int)(c % 3);
-        const int64_t sl = c / 3;
-        const unsigned bit = 1u << (int)(sl & 31);
+        const uint32_t c = (uint32_t)(p - 2);
+        const int r = (int)(c % 3u);
+        const uint32_t sl = c / 3u;
+        const unsigned bit = 1u << (sl & 31u);
         if (__ldg(cb + (size_t)r * nwc + (sl >> 5)).y & bit) n += orf_fwd_closed(cb, nwc, a, L, q, P, &rec[n]);
         if (__ldg(cb + (size_t)(3 + r) * nwc + (sl >> 5)).y & bit) n += orf_rev_closed(cb, nwc, a, L, q, false, P, &rec[n]);
       }
