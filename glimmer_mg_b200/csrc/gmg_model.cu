@@ -268,8 +268,9 @@ static int icm_upload(gmg_icm* m) {
       memcpy(&eff[((size_t)f * N + i) * 4], &m->prob[((size_t)f * N + src) * 4], 4 * sizeof(float));
     }
   }
-  GMG_CUDA(cudaMalloc(&m->d_mip, mip8.size() + 16));
-  GMG_CUDA(cudaMalloc(&m->d_prob, eff.size() * sizeof(float) + 16));
+  // model tables come from the device's stream-ordered pool (cached blocks: no driver call per model)
+  GMG_CUDA(cudaMallocAsync(&m->d_mip, mip8.size() + 16, ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&m->d_prob, eff.size() * sizeof(float) + 16, ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(m->d_mip, mip8.data(), mip8.size(), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(m->d_prob, eff.data(), eff.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -334,9 +335,9 @@ static int icm_upload(gmg_icm* m) {
         wbase += width;
       }
     }
-    GMG_CUDA(cudaMalloc(&m->d_msh, mw.size() * sizeof(uint32_t) + 64));
+    GMG_CUDA(cudaMallocAsync(&m->d_msh, mw.size() * sizeof(uint32_t) + 64, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(m->d_msh, mw.data(), mw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    GMG_CUDA(cudaMalloc(&m->d_bleaf, bleaf.size() * sizeof(float) + 64));
+    GMG_CUDA(cudaMallocAsync(&m->d_bleaf, bleaf.size() * sizeof(float) + 64, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(m->d_bleaf, bleaf.data(), bleaf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     m->fast.N = N;
@@ -365,7 +366,7 @@ static int icm_upload(gmg_icm* m) {
       }
       lut[i] = eff[((size_t)f * N + node) * 4 + ((ctx >> 4) & 3)];
     }
-    GMG_CUDA(cudaMalloc(&m->d_lut3, 384 * sizeof(float)));
+    GMG_CUDA(cudaMallocAsync(&m->d_lut3, 384 * sizeof(float), ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(m->d_lut3, lut.data(), 384 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     m->dev.lut3 = m->d_lut3;
@@ -530,11 +531,9 @@ extern "C" int gmg_icm_mut_info(const gmg_icm* m, float* h_out) {
 extern "C" void gmg_icm_free(gmg_icm* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
-  if (m->d_mip) cudaFree(m->d_mip);
-  if (m->d_prob) cudaFree(m->d_prob);
-  if (m->d_msh) cudaFree(m->d_msh);
-  if (m->d_bleaf) cudaFree(m->d_bleaf);
-  if (m->d_lut3) cudaFree(m->d_lut3);
+  void* ptrs[] = {m->d_mip, m->d_prob, m->d_msh, m->d_bleaf, m->d_lut3};
+  for (void* q : ptrs)
+    if (q) cudaFreeAsync(q, m->ctx->stream);  // ordered after every kernel of this context that reads the tables
   delete m;
 }
 

@@ -221,13 +221,13 @@ extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int
   t->d_hist = NULL;
   t->hist_ready = 0;
   GMG_CUDA(cudaSetDevice(ctx->device));
-  GMG_CUDA(cudaMalloc(&t->d_mip, (size_t)p * t->N));
+  GMG_CUDA(cudaMallocAsync(&t->d_mip, (size_t)p * t->N, ctx->stream));
   GMG_CUDA(cudaMemsetAsync(t->d_mip, 0xFF, (size_t)p * t->N, ctx->stream));
   // the count slab (and the window histogram) live in the context's scratch: no cudaMalloc / cudaFree per model
   size_t cap = (size_t)p * level_nodes(d) * (w - 1) * 16;
   void* d_slab;
   if (gmg_scratch(ctx, SCR_TMP, cap * sizeof(int32_t), &d_slab)) {
-    cudaFree(t->d_mip);
+    cudaFreeAsync(t->d_mip, ctx->stream);
     delete t;
     return 1;
   }
@@ -240,8 +240,7 @@ extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int
 extern "C" void gmg_trainer_free(gmg_trainer* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
-  cudaStreamSynchronize(t->ctx->stream);
-  if (t->d_mip) cudaFree(t->d_mip);
+  if (t->d_mip) cudaFreeAsync(t->d_mip, t->ctx->stream);
   delete t;
 }
 
