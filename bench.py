@@ -881,9 +881,9 @@ def run_b200_train(args):
 
 
 def main():
-    # the bench contract is ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # the bench contract is ONE JSON line on stdout: NCCL's banner / debug output (NCCL_DEBUG set on the box) goes
+    # to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     if args.workload in ("reads400", "reads100"):
         (run_reference_reads if args.impl == "reference" else run_b200_reads)(args, args.workload)
