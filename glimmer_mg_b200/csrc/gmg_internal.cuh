@@ -78,6 +78,8 @@ struct gmg_ctx {
   double* h_penalty;  // pinned staging
   int64_t* h_scalars;  // pinned: small device -> host results (totals) that must not serialise the stream
   cudaEvent_t ev_scalars;
+  cudaStream_t side;   // second stream: small kernels that do not depend on the walks run beside K1 (gmg_score_orfs_g3)
+  cudaEvent_t ev_fork, ev_join;
   double mg_rate[4];   // start records per base seen by the last gmg_score_orfs_mg call, by (indels, subs) mode
   void* h_stage;       // pinned staging for larger device -> host results (training count slabs), grown on demand
   size_t h_stage_bytes;

@@ -63,6 +63,9 @@ extern "C" int gmg_ctx_create(int device, void* stream, gmg_ctx** out) {
   }
   GMG_CUDA(cudaMallocHost(&c->h_scalars, 16 * sizeof(int64_t)));
   GMG_CUDA(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
+  GMG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  GMG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  GMG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -86,6 +89,9 @@ extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev_scalars) cudaEventDestroy(c->ev_scalars);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side) cudaStreamDestroy(c->side);
   for (int k = 0; k < GMG_NPROF; k++)
     for (int i = 0; i < GMG_PROF_RING; i++)
       for (int e = 0; e < 2; e++)

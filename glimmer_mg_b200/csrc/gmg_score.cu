@@ -986,14 +986,17 @@ __global__ void k_orf_seq_from_off(const int64_t* __restrict__ orf_off, int64_t 
   orf_seq[o] = (int32_t)lo;
 }
 
-static int exclusive_sum_i64(gmg_ctx* ctx, int64_t* d_in, int64_t* d_out, int64_t n) {
+static int exclusive_sum_i64_on(gmg_ctx* ctx, cudaStream_t stream, int64_t* d_in, int64_t* d_out, int64_t n) {
   size_t tmp_bytes = 0;
-  GMG_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_in, d_out, n, ctx->stream));
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_in, d_out, n, stream));
   void* tmp;
   if (gmg_scratch(ctx, SCR_TMP4, tmp_bytes, &tmp)) return 1;
-  GMG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, n, ctx->stream));
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, n, stream));
   ctx->launches += 2;
   return 0;
+}
+static int exclusive_sum_i64(gmg_ctx* ctx, int64_t* d_in, int64_t* d_out, int64_t n) {
+  return exclusive_sum_i64_on(ctx, ctx->stream, d_in, d_out, n);
 }
 
 static int ensure_orf_capacity(gmg_seqset* s, int64_t n_orfs) {
@@ -3071,35 +3074,19 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   }
   const bool exact = exact_len >= 0;
   GMG_CUDA(cudaMemsetAsync(s->d_gc + 1, 0, sizeof(unsigned long long), ctx->stream));
-  // Start counts first: they only need the codon bitmaps, and the host has to learn the total before it can size
-  // the output.  The total travels to pinned memory behind an event, so the walks and sums below are already
-  // queued -- the stream never drains -- by the time the host reads it.
+  // Start counts, their scan and the head sums only need the codon bitmaps and the packed bases: they run on the
+  // context's side stream BESIDE the walks (K1) and the codon sums (K2), which fill the machine on the main stream.
+  // The total travels to pinned memory behind an event, so the host sizes the output while K1 is still running; the
+  // emit pass joins both streams.
   void *d_counts, *d_first;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n_orfs * sizeof(int32_t), &d_first)) return 1;
   int64_t* counts = (int64_t*)d_counts;
   int* d_maxlen = (int*)(counts + s->n_orfs + 1);
-  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
-  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_g3_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_orfs,
-                                                                            s->d_orf_seq, s->n_orfs, dp, counts,
-                                                                            (int32_t*)d_first, d_maxlen);
-  ctx->launches++;
-  gmg_prof_end(ctx, GMG_PROF_K3);
-  GMG_CUDA(cudaGetLastError());
-  if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
-  ctx->h_scalars[0] = 0;
-  ctx->h_scalars[1] = 0;
-  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[0], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[1], d_maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  GMG_CUDA(cudaEventRecord(ctx->ev_scalars, ctx->stream));
-
-  float* planes;
-  if (launch_k1(ctx, gene, s, &planes)) return 1;
   double *cumc = NULL, *tileT = NULL, *heads = NULL;
   const int64_t ntiles = s->total / (3 * G3_TS) + 1, tot3 = ntiles * 3 * G3_TS;
   const int nh = (ja + 1) / 3;
-  if (exact) {  // K2 (glimmer3 path): codon-boundary cumulative sums, tile by tile
+  if (exact) {
     void *d_cum, *d_tiles, *d_heads;
     if (gmg_scratch(ctx, SCR_CUM, (size_t)2 * tot3 * sizeof(double), &d_cum)) return 1;
     if (gmg_scratch(ctx, SCR_QUAL, (size_t)ntiles * 6 * sizeof(double), &d_tiles)) return 1;
@@ -3107,23 +3094,46 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     cumc = (double*)d_cum;
     tileT = (double*)d_tiles;
     heads = (double*)d_heads;
+  }
+  float* planes = NULL;
+  void* d_planes;
+  if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &d_planes)) return 1;  // before the fork
+  cudaStream_t side = ctx->side;
+  GMG_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  GMG_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), side));
+  k3_g3_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, side>>>(s->d_cbits, s->nwc, s->d_off, s->d_orfs, s->d_orf_seq,
+                                                                     s->n_orfs, dp, counts, (int32_t*)d_first, d_maxlen);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  if (exclusive_sum_i64_on(ctx, side, counts, s->d_start_off, s->n_orfs + 1)) return 1;
+  ctx->h_scalars[0] = 0;
+  ctx->h_scalars[1] = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[0], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, side));
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[1], d_maxlen, sizeof(int), cudaMemcpyDeviceToHost, side));
+  GMG_CUDA(cudaEventRecord(ctx->ev_scalars, side));
+  if (exact) {
+    if (ja < 16)
+      k3_g3_heads<16><<<(unsigned)((s->n_orfs * 16 + 127) / 128), 128, 0, side>>>(
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
+    else
+      k3_g3_heads<32><<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, side>>>(
+          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+  }
+  GMG_CUDA(cudaEventRecord(ctx->ev_join, side));
+
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  if (exact) {  // K2 (glimmer3 path): codon-boundary cumulative sums, tile by tile
     if (gmg_prof_begin(ctx, GMG_PROF_K2)) return 1;
     k2_g3_codon_cum<<<(unsigned)ntiles, G3_TS, 0, ctx->stream>>>(indep->dev.lut3, s->d_words, s->total, planes,
                                                                 s->d_bktidx, cumc, tot3, tileT);
     gmg_prof_end(ctx, GMG_PROF_K2);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
-    if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-    if (ja < 16)
-      k3_g3_heads<16><<<(unsigned)((s->n_orfs * 16 + 127) / 128), 128, 0, ctx->stream>>>(
-          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
-    else
-      k3_g3_heads<32><<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-          gene->dev, indep->dev, s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, dp, counts, ja, heads);
-    ctx->launches++;
-    gmg_prof_end(ctx, GMG_PROF_K3);
-    GMG_CUDA(cudaGetLastError());
   }
+  GMG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   GMG_CUDA(cudaEventSynchronize(ctx->ev_scalars));
   const int64_t total_starts = ctx->h_scalars[0];
   const int max_orf_len = (int)(ctx->h_scalars[1] & 0xffffffff);
