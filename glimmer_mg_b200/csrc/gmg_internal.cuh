@@ -11,6 +11,9 @@
 
 #define GMG_MAX_W 32      // window bases held in one 64-bit register
 #define GMG_MAX_DEPTH 12
+// zero entries after the walk-ready context arrays (d_ctxf / d_ctxr): K1's software pipeline reads whole trips past the
+// end of a share (k1_planes_bucketed); sized for every (contexts per thread, threads per CTA) variant it is built in
+#define GMG_CTX_PAD 16384
 #define GMG_PAD_WORDS 8   // 64-bit words of zero padding before/after the packed bases
 #define GMG_NPROF 8
 #define GMG_PROF_RING 64

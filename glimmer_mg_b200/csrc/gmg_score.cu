@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
 // 4 SM cycles from shared memory against 11 from an L1-resident and 28 from an L2-resident table).
 // The 24 (f, pb, strand) segments are linearised; CTA c takes the c-th equal share of the 6 * total walks, which
 // spans at most two roles unless the batch is tiny.
-#define K1_PAD 8192  // entries of padding after the context arrays: two trips of two entries per thread
+#define K1_PAD GMG_CTX_PAD  // entries of padding after the context arrays (gmg_internal.cuh)
 struct K1Segs {
   long long lo[25];        // linearised start of segment (f * 4 + pb) * 2 + strand; lo[24] = 6 * total
   unsigned bucket_lo[4];   // plane index of the first position of each base bucket
@@ -286,8 +286,8 @@ __device__ __forceinline__ bool k1_step2_tested(uint32_t w, uint32_t c, unsigned
   return false;
 }
 
-template <int kU>
-__global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
+template <int kU, int NT = 1024>
+__global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
                                                               const uint32_t* __restrict__ ctxr, unsigned total,
                                                               K1Segs segs, float* __restrict__ planes) {
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -295,7 +295,6 @@ __global__ void __launch_bounds__(1024, 2) k1_planes_bucketed(DevIcmFast gm, con
   constexpr uint32_t OFF7 = (16384 - 1) / 3;  // dense number of the first level-7 node
   uint32_t* s_mw = reinterpret_cast<uint32_t*>(s_raw);
   float* s_leaf = reinterpret_cast<float*>(s_raw + NWORDS * 4);
-  constexpr int NT = 1024;  // threads per CTA (launch_k1)
   const int W = gm.W, nt = NT, np = gm.np;
   const int wsh = 32 - 2 * W;
   const long long all = segs.lo[24];
@@ -428,19 +427,31 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
       bl += (unsigned)s->n_base[b];
     }
     const size_t smem = (size_t)(4 + 64 + 1024) * 4 + (size_t)gene->fast.np * sizeof(float);
-    static const int ku = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 2;
-    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (contexts per thread and trip, threads per CTA).  Default (4, 512): four walks in flight per thread hide the
+    // shared-memory latency with half the warps, and the loop overhead is paid once per four walks: 72.5 us per
+    // 5 Mbp against 77.8 us for (2, 1024) and 72.8 us for (3, 768); GMG_K1_U / GMG_K1_NT select the other variants.
+    // Short reads keep (2, 1024): a trip takes the tested path when ANY of its kU x 32 windows per warp is partial,
+    // and reads have W-1 partial windows at either end (reads100: 0.70 ms against 0.76 ms with four per thread).
+    static const int ku_env = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 0;
+    static const int knt_env = getenv("GMG_K1_NT") ? atoi(getenv("GMG_K1_NT")) : 0;
+    const bool long_seqs = s->total / (s->n > 0 ? s->n : 1) >= 4096;
+    const int ku = ku_env ? ku_env : (long_seqs ? 4 : 2);
+    const int knt = knt_env ? knt_env : (long_seqs ? 512 : 1024);
     long long need = (acc + 4095) / 4096;
     long long cap = (long long)ctx->sm_count * 2;
     int grid = (int)(need < cap ? need : cap);
     if (gmg_prof_begin(ctx, GMG_PROF_K1)) return 1;
-    if (ku == 1)
-      k1_planes_bucketed<1><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,
-                                                              (float*)planes);
-    else
-      k1_planes_bucketed<2><<<grid, 1024, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,
-                                                              (float*)planes);
+#define GMG_K1_LAUNCH(U, T)                                                                                             \
+  do {                                                                                                                  \
+    GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k1_planes_bucketed<U, T><<<grid, T, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,  \
+                                                            (float*)planes);                                            \
+  } while (0)
+    if (ku == 1) GMG_K1_LAUNCH(1, 1024);
+    else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
+    else if (ku == 3 && knt == 768) GMG_K1_LAUNCH(3, 768);
+    else GMG_K1_LAUNCH(4, 512);
+#undef GMG_K1_LAUNCH
     gmg_prof_end(ctx, GMG_PROF_K1);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
@@ -3098,7 +3109,8 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   float* planes = NULL;
   void* d_planes;
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &d_planes)) return 1;  // before the fork
-  cudaStream_t side = ctx->side;
+  static const int no_side = getenv("GMG_G3_NO_SIDE") ? atoi(getenv("GMG_G3_NO_SIDE")) : 0;  // diagnostic: one stream
+  cudaStream_t side = no_side ? ctx->stream : ctx->side;
   GMG_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   GMG_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
   GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), side));

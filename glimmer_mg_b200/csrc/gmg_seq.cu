@@ -152,10 +152,10 @@ static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
   const int64_t nblk = (s->total + 31) >> 5;
   GMG_CHECK(s->total < (1ll << 32), "batches of 2^32 bases or more are not supported (got %lld)", (long long)s->total);
   GMG_CUDA(cudaMallocAsync(&s->d_bktidx, (size_t)(nblk + 1) * sizeof(uint4), ctx->stream));
-  GMG_CUDA(cudaMallocAsync(&s->d_ctxf, (size_t)(s->total + 8192) * sizeof(uint32_t), ctx->stream));
-  GMG_CUDA(cudaMallocAsync(&s->d_ctxr, (size_t)(s->total + 8192) * sizeof(uint32_t), ctx->stream));
-  GMG_CUDA(cudaMemsetAsync(s->d_ctxf + s->total, 0, 8192 * sizeof(uint32_t), ctx->stream));
-  GMG_CUDA(cudaMemsetAsync(s->d_ctxr + s->total, 0, 8192 * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_ctxf, (size_t)(s->total + GMG_CTX_PAD) * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMallocAsync(&s->d_ctxr, (size_t)(s->total + GMG_CTX_PAD) * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMemsetAsync(s->d_ctxf + s->total, 0, GMG_CTX_PAD * sizeof(uint32_t), ctx->stream));
+  GMG_CUDA(cudaMemsetAsync(s->d_ctxr + s->total, 0, GMG_CTX_PAD * sizeof(uint32_t), ctx->stream));
   void *d_cnt, *d_tmp;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)2 * nblk * sizeof(uint4), &d_cnt)) return 1;
   uint4* cnt = (uint4*)d_cnt;
