@@ -427,16 +427,18 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
       bl += (unsigned)s->n_base[b];
     }
     const size_t smem = (size_t)(4 + 64 + 1024) * 4 + (size_t)gene->fast.np * sizeof(float);
-    // (contexts per thread and trip, threads per CTA).  Default (4, 512): four walks in flight per thread hide the
-    // shared-memory latency with half the warps, and the loop overhead is paid once per four walks: 72.5 us per
-    // 5 Mbp against 77.8 us for (2, 1024) and 72.8 us for (3, 768); GMG_K1_U / GMG_K1_NT select the other variants.
+    // (contexts per thread and trip, threads per CTA).  Long sequences use (6, 384): six walks in flight per thread
+    // hide the shared-memory latency with a third of the warps and the loop overhead is paid once per six walks
+    // (72 us per 5 Mbp against 77.8 us for (2, 1024); (4, 512) and (3, 768) also 72-73 us, (8, 256) 76 us), and the
+    // 768 threads per SM leave room for the side-stream kernels of gmg_score_orfs_g3 to run beside K1 (0.242 ms per
+    // step against 0.255 ms with (4, 512)).  GMG_K1_U / GMG_K1_NT select the other variants.
     // Short reads keep (2, 1024): a trip takes the tested path when ANY of its kU x 32 windows per warp is partial,
     // and reads have W-1 partial windows at either end (reads100: 0.70 ms against 0.76 ms with four per thread).
     static const int ku_env = getenv("GMG_K1_U") ? atoi(getenv("GMG_K1_U")) : 0;
     static const int knt_env = getenv("GMG_K1_NT") ? atoi(getenv("GMG_K1_NT")) : 0;
     const bool long_seqs = s->total / (s->n > 0 ? s->n : 1) >= 4096;
-    const int ku = ku_env ? ku_env : (long_seqs ? 4 : 2);
-    const int knt = knt_env ? knt_env : (long_seqs ? 512 : 1024);
+    const int ku = ku_env ? ku_env : (long_seqs ? 6 : 2);
+    const int knt = knt_env ? knt_env : (long_seqs ? 384 : 1024);
     long long need = (acc + 4095) / 4096;
     long long cap = (long long)ctx->sm_count * 2;
     int grid = (int)(need < cap ? need : cap);
@@ -450,7 +452,9 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     if (ku == 1) GMG_K1_LAUNCH(1, 1024);
     else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
     else if (ku == 3 && knt == 768) GMG_K1_LAUNCH(3, 768);
-    else GMG_K1_LAUNCH(4, 512);
+    else if (ku == 8 && knt == 256) GMG_K1_LAUNCH(8, 256);
+    else if (ku == 4) GMG_K1_LAUNCH(4, 512);
+    else GMG_K1_LAUNCH(6, 384);
 #undef GMG_K1_LAUNCH
     gmg_prof_end(ctx, GMG_PROF_K1);
     ctx->launches++;
