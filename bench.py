@@ -479,8 +479,9 @@ def run_reference_reads(args, kind):
         have = ref_bin("glimmer-mg") is not None
         fastas, bases = [], 0
         n_avail = len(off) - 1
+        n_sample = min(n_sample, n_avail)
         for i in range(cores if have else 1):
-            lo = (i * n_sample) % max(1, n_avail - n_sample)
+            lo = (i * n_sample) % max(1, n_avail - n_sample + 1)
             sa, so = a[off[lo]:off[lo + n_sample]], off[lo:lo + n_sample + 1] - off[lo]
             bases += int(so[-1])
             if have:

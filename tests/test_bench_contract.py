@@ -1,0 +1,44 @@
+"""bench.py's output contract on CPU: the reference arm (no GPU needed) prints exactly one JSON line with the
+keys the driver reads, for every workload; the b200 arm refuses to run without a CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def _run(args, timeout=600):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.parametrize("workload,extra", [("train500m", ["--scale", "0.001"]), ("reads100", ["--scale", "0.01"]),
+                                            ("reads400", ["--scale", "0.05"])])
+def test_reference_arm_prints_one_json_line(workload, extra):
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    r = _run(["--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0", *extra])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert isinstance(d["config"].get("workload"), str) and "model" not in {k for k in d["config"] if k == "model_family"}
+
+
+def test_b200_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run(["--steps", "1", "--warmup", "1"])
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
