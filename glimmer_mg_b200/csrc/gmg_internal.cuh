@@ -51,6 +51,7 @@ struct DevIcm {
   const int8_t* mip;
   const float* prob;
   const float* lut3;
+  const float* lutp;  // W == 3 models: partial-window values [strand][lim - 1][period][raw], lim = 1, 2 unavailable positions
 };
 
 // Tables of the bucketed K1 kernel (W <= 16, D == 7, P == 3), see icm_upload:
@@ -110,6 +111,7 @@ struct gmg_icm {
   uint8_t* d_msh;
   float* d_bleaf;
   float* d_lut3;
+  float* d_lutp;
   DevIcmFast fast;
   // value statistics of `prob` (lazily computed, see gmg_icm_value_stats)
   int stat_valid, stat_ulp_exp;

@@ -357,6 +357,7 @@ static int icm_upload(gmg_icm* m) {
   }
   // full-window lookup table of W == 3 models (Build_Indep_WO_Stops makes an ICM_t(3,2,3))
   m->dev.lut3 = NULL;
+  m->dev.lutp = NULL;
   if (m->W == 3 && P == 3) {
     std::vector<float> lut(384);
     for (int i = 0; i < 384; i++) {
@@ -372,10 +373,29 @@ static int icm_upload(gmg_icm* m) {
       }
       lut[i] = eff[((size_t)f * N + node) * 4 + ((ctx >> 4) & 3)];
     }
+    // the same for the partial windows at a sequence's ends (Partial_Window_Prob, icm.cc:807-842): window positions
+    // below lim are not available, the walk stops at the first node that asks for one -- so the entry does not depend
+    // on the raw code's bits at those positions and the caller may index with whatever bases lie there
+    std::vector<float> lutp(768);
+    for (int i = 0; i < 768; i++) {
+      const int raw = i & 63, f = (i >> 6) % 3, lim = 1 + (i / 192) % 2, strand = i / 384;
+      const unsigned ctx = strand == 0 ? (unsigned)(((raw >> 4) & 3) | (((raw >> 2) & 3) << 2) | ((raw & 3) << 4))
+                                       : (unsigned)((~raw) & 63);
+      int node = 0;
+      for (int l = 0; l < D; l++) {
+        const int pos = m->mip[(size_t)f * N + node];
+        if (pos < lim) break;
+        node = 4 * node + (int)((ctx >> (2 * pos)) & 3) + 1;
+      }
+      lutp[i] = eff[((size_t)f * N + node) * 4 + ((ctx >> 4) & 3)];
+    }
     GMG_CUDA(cudaMallocAsync(&m->d_lut3, 384 * sizeof(float), ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(m->d_lut3, lut.data(), 384 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaMallocAsync(&m->d_lutp, 768 * sizeof(float), ctx->stream));
+    GMG_CUDA(cudaMemcpyAsync(m->d_lutp, lutp.data(), 768 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     m->dev.lut3 = m->d_lut3;
+    m->dev.lutp = m->d_lutp;
   }
   m->dev.W = m->W;
   m->dev.D = D;
@@ -411,6 +431,7 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
   m->d_msh = NULL;
   m->d_bleaf = NULL;
   m->d_lut3 = NULL;
+  m->d_lutp = NULL;
   for (size_t i = 0; i < m->mip.size(); i++)
     if (m->mip[i] >= w - 1 && w > 1) {
       gmg_set_error("ICM node %zu has mut_info_pos %d outside the context window (len %d)", i, m->mip[i], w);
@@ -537,7 +558,7 @@ extern "C" int gmg_icm_mut_info(const gmg_icm* m, float* h_out) {
 extern "C" void gmg_icm_free(gmg_icm* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
-  void* ptrs[] = {m->d_mip, m->d_prob, m->d_msh, m->d_bleaf, m->d_lut3};
+  void* ptrs[] = {m->d_mip, m->d_prob, m->d_msh, m->d_bleaf, m->d_lut3, m->d_lutp};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, m->ctx->stream);  // ordered after every kernel of this context that reads the tables
   delete m;

@@ -1957,6 +1957,11 @@ __global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint6
             n0 = s_lut[192 + raw_rev];
             n1 = s_lut[256 + raw_rev];
             n2 = s_lut[320 + raw_rev];
+          } else if (have_lut) {  // q = 0, 1: two / one window positions missing
+            const float* lp = indep.lutp + 384 + (1 - q) * 192 + raw_rev;
+            n0 = __ldg(lp);
+            n1 = __ldg(lp + 64);
+            n2 = __ldg(lp + 128);
           } else {
             n0 = icm_rev(indep, words, a + q, q, 0, 0);
             n1 = icm_rev(indep, words, a + q, q, 0, 1);
@@ -2125,6 +2130,11 @@ __global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint6
             n0 = s_lut[raw_fwd];
             n1 = s_lut[64 + raw_fwd];
             n2 = s_lut[128 + raw_fwd];
+          } else if (have_lut) {  // q = L-2, L-1: one / two window positions missing
+            const float* lp = indep.lutp + (q - (L - 2)) * 192 + raw_fwd;
+            n0 = __ldg(lp);
+            n1 = __ldg(lp + 64);
+            n2 = __ldg(lp + 128);
           } else {
             n0 = icm_fwd(indep, words, a + q, q, L, 0);
             n1 = icm_fwd(indep, words, a + q, q, L, 1);
