@@ -882,9 +882,13 @@ def run_b200_train(args):
 
 
 def main():
-    # the bench contract is ONE JSON line on stdout: NCCL's banner / debug output (NCCL_DEBUG set on the box) goes
-    # to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # the bench contract is ONE JSON line on stdout.  With NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its
+    # version banner to stdout and ignores NCCL_DEBUG_FILE; at WARN and above the file is honoured: keep the banner,
+    # send it to stderr
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     if args.workload in ("reads400", "reads100"):
         (run_reference_reads if args.impl == "reference" else run_b200_reads)(args, args.workload)
