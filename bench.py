@@ -47,8 +47,8 @@ K1_BYTES_PER_BASE = 0.25 + 6 * 4  # packed read + six float planes written (DESI
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)  # a 0.25 ms step: 100 of them average out host jitter
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="contig5m", choices=["contig5m", "reads400", "reads100", "train500m"])
     ap.add_argument("--scale", type=float, default=1.0,
@@ -194,7 +194,8 @@ def run_reference(args):
         return
     import workloads as W
     cores = host_cores()
-    slice_len = 500_000
+    # bounded sample per step: the whole --steps K --warmup W run stays around a minute (0.8 us per base and core)
+    slice_len = max(50_000, min(500_000, int(75e6 / max(1, args.steps + args.warmup))))
     tmp = tempfile.mkdtemp(prefix="gmg_ref_")
     try:
         kind = "reference" if ref_bin("glimmer3") else "port"
@@ -471,6 +472,7 @@ def run_reference_reads(args, kind):
     import workloads as W
     cores = host_cores()
     n_sample = 1500 if kind == "reads400" else 15000
+    n_sample = max(n_sample // 15, min(n_sample, n_sample * 47 // max(1, args.steps + args.warmup)))  # ~ a minute in total
     flags = ["-i"] if kind == "reads400" else []
     tmp = tempfile.mkdtemp(prefix="gmg_ref_")
     try:
@@ -732,7 +734,7 @@ def run_reference_train(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     n_seqs = max(16, int(TRAIN_SEQS * args.scale))
-    n_sample = min(n_seqs, 2500)
+    n_sample = min(n_seqs, max(100, min(2500, 2500 * 20 // max(1, args.steps + args.warmup))))  # ~ a minute in total
     times = []
     for k in range(args.warmup + args.steps):
         bases, sec, kind = train_cpu(n_sample)
