@@ -240,6 +240,58 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
   }
 }
 
+// Partial windows of short sequences, separately: the W-1 first positions of a sequence have a partial reverse-strand
+// window and the W-1 last ones a partial forward window (icm.cc:807-842).  In bucket order nearly every warp of the
+// bucketed kernel would meet one and fall to its tested path, so for read sets that kernel walks EVERY window as if
+// it were full and this kernel then overwrites the 2 (W-1) x 3 partial entries of every sequence with the generic
+// walk (branch table in shared memory, leaf gathers from L2).  One thread per (sequence, end, offset).
+__global__ void __launch_bounds__(256) k1_partial_fix(DevIcm gene, const uint64_t* __restrict__ words,
+                                                      const int64_t* __restrict__ off, int64_t n_seq,
+                                                      const uint32_t* __restrict__ bktidx, int64_t total,
+                                                      float* __restrict__ planes) {
+  extern __shared__ int8_t s_mip[];
+  const int nmip = gene.P * gene.inner;
+  for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip[i] = gene.mip[i];
+  __syncthreads();
+  const int W = gene.W, D = gene.D, per = 2 * (W - 1);
+  const int64_t items = n_seq * per;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t sq = it / per;
+    const int k = (int)(it - sq * per);
+    const int64_t a = __ldg(off + sq);
+    const int L = (int)(__ldg(off + sq + 1) - a);
+    const bool tail = k >= W - 1;            // forward-strand partial windows at the end of the sequence
+    const int q = tail ? L - 1 - (k - (W - 1)) : k;
+    if (q < 0 || q >= L) continue;
+    const int64_t p = a + q;
+    int lf = q + W - L;
+    lf = lf > 0 ? lf : 0;
+    int lr = W - 1 - q;
+    lr = lr > 0 ? lr : 0;
+    // the strand whose window is partial at this end; the other strand's entry is a full window and already right
+    // (unless the sequence is so short that it is partial too: then the item of the other end rewrites it)
+    const bool rev = !tail;
+    if ((rev ? lr : lf) == 0) continue;
+    const uint64_t cx = rev ? ctx_rev(words, p, W) : ctx_fwd(words, p, W);
+    const int8_t* mipf[3];
+    const float* probf[3];
+    uint64_t ctx[3];
+    int lim[3];
+    float v[3];
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      mipf[f] = s_mip + f * gene.inner;
+      probf[f] = gene.prob + (size_t)f * gene.N * 4;
+      ctx[f] = cx;
+      lim[f] = rev ? lr : lf;
+    }
+    walk_many<3>(mipf, probf, ctx, lim, W, D, v);
+    const size_t pi = gmg_plane_index(words, bktidx, p);
+#pragma unroll
+    for (int f = 0; f < 3; f++) planes[(size_t)(rev ? 3 + f : f) * total + pi] = v[f];
+  }
+}
+
 // K1, bucketed form (the default for W <= 16, D <= 7): role-persistent CTAs.  The planes are stored bucketed by
 // the base at each position (gmg_plane_index), so all positions whose PREDICTED base is pb -- the base itself on the
 // forward strand, its complement on the reverse strand -- are one dense run of plane indices.  A CTA keeps the
@@ -286,7 +338,7 @@ __device__ __forceinline__ bool k1_step2_tested(uint32_t w, uint32_t c, unsigned
   return false;
 }
 
-template <int kU, int NT = 1024>
+template <int kU, int NT = 1024, bool kAllFull = false>
 __global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
                                                               const uint32_t* __restrict__ ctxr, unsigned total,
                                                               K1Segs segs, float* __restrict__ planes) {
@@ -346,7 +398,7 @@ __global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const
 #pragma unroll
       for (int u = 0; u < kU; u++) {
         c[u] = nc[u];
-        partial |= (int)(c[u] & 15u) < W - 1;  // some window position does not exist
+        if (!kAllFull) partial |= (int)(c[u] & 15u) < W - 1;  // some window position does not exist
         nc[u] = __ldg(pc + NT * u);
       }
       uint32_t idx[kU];
@@ -449,7 +501,20 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     k1_planes_bucketed<U, T><<<grid, T, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,  \
                                                             (float*)planes);                                            \
   } while (0)
-    if (ku == 1) GMG_K1_LAUNCH(1, 1024);
+    // read sets: every window walked as full, the partial ones redone by k1_partial_fix (GMG_K1_FIX=0 disables)
+    static const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 1;
+    const size_t fix_smem = (size_t)gene->dev.P * gene->dev.inner;
+    const bool fix = fix_env && !long_seqs && !ku_env && fix_smem <= 48 * 1024;
+    if (fix) {
+      GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<6, 384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k1_planes_bucketed<6, 384, true><<<grid, 384, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr,
+                                                                         (unsigned)s->total, segs, (float*)planes);
+      const int64_t items = s->n * 2 * (gene->W - 1);
+      int64_t fg = (items + 255) / 256, fcap = (int64_t)ctx->sm_count * 8;
+      k1_partial_fix<<<(unsigned)(fg < fcap ? fg : fcap), 256, fix_smem, ctx->stream>>>(
+          gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
+      ctx->launches++;
+    } else if (ku == 1) GMG_K1_LAUNCH(1, 1024);
     else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
     else if (ku == 3 && knt == 768) GMG_K1_LAUNCH(3, 768);
     else if (ku == 8 && knt == 256) GMG_K1_LAUNCH(8, 256);
