@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)  # a 0.25 ms step: 100 of them average out host jitter
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="contig5m", choices=["contig5m", "reads400", "reads100", "train500m"])
+    ap.add_argument("--workload", default="contig5m", choices=["contig5m", "reads400", "reads100", "train500m", "simplescore"])
     ap.add_argument("--scale", type=float, default=1.0,
                     help="shrink a non-default workload (fraction of its reads / training strings); 1.0 = BASELINE size")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
@@ -883,6 +883,207 @@ def run_b200_train(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# simplescore: the many-model read scoring that precedes glimmer-mg in the full pipeline (SURVEY.md section 8(f) row 4;
+# Phymm / Scimm `simple-score`, scripts/scoreReadsGlim.pl:450,482): Score_String of every read under every
+# classification ICM.  16 period-1 ICMs (12/7/1) trained from the 16 synthetic genomes' coding strings, 250 000 reads x
+# 400 bp drawn from the config-2 contig; a step scores all reads against all models in one call.  The metric counts
+# read bases x models ("model-bases").
+SIMPLE_MODELS, SIMPLE_READS, SIMPLE_LEN, SIMPLE_TRAIN_SEQS = 16, 250_000, 400, 300
+SIMPLE_METRIC = "ICM-scored Gbp/s"
+
+
+def simple_reads(rank, scale):
+    import workloads as W
+    contig = W.contig(W.CONTIG_SEED, CONTIG_LEN)
+    n = max(64, int(SIMPLE_READS * scale))
+    return W.reads(contig, n, SIMPLE_LEN, 11 + rank, indel=False)
+
+
+def simple_training(k):
+    import numpy as np
+    import workloads as W
+    gc = float(np.linspace(0.30, 0.70, SIMPLE_MODELS)[k])
+    return W.coding(SIMPLE_TRAIN_SEQS, 333, seed=W.READS100_SEED * 1000 + 700 + k, freq=W.reweight_gc(W.codon_freq(), gc))
+
+
+def simple_desc(n_reads):
+    return (f"simplescore: Score_String of {n_reads} reads x {SIMPLE_LEN} bp under {SIMPLE_MODELS} period-1 ICMs (12/7/1, "
+            f"trained from {SIMPLE_TRAIN_SEQS} x 999 bp coding strings of 16 synthetic genomes) in one call; Gbp/s counts "
+            f"read bases x models (SURVEY.md section 8(f) row 4)")
+
+
+def _simple_ref_worker(job):
+    """One reference process: Score_String (the unmodified ICM library through oracle/_ref's ctypes shim) of a slice
+    of reads under every model; returns seconds."""
+    model_paths, seqs = job
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    R = O.ref()
+    hs = [R.ref_icm_read(p.encode()) for p in model_paths]
+    t0 = time.perf_counter()
+    acc = 0.0
+    for h in hs:
+        for s in seqs:
+            acc += R.ref_score_string(h, s, len(s), 0)
+    return time.perf_counter() - t0
+
+
+def run_reference_simple(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    import workloads as W
+    cores = host_cores()
+    n_sample = max(50, min(1500, 1500 * 40 // max(1, args.steps + args.warmup)))
+    a, off = simple_reads(0, min(1.0, max(args.scale, 1e-9)))
+    n_avail = len(off) - 1
+    n_sample = min(n_sample, n_avail)
+    tmp = tempfile.mkdtemp(prefix="gmg_ref_")
+    try:
+        exe = ref_bin("build-icm")
+        if exe is None or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "lib", "libref_icm.so")):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) missing"}), flush=True)
+            return
+        paths = []
+        for k in range(SIMPLE_MODELS):  # the reference's own build-icm trains the models (not timed)
+            ts, toff = simple_training(k)
+            fa = os.path.join(tmp, f"train{k}.fa")
+            W.write_fasta(fa, ts, toff, prefix="g")
+            mp = os.path.join(tmp, f"m{k}.icm")
+            with open(fa, "rb") as fin:
+                subprocess.run([exe, "-d", "7", "-w", "12", "-p", "1", mp], stdin=fin, check=True,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            paths.append(mp)
+        raw = a.tobytes()
+        jobs = []
+        for i in range(cores):
+            lo = (i * n_sample) % max(1, n_avail - n_sample + 1)
+            jobs.append((paths, [raw[off[j]:off[j + 1]] for j in range(lo, lo + n_sample)]))
+        times = []
+        with ProcessPoolExecutor(max_workers=cores) as ex:
+            for k in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                list(ex.map(_simple_ref_worker, jobs))
+                if k >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+        bases = cores * n_sample * SIMPLE_LEN * SIMPLE_MODELS
+        value = bases * len(times) / sum(times) / 1e9
+        line = {"metric": SIMPLE_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": simple_desc(n_avail)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                                 "sample": f"each step: {cores} processes, each ICM_t::Score_String of its own {n_sample} reads "
+                                           f"under all {SIMPLE_MODELS} models (the unmodified ICM library through a ctypes shim)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_b200_simple(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import glimmer_mg_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    K, Wu = args.steps, max(args.warmup, 3)
+    with torch.cuda.stream(stream):
+        ctx = g.Context(local, stream.cuda_stream)
+        models = []
+        for k in range(SIMPLE_MODELS):
+            ts, toff = simple_training(k)
+            models.append(g.ICMTraining(ctx, 12, 7, 1).Train_Model(g.SeqSet(ctx, ascii=ts, offsets=toff), reverse=False))
+        a, off = simple_reads(rank, args.scale)
+        h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
+        h.numpy()[:] = a
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
+        n_reads, n_bases = ss.n, ss.total
+        for _ in range(Wu):
+            out = g.score_strings_many(ctx, models, ss, 0)
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_read("fs")
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        clocks = ClockSampler(local) if rank == 0 else None
+        barrier()
+        launches0 = ctx.launches
+        t_wall0 = time.time()
+        for k in range(K):
+            flush.zero_()
+            e0[k].record(stream)
+            out = g.score_strings_many(ctx, models, ss, 0)  # includes the D2H of the score matrix
+            e1[k].record(stream)
+        barrier()
+        t_wall1 = time.time()
+        launches = ctx.launches - launches0
+        ms = sum(x.elapsed_time(y) for x, y in zip(e0, e1))
+        k_ms, k_n = ctx.profile_read("fs")
+        clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+        ss.close()
+        e2e_ms = 0.0
+        for k in range(Wu + K):
+            flush.zero_()
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            x.record(stream)
+            s2 = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
+            out = g.score_strings_many(ctx, models, s2, 0)
+            y.record(stream)
+            torch.cuda.synchronize()
+            if k >= Wu:
+                e2e_ms += x.elapsed_time(y)
+            s2.close()
+        ctx.profile(False)
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = t.tolist()
+    if rank == 0:
+        mb = n_bases * SIMPLE_MODELS * world
+        peak, peak_src = measured_peak()
+        kern_ms = k_ms / max(k_n, 1)
+        # algorithmic HBM bytes of the kernel: the packed reads once per model (L2 keeps them) + one double per (model, read)
+        alg = n_bases * 0.25 + n_reads * SIMPLE_MODELS * 8
+        line = {"metric": SIMPLE_METRIC, "value": mb * K / (ms_max / 1e3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": Wu, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": simple_desc(n_reads), "reads_per_gpu": int(n_reads), "models": SIMPLE_MODELS,
+                           "l2": "256 MB flush write before every timed step", "sharding": "reads dealt to ranks, no collective"},
+                "roofline": {"bound": "hbm", "kernel": "k_score_many", "achieved": alg / (kern_ms / 1e3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": alg / (kern_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms, "kernel_share_of_step": k_ms / ms,
+                             "note": "gather-bound: 8 shared-memory byte lookups and one L2 leaf gather per (model, base); "
+                                     "HBM only carries 0.25 B/base in and 8 B per (model, read) out"},
+                "e2e": {"value": mb * K / (e2e_max / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(len(a) + off.nbytes),
+                        "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_max / K},
+                "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     # the bench contract is ONE JSON line on stdout.  With NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its
     # version banner to stdout and ignores NCCL_DEBUG_FILE; at WARN and above the file is honoured: keep the banner,
@@ -896,6 +1097,8 @@ def main():
         (run_reference_reads if args.impl == "reference" else run_b200_reads)(args, args.workload)
     elif args.workload == "train500m":
         (run_reference_train if args.impl == "reference" else run_b200_train)(args)
+    elif args.workload == "simplescore":
+        (run_reference_simple if args.impl == "reference" else run_b200_simple)(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -20,7 +20,8 @@ def _run(args, timeout=600):
 
 
 @pytest.mark.parametrize("workload,extra", [("train500m", ["--scale", "0.001"]), ("reads100", ["--scale", "0.01"]),
-                                            ("reads400", ["--scale", "0.05"])])
+                                            ("reads400", ["--scale", "0.05"]),
+                                            ("simplescore", ["--scale", "0.004"])])
 def test_reference_arm_prints_one_json_line(workload, extra):
     if not O.have_ref():
         pytest.skip("oracle/_ref not built")
