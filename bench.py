@@ -1020,7 +1020,7 @@ def run_b200_simple(args):
         ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
         n_reads, n_bases = ss.n, ss.total
         for _ in range(Wu):
-            out = g.score_strings_many(ctx, models, ss, 0)
+            out = g.score_strings_many(ctx, models, ss, 0, pinned=True)
         ctx.sync()
         ctx.profile(True)
         ctx.profile_read("fs")
@@ -1033,7 +1033,7 @@ def run_b200_simple(args):
         for k in range(K):
             flush.zero_()
             e0[k].record(stream)
-            out = g.score_strings_many(ctx, models, ss, 0)  # includes the D2H of the score matrix
+            out = g.score_strings_many(ctx, models, ss, 0, pinned=True)  # includes the D2H of the score matrix
             e1[k].record(stream)
         barrier()
         t_wall1 = time.time()
@@ -1049,7 +1049,7 @@ def run_b200_simple(args):
             torch.cuda.synchronize()
             x.record(stream)
             s2 = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
-            out = g.score_strings_many(ctx, models, s2, 0)
+            out = g.score_strings_many(ctx, models, s2, 0, pinned=True)
             y.record(stream)
             torch.cuda.synchronize()
             if k >= Wu:

@@ -664,12 +664,14 @@ static int string_scores(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int fram
 // classification that precedes glimmer-mg, scripts/scoreReadsGlim.pl:450,482 -- Score_String of every read
 // against every ICM).  gridDim.y = model: a CTA stages its model's branch-position table (int8, levels
 // 0..D-1) in shared memory and gathers leaf probabilities from the L2-resident table; one warp per read, lanes
-// stride the positions and sum in FP64.  Summation order is free because gmg_icm_score_strings_many only routes a
-// model here when its static certificate holds for the longest read (every value an integer multiple of 2^g, and
-// len * max|value| < 2^(g+52): no addition can round); any other model goes through the ordered kernel.
+// stride the positions and sum in FP64.  Summation order is free whenever the read's certificate holds (every term an
+// integer multiple of 2^g, g from the smallest float exponent the read meets, and sum|term| < 2^(g+52): no addition
+// can round); the kernel flags the (model, read) pairs where it does not and k_score_many_redo repeats just those in
+// the reference's serial order.
 __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ models, const int* __restrict__ slot,
                                                     const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                    int64_t n, int frame0, double* __restrict__ out) {
+                                                    int64_t n, int frame0, double* __restrict__ out,
+                                                    uint8_t* __restrict__ redo) {
   extern __shared__ int8_t s_mipm[];
   const DevIcm m = models[slot[blockIdx.y]];
   const int nmip = m.P * m.inner;
@@ -678,20 +680,65 @@ __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ m
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int fr0 = m.P == 1 ? 0 : frame0;
   double* row = out + (size_t)slot[blockIdx.y] * n;
+  uint8_t* flag = redo + (size_t)slot[blockIdx.y] * n;
   for (int64_t s = (int64_t)blockIdx.x * nw + wid; s < n; s += (int64_t)gridDim.x * nw) {
     const int64_t a = off[s];
     const int len = (int)(off[s + 1] - a);
     double sum = 0.0;
+    unsigned umin = 0x7fffffffu;  // certificate inputs, as in K2: smallest magnitude bits, sum of magnitudes
+    float asum = 0.f;
     for (int q = lane; q < len; q += 32) {
       const int f = m.P == 1 ? 0 : (fr0 + q) % m.P;
       const int lim = m.W - 1 - q;
-      sum += (double)gmg_walk(s_mipm + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_str(words, a + q, m.W), m.W,
-                              m.D, lim > 0 ? lim : 0);
+      const float v = gmg_walk(s_mipm + (size_t)f * m.inner, m.prob + (size_t)f * m.N * 4, ctx_str(words, a + q, m.W), m.W,
+                               m.D, lim > 0 ? lim : 0);
+      sum += (double)v;
+      const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+      umin = min(umin, u ? u : 0x7fffffffu);
+      asum += fabsf(v);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    if (lane == 0) row[s] = sum;
+    for (int d = 16; d > 0; d >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, d));
+      asum += __shfl_xor_sync(0xffffffffu, asum, d);
+    }
+    if (lane == 0) {
+      // every term is a multiple of 2^g and every partial sum of ANY order is bounded by the sum of magnitudes:
+      // below 2^(g+52) no addition can round and this sum has the bits of the reference's serial one
+      const int e = (int)(umin >> 23);
+      const int g = (e > 0 ? e : 1) - 150;
+      const bool exact = umin == 0x7fffffffu || (double)asum * 1.001 < ldexp(1.0, g + 52);
+      row[s] = sum;
+      flag[s] = exact ? 0 : 1;
+    }
   }
+}
+
+// the (model, read) pairs whose certificate failed, again in the reference's serial order (icm.cc:886-900)
+__global__ void __launch_bounds__(128) k_score_many_redo(const DevIcm* __restrict__ models, const int* __restrict__ slot,
+                                                         int n_slots, const uint64_t* __restrict__ words,
+                                                         const int64_t* __restrict__ off, int64_t n, int frame0,
+                                                         double* __restrict__ out, const uint8_t* __restrict__ redo) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (int64_t)n_slots * n) return;
+  const int k = slot[w / n];
+  const int64_t s = w % n;
+  if (!redo[(size_t)k * n + s]) return;
+  const DevIcm m = models[k];
+  const int64_t a = off[s];
+  const int len = (int)(off[s + 1] - a);
+  const int fr0 = m.P == 1 ? 0 : frame0;
+  double total = 0.0;
+  for (int base = 0; base < len; base += 32) {
+    const int q = base + lane;
+    double x = 0.0;
+    if (q < len) x = (double)icm_str(m, words, a + q, q, (fr0 + q) % m.P);
+    const int cnt = min(32, len - base);
+    for (int l = 0; l < cnt; l++) total += __shfl_sync(0xffffffffu, x, l);
+  }
+  if (lane == 0) out[(size_t)k * n + s] = total;
 }
 
 extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* models, int n_models, gmg_seqset* s,
@@ -706,23 +753,20 @@ extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* mo
     GMG_CHECK(m != NULL, "gmg_icm_score_strings_many: model %d is NULL", k);
     GMG_CHECK(frame >= 0 && (frame < m->P || m->P == 1), "frame %d out of range for periodicity %d (model %d)", frame, m->P, k);
     dev[(size_t)k] = m->dev;
-    int g;
-    float mx;
-    gmg_icm_value_stats(m, &g, &mx);
     const size_t need = (size_t)m->dev.P * m->dev.inner;
-    const bool exact = (double)s->max_len * (double)mx * 1.01 < ldexp(1.0, g + 52);
-    if (exact && need <= 64 * 1024) {
+    if (need <= 64 * 1024) {  // branch table fits in shared memory; exactness is certified per read in the kernel
       fast_slots.push_back(k);
       if (need > smem) smem = need;
     } else {
       ordered_slots.push_back(k);
     }
   }
-  void *d_out, *d_models;
+  void *d_out, *d_models, *d_redo;
   if (gmg_scratch(ctx, SCR_CUM, (size_t)n_models * s->n * sizeof(double), &d_out)) return 1;
   if (!fast_slots.empty()) {
     const size_t mb = (size_t)n_models * sizeof(DevIcm), sb = fast_slots.size() * sizeof(int);
     if (gmg_scratch(ctx, SCR_TMP3, mb + sb + 64, &d_models)) return 1;
+    if (gmg_scratch(ctx, SCR_TMP2, (size_t)n_models * s->n + 64, &d_redo)) return 1;
     int* d_slot = (int*)((char*)d_models + ((mb + 15) & ~(size_t)15));
     GMG_CUDA(cudaMemcpyAsync(d_models, dev.data(), mb, cudaMemcpyHostToDevice, ctx->stream));
     GMG_CUDA(cudaMemcpyAsync(d_slot, fast_slots.data(), sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -735,13 +779,17 @@ extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* mo
     dim3 grid((unsigned)gx, (unsigned)fast_slots.size());
     if (gmg_prof_begin(ctx, GMG_PROF_FS)) return 1;
     k_score_many<<<grid, 256, smem, ctx->stream>>>((const DevIcm*)d_models, d_slot, s->d_words, s->d_off, s->n, frame,
-                                                  (double*)d_out);
+                                                  (double*)d_out, (uint8_t*)d_redo);
+    const int64_t pairs = (int64_t)fast_slots.size() * s->n;
+    k_score_many_redo<<<(unsigned)((pairs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        (const DevIcm*)d_models, d_slot, (int)fast_slots.size(), s->d_words, s->d_off, s->n, frame, (double*)d_out,
+        (const uint8_t*)d_redo);
     gmg_prof_end(ctx, GMG_PROF_FS);
-    ctx->launches++;
+    ctx->launches += 2;
     GMG_CUDA(cudaGetLastError());
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // dev / fast_slots are host temporaries
   }
-  for (int k : ordered_slots) {  // serial FP64 order of the reference (icm.cc:886-900)
+  for (int k : ordered_slots) {  // branch table too large for shared memory: the ordered kernel, model by model
     const gmg_icm* m = models[k];
     int64_t threads = s->n * 32;
     k_string_scores<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(m->dev, s->d_words, s->d_off, s->n, frame, 0,

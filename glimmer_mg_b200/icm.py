@@ -482,11 +482,14 @@ class ICM:
         return out
 
 
-def score_strings_many(ctx, models, strings, frame=0):
+def score_strings_many(ctx, models, strings, frame=0, pinned=False):
     """Score_String of every string against every model (list of ICM) in one launch -> float64 [n_models, n_strings]."""
     ss = strings if isinstance(strings, SeqSet) else SeqSet(ctx, seqs=strings)
     arr = (C.c_void_p * len(models))(*[m.h for m in models])
-    out = np.zeros((len(models), ss.n), np.float64)
+    if pinned:  # page-locked staging owned by the context (valid until the next pinned call): D2H at PCIe rate
+        out = ctx.pinned("score_many", len(models) * ss.n, np.float64).reshape(len(models), ss.n)
+    else:
+        out = np.zeros((len(models), ss.n), np.float64)
     _check(lib().gmg_icm_score_strings_many(ctx.h, arr, len(models), ss.h, frame, out.ctypes.data))
     return out
 
