@@ -671,7 +671,7 @@ static int string_scores(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int fram
 __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ models, const int* __restrict__ slot,
                                                     const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
                                                     int64_t n, int frame0, double* __restrict__ out,
-                                                    uint8_t* __restrict__ redo) {
+                                                    uint8_t* __restrict__ redo, int force_redo) {
   extern __shared__ int8_t s_mipm[];
   const DevIcm m = models[slot[blockIdx.y]];
   const int nmip = m.P * m.inner;
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ m
       const int g = (e > 0 ? e : 1) - 150;
       const bool exact = umin == 0x7fffffffu || (double)asum * 1.001 < ldexp(1.0, g + 52);
       row[s] = sum;
-      flag[s] = exact ? 0 : 1;
+      flag[s] = (exact && !force_redo) ? 0 : 1;
     }
   }
 }
@@ -777,9 +777,11 @@ extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* mo
     if (gx > need_ctas) gx = need_ctas;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)fast_slots.size());
+    const char* env_redo = getenv("GMG_MANY_FORCE_REDO");  // test hook: every pair through the serial-order kernel
+    const int force_redo = env_redo ? atoi(env_redo) : 0;
     if (gmg_prof_begin(ctx, GMG_PROF_FS)) return 1;
     k_score_many<<<grid, 256, smem, ctx->stream>>>((const DevIcm*)d_models, d_slot, s->d_words, s->d_off, s->n, frame,
-                                                  (double*)d_out, (uint8_t*)d_redo);
+                                                  (double*)d_out, (uint8_t*)d_redo, force_redo);
     const int64_t pairs = (int64_t)fast_slots.size() * s->n;
     k_score_many_redo<<<(unsigned)((pairs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
         (const DevIcm*)d_models, d_slot, (int)fast_slots.size(), s->d_words, s->d_off, s->n, frame, (double*)d_out,

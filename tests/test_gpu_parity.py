@@ -161,6 +161,20 @@ def test_score_strings_many_models(gm, ctx, reads):
             assert "%.4f" % v == "%.4f" % float(gv)
 
 
+def test_score_strings_many_redo_path(gm, ctx, reads, monkeypatch):
+    """(model, read) pairs whose exactness certificate fails are repeated in the reference's serial order: forced for
+    every pair here, the matrix must keep its bits."""
+    names = ["cluster-4.icm", "NC_000915.icm"]
+    models = [gm.ICM.Read(ctx, os.path.join(G, nm)) for nm in names]
+    ss = gm.SeqSet(ctx, seqs=[s for _, s in reads[:300]] + [b"", b"ac"])
+    want = gm.score_strings_many(ctx, models, ss, 1).copy()
+    monkeypatch.setenv("GMG_MANY_FORCE_REDO", "1")
+    got = gm.score_strings_many(ctx, models, ss, 1)
+    assert (got.view(np.uint64) == want.view(np.uint64)).all()
+    for k, m in enumerate(models):
+        assert (got[k].view(np.uint64) == m.score_strings(ss, 1).view(np.uint64)).all()
+
+
 def test_scalar_surface_matches_oracle(gm, ctx, reads):
     path = os.path.join(G, "NC_000915.icm")
     m = gm.ICM.Read(ctx, path)
