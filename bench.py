@@ -3,26 +3,34 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-Workload (default ``contig5m`` = BASELINE.json configs[1]): one synthetic 5 Mbp bacterial contig per GPU
-(seed 20261017 + rank), gene model tests/golden/NC_000915.icm, the
-glimmer3 whole-genome scoring half: K1 six-frame ICM walks of every base + per-ORF start enumeration
-(Score_Orfs, glimmer3.cc:1275).  A "step" is one pass of that path over the contig.
+Default workload ``reads100`` = BASELINE.json configs[4], the sharded read set north_star's scaling target names
+(SURVEY.md section 8(d) config 5): 16 synthetic genomes (GC 0.30..0.70) with their own ICMs trained on the device,
+625 000 error-free 100 bp reads each (seed 5); a "step" is one half-cluster batch of 312 500 reads (31.25 Mbp)
+through the glimmer-mg scoring half (K1 six-frame walks, K2 prefix sums / stop tables, K3 start enumeration) with
+its cluster's ICM; rank r takes batches r, r+N, ... (no collective: reads never interact).  It fits one GPU, so the
+N=1 line and the 1/2/4/8 scaling lines measure the same thing.  A default run (no --workload) also runs the other
+BASELINE configs with fewer steps and nests their lines under "extra": contig5m (configs[1], glimmer3 whole-genome
+half), train500m (configs[3], build-icm with the per-level count exchange) and reads400 (configs[2], glimmer-mg -i).
 
-  value  whole-job Gbp/s with the packed contig and its ORF table already resident in HBM
-         (gmg_score_orfs_g3: K1 + K3 count/scan/write), CUDA events, L2 flushed before every step.
+  value  whole-job Gbp/s with the packed batch and its ORF table already resident in HBM, CUDA events on the
+         launching stream, L2 flushed (256 MB write) before every step, max over ranks.
   e2e    the same metric through the C-ABI call sequence a host makes with HOST buffers: pinned ASCII ->
-         gmg_seqset_create (H2D + Filter/2-bit pack) -> gmg_find_orfs -> gmg_score_orfs_g3 ->
-         gmg_get_orfs + gmg_get_starts (D2H), copies inside the timed region.
-  roofline   K1 (k1_planes), the dominant kernel: algorithmic HBM bytes per launch
-             (0.25 B/base packed read + 6 planes x 4 B/base written = 24.25 B/base) divided by
-             its CUDA-event duration measured live in the timed region (gmg_ctx_profile).
-  cpu_baseline   the unmodified reference glimmer3 binary (oracle/_ref, built from /root/reference by
-             oracle/Makefile) on the same contig on one host core (it is single-threaded).
+         gmg_seqset_create (H2D + Filter / 2-bit pack) -> gmg_find_orfs -> gmg_score_orfs_* -> gmg_get_orfs +
+         gmg_get_starts (D2H), copies inside the timed region.
+  roofline   the dominant streaming kernel of the workload: algorithmic HBM bytes per launch
+         divided by its CUDA-event duration measured live in the timed region (gmg_ctx_profile).
+  parity_checked / parity   the results of the last end-to-end step compared with the oracle port (tests/config_parity.py)
+         OUTSIDE the timed region: ORF tables, start lists incl. FP64 score bits, model files.  A difference aborts
+         the run -- a number without parity is not printed.
+  cpu_baseline   the unmodified reference binary (oracle/_ref, built from /root/reference by oracle/Makefile) on a
+         bounded sample of the same workload on one host core (it is single-threaded).
+  e2e_app    whole-application wall time: the reference's own driver compiled over the C-ABI
+         (oracle/_ref/bin/*-gmg, glimmer_mg_b200/host/bin/build-icm) against the unmodified binary on the same
+         input file, outputs compared byte for byte.
 
-``--impl reference`` times the reference's own CPU implementation with every host core: one glimmer3
-process per core, each on its own bounded slice of the workload (the reference's only parallelism is
-process-per-sequence-set, scripts/train_all.py:58).  Multi-GPU: contigs are independent, so ranks shard
-them with no collective ("weak" scaling: one contig per GPU).
+``--impl reference`` times the reference's own CPU implementation with every host core: one process per core, each
+on its own bounded slice of the workload (the reference's only parallelism is process-per-sequence-set,
+scripts/train_all.py:58).
 """
 import argparse
 import json
@@ -50,7 +58,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)  # a 0.25 ms step: 100 of them average out host jitter
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="contig5m", choices=["contig5m", "reads400", "reads100", "train500m", "simplescore"])
+    ap.add_argument("--workload", default=None, choices=["contig5m", "reads400", "reads100", "train500m", "simplescore"],
+                    help="default: reads100 (BASELINE.json configs[4], the sharded read set north_star's scaling target names), "
+                         "with the contig5m / train500m / reads400 lines of the same run nested under \"extra\"")
+    ap.add_argument("--no-extra", action="store_true", help="default workload only, no nested lines")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the results (profiling runs)")
     ap.add_argument("--scale", type=float, default=1.0,
                     help="shrink a non-default workload (fraction of its reads / training strings); 1.0 = BASELINE size")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
@@ -120,6 +132,45 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class Env:
+    """Per-process CUDA / torch.distributed state shared by every workload of one bench.py run."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.destroy_process_group()
+
+
+def parity_mod():
+    """The checker (tests/config_parity.py over the oracle port); only ever called outside timed regions."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import config_parity as CP
+    return CP
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -187,6 +238,78 @@ def cpu_baseline(contig_arr):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def _timed(cmd, stdin_path=None, cwd=None):
+    fin = open(stdin_path, "rb") if stdin_path else None
+    t0 = time.perf_counter()
+    try:
+        rc = subprocess.run(cmd, stdin=fin, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=cwd).returncode
+    finally:
+        if fin:
+            fin.close()
+    if rc != 0:
+        raise RuntimeError(f"{cmd[0]} failed (exit {rc})")
+    return time.perf_counter() - t0
+
+
+def _app_pair(ref_exe, gmg_exe, args_of, files, what, bases, stdin_path=None):
+    """Wall time of the whole APPLICATION: the unmodified reference binary against the same driver compiled over
+    the C-ABI (process start, CUDA context creation, file I/O, host DP and output included), same input file,
+    output files compared byte for byte.  `args_of(tag)` -> argument list writing output files `files(tag)`."""
+    if not (ref_exe and gmg_exe and os.path.exists(ref_exe) and os.path.exists(gmg_exe)):
+        return {"unavailable": "drop-in or reference binary not built (needs the reference checkout at build time)"}
+    _timed([gmg_exe, *args_of("warm")], stdin_path)  # first CUDA context of this process tree: driver / module load
+    t_ref = _timed([ref_exe, *args_of("ref")], stdin_path)
+    t_gmg = min(_timed([gmg_exe, *args_of("gmg")], stdin_path) for _ in range(2))
+    same = all(open(a, "rb").read() == open(b, "rb").read() for a, b in zip(files("ref"), files("gmg")))
+    return {"what": what, "reference_s": t_ref, "b200_s": t_gmg, "speedup": t_ref / t_gmg, "bases": int(bases),
+            "reference_gbps": bases / t_ref / 1e9, "b200_gbps": bases / t_gmg / 1e9, "outputs_identical": bool(same)}
+
+
+def app_glimmer3(contig_arr):
+    import workloads as W
+    tmp = tempfile.mkdtemp(prefix="gmg_app_")
+    try:
+        fa = os.path.join(tmp, "contig.fa")
+        W.write_fasta(fa, contig_arr, prefix="contig")
+        return _app_pair(ref_bin("glimmer3"), ref_bin("glimmer3-gmg"),
+                         lambda tag: ["-u", "-12", "-m", W.gene_model_path(), fa, os.path.join(tmp, tag)],
+                         lambda tag: [os.path.join(tmp, tag + ".predict")],
+                         "glimmer3 -u -12 -m NC_000915.icm on the contig's FASTA file -> .predict, whole process wall time; "
+                         "b200 = the reference's own driver with Score_Orfs bound to gmg_score_orfs_g3", len(contig_arr))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def app_glimmer_mg(ascii_arr, off, n_reads, flags, model_path):
+    import workloads as W
+    tmp = tempfile.mkdtemp(prefix="gmg_app_")
+    try:
+        fa = os.path.join(tmp, "reads.fa")
+        W.write_fasta(fa, ascii_arr[:off[n_reads]], off[:n_reads + 1], prefix="r")
+        return _app_pair(ref_bin("glimmer-mg"), ref_bin("glimmer-mg-gmg"),
+                         lambda tag: ["-u", "1.0", *flags, "-m", model_path, fa, os.path.join(tmp, tag)],
+                         lambda tag: [os.path.join(tmp, tag + ".predict")],
+                         f"glimmer-mg -u 1.0 {' '.join(flags)} -m <icm> on the first {n_reads} reads of the batch (FASTA file) -> "
+                         f".predict, whole process wall time", int(off[n_reads]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def app_build_icm(ascii_arr, off):
+    import workloads as W
+    tmp = tempfile.mkdtemp(prefix="gmg_app_")
+    try:
+        fa = os.path.join(tmp, "train.fa")
+        W.write_fasta(fa, ascii_arr, off, prefix="g")
+        ours = os.path.join(ROOT, "glimmer_mg_b200", "host", "bin", "build-icm")
+        return _app_pair(ref_bin("build-icm"), ours, lambda tag: ["-r", os.path.join(tmp, tag + ".icm")],
+                         lambda tag: [os.path.join(tmp, tag + ".icm")],
+                         f"build-icm -r < {len(off) - 1} training strings (FASTA on stdin) -> model file, whole process wall "
+                         f"time; b200 = glimmer_mg_b200/host/bin/build-icm", int(off[-1]), stdin_path=fa)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -243,29 +366,14 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_b200(args):
+def run_b200(args, env):
     import numpy as np
     import torch
     import torch.distributed as dist
     import glimmer_mg_b200 as g
     import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, world, local, dev, barrier = env.rank, env.world, env.local, env.dev, env.barrier
 
     stream = torch.cuda.Stream(device=dev)
     K, Wu = args.steps, max(args.warmup, 3)
@@ -277,7 +385,7 @@ def run_b200(args):
         h_ascii.numpy()[:] = contig
         off = np.array([0, n], np.int64)
         gene = g.ICM.Read(ctx, W.gene_model_path())
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        flush = env.flush
 
         # ---- resident phase: packed contig + ORF table live in HBM ----
         ss = g.SeqSet(ctx, ascii=h_ascii.numpy(), offsets=off)
@@ -329,8 +437,19 @@ def run_b200(args):
             if k >= Wu:
                 e2e_ms += a.elapsed_time(b)
                 d2h = orfs.nbytes + ooff.nbytes + starts.nbytes + soff.nbytes
-            s2.close()
+            if k + 1 < Wu + K:
+                s2.close()
         ctx.profile(False)
+        # ---- parity (outside the timed region): the last end-to-end step's ORF table and start lists of the WHOLE
+        # contig against the oracle port, bit for bit
+        parity = None
+        if rank == 0 and not args.no_parity:
+            CP = parity_mod()
+            st = CP.check_scoring("g3", contig, off, [0], orfs, ooff, starts, soff, CP.oracle_model(path=W.gene_model_path()),
+                                  gc, p.stop_codons, ignore_score_len=p.ignore_score_len)
+            parity = {"checked": "ORF table + start lists (order, j, pos, which, flags, FP64 score bits) of the whole contig "
+                                 "identical to the oracle port", **st, "ordered_fallback_orfs": int(s2.ordered_fallbacks)}
+        s2.close()
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -359,12 +478,13 @@ def run_b200(args):
                              "k3_ms_per_step": k3_ms / K},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(n + off.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max / K},
-                "gpu_launches": int(launches), "clocks": clk}
+                "gpu_launches": int(launches), "clocks": clk,
+                "parity_checked": parity is not None, "parity": parity}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(contig)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            line["e2e_app"] = app_glimmer3(contig)
+        return line
+    return None
 
 
 # ===================================================================================================
@@ -513,29 +633,14 @@ def run_reference_reads(args, kind):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def run_b200_reads(args, kind):
+def run_b200_reads(args, env, kind):
     import numpy as np
     import torch
     import torch.distributed as dist
     import glimmer_mg_b200 as g
     import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, world, local, dev, barrier = env.rank, env.world, env.local, env.dev, env.barrier
 
     stream = torch.cuda.Stream(device=dev)
     K, Wu = args.steps, max(args.warmup, 3)
@@ -544,7 +649,7 @@ def run_b200_reads(args, kind):
         ctx = g.Context(local, stream.cuda_stream)
         batches, desc = reads_batches(kind, rank, world, args.scale, K + Wu)
         nb = len(batches)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = env.flush
         # models: the sample genome's ICM (reads400) or one device-trained ICM per cluster (reads100)
         genes = {}
         for _, _, k in batches:
@@ -622,8 +727,23 @@ def run_b200_reads(args, kind):
                 e2e_bases += bases[j]
                 d2h = orfs.nbytes + ooff.nbytes + starts.nbytes + soff.nbytes
                 h2d = len(batches[j][0]) + batches[j][1].nbytes
-            s2.close()
+            if k + 1 < We + K:
+                s2.close()
         ctx.profile(False)
+        # ---- parity (outside the timed region): a sample of the last end-to-end batch against the oracle port
+        parity = None
+        if rank == 0 and not args.no_parity:
+            CP = parity_mod()
+            ba, boff, bk = batches[j]
+            ids = CP.sample_ids(len(boff) - 1, 600 if indels else 3000)
+            og = CP.oracle_model(path=W.gene_model_path()) if indels else CP.oracle_model(genes[bk])
+            st = CP.check_scoring("mg", ba, boff, ids, orfs, ooff, starts, soff, og, s2.gc_fraction(),
+                                  params[j].stop_codons, allow_indels=1 if indels else 0,
+                                  ignore_score_len=params[j].ignore_score_len)
+            parity = {"checked": f"ORF tables + start lists (order, j, pos, which, flags, error lists, FP64 score bits) of "
+                                 f"{len(ids)} reads of the last end-to-end batch ({int(s2.n_starts)} starts in the batch) "
+                                 f"identical to the oracle port", **st, "uncertified_reads": int(s2.uncertified)}
+        s2.close()
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     tb = torch.tensor([done_bases, e2e_bases], dtype=torch.float64, device=dev)
@@ -659,7 +779,8 @@ def run_b200_reads(args, kind):
                                      "HBM roofline; its time is listed beside the two streaming kernels"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / K},
-                "gpu_launches": int(launches), "clocks": clk}
+                "gpu_launches": int(launches), "clocks": clk,
+                "parity_checked": parity is not None, "parity": parity}
         if world == 1 and not args.no_cpu_baseline:
             tmp = tempfile.mkdtemp(prefix="gmg_bench_")
             try:
@@ -676,11 +797,15 @@ def run_b200_reads(args, kind):
                                         "sample": f"first {n_s} reads of the first batch through glimmer-mg -u 1.0"
                                                   f"{' -i' if indels else ''} on one core (single-threaded binary; "
                                                   f"sample-genome ICM), {sec:.2f} s"}
+                mp = W.gene_model_path()
+                if not indels:  # the cluster's own ICM, as the pipeline would use it
+                    mp = os.path.join(tmp, "cluster.icm")
+                    genes[batches[0][2]].Output(mp)
+                line["e2e_app"] = app_glimmer_mg(a, off, n_s, ["-i"] if indels else [], mp)
             finally:
                 shutil.rmtree(tmp, ignore_errors=True)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -724,6 +849,41 @@ def train_cpu(n_seqs):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def train_reference_sha(n_seqs):
+    """sha256 of the model file the reference writes for the first n_seqs training strings -> (digest, how)."""
+    import hashlib
+    import workloads as W
+    if n_seqs == TRAIN_SEQS:
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "train500m.sha256.json")) as fp:
+                rec = json.load(fp)
+            if rec["n_seqs"] == n_seqs and rec["seed"] == W.TRAIN_SEED:
+                return rec["model_file_sha256"], ("the unmodified reference build-icm -r on the same 500 Mbp (committed digest, "
+                                                  "tests/golden/train500m.sha256.json)")
+        except Exception:
+            return None, None
+        return None, None
+    if n_seqs > 6000:
+        return None, None
+    a, off = W.coding(n_seqs, TRAIN_CODONS, W.TRAIN_SEED)
+    tmp = tempfile.mkdtemp(prefix="gmg_bench_")
+    try:
+        out = os.path.join(tmp, "m.icm")
+        if ref_bin("build-icm"):
+            ref_build_icm_seconds(a, off, tmp)
+            how = "the unmodified reference build-icm -r run on the same strings"
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            raw = a.tobytes()
+            rev = [raw[off[i]:off[i + 1]][::-1] for i in range(len(off) - 1)]
+            O.lib().orc_icm_write(O.lib().orc_icm_train(O.cstr_array(rev), len(rev), 12, 7, 3), out.encode())
+            how = "the oracle port's Train_Model on the same strings"
+        return hashlib.sha256(open(out, "rb").read()).hexdigest(), how
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def train_desc(n_seqs):
     return (f"train500m: build-icm -r (Train_Model, 12/7/3) on {n_seqs} stop-free coding strings x {3 * TRAIN_CODONS} bp "
             f"(seed 7), strings dealt round-robin to ranks, one int32 count-slab all-reduce per tree level "
@@ -752,7 +912,7 @@ def run_reference_train(args):
     print(json.dumps(line), flush=True)
 
 
-def run_b200_train(args):
+def run_b200_train(args, env):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -760,22 +920,7 @@ def run_b200_train(args):
     from glimmer_mg_b200 import shard
     import workloads as W
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, world, local, dev, barrier = env.rank, env.world, env.local, env.dev, env.barrier
 
     stream = torch.cuda.Stream(device=dev)
     K, Wu = args.steps, max(args.warmup, 3)
@@ -792,7 +937,7 @@ def run_b200_train(args):
         h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
         h.numpy()[:] = a
         ar = shard.torch_allreduce(local) if world > 1 else None
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = env.flush
         ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
         trainer = g.ICMTraining(ctx, 12, 7, 3)
         model = None
@@ -838,10 +983,36 @@ def run_b200_train(args):
                 e2e_ms += x.elapsed_time(y)
                 d2h = mip.nbytes + prob.nbytes
             s2.close()
-            m2.close()
+            if k + 1 < Wu + K:
+                m2.close()
         ctx.profile(False)
         import hashlib
         digest = hashlib.sha256(mip.tobytes() + prob.tobytes()).hexdigest()[:16]
+        # ---- parity (outside the timed region): the model FILE of the last end-to-end step against the unmodified
+        # reference build-icm's -- the committed digest of its 25-minute run at full size
+        # (tests/golden/train500m.sha256.json, tools/make_train500m_golden.py), a live run below 6 000 strings
+        tmpd = tempfile.mkdtemp(prefix="gmg_bench_")
+        try:
+            mfile = os.path.join(tmpd, "dev.icm")
+            m2.Output(mfile)
+            file_sha = hashlib.sha256(open(mfile, "rb").read()).hexdigest()
+        finally:
+            shutil.rmtree(tmpd, ignore_errors=True)
+        m2.close()
+        all_sha = [file_sha]
+        if world > 1:
+            all_sha = [None] * world
+            dist.all_gather_object(all_sha, file_sha)
+        parity = None
+        if rank == 0 and not args.no_parity:
+            want, how = train_reference_sha(n_seqs)
+            if want is not None:
+                if any(x != want for x in all_sha):
+                    raise SystemExit(f"bench.py: PARITY FAILURE: trained model file sha256 {all_sha} != reference {want} ({how})")
+                parity = {"checked": f"model file written from every rank's trained model byte-identical (sha256) to {how}",
+                          "model_file_sha256": file_sha, "ranks": world}
+            elif len(set(all_sha)) != 1:
+                raise SystemExit(f"bench.py: PARITY FAILURE: ranks hold different models {all_sha}")
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -872,15 +1043,17 @@ def run_b200_train(args):
                                      "re-read (8 x 0.25 B/base) and is expected to be a small fraction of peak"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(len(a) + off.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max / K},
-                "gpu_launches": int(launches), "clocks": clk}
+                "gpu_launches": int(launches), "clocks": clk,
+                "parity_checked": parity is not None, "parity": parity}
         if world == 1 and not args.no_cpu_baseline:
+            an, offn = W.coding(min(n_seqs, 5000), TRAIN_CODONS, W.TRAIN_SEED)
+            line["e2e_app"] = app_build_icm(an, offn)
             bases, sec, kind = train_cpu(min(n_seqs, 5000))
             line["cpu_baseline"] = {"value": bases / sec / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": f"build-icm -r on the first {min(n_seqs, 5000)} training strings ({bases} bp) on "
                                               f"one core (one model cannot be split over processes), {sec:.2f} s"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -982,28 +1155,13 @@ def run_reference_simple(args):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def run_b200_simple(args):
+def run_b200_simple(args, env):
     import numpy as np
     import torch
     import torch.distributed as dist
     import glimmer_mg_b200 as g
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, world, local, dev, barrier = env.rank, env.world, env.local, env.dev, env.barrier
 
     stream = torch.cuda.Stream(device=dev)
     K, Wu = args.steps, max(args.warmup, 3)
@@ -1016,7 +1174,7 @@ def run_b200_simple(args):
         a, off = simple_reads(rank, args.scale)
         h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
         h.numpy()[:] = a
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = env.flush
         ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
         n_reads, n_bases = ss.n, ss.total
         for _ in range(Wu):
@@ -1056,6 +1214,21 @@ def run_b200_simple(args):
                 e2e_ms += x.elapsed_time(y)
             s2.close()
         ctx.profile(False)
+        parity = None
+        if rank == 0 and not args.no_parity:  # 200 reads x every model against the oracle port's Score_String, bit for bit
+            CP = parity_mod()
+            import oracle_lib as O
+            raw = a.tobytes()
+            ids = CP.sample_ids(n_reads, 200)
+            for km, m in enumerate(models):
+                om = CP.oracle_model(m)
+                for i in ids:
+                    sq = raw[off[i]:off[i + 1]]
+                    want = O.lib().orc_score_string(om, sq, len(sq), 0)
+                    if np.float64(out[km, i]).view(np.uint64) != np.float64(want).view(np.uint64):
+                        raise SystemExit(f"bench.py: PARITY FAILURE: Score_String model {km} read {i}: {out[km, i]!r} != {want!r}")
+            parity = {"checked": f"Score_String of {len(ids)} reads under each of the {len(models)} models bit-identical to the "
+                                 f"oracle port"}
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -1078,10 +1251,9 @@ def run_b200_simple(args):
                                      "HBM only carries 0.25 B/base in and 8 B per (model, read) out"},
                 "e2e": {"value": mb * K / (e2e_max / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(len(a) + off.nbytes),
                         "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_max / K},
-                "gpu_launches": int(launches), "clocks": clk}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                "gpu_launches": int(launches), "clocks": clk, "parity_checked": parity is not None, "parity": parity}
+        return line
+    return None
 
 
 def main():
@@ -1093,16 +1265,43 @@ def main():
     if os.environ.get("NCCL_DEBUG"):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
-    if args.workload in ("reads400", "reads100"):
-        (run_reference_reads if args.impl == "reference" else run_b200_reads)(args, args.workload)
-    elif args.workload == "train500m":
-        (run_reference_train if args.impl == "reference" else run_b200_train)(args)
-    elif args.workload == "simplescore":
-        (run_reference_simple if args.impl == "reference" else run_b200_simple)(args)
-    elif args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    default_run = args.workload is None
+    if default_run:
+        args.workload = "reads100"
+    if args.impl == "reference":
+        if args.workload in ("reads400", "reads100"):
+            run_reference_reads(args, args.workload)
+        elif args.workload == "train500m":
+            run_reference_train(args)
+        elif args.workload == "simplescore":
+            run_reference_simple(args)
+        else:
+            run_reference(args)
+        return
+    runners = {"contig5m": run_b200, "reads400": lambda a, e: run_b200_reads(a, e, "reads400"),
+               "reads100": lambda a, e: run_b200_reads(a, e, "reads100"), "train500m": run_b200_train,
+               "simplescore": run_b200_simple}
+    env = Env()
+    try:
+        line = runners[args.workload](args, env)
+        if default_run and not args.no_extra:
+            # the other BASELINE configs in the same run (fewer steps each: the whole default run stays within minutes)
+            import copy
+            extra = {}
+            for wl, steps in (("contig5m", 50), ("train500m", 8), ("reads400", 10)):
+                sub = copy.copy(args)
+                sub.workload = wl
+                sub.steps = min(args.steps, steps)
+                sub.warmup = min(max(args.warmup, 3), 5)
+                sub_line = runners[wl](sub, env)
+                if sub_line is not None:
+                    extra[wl] = sub_line
+            if line is not None:
+                line["extra"] = extra
+        if line is not None:
+            print(json.dumps(line), flush=True)
+    finally:
+        env.close()
 
 
 if __name__ == "__main__":

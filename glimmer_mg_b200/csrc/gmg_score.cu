@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ m
     const int len = (int)(off[s + 1] - a);
     double sum = 0.0;
     unsigned umin = 0x7fffffffu;  // certificate inputs, as in K2: smallest magnitude bits, sum of magnitudes
-    float asum = 0.f;
+    double asum = 0.0;            // FP64: a float sum of len / 32 terms would eat the margin on long sequences
     for (int q = lane; q < len; q += 32) {
       const int f = m.P == 1 ? 0 : (fr0 + q) % m.P;
       const int lim = m.W - 1 - q;
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ m
       sum += (double)v;
       const unsigned u = __float_as_uint(v) & 0x7fffffffu;
       umin = min(umin, u ? u : 0x7fffffffu);
-      asum += fabsf(v);
+      asum += (double)fabsf(v);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(256) k_score_many(const DevIcm* __restrict__ m
       // below 2^(g+52) no addition can round and this sum has the bits of the reference's serial one
       const int e = (int)(umin >> 23);
       const int g = (e > 0 ? e : 1) - 150;
-      const bool exact = umin == 0x7fffffffu || (double)asum * 1.001 < ldexp(1.0, g + 52);
+      const bool exact = umin == 0x7fffffffu || asum * 1.001 < ldexp(1.0, g + 52);
       row[s] = sum;
       flag[s] = (exact && !force_redo) ? 0 : 1;
     }

@@ -33,12 +33,12 @@ struct gmg_trainer {
   std::vector<float> prob;   // [P][N][4] probabilities (logs only after finish)
   std::vector<float> mut_info;  // [P][N] mutual information of the chosen position (icm.cc:1156, 1438)
   int8_t* d_mip;             // [P][N] current tree (levels not built yet are -1)
-  int32_t* d_counts;         // slab of the level being counted
-  size_t counts_cap;
+  int32_t* d_counts;         // slab of the level being counted: the trainer's own stream-ordered allocation (no other
+  size_t counts_cap;         // call on the context can invalidate it between levels)
   std::vector<int32_t> h_counts;
   int next_level;
-  unsigned* d_hist;          // [P][4^W] windows by (frame, content): built once, walked by every level (large sets)
-  int hist_ready;
+  unsigned* d_hist;          // [P][4^W] windows by (frame, content): built once, walked by every level (large sets);
+  int hist_ready;            // owned by the trainer like the slab
 };
 
 static inline int64_t level_nodes(int level) {
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(512) k4_hist_level(const unsigned* __restrict_
   const int64_t all = cells * P;
   const int lane = threadIdx.x & 31;
   for (int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; g0 < all; g0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g = g0 + lane;  // cells is a multiple of 32: a warp never straddles two frames
-    const unsigned cnt = __ldg(hist + g);
+    const int64_t g = g0 + lane;  // cells is a multiple of 32 (W >= 3, checked by the caller): a warp never straddles two frames
+    const unsigned cnt = g < all ? __ldg(hist + g) : 0u;
     if (__ballot_sync(0xffffffffu, cnt != 0) == 0) continue;
-    const int f = (int)(g / cells);
+    const int f = g < all ? (int)(g / cells) : 0;
     const uint64_t ctx = (uint64_t)(g - (int64_t)f * cells);
     int node = 0;
     bool ok = true;
@@ -223,15 +223,16 @@ extern "C" int gmg_trainer_create(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int
   GMG_CUDA(cudaSetDevice(ctx->device));
   GMG_CUDA(cudaMallocAsync(&t->d_mip, (size_t)p * t->N, ctx->stream));
   GMG_CUDA(cudaMemsetAsync(t->d_mip, 0xFF, (size_t)p * t->N, ctx->stream));
-  // the count slab (and the window histogram) live in the context's scratch: no cudaMalloc / cudaFree per model
+  // the count slab (and the window histogram) are the trainer's own allocations from the stream-ordered pool (the
+  // pool keeps freed blocks, so a model costs no cudaMalloc / cudaFree); context scratch would be invalidated by any
+  // other call on the context between two levels of the step API
   size_t cap = (size_t)p * level_nodes(d) * (w - 1) * 16;
-  void* d_slab;
-  if (gmg_scratch(ctx, SCR_TMP, cap * sizeof(int32_t), &d_slab)) {
+  if (cudaMallocAsync(&t->d_counts, cap * sizeof(int32_t), ctx->stream) != cudaSuccess) {
+    gmg_set_error("gmg_trainer_create: cannot allocate the %zu-byte count slab", cap * sizeof(int32_t));
     cudaFreeAsync(t->d_mip, ctx->stream);
     delete t;
     return 1;
   }
-  t->d_counts = (int32_t*)d_slab;
   t->counts_cap = cap;
   *out = t;
   return 0;
@@ -241,6 +242,8 @@ extern "C" void gmg_trainer_free(gmg_trainer* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   if (t->d_mip) cudaFreeAsync(t->d_mip, t->ctx->stream);
+  if (t->d_counts) cudaFreeAsync(t->d_counts, t->ctx->stream);
+  if (t->d_hist) cudaFreeAsync(t->d_hist, t->ctx->stream);
   delete t;
 }
 
@@ -256,17 +259,14 @@ extern "C" int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_count
   // window histogram for large sets (W <= 12): GMG_K4_HIST=0/1 forces the direct / histogram path (tests)
   const char* hist_env = getenv("GMG_K4_HIST");
   const int hist_mode = hist_env ? atoi(hist_env) : -1;
-  const bool use_hist = t->W <= 12 && (hist_mode == 1 || (hist_mode < 0 && s->total >= ((int64_t)t->P << (2 * t->W)) / 2));  // >= 25 M windows at 12/7/3
+  // (W >= 3: 4^W cells per frame must be a multiple of the warp size, see k4_hist_level)
+  const bool use_hist = t->W >= 3 && t->W <= 12 && (hist_mode == 1 || (hist_mode < 0 && s->total >= ((int64_t)t->P << (2 * t->W)) / 2));  // >= 25 M windows at 12/7/3
   if (s->total > 0 && use_hist) {
     const size_t cells = (size_t)t->P << (2 * t->W);
     const int threads = 512;
     if (gmg_prof_begin(ctx, GMG_PROF_K4)) return 1;
     if (!t->hist_ready) {
-      if (!t->d_hist) {
-        void* d_h;
-        if (gmg_scratch(ctx, SCR_CUM, cells * sizeof(unsigned), &d_h)) return 1;
-        t->d_hist = (unsigned*)d_h;
-      }
+      if (!t->d_hist) GMG_CUDA(cudaMallocAsync(&t->d_hist, cells * sizeof(unsigned), ctx->stream));
       GMG_CUDA(cudaMemsetAsync(t->d_hist, 0, cells * sizeof(unsigned), ctx->stream));
       int64_t need = (s->total + threads - 1) / threads;
       int64_t cap = (int64_t)ctx->sm_count * 4;

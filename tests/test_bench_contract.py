@@ -19,13 +19,15 @@ def _run(args, timeout=600):
                           timeout=timeout, cwd=ROOT)
 
 
-@pytest.mark.parametrize("workload,extra", [("train500m", ["--scale", "0.001"]), ("reads100", ["--scale", "0.01"]),
+@pytest.mark.parametrize("workload,extra", [(None, ["--scale", "0.01"]), ("contig5m", []),
+                                            ("train500m", ["--scale", "0.001"]), ("reads100", ["--scale", "0.01"]),
                                             ("reads400", ["--scale", "0.05"]),
                                             ("simplescore", ["--scale", "0.004"])])
 def test_reference_arm_prints_one_json_line(workload, extra):
     if not O.have_ref():
         pytest.skip("oracle/_ref not built")
-    r = _run(["--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0", *extra])
+    wl = ["--workload", workload] if workload else []  # no --workload: the default (reads100)
+    r = _run(["--impl", "reference", *wl, "--steps", "1", "--warmup", "0", *extra])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -34,6 +36,8 @@ def test_reference_arm_prints_one_json_line(workload, extra):
     assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if workload is None:
+        assert d["config"]["workload"].startswith("reads100")
     assert isinstance(d["config"].get("workload"), str) and "model" not in {k for k in d["config"] if k == "model_family"}
 
 
