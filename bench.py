@@ -25,7 +25,7 @@ half), train500m (configs[3], build-icm with the per-level count exchange) and r
   cpu_baseline   the unmodified reference binary (oracle/_ref, built from /root/reference by oracle/Makefile) on a
          bounded sample of the same workload on one host core (it is single-threaded).
   e2e_app    whole-application wall time: the reference's own driver compiled over the C-ABI
-         (oracle/_ref/bin/*-gmg, glimmer_mg_b200/host/bin/build-icm) against the unmodified binary on the same
+         (glimmer_mg_b200/host/bin/glimmer3-gmg, glimmer-mg-gmg, build-icm) against the unmodified binary on the same
          input file, outputs compared byte for byte.
 
 ``--impl reference`` times the reference's own CPU implementation with every host core: one process per core, each
@@ -179,7 +179,9 @@ def host_cores():
 
 
 def ref_bin(name):
-    p = os.path.join(ROOT, "oracle", "_ref", "bin", name)
+    """oracle/_ref/bin: the unmodified reference; glimmer_mg_b200/host/bin: its drivers compiled over the C-ABI (*-gmg)."""
+    d = os.path.join(ROOT, "glimmer_mg_b200", "host", "bin") if name.endswith("-gmg") else os.path.join(ROOT, "oracle", "_ref", "bin")
+    p = os.path.join(d, name)
     return p if os.path.exists(p) else None
 
 
@@ -708,6 +710,8 @@ def run_b200_reads(args, env, kind):
         for s in sets:
             s.close()
         e2e_ms, d2h, h2d, e2e_bases = 0.0, 0, 0, 0
+        # glimmer-mg -u 1.0 without a feature file: prior -1 + 1, default start-codon log-odds, length log-odds 0
+        event_model = g.EventModel(prior=0.0, len_lo=np.zeros((1, 2, 2, (READS400_LEN if indels else READS100_LEN) // 3 + 64)))
         We = max(Wu, nb)  # every resident batch once before timing (pinned staging and pool blocks sized)
         for k in range(We + K):
             j = k % nb
@@ -715,18 +719,21 @@ def run_b200_reads(args, env, kind):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record(stream)
+            # the call sequence of the chunk-level glimmer-mg binding (host/mg_score_orfs_dropin.inc): ORF table and the
+            # REDUCED start lists (one candidate per ORF and start position, row a11b) come back to the host
             s2 = g.SeqSet(ctx, ascii=pinned[j].numpy(), offsets=batches[j][1])
             s2.find_orfs(params[j])
-            s2.score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
             orfs, ooff = s2.get_orfs(pinned=True)
-            starts, soff = s2.get_starts(pinned=True)
+            s2.score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
+            s2.reduce_starts_mg(params[j], event_model)
+            red, rfirst, rcnt, rstatus = s2.get_reduced_starts(pinned=True)
             b.record(stream)
             torch.cuda.synchronize()
             if k >= We:
                 e2e_ms += a.elapsed_time(b)
                 e2e_bases += bases[j]
-                d2h = orfs.nbytes + ooff.nbytes + starts.nbytes + soff.nbytes
-                h2d = len(batches[j][0]) + batches[j][1].nbytes
+                d2h = orfs.nbytes + ooff.nbytes + red.nbytes + rfirst.nbytes + rcnt.nbytes + rstatus.nbytes
+                h2d = len(batches[j][0]) + batches[j][1].nbytes + event_model.len_lo.nbytes
             if k + 1 < We + K:
                 s2.close()
         ctx.profile(False)
@@ -737,12 +744,19 @@ def run_b200_reads(args, env, kind):
             ba, boff, bk = batches[j]
             ids = CP.sample_ids(len(boff) - 1, 600 if indels else 3000)
             og = CP.oracle_model(path=W.gene_model_path()) if indels else CP.oracle_model(genes[bk])
+            starts, soff = s2.get_starts()  # the raw lists stay on the device; fetched here only for the check
             st = CP.check_scoring("mg", ba, boff, ids, orfs, ooff, starts, soff, og, s2.gc_fraction(),
                                   params[j].stop_codons, allow_indels=1 if indels else 0,
                                   ignore_score_len=params[j].ignore_score_len)
-            parity = {"checked": f"ORF tables + start lists (order, j, pos, which, flags, error lists, FP64 score bits) of "
-                                 f"{len(ids)} reads of the last end-to-end batch ({int(s2.n_starts)} starts in the batch) "
-                                 f"identical to the oracle port", **st, "uncertified_reads": int(s2.uncertified)}
+            orf_ids = [o for i in ids[:200] for o in range(int(ooff[i]), int(ooff[i + 1]))]
+            rs = CP.check_reduction(orfs, ooff, np.diff(boff), starts, soff, red, rfirst, rcnt, rstatus, params[j].min_gene_len,
+                                    event_model, orf_ids=orf_ids)
+            parity = {"checked": f"ORF tables + raw start lists (order, j, pos, which, flags, error lists, FP64 score bits) of "
+                                 f"{len(ids)} reads of the last end-to-end batch ({int(s2.n_starts)} raw starts in the batch) "
+                                 f"identical to the oracle port; the device-side reduction of {len(orf_ids)} ORFs identical to the "
+                                 f"reference's filter + per-position arg-max restated on the raw lists", **st,
+                      "reduction": rs, "raw_starts": int(s2.n_starts), "surviving_starts": int(len(red)),
+                      "uncertified_reads": int(s2.uncertified)}
         s2.close()
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)

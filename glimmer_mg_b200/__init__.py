@@ -5,8 +5,8 @@ package is the thin Python mirror of the reference's operator surface (``ICM_t``
 ``src/ICM/icm.hh:116-213``) used by the tests and the benchmark; the C++ hosts in ``host/`` link the same
 library.  There is no CPU fallback: importing works without a GPU, creating a :class:`Context` does not.
 """
-from .icm import (Context, ICM, ICMTraining, Params, SeqSet, GmgError, ORF_DTYPE, START_DTYPE, lib, lib_path,
+from .icm import (Context, EventModel, ICM, ICMTraining, Params, SeqSet, GmgError, ORF_DTYPE, START_DTYPE, lib, lib_path,
                   build_indep_wo_stops, score_strings_many)
 
-__all__ = ["Context", "ICM", "ICMTraining", "Params", "SeqSet", "GmgError", "ORF_DTYPE", "START_DTYPE", "lib",
+__all__ = ["Context", "EventModel", "ICM", "ICMTraining", "Params", "SeqSet", "GmgError", "ORF_DTYPE", "START_DTYPE", "lib",
            "lib_path", "build_indep_wo_stops", "score_strings_many"]

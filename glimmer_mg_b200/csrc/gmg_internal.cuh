@@ -16,6 +16,7 @@
 #define GMG_CTX_PAD 16384
 #define GMG_PAD_WORDS 8   // 64-bit words of zero padding before/after the packed bases
 #define GMG_NPROF 8
+#define GMG_NSCRATCH 16
 #define GMG_PROF_RING 64
 
 void gmg_set_error(const char* fmt, ...);
@@ -77,8 +78,8 @@ struct gmg_ctx {
   int sm_count;
   int64_t launches;
   // scratch (grown on demand, reused across calls)
-  void* scratch[8];
-  size_t scratch_bytes[8];
+  void* scratch[GMG_NSCRATCH];
+  size_t scratch_bytes[GMG_NSCRATCH];
   double* h_penalty;  // pinned staging
   int64_t* h_scalars;  // pinned: small device -> host results (totals) that must not serialise the stream
   cudaEvent_t ev_scalars;
@@ -159,10 +160,19 @@ struct gmg_seqset {
   int64_t* d_start_off;      // n_orfs+1
   int64_t uncertified;
   size_t cap_orfs, cap_starts;
+  // reduced start lists of the last gmg_reduce_starts_mg call (they live in the context's SCR_RED scratch)
+  int64_t n_red, n_red_fallback;
+  gmg_start* d_red;
+  int64_t* d_red_first;
+  int32_t* d_red_cnt;
+  uint8_t* d_red_status;
 };
 
 // scratch slots
-enum { SCR_PLANES = 0, SCR_CUM = 1, SCR_TMP = 2, SCR_TMP2 = 3, SCR_FLAGS = 4, SCR_TMP3 = 5, SCR_QUAL = 6, SCR_TMP4 = 7 };
+enum { SCR_PLANES = 0, SCR_CUM = 1, SCR_TMP = 2, SCR_TMP2 = 3, SCR_FLAGS = 4, SCR_TMP3 = 5, SCR_QUAL = 6, SCR_TMP4 = 7,
+       // flat glimmer-mg start enumeration (gmg_mg_flat.cuh): gates, root calls, per-level work arrays; reduction output
+       SCR_MG_GATE = 8, SCR_MG_ROOT = 9, SCR_MG_L0 = 10, SCR_MG_CALL1 = 11, SCR_MG_L1 = 12, SCR_MG_L2 = 13, SCR_RED = 14,
+       SCR_MISC = 15 };
 int gmg_scratch(gmg_ctx* ctx, int slot, size_t bytes, void** out);
 
 // ---- device helpers ---------------------------------------------------------------------

@@ -83,7 +83,7 @@ extern "C" void gmg_host_free(void* p) {
 extern "C" void gmg_ctx_destroy(gmg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < GMG_NSCRATCH; i++)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->h_penalty) cudaFreeHost(c->h_penalty);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);

@@ -31,6 +31,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "gmg_internal.cuh"
+#include "gmg_mg_flat.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -102,21 +103,6 @@ __device__ __forceinline__ int codon_rev_starting_at(const uint64_t* __restrict_
   const int c = 63 - codon6_at(words, a + q);
   return ((c & 3) << 4) | (c & 12) | (c >> 4);
 }
-
-struct CodonSets {
-  unsigned long long start_mask;  // bit c set: 6-bit codon c is a start codon
-  unsigned long long stop_mask;
-  // the same sets over the RAW packed code  b(c) | b(c+1) << 2 | b(c+2) << 4  of the bases at c, c+1, c+2:
-  // [0] forward start, [1] forward stop, [2] reverse-strand start, [3] reverse-strand stop (k_codon_bits)
-  unsigned long long raw_mask[4];
-  unsigned char which[64];        // index of the first matching start codon (Can_Be order)
-};
-
-struct DevParams {
-  int min_gene_len, allow_truncated, allow_indels, allow_subs, min_indel_orf_len, indel_q_thresh, indel_max,
-      ignore_score_len, have_quality_file;
-  double indel_suffix_thresh;
-};
 
 static int code_of(char ch) {
   switch (ch | 0x20) {
@@ -1223,6 +1209,21 @@ extern "C" int gmg_set_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_orf* h_orfs, 
   int64_t n_orfs = h_orf_off[s->n];
   GMG_CHECK(n_orfs >= 0 && h_orf_off[0] == 0, "gmg_set_orfs: bad offsets");
   GMG_CHECK(n_orfs == 0 || h_orfs, "gmg_set_orfs: NULL ORF table");
+  // geometry: the kernels score linear sequences; a wrap-around ORF of a circular genome (Find_Orfs with
+  // Genome_Is_Circular, glimmer_base.cc:760-777) would be read from the neighbouring sequence
+  for (int64_t q = 0; q < s->n; q++) {
+    GMG_CHECK(h_orf_off[q + 1] >= h_orf_off[q], "gmg_set_orfs: offsets not monotone at sequence %lld", (long long)q);
+    const int64_t L = s->off[(size_t)q + 1] - s->off[(size_t)q];
+    for (int64_t o = h_orf_off[q]; o < h_orf_off[q + 1]; o++) {
+      const gmg_orf& f = h_orfs[o];
+      const int af = f.frame < 0 ? -f.frame : f.frame;
+      GMG_CHECK(af >= 1 && af <= 3 && f.orf_len >= 0, "gmg_set_orfs: ORF %lld has frame %d, orf_len %d", (long long)o, f.frame, f.orf_len);
+      const int64_t lo = f.frame > 0 ? (int64_t)f.stop_position - 1 - f.orf_len : (int64_t)f.stop_position + 2;
+      const int64_t hi = f.frame > 0 ? (int64_t)f.stop_position - 1 : (int64_t)f.stop_position + 2 + f.orf_len;
+      GMG_CHECK(lo >= 0 && hi <= L, "gmg_set_orfs: ORF %lld (frame %d, stop %d, length %d) does not lie inside its %lld bp sequence: "
+                "wrap-around ORFs of circular sequences are not supported", (long long)o, f.frame, f.stop_position, f.orf_len, (long long)L);
+    }
+  }
   if (ensure_orf_capacity(s, n_orfs)) return 1;
   if (n_orfs)
     GMG_CUDA(cudaMemcpyAsync(s->d_orfs, h_orfs, (size_t)n_orfs * sizeof(gmg_orf), cudaMemcpyHostToDevice, ctx->stream));
@@ -2387,7 +2388,23 @@ struct MgSeq {
   const double* penalty;   // [256] log(pe/2) - log(1-pe), pe = 10^(-q/10)   (host glibc, Score_Indels :1520-1521)
   const double* stop_pen;  // [4]   Pass_Stop_Penalty without a quality file, index = 2*a1 + a2
   const double* codon_p;   // [256] 1 - 10^(-q/10)
+  const double* sub_pen;   // [n_orfs] Pass_Stop_Penalty of every root call with a quality file (log taken on the host)
+  // ordered mode (sequences whose exactness certificate failed): score[] of a call is re-summed in the reference's
+  // own order from the six Frame_Scores rows instead of read off the prefix sums
+  int ordered;
+  const float* planes;
+  const uint32_t* bktidx;
+  DevIcm indep;
 };
+
+// Frame_Scores[plane][q] (Score_All_Frames glimmer-mg.cc:1468-1510): gene - indep in FP64
+__device__ double mg_frame_score_at(const MgSeq& S, int plane, int q) {
+  if (q < 0 || q >= S.L) return 0.0;
+  const int64_t p = S.a + q;
+  const float g = S.planes[(size_t)plane * S.total + gmg_plane_index(S.words, S.bktidx, p)];
+  const float n = plane < 3 ? icm_fwd(S.indep, S.words, p, q, S.L, plane) : icm_rev(S.indep, S.words, p, q, 0, plane - 3);
+  return (double)g - (double)n;
+}
 
 struct MgCall {
   int lo, hi, m;       // geometry of this call (1-based lo/hi as in the reference)
@@ -2411,6 +2428,16 @@ __device__ __forceinline__ double mg_cum_r(const MgSeq& S, int c, int q) {  // p
 
 // score[j] of a call (Cumulative_Frame_Score glimmer-mg.cc:561-604)
 __device__ __forceinline__ double mg_score(const MgSeq& S, int frame, const MgCall& c, int j) {
+  if (S.ordered) {  // Cumulative_Frame_Score (glimmer-mg.cc:561-604), term by term from the call's end
+    double cum_score = 0.0;
+    int f = 1, si = frame > 0 ? c.hi - 1 : c.lo - 1;
+    for (int i = 0; i <= j; i++) {
+      cum_score = cum_score + mg_frame_score_at(S, frame > 0 ? f : 3 + f, si);
+      si += frame > 0 ? -1 : 1;
+      f = f == 2 ? 0 : f + 1;
+    }
+    return cum_score;
+  }
   if (frame > 0) {
     const int cls = mod3(c.hi);
     return mg_cum_f(S, cls, c.hi - 1 - j) - c.cbase;
@@ -2444,7 +2471,8 @@ __device__ __forceinline__ void mg_open_call(const MgSeq& S, const DevParams& P,
   c.first_pos = 0;
 }
 
-__device__ double mg_pass_stop_penalty(const MgSeq& S, const DevParams& P, int frame, int lo, int hi) {
+__device__ double mg_pass_stop_penalty(const MgSeq& S, const DevParams& P, int frame, int lo, int hi, int64_t oi) {
+  if (S.sub_pen) return S.sub_pen[oi];  // quality file: p_stop from the device, its log-odds from the host (glibc)
   int i0, i1, i2;
   if (frame > 0) { i0 = lo - 3; i1 = lo - 2; i2 = lo - 1; }
   else { i0 = hi + 1; i1 = hi; i2 = hi - 1; }
@@ -2461,7 +2489,7 @@ __device__ double mg_pass_stop_penalty(const MgSeq& S, const DevParams& P, int f
   return log(1.0 - p_stop) - log(p_stop);
 }
 
-__device__ void mg_orf_starts(const MgSeq& S, const DevParams& P, const CodonSets& cs, const gmg_orf& o, Emit& e) {
+__device__ void mg_orf_starts(const MgSeq& S, const DevParams& P, const CodonSets& cs, const gmg_orf& o, int64_t oi, Emit& e) {
   const int frame = o.frame;
   const int lowest_j = min(3, P.min_gene_len - 3);
   MgCall st[5];
@@ -2481,7 +2509,7 @@ __device__ void mg_orf_starts(const MgSeq& S, const DevParams& P, const CodonSet
         if (frame > 0) { eep = c.lo - 3; epos = c.lo - 2; }
         else { eep = c.hi + 3; epos = c.hi + 2; }
         if (eep >= 0 && eep - 2 < S.L) {
-          double ess = c.suffix_score + mg_pass_stop_penalty(S, P, frame, c.lo, c.hi);
+          double ess = c.suffix_score + mg_pass_stop_penalty(S, P, frame, c.lo, c.hi, oi);
           if (c.m > 0) ess += mg_score(S, frame, c, c.m - 1) - 0.0;
           MgCall& nc = st[sp + 1];
           mg_open_call(S, P, frame, eep, nc);
@@ -2567,598 +2595,314 @@ __device__ void mg_orf_starts(const MgSeq& S, const DevParams& P, const CodonSet
   }
 }
 
+// One thread per ORF: the recursion as the reference runs it (explicit stack).  Used for read sets without error
+// branches (plain glimmer-mg: one short linear walk per ORF) and, with kOnlyUncert, as the ORDERED path of the
+// sequences whose FP64 exactness certificate failed in K2 (their sums are re-formed in the reference's own order).
 template <bool kWrite>
-__global__ void __launch_bounds__(128) k3_mg_starts(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                    const gmg_orf* __restrict__ orfs,
-                                                    const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                    const double* __restrict__ cum, const int32_t* __restrict__ fwd_prev,
-                                                    const int32_t* __restrict__ rev_next, const uint8_t* __restrict__ qual,
-                                                    const double* __restrict__ tables, CodonSets cs, DevParams P,
+__global__ void __launch_bounds__(128) k3_mg_starts(MgfBatch B, int64_t n_orfs, const gmg_orf* __restrict__ orfs,
+                                                    const int32_t* __restrict__ orf_seq, CodonSets cs, DevParams P,
+                                                    int only_uncert, const float* __restrict__ planes,
+                                                    const uint32_t* __restrict__ bktidx, DevIcm indep,
                                                     int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
                                                     gmg_start* __restrict__ starts) {
   const int64_t oi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (oi >= n_orfs) return;
   const int32_t s = orf_seq[oi];
+  const bool uncert = B.cert != NULL && B.cert[s] == 0;
+  if (only_uncert && !uncert) return;
   MgSeq S;
-  S.words = words;
-  S.a = off[s];
-  S.L = (int)(off[s + 1] - S.a);
-  S.total = total;
-  S.cum = cum;
-  S.fwd_prev = fwd_prev;
-  S.rev_next = rev_next;
-  S.qual = qual;
-  S.penalty = tables;
-  S.stop_pen = tables + 256;
-  S.codon_p = tables + 260;
+  S.words = B.words;
+  S.a = B.off[s];
+  S.L = (int)(B.off[s + 1] - S.a);
+  S.total = B.total;
+  S.cum = B.cum;
+  S.fwd_prev = B.fwd_prev;
+  S.rev_next = B.rev_next;
+  S.qual = B.qual;
+  S.penalty = B.tables;
+  S.stop_pen = B.tables + 256;
+  S.codon_p = B.tables + 260;
+  S.sub_pen = B.sub_pen;
+  S.ordered = uncert ? 1 : 0;
+  S.planes = planes;
+  S.bktidx = bktidx;
+  S.indep = indep;
   Emit e;
   e.out = kWrite ? starts + start_off[oi] : NULL;
   e.n = 0;
-  mg_orf_starts(S, P, cs, orfs[oi], e);
+  mg_orf_starts(S, P, cs, orfs[oi], oi, e);
   if (!kWrite) counts[oi] = e.n;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 (glimmer-mg), warp-cooperative form (the default): one WARP per ORF runs the same recursion with
-// warp-uniform control flow.  The frame on top of the stack is walked 32 positions (j values) at a time: every
-// lane evaluates its position -- quality gate and the two indel branch scores, start codon / truncation test --
-// and ballots turn that into three event masks (deletion branch, insertion branch, own start) which are
-// consumed in the reference's order (position descending; deletion, insertion, then the position's own start,
-// glimmer-mg.cc:1809-1856).  Runs of starts with no branch in between are written by their lanes in parallel;
-// a taken branch pushes a child frame (parameters broadcast from the branching lane) and the parent chunk is
-// re-evaluated when the child returns.  Frames live in shared memory (5 per warp); everything a lane needs is
-// a coalesced load (qualities, prefix sums) or a broadcast (stop tables).
-struct MgFrame {
-  int lo, hi, m, trunc;
-  int jtop;        // highest j of the chunk being walked
-  int cur;         // events with key (lane * 4 + phase) < cur are done; phase 0 deletion, 1 insertion, 2 own start
-  int suffix_j, n_err;
-  int first_zero;  // first_pos == 0 at the start of the chunk
-  int fresh;       // substitution pre-step not run yet
-  int err_pos[2], err_type[2];
-  double suffix_score, cbase;
-  const double* row;  // this call's prefix-sum plane, offset to the sequence: score[j] = row[idx(j)] - cbase
-};
+// K3 (glimmer-mg), flat form (the default for -i / -s): the reference's recursion enumerated level by level with
+// one thread per CANDIDATE call, see gmg_mg_flat.cuh for the passes.  The kernels below only map a thread to an
+// item; the bodies are the __host__ __device__ functions of that header (checked on the host against the oracle
+// by tests/test_mgflat_host.py, on the device by the start-list parity tests).
 
-__device__ __forceinline__ void mg_open_frame(const MgSeq& S, const DevParams& P, int frame, int end_point, MgFrame& c) {
-  const int L = S.L;
-  if (frame > 0) {
-    c.hi = end_point;
-    const int e = end_point - 1;
-    c.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
-    c.m = c.hi - c.lo;
-    c.trunc = (c.lo < 3 && P.allow_truncated);
-    c.row = S.cum + (size_t)mod3(c.hi) * S.total + S.a;
-    c.cbase = ((unsigned)c.hi < (unsigned)L) ? c.row[c.hi] : 0.0;
+// gates: positions whose quality allows an indel branch (Score_Orf_Starts glimmer-mg.cc:1816)
+__global__ void __launch_bounds__(256) k_gate_bits(const uint8_t* __restrict__ qual, int64_t total, int thresh, int64_t nblk,
+                                                   uint32_t* __restrict__ bits, uint32_t* __restrict__ cnt) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nblk) return;
+  uint32_t m = 0;
+  const int64_t p0 = w << 5;
+  if (p0 + 32 <= total) {
+    const uint4* q4 = reinterpret_cast<const uint4*>(qual + p0);
+    const uint4 x = __ldg(q4), y = __ldg(q4 + 1);
+    const uint32_t v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) m |= (uint32_t)((int)((v[k] >> (8 * b)) & 255u) <= thresh) << (4 * k + b);
   } else {
-    c.lo = end_point;
-    const int e = end_point - 1;
-    c.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
-    c.m = c.hi - c.lo;
-    c.trunc = (L - (c.hi - 1) < 3 && P.allow_truncated);
-    c.row = S.cum + (size_t)(3 + mod3(c.lo - 1)) * S.total + S.a;
-    c.cbase = ((unsigned)(c.lo - 2) < (unsigned)L) ? c.row[c.lo - 2] : 0.0;
+    for (int i = 0; i < 32 && p0 + i < total; i++) m |= (uint32_t)((int)qual[p0 + i] <= thresh) << i;
   }
-  if (c.m < 0) c.m = 0;
-  c.jtop = c.m - 1;
-  c.cur = 0;
-  c.first_zero = 1;
-  c.fresh = 1;
+  bits[w] = m;
+  cnt[w] = (uint32_t)__popc(m);
+}
+__global__ void __launch_bounds__(256) k_gate_pos(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank, int64_t nblk,
+                                                  uint32_t* __restrict__ pos) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nblk) return;
+  uint32_t m = bits[w], r = rank[w];
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    pos[r++] = (uint32_t)(w << 5) + (uint32_t)b;
+  }
 }
 
-__device__ __forceinline__ double mg_frame_score(const MgSeq& S, int frame, const MgFrame& c, int j) {
-  const int q = frame > 0 ? c.hi - 1 - j : c.lo - 1 + j;
-  return (((unsigned)q < (unsigned)S.L) ? c.row[q] : 0.0) - c.cbase;
+// Pass_Stop_Penalty with a quality file: the stop probability of every root call (the host takes the logs)
+__global__ void __launch_bounds__(128) k_mg_sub_pstop(MgfBatch B, DevParams P, const gmg_orf* __restrict__ orfs,
+                                                      const int32_t* __restrict__ orf_seq, uint32_t n_orfs, double* __restrict__ pstop) {
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_orfs) return;
+  const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+  const bool fwd = orfs[o].frame > 0;
+  int lo, hi;
+  mgf_open(B, S, fwd, fwd ? orfs[o].stop_position - 1 : orfs[o].stop_position + 3, &lo, &hi);
+  pstop[o] = mgf_stop_pstop(B, S, fwd, lo, hi);
 }
 
-// A LEAF call: a call that can neither branch nor substitute any further (n_err == indel_max, or a substitution
-// child) only enumerates its own starts, so one lane handles it alone: the candidate start codons are a contiguous
-// slot range of one codon-bitmap stream (k_codon_bits), counted with popcounts; only emitted positions touch
-// the prefix sums.  Most calls of an -i run are leaves (the call tree fans out ~0.1 x positions per level).
-struct MgLeaf {
-  int lo, hi, m, trunc;
-  int j_lo, j_hi, j_hs;  // eligible j (multiples of 3): j_lo..j_hi; start-codon test only for j <= j_hs
-  const uint2* st;       // bitmap stream
-  uint32_t cpos;         // forward: slot(j) = (cpos - j) / 3; reverse: slot(j) = (cpos + j) / 3 (batches < 2^32 bases)
+__global__ void __launch_bounds__(128) k_mgf_a(MgfBatch B, DevParams P, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.n_orfs) mgf_pass_a(B, P, W, i);
+}
+__global__ void __launch_bounds__(128) k_mgf_b(MgfBatch B, DevParams P, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.c1) mgf_pass_b(B, P, W, i);
+}
+__global__ void __launch_bounds__(128) k_mgf_c(MgfBatch B, DevParams P, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.c2) mgf_pass_c(B, P, W, i);
+}
+__global__ void __launch_bounds__(256) k_mgf_d(MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.c1) mgf_pass_d(W, i);
+}
+__global__ void __launch_bounds__(256) k_mgf_e(MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.n_orfs) mgf_pass_e(W, i);
+}
+__global__ void __launch_bounds__(128) k_mgf_w0(MgfBatch B, DevParams P, CodonSets cs, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.n_orfs) mgf_write_0(B, P, cs, W, i);
+}
+__global__ void __launch_bounds__(128) k_mgf_w1(MgfBatch B, DevParams P, CodonSets cs, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.c1) mgf_write_1(B, P, cs, W, i);
+}
+__global__ void __launch_bounds__(128) k_mgf_w2(MgfBatch B, DevParams P, CodonSets cs, MgfWork W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.c2) mgf_write_2(B, P, cs, W, i);
+}
+
+// test hook (GMG_MG_FORCE_UNCERT=k): withdraw the certificate of every k-th sequence so that the ordered path runs
+__global__ void k_force_uncert(uint8_t* __restrict__ cert, int64_t n, int k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && i % k == 0) cert[i] = 0;
+}
+
+static int exclusive_sum_u32(gmg_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, int64_t n) {
+  size_t tmp_bytes = 0;
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(NULL, tmp_bytes, d_in, d_out, n, ctx->stream));
+  void* tmp;
+  if (gmg_scratch(ctx, SCR_TMP4, tmp_bytes, &tmp)) return 1;
+  GMG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, n, ctx->stream));
+  ctx->launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Start-list reduction: what Score_Orfs_Errors' filter (glimmer-mg.cc:1656-1684) and
+// Add_Events_Fwd / Add_Events_Rev (glimmer_base.cc:65-128, 175-235) keep of an ORF's raw start_list -- at most one
+// candidate per start position -- decided on the device so that only survivors cross PCIe.
+//
+// One warp per ORF, two sweeps over its records and a shared-memory table indexed by start position:
+//   gate 1  first_j + 1 >= Min_Gene_Len, first_j = j of the record at the lowest (forward) / highest (reverse)
+//           position.  Several records can share that position with different j (std::sort is not stable): the ORF
+//           is decided here only when they all agree, else it is handed back (status 2).
+//   gate 2  best raw score > Start_Threshold.
+//   per start position: candidates with 1 + j >= Min_Gene_Len are ranked by
+//           x = ((score + prior) [+ LogOdds_Start(which)]) + LogOdds_Length(...)
+//           -- the reference's event score, formed in its order, WITHOUT the RBS term: Add_PWM_Score adds the same
+//           value to every candidate of a position, so it shifts all of them alike up to a rounding of the last
+//           bits.  The maximum survives if x + pwm_bonus_max can exceed Event_Threshold; if a second candidate of
+//           the position lies within 1e-9 of it (a tie, or close enough for the RBS term's rounding to matter) the
+//           ORF is handed back as well.  The host then runs the reference's own Add_Events on the survivors (exact
+//           scores, exact threshold) or, for status 2, on the raw list it fetches for that ORF.
+struct DevEventModel {
+  double prior, start_threshold, event_threshold, pwm_bonus_max;
+  double start_lo[8];
+  int n_len, n_class, min_gene_len;
+  const double* len_lo;      // [n_class][2][2][n_len]
+  const int32_t* seq_class;  // [n_seq] or NULL
 };
-
-__device__ __forceinline__ void mg_leaf_open(const MgSeq& S, const DevParams& P, int frame, int end_point, int suffix_j,
-                                             int lowest_j, const uint2* __restrict__ cb, int64_t nwc, MgLeaf& f) {
-  const int L = S.L;
-  const int e = end_point - 1;
-  if (frame > 0) {
-    f.hi = end_point;
-    f.lo = ((e >= 0 && e < L) ? S.fwd_prev[S.a + e] : e) + 1;
-    f.trunc = (f.lo < 3 && P.allow_truncated);
-  } else {
-    f.lo = end_point;
-    f.hi = ((e >= 0 && e < L) ? S.rev_next[S.a + e] : e) + 1;
-    f.trunc = (L - (f.hi - 1) < 3 && P.allow_truncated);
-  }
-  f.m = f.hi - f.lo;
-  if (f.m < 0) f.m = 0;
-  int jl = max(lowest_j, P.min_gene_len - 3 - suffix_j);
-  if (jl < 0) jl = 0;
-  f.j_lo = jl + (3 - jl % 3) % 3;
-  f.j_hi = (f.m - 1) >= 0 ? (f.m - 1) - (f.m - 1) % 3 : -3;
-  f.j_hs = (f.m - 3) >= 0 ? (f.m - 3) - (f.m - 3) % 3 : -3;
-  if (frame > 0) {
-    f.cpos = (uint32_t)(S.a + f.hi - 3);  // first base of the codon ending at bidx = hi-1-j is cpos - j
-    const int r = (int)(f.cpos % 3u);
-    f.st = cb + (size_t)r * nwc;
-  } else {
-    f.cpos = (uint32_t)(S.a + f.lo - 1);  // first base of the reverse codon starting at bidx = lo-1+j is cpos + j
-    const int r = (int)(f.cpos % 3u);
-    f.st = cb + (size_t)(3 + r) * nwc;
-  }
-}
-
-__device__ __forceinline__ bool mg_leaf_bit(const MgLeaf& f, bool fwd, int j) {
-  const uint32_t sl = (fwd ? f.cpos - (uint32_t)j : f.cpos + (uint32_t)j) / 3u;
-  return (__ldg(f.st + (sl >> 5)).x >> (sl & 31u)) & 1u;
-}
-
-// number of start bits at eligible j in [ja, jb] (multiples of 3, ja <= jb)
-__device__ __forceinline__ int mg_leaf_popc(const MgLeaf& f, bool fwd, int ja, int jb) {
-  const uint32_t s1 = (fwd ? f.cpos - (uint32_t)jb : f.cpos + (uint32_t)ja) / 3u;
-  const uint32_t s2 = (fwd ? f.cpos - (uint32_t)ja : f.cpos + (uint32_t)jb) / 3u;
-  const uint32_t w1 = s1 >> 5, w2 = s2 >> 5;
-  const unsigned m1 = ~0u << (s1 & 31u), m2 = (2u << (s2 & 31u)) - 1u;
-  int cnt = 0;
-  for (uint32_t w = w1; w <= w2; w++)
-    cnt += __popc(__ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u));
-  return cnt;
-}
-
-// Records of a leaf call in the reference's order (j descending).  out == NULL: count only.
-__device__ int mg_leaf_run(const MgSeq& S, const DevParams& P, const CodonSets& cs, int frame, const MgLeaf& f,
-                           double suffix_score, int suffix_j, int n_err, const int* err_pos, const int* err_type,
-                           gmg_start* __restrict__ out) {
-  const bool fwd = frame > 0;
-  if (f.j_hi < f.j_lo) return 0;
-  int cnt = 0;
-  int jt = f.j_hi;
-  bool state = true;  // first_pos == 0
-  double cbase = 0.0;
-  if (out) cbase = fwd ? mg_cum_f(S, mod3(f.hi), f.hi) : mg_cum_r(S, mod3(f.lo - 1), f.lo - 2);
-  auto put = [&](int j, int which, int truncated, int first) {
-    if (out) {
-      const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
-      const double raw = fwd ? mg_cum_f(S, mod3(f.hi), f.hi - j) : mg_cum_r(S, mod3(f.lo - 1), f.lo - 2 + j);  // score[j-1]
-      const double sc = ((raw - cbase) - 0.0) + suffix_score;
-      const int jj = j + 2 + suffix_j;
-      gmg_start st;
-      st.j = jj;
-      st.pos = k;
-      st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
-      st.which = which;
-      st.truncated = truncated;
-      st.first = first;
-      st.n_err = n_err;
-      st.err_pos[0] = n_err > 0 ? err_pos[0] : 0;
-      st.err_pos[1] = n_err > 1 ? err_pos[1] : 0;
-      st.err_type[0] = n_err > 0 ? err_type[0] : 0;
-      st.err_type[1] = n_err > 1 ? err_type[1] : 0;
-      out[cnt] = st;
-    }
-    cnt++;
-  };
-  auto which_at = [&](int j) -> int {
-    const int bidx = fwd ? f.hi - 1 - j : f.lo - 1 + j;
-    const int cd = fwd ? codon_fwd_ending_at(S.words, S.a, bidx) : codon_rev_starting_at(S.words, S.a, bidx);
-    return (int)cs.which[cd];
-  };
-  if (f.trunc) {  // every eligible position emits while first_pos is still 0 (glimmer-mg.cc:1836-1853)
-    while (state && jt >= f.j_lo) {
-      const bool is_start = jt <= f.j_hs && mg_leaf_bit(f, fwd, jt);
-      if (is_start) {
-        put(jt, -1, 1, 1);
-        put(jt, out ? which_at(jt) : 0, 0, 0);
-      } else {
-        put(jt, -1, 1, 1);
-      }
-      const int k = fwd ? f.lo + f.m - 2 - jt : f.lo + jt + 2;
-      if (k != 0) state = false;
-      jt -= 3;
-    }
-  }
-  const int jb = min(jt, f.j_hs);
-  if (jb < f.j_lo) return cnt;
-  if (!out) return cnt + mg_leaf_popc(f, fwd, f.j_lo, jb);
-  // write: walk the set bits in descending j
-  const uint32_t s1 = (fwd ? f.cpos - (uint32_t)jb : f.cpos + (uint32_t)f.j_lo) / 3u;
-  const uint32_t s2 = (fwd ? f.cpos - (uint32_t)f.j_lo : f.cpos + (uint32_t)jb) / 3u;
-  const uint32_t w1 = s1 >> 5, w2 = s2 >> 5;
-  const unsigned m1 = ~0u << (s1 & 31u), m2 = (2u << (s2 & 31u)) - 1u;
-  const uint32_t rr = f.cpos % 3u;  // (cpos -/+ j) = 3 sl + rr
-  for (uint32_t wi = 0; wi <= w2 - w1; wi++) {
-    const uint32_t w = fwd ? w1 + wi : w2 - wi;
-    unsigned x = __ldg(f.st + w).x & (w == w1 ? m1 : ~0u) & (w == w2 ? m2 : ~0u);
-    while (x) {
-      const int b = fwd ? __ffs(x) - 1 : 31 - __clz(x);
-      x &= ~(1u << b);
-      const uint32_t sl = (w << 5) + (uint32_t)b;
-      const int j = (int)(fwd ? f.cpos - rr - 3u * sl : 3u * sl + rr - f.cpos);
-      const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
-      put(j, which_at(j), 0, state ? 1 : 0);
-      if (k != 0) state = false;
-    }
-  }
-  return cnt;
-}
-
-// kMode 0: count only.  1: write into the CSR ranges given by start_off (second pass).  2: SINGLE PASS -- every run
-// of records reserves its exact size from a pool (one atomicAdd per run; consecutive reservations of a warp merge
-// into one extent), the per-ORF extent lists and counts are kept, and k3_mg_compact moves the records to their
-// CSR places after the scan: the recursion runs once instead of twice.  A pool or extent-table overflow only
-// drops writes (counts stay exact), and the caller then runs the write pass.
-struct MgExt {
-  long long start;
-  int len, next;
+struct RedSlot {
+  unsigned long long best;
+  unsigned int win, cnt;
 };
-struct MgPool {
-  gmg_start* pool;
-  unsigned long long cap;
-  unsigned long long* cur;   // [0] pool cursor, [1] extent cursor, [2] overflow flag
-  MgExt* ext;
-  unsigned long long ext_cap;
-  int* orf_head;
-};
+__device__ __forceinline__ unsigned long long red_key(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double red_unkey(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
 
-template <int kMode>
-__global__ void __launch_bounds__(128, 8) k3_mg_starts_warp(const uint64_t* __restrict__ words, const int64_t* __restrict__ off,
-                                                         const gmg_orf* __restrict__ orfs,
-                                                         const int32_t* __restrict__ orf_seq, int64_t n_orfs, int64_t total,
-                                                         const double* __restrict__ cum, const int32_t* __restrict__ fwd_prev,
-                                                         const int32_t* __restrict__ rev_next, const uint8_t* __restrict__ qual,
-                                                         const double* __restrict__ tables, CodonSets cs, DevParams P,
-                                                         int64_t* __restrict__ counts, const int64_t* __restrict__ start_off,
-                                                         gmg_start* __restrict__ starts, const uint2* __restrict__ cb,
-                                                         int64_t nwc, MgPool pool) {
+__global__ void __launch_bounds__(128) k3_mg_reduce(const gmg_start* __restrict__ starts, const int64_t* __restrict__ soff,
+                                                    const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                    const int64_t* __restrict__ off, int64_t n_orfs, DevEventModel M,
+                                                    int slots_per_warp, gmg_start* __restrict__ out,
+                                                    unsigned long long* __restrict__ cursor, int64_t* __restrict__ red_first,
+                                                    int32_t* __restrict__ red_cnt, uint8_t* __restrict__ status) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr bool kWrite = kMode != 0;
-  __shared__ MgFrame s_stack[4][5];
+  constexpr double TOL = 1e-9;
+  extern __shared__ __align__(16) unsigned char s_red[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (oi >= n_orfs) return;  // warp-uniform
-  const int32_t sq = orf_seq[oi];
-  MgSeq S;
-  S.words = words;
-  S.a = off[sq];
-  S.L = (int)(off[sq + 1] - S.a);
-  S.total = total;
-  S.cum = cum;
-  S.fwd_prev = fwd_prev;
-  S.rev_next = rev_next;
-  S.qual = qual;
-  S.penalty = tables;
-  S.stop_pen = tables + 256;
-  S.codon_p = tables + 260;
-  const gmg_orf o = orfs[oi];
-  const int frame = o.frame;
-  const bool fwd = frame > 0;
-  const int lowest_j = min(3, P.min_gene_len - 3);
-  gmg_start* out = kMode == 1 ? starts + start_off[oi] : NULL;
-  int64_t n = 0;  // records so far (warp-uniform)
-  // single pass: the warp's open extent and its list
-  long long ext_start = -1;
-  int ext_len = 0, ext_head = -1, ext_tail = -1;
-  auto flush_extent = [&]() {
-    if (ext_start < 0) return;
-    int e = 0;
-    if (lane == 0) {
-      e = (int)atomicAdd(pool.cur + 1, 1ull);
-      if ((unsigned long long)e < pool.ext_cap) {
-        MgExt x;
-        x.start = ext_start;
-        x.len = ext_len;
-        x.next = -1;
-        pool.ext[e] = x;
-        if (ext_tail >= 0 && (unsigned long long)ext_tail < pool.ext_cap) pool.ext[ext_tail].next = e;
-      } else {
-        pool.cur[2] = 1ull;
-      }
+  const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (o >= n_orfs) return;  // warp-uniform
+  RedSlot* tab = reinterpret_cast<RedSlot*>(s_red) + (size_t)wid * slots_per_warp;
+  const int64_t a = soff[o];
+  const int n = (int)(soff[o + 1] - a);
+  const gmg_start* rec = starts + a;
+  int st = 0, kept = 0;
+  long long first = 0;
+  if (n > 0) {
+    const gmg_orf orf = orfs[o];
+    const bool fwd = orf.frame > 0;
+    const int32_t sq = orf_seq[o];
+    const int L = (int)(off[sq + 1] - off[sq]);
+    // sweep 1: position range, best raw score
+    int pmin = INT_MAX, pmax = INT_MIN;
+    double best = -DBL_MAX;
+    for (int i = lane; i < n; i += 32) {
+      const int p = rec[i].pos;
+      pmin = min(pmin, p);
+      pmax = max(pmax, p);
+      best = fmax(best, rec[i].score);
     }
-    e = __shfl_sync(FULL, e, 0);
-    if (ext_head < 0) ext_head = e;
-    ext_tail = e;
-    ext_start = -1;
-  };
-  // where the next `cnt` records of this ORF go (NULL: nowhere -- counting, or the pool is full)
-  auto place = [&](int cnt) -> gmg_start* {
-    if (kMode == 1) return out + n;
-    if (kMode == 0 || cnt == 0) return NULL;
-    unsigned long long st = 0;
-    if (lane == 0) st = atomicAdd(pool.cur, (unsigned long long)cnt);
-    st = __shfl_sync(FULL, st, 0);
-    if (st + (unsigned long long)cnt > pool.cap) {
-      if (lane == 0) pool.cur[2] = 1ull;
-      return NULL;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      pmin = min(pmin, __shfl_xor_sync(FULL, pmin, d));
+      pmax = max(pmax, __shfl_xor_sync(FULL, pmax, d));
+      best = fmax(best, __shfl_xor_sync(FULL, best, d));
     }
-    if (ext_start >= 0 && (long long)st == ext_start + ext_len) {
-      ext_len += cnt;
+    const int range = pmax - pmin + 1;
+    if (range > slots_per_warp) {
+      st = 2;
     } else {
-      flush_extent();
-      ext_start = (long long)st;
-      ext_len = cnt;
-    }
-    return pool.pool + st;
-  };
-  MgFrame* stk = s_stack[wid];
-  int sp = 0;
-  MgFrame c;
-  mg_open_frame(S, P, frame, fwd ? o.stop_position - 1 : o.stop_position + 3, c);
-  c.suffix_score = 0.0;
-  c.suffix_j = 0;
-  c.n_err = 0;
-  c.err_pos[0] = c.err_pos[1] = c.err_type[0] = c.err_type[1] = 0;
-  for (;;) {
-    if (c.fresh) {
-      c.fresh = 0;
-      // substitution through the previous stop (glimmer-mg.cc:1771-1806)
-      if (P.allow_subs && c.n_err < 1) {
-        int eep, epos;
-        if (fwd) { eep = c.lo - 3; epos = c.lo - 2; }
-        else { eep = c.hi + 3; epos = c.hi + 2; }
-        if (eep >= 0 && eep - 2 < S.L) {
-          double ess = c.suffix_score + mg_pass_stop_penalty(S, P, frame, c.lo, c.hi);
-          if (c.m > 0) ess += mg_frame_score(S, frame, c, c.m - 1) - 0.0;
-          __syncwarp();
-          if (lane == 0) stk[sp] = c;
-          __syncwarp();
-          MgFrame nc;
-          mg_open_frame(S, P, frame, eep, nc);
-          nc.suffix_score = ess;
-          nc.suffix_j = c.suffix_j + c.m;
-          nc.n_err = c.n_err + 1;
-          nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
-          nc.err_pos[1] = c.err_pos[1]; nc.err_type[1] = c.err_type[1];
-          if (c.n_err == 0) { nc.err_pos[0] = epos; nc.err_type[0] = 2; }
-          else { nc.err_pos[1] = epos; nc.err_type[1] = 2; }
-          c = nc;
-          sp++;
-          continue;
+      for (int i = lane; i < range; i += 32) {
+        tab[i].best = 0ull;
+        tab[i].win = 0xffffffffu;
+        tab[i].cnt = 0u;
+      }
+      __syncwarp();
+      const int ext = fwd ? pmin : pmax;
+      const int cls = M.seq_class ? M.seq_class[sq] : 0;
+      const bool t3 = fwd ? orf.stop_position > L - 2 : orf.stop_position < 1;
+      const double* lenrow = M.len_lo + (size_t)cls * 4 * M.n_len;
+      bool pass_any = false, fail_any = false, too_long = false;
+      // sweep 2: first_j gate inputs; per-position maxima of the candidates
+      for (int i = lane; i < n; i += 32) {
+        const gmg_start r = rec[i];
+        if (r.pos == ext) {
+          if (r.j + 1 >= M.min_gene_len) pass_any = true;
+          else fail_any = true;
+        }
+        if (1 + r.j >= M.min_gene_len) {
+          const int l = (1 + r.j) / 3;
+          if (l >= M.n_len) {
+            too_long = true;
+            continue;
+          }
+          double x = r.score + M.prior;
+          if (r.which >= 0) x += M.start_lo[r.which & 7];
+          x += lenrow[(size_t)((r.truncated ? 2 : 0) + (t3 ? 1 : 0)) * M.n_len + l];
+          if (x + M.pwm_bonus_max > M.event_threshold - TOL) atomicMax(&tab[r.pos - pmin].best, red_key(x));
         }
       }
-    }
-    if (c.jtop < lowest_j) {  // this call is finished
-      if (sp == 0) break;
-      sp--;
+      pass_any = __any_sync(FULL, pass_any);
+      fail_any = __any_sync(FULL, fail_any);
+      too_long = __any_sync(FULL, too_long);
       __syncwarp();
-      c = stk[sp];
-      continue;
-    }
-    // ---- evaluate the chunk: lane l looks at j = jtop - l ----
-    const int j = c.jtop - lane;
-    const bool valid = j >= lowest_j;
-    const int k = fwd ? c.lo + c.m - 2 - j : c.lo + j + 2;
-    const int bidx = fwd ? c.hi - 1 - j : c.lo - 1 + j;
-    const int jm3 = valid ? j % 3 : 0;
-    bool del_ok = false, ins_ok = false;
-    double ess_del = 0.0, ess_ins = 0.0;
-    double sc_prev = 0.0;  // score[j - 1] of this call
-    const bool can_branch = P.allow_indels && c.n_err < P.indel_max;
-    if (valid) {
-      const bool need_emit_score = kWrite && (jm3 == 0);  // the counting pass never needs a start's score
-      int qv = 255;
-      if (can_branch) qv = S.qual[S.a + bidx];
-      const bool gate = can_branch && qv <= P.indel_q_thresh;
-      if (gate || need_emit_score) sc_prev = mg_frame_score(S, frame, c, j - 1);
-      if (gate) {
-        const double pen = S.penalty[qv];
-        ess_del = c.suffix_score + mg_frame_score(S, frame, c, j) - 0.0 + pen;
-        ess_ins = c.suffix_score + sc_prev - 0.0 + pen;
-        del_ok = ess_del > P.indel_suffix_thresh;
-        ins_ok = ess_ins > P.indel_suffix_thresh;
-      }
-    }
-    int which = -1;
-    bool len_ok = false;
-    if (valid && jm3 == 0) {
-      if (j <= c.m - 3) {
-        const int cd = fwd ? codon_fwd_ending_at(S.words, S.a, bidx) : codon_rev_starting_at(S.words, S.a, bidx);
-        if ((cs.start_mask >> cd) & 1) which = cs.which[cd];
-      }
-      len_ok = j + 3 + c.suffix_j >= P.min_gene_len;
-    }
-    const unsigned D = __ballot_sync(FULL, del_ok), I = __ballot_sync(FULL, ins_ok);
-    const unsigned A = __ballot_sync(FULL, len_ok && which >= 0);         // start codon that may be emitted
-    const unsigned T = __ballot_sync(FULL, len_ok && c.trunc);            // emitted while first_pos == 0
-    const unsigned Z = __ballot_sync(FULL, valid && k == 0);              // an emit here leaves first_pos == 0
-    // own starts of the chunk and their `first` flags, from the chunk-start state (glimmer-mg.cc:1836-1853)
-    unsigned EM = A, FI = 0;
-    int state = c.first_zero;
-    {
-      unsigned rem = A | T;
-      while (state && rem) {
-        const int l = __ffs(rem) - 1;
-        rem &= rem - 1;
-        EM |= 1u << l;
-        FI |= 1u << l;
-        if (!((Z >> l) & 1u)) state = 0;
-      }
-    }
-    const unsigned DB = EM & FI & A & T;  // truncated copy + real start at the same position: two records
-    // ---- children that are leaves: every lane runs its own (up to two) children, no push ----
-    {
-      const int cn = c.n_err + 1;
-      const bool child_is_leaf = !(P.allow_indels && cn < P.indel_max) && !(P.allow_subs && cn < 1);
-      if (child_is_leaf) {
-        if (D | I | EM) {
-          int eperr[2] = {c.err_pos[0], c.err_pos[1]}, etype[2] = {c.err_type[0], c.err_type[1]};
-          int cnt_b[2] = {0, 0};  // records of the deletion child, of the insertion child
-          const int esj = c.suffix_j + j + 2 - jm3;
-#pragma unroll 1
-          for (int ph = 0; ph < 2; ph++) {
-            if (ph == 0 ? del_ok : ins_ok) {
-              MgLeaf lf;
-              const int eep = ph == 0 ? (fwd ? k + jm3 : k - jm3) : (fwd ? k - (2 - jm3) : k + 2 - jm3);
-              mg_leaf_open(S, P, frame, eep, esj, lowest_j, cb, nwc, lf);
-              cnt_b[ph] = mg_leaf_run(S, P, cs, frame, lf, 0.0, esj, cn, eperr, etype, NULL);
+      if (too_long || (pass_any && fail_any)) {
+        st = 2;
+      } else if (!pass_any || !(best > M.start_threshold)) {
+        st = 0;
+      } else {
+        // sweep 3: who is (within TOL of) the maximum of its position
+        for (int i = lane; i < n; i += 32) {
+          const gmg_start r = rec[i];
+          if (1 + r.j >= M.min_gene_len) {
+            const int l = (1 + r.j) / 3;
+            double x = r.score + M.prior;
+            if (r.which >= 0) x += M.start_lo[r.which & 7];
+            x += lenrow[(size_t)((r.truncated ? 2 : 0) + (t3 ? 1 : 0)) * M.n_len + l];
+            RedSlot* t = &tab[r.pos - pmin];
+            if (t->best != 0ull && x + M.pwm_bonus_max > M.event_threshold - TOL && x >= red_unkey(t->best) - TOL) {
+              atomicAdd(&t->cnt, 1u);
+              atomicMin(&t->win, (unsigned)i);
             }
           }
-          const int cnt_d = cnt_b[0], cnt_i = cnt_b[1];
-          const int own = ((EM >> lane) & 1u) ? (((DB >> lane) & 1u) ? 2 : 1) : 0;
-          const int tot = cnt_d + cnt_i + own;
-          int incl = tot;
+        }
+        __syncwarp();
+        bool amb = false;
+        int mine = 0;
+        for (int i = lane; i < range; i += 32) {
+          if (tab[i].cnt > 1u) amb = true;
+          if (tab[i].cnt >= 1u) mine++;
+        }
+        amb = __any_sync(FULL, amb);
+        if (amb) {
+          st = 2;
+        } else {
+          st = 1;
+          int incl = mine;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) incl += t;
           }
-          const int all = __shfl_sync(FULL, incl, 31);
-          gmg_start* const dstb = place(all);
-          if (kWrite && tot && dstb) {
-            gmg_start* o = dstb + (incl - tot);
-#pragma unroll 1
-            for (int ph = 0; ph < 2; ph++) {
-              if (cnt_b[ph]) {
-                MgLeaf lf;
-                const int eep = ph == 0 ? (fwd ? k + jm3 : k - jm3) : (fwd ? k - (2 - jm3) : k + 2 - jm3);
-                mg_leaf_open(S, P, frame, eep, esj, lowest_j, cb, nwc, lf);
-                eperr[c.n_err] = ph == 0 ? (fwd ? k + 3 : k - 1) : (fwd ? k + 2 : k - 2);
-                etype[c.n_err] = ph == 0 ? 1 : 0;
-                mg_leaf_run(S, P, cs, frame, lf, ph == 0 ? ess_del : ess_ins, esj, cn, eperr, etype, o);
-                o += cnt_b[ph];
-              }
-            }
-            if (own) {
-              const double sc = (sc_prev - 0.0) + c.suffix_score;
-              const int jj = j + 2 + c.suffix_j;
-              const int first = (FI >> lane) & 1u;
-              gmg_start st;
-              st.j = jj;
-              st.pos = k;
-              st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
-              st.n_err = c.n_err;
-              st.err_pos[0] = c.n_err > 0 ? c.err_pos[0] : 0;
-              st.err_pos[1] = c.n_err > 1 ? c.err_pos[1] : 0;
-              st.err_type[0] = c.n_err > 0 ? c.err_type[0] : 0;
-              st.err_type[1] = c.n_err > 1 ? c.err_type[1] : 0;
-              if (own == 2) {
-                st.which = -1; st.truncated = 1; st.first = first;
-                o[0] = st;
-                st.which = which; st.truncated = 0; st.first = 0;
-                o[1] = st;
-              } else {
-                st.which = which; st.truncated = which < 0; st.first = first;
-                o[0] = st;
-              }
-            }
-          }
-          n += all;
+          kept = __shfl_sync(FULL, incl, 31);
+          unsigned long long base = 0;
+          if (lane == 0 && kept) base = atomicAdd(cursor, (unsigned long long)kept);
+          base = __shfl_sync(FULL, base, 0);
+          first = (long long)base;
+          // lane's slots are i = lane, lane + 32, ...: survivors go out in that (deterministic) order
+          unsigned long long at = base + (unsigned long long)(incl - mine);
+          for (int i = lane; i < range; i += 32)
+            if (tab[i].cnt >= 1u) out[at++] = rec[tab[i].win];
         }
-        c.jtop -= 32;
-        c.cur = 0;
-        c.first_zero = state;
-        continue;
       }
     }
-    // ---- consume events from the cursor on ----
-    bool pushed = false;
-    for (;;) {
-      const int cl = c.cur >> 2, cp = c.cur & 3;
-      const unsigned ge = cl >= 32 ? 0u : (FULL << cl);          // lanes >= cursor lane
-      const unsigned gt = cl >= 31 ? 0u : (FULL << (cl + 1));    // lanes > cursor lane
-      const unsigned Dr = D & (cp <= 0 ? ge : gt), Ir = I & (cp <= 1 ? ge : gt), Er = EM & (cp <= 2 ? ge : gt);
-      const unsigned Br = Dr | Ir;
-      if (!(Br | Er)) break;
-      const int lb = Br ? __ffs(Br) - 1 : 32, le = Er ? __ffs(Er) - 1 : 32;
-      if (le < lb) {
-        // run of own starts before the next branch: lanes le .. lb-1 of Er write their records in parallel
-        const unsigned run = Er & (lb >= 32 ? FULL : ((1u << lb) - 1u));
-        const unsigned below = (1u << lane) - 1u;
-        gmg_start* const dstb = place(__popc(run) + __popc(run & DB));
-        if ((run >> lane) & 1u) {
-          const int at = __popc(run & below) + __popc(run & DB & below);
-          if (kWrite && dstb) {
-            const double sc = (sc_prev - 0.0) + c.suffix_score;
-            const int jj = j + 2 + c.suffix_j;
-            const int first = (FI >> lane) & 1u;
-            gmg_start st;
-            st.j = jj;
-            st.pos = k;
-            st.score = (jj > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
-            st.n_err = c.n_err;
-            st.err_pos[0] = c.n_err > 0 ? c.err_pos[0] : 0;
-            st.err_pos[1] = c.n_err > 1 ? c.err_pos[1] : 0;
-            st.err_type[0] = c.n_err > 0 ? c.err_type[0] : 0;
-            st.err_type[1] = c.n_err > 1 ? c.err_type[1] : 0;
-            if ((DB >> lane) & 1u) {
-              st.which = -1; st.truncated = 1; st.first = first;
-              dstb[at] = st;
-              st.which = which; st.truncated = 0; st.first = 0;
-              dstb[at + 1] = st;
-            } else {
-              st.which = which; st.truncated = which < 0; st.first = first;
-              dstb[at] = st;
-            }
-          }
-        }
-        n += __popc(run) + __popc(run & DB);
-        c.cur = (31 - __clz(run)) * 4 + 3;
-        continue;
-      }
-      // branch at lane lb: deletion first, then insertion
-      const bool is_del = (Dr >> lb) & 1u;
-      const int ph = is_del ? 0 : 1;
-      const int bj = c.jtop - lb;
-      const int bk = fwd ? c.lo + c.m - 2 - bj : c.lo + bj + 2;
-      const int b3 = bj % 3;
-      const double ess = __shfl_sync(FULL, is_del ? ess_del : ess_ins, lb);
-      int eep, epos;
-      if (ph == 0) {  // deletion
-        eep = fwd ? bk + b3 : bk - b3;
-        epos = fwd ? bk + 3 : bk - 1;
-      } else {        // insertion
-        eep = fwd ? bk - (2 - b3) : bk + 2 - b3;
-        epos = fwd ? bk + 2 : bk - 2;
-      }
-      c.cur = lb * 4 + ph + 1;
-      __syncwarp();
-      if (lane == 0) stk[sp] = c;
-      __syncwarp();
-      MgFrame nc;
-      mg_open_frame(S, P, frame, eep, nc);
-      nc.suffix_score = ess;
-      nc.suffix_j = c.suffix_j + bj + 2 - b3;
-      nc.n_err = c.n_err + 1;
-      nc.err_pos[0] = c.err_pos[0]; nc.err_type[0] = c.err_type[0];
-      nc.err_pos[1] = c.err_pos[1]; nc.err_type[1] = c.err_type[1];
-      if (c.n_err == 0) { nc.err_pos[0] = epos; nc.err_type[0] = (ph == 0) ? 1 : 0; }
-      else { nc.err_pos[1] = epos; nc.err_type[1] = (ph == 0) ? 1 : 0; }
-      c = nc;
-      sp++;
-      pushed = true;
-      break;
-    }
-    if (pushed) continue;
-    // chunk done: next 32 positions
-    c.jtop -= 32;
-    c.cur = 0;
-    c.first_zero = state;
+    __syncwarp();
   }
-  if (kMode == 2) {
-    flush_extent();
-    if (lane == 0) pool.orf_head[oi] = ext_head;
-  }
-  if (kMode != 1 && lane == 0) counts[oi] = n;
-}
-
-// single pass, step 2: the extents of ORF oi, in order, copied to its CSR range (48-byte records as 3 x 16 bytes)
-__global__ void __launch_bounds__(128) k3_mg_compact(MgPool pool, const int64_t* __restrict__ start_off, int64_t n_orfs,
-                                                     gmg_start* __restrict__ starts) {
-  const int64_t oi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (oi >= n_orfs) return;
-  uint4* dst = reinterpret_cast<uint4*>(starts + start_off[oi]);
-  for (int e = pool.orf_head[oi]; e >= 0;) {
-    const MgExt x = pool.ext[e];
-    const uint4* src = reinterpret_cast<const uint4*>(pool.pool + x.start);
-    const int q = 3 * x.len;
-    for (int i = lane; i < q; i += 32) dst[i] = src[i];
-    dst += q;
-    e = x.next;
+  if (lane == 0) {
+    status[o] = (uint8_t)st;
+    red_cnt[o] = st == 1 ? kept : 0;
+    red_first[o] = first;
   }
 }
 
@@ -3311,34 +3055,40 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CHECK(!(p->have_quality_file && !s->d_qual), "have_quality_file set but the seqset has no quality values");
   s->n_starts = 0;
   s->uncertified = 0;
+  s->n_red = s->n_red_fallback = 0;
+  s->d_red = NULL;
   if (n_starts) *n_starts = 0;
   if (s->n_orfs == 0) return 0;
-  if (ensure_codon_bits(ctx, s, cs)) return 1;  // start-codon bitmaps for the leaf calls of K3
+  GMG_CHECK(s->n_orfs < 0x7fffffffll && s->total < 0xffffffffll, "gmg_score_orfs_mg: batch too large (%lld ORFs): split it",
+            (long long)s->n_orfs);
+  if (ensure_codon_bits(ctx, s, cs)) return 1;  // start-codon bitmaps: the own starts of every call
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
   // K2
   void *d_cum, *d_tab, *d_qual, *d_cert;
   if (gmg_scratch(ctx, SCR_CUM, (size_t)6 * s->total * sizeof(double), &d_cum)) return 1;
   if (gmg_scratch(ctx, SCR_TMP, (size_t)2 * s->total * sizeof(int32_t), &d_tab)) return 1;
-  if (gmg_scratch(ctx, SCR_QUAL, (size_t)s->total, &d_qual)) return 1;
+  if (gmg_scratch(ctx, SCR_QUAL, (size_t)s->total + 64, &d_qual)) return 1;
   if (gmg_scratch(ctx, SCR_TMP3, (size_t)s->n + 64 + 520 * sizeof(double), &d_cert)) return 1;
   int32_t* fwd_prev = (int32_t*)d_tab;
   int32_t* rev_next = fwd_prev + s->total;
   // penalty tables (host libm, FP64): indices 0..255 indel penalty, 256..259 stop penalty, 260..515 codon_p
   double* d_tables = (double*)d_cert;
   uint8_t* cert = (uint8_t*)(d_tables + 516);
-  if (!ctx->h_penalty) GMG_CUDA(cudaMallocHost(&ctx->h_penalty, 516 * sizeof(double)));
-  for (int q = 0; q < 256; q++) {
-    double pe = pow(10.0, -(double)q / 10.0);
-    ctx->h_penalty[q] = log(pe / 2.0) - log(1.0 - pe);
-    ctx->h_penalty[260 + q] = 1.0 - pe;
-  }
-  for (int t = 0; t < 4; t++) {
-    const double dpv = 0.999;
-    double ps = dpv;
-    ps *= (t & 2) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
-    ps *= (t & 1) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
-    ctx->h_penalty[256 + t] = log(1.0 - ps) - log(ps);
+  if (!ctx->h_penalty) {
+    GMG_CUDA(cudaMallocHost(&ctx->h_penalty, 516 * sizeof(double)));
+    for (int q = 0; q < 256; q++) {
+      double pe = pow(10.0, -(double)q / 10.0);
+      ctx->h_penalty[q] = log(pe / 2.0) - log(1.0 - pe);
+      ctx->h_penalty[260 + q] = 1.0 - pe;
+    }
+    for (int t = 0; t < 4; t++) {
+      const double dpv = 0.999;
+      double ps = dpv;
+      ps *= (t & 2) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
+      ps *= (t & 1) ? (2.0 / 3.0 * dpv + 1.0 / 3.0) : dpv;
+      ctx->h_penalty[256 + t] = log(1.0 - ps) - log(ps);
+    }
   }
   GMG_CUDA(cudaMemcpyAsync(d_tables, ctx->h_penalty, 516 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   const bool need_qual = p->allow_indels || p->have_quality_file;
@@ -3350,99 +3100,291 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
                                                  dp, p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev,
                                                  rev_next, need_qual ? (uint8_t*)d_qual : NULL, cert);
   else
-  k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, s->d_bktidx, cs, dp,
-                                         p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
-                                         need_qual ? (uint8_t*)d_qual : NULL, cert);
+    k2_prefix<<<g2, 128, 0, ctx->stream>>>(indep->dev, s->d_words, s->d_off, s->n, s->total, planes, s->d_bktidx, cs, dp,
+                                           p->have_quality_file ? s->d_qual : NULL, (double*)d_cum, fwd_prev, rev_next,
+                                           need_qual ? (uint8_t*)d_qual : NULL, cert);
   gmg_prof_end(ctx, GMG_PROF_K2);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
-  // K3: count, scan, write
+  {  // test hook: withdraw every k-th sequence's certificate (exercises the ordered path)
+    const char* fu = getenv("GMG_MG_FORCE_UNCERT");
+    const int k = fu ? atoi(fu) : 0;
+    if (k > 0) {
+      k_force_uncert<<<(unsigned)((s->n + 255) / 256), 256, 0, ctx->stream>>>(cert, s->n, k);
+      ctx->launches++;
+    }
+  }
+
+  // ---- K3 ----
+  MgfBatch B;
+  memset(&B, 0, sizeof B);
+  B.words = s->d_words;
+  B.off = s->d_off;
+  B.total = s->total;
+  B.cum = (const double*)d_cum;
+  B.fwd_prev = fwd_prev;
+  B.rev_next = rev_next;
+  B.qual = need_qual ? (const uint8_t*)d_qual : NULL;
+  B.cert = cert;
+  B.cb = s->d_cbits;
+  B.nwc = s->nwc;
+  B.tables = d_tables;
   void* d_counts;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
   int64_t* counts = (int64_t*)d_counts;
-  GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
-  unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
-  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  // warp per ORF when calls can branch (-i / -s); without error branches an ORF is one short linear walk and one
-  // thread per ORF keeps 32x more ORFs in flight.  GMG_K3MG_MODE = 0 / 1 forces warp / thread per ORF (tests).
-  static const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
+  GMG_CUDA(cudaMemsetAsync(counts, 0, (size_t)(s->n_orfs + 2) * sizeof(int64_t), ctx->stream));
+  const unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
+  // flat form when calls can branch (-i / -s); without error branches an ORF is one short linear walk and the
+  // thread-per-ORF kernel does it directly.  GMG_K3MG_MODE = 0 / 1 forces the flat / thread-per-ORF form (tests).
+  const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
   const int k3mg_mode = k3mg_env >= 0 ? k3mg_env : ((p->allow_indels || p->allow_subs) ? 0 : 1);
-  const unsigned g3w = (unsigned)((s->n_orfs * 32 + 127) / 128);
-  // single pass (warp kernel only): pool sized from the rate of the previous call in the same error mode
-  const int rate_key = (p->allow_indels ? 1 : 0) | (p->allow_subs ? 2 : 0);
-  const char* env_two = getenv("GMG_K3MG_TWO_PASS");      // test hooks: force the two-pass form,
-  const char* env_scale = getenv("GMG_K3MG_POOL_SCALE");  // shrink the pool (overflow -> write pass)
-  const int k3mg_two_pass = env_two ? atoi(env_two) : 0;
-  const double pool_scale = env_scale ? atof(env_scale) : 1.25;
-  MgPool pool;
-  memset(&pool, 0, sizeof pool);
-  bool single = false;
-  if (k3mg_mode == 0 && !k3mg_two_pass && ctx->mg_rate[rate_key] > 0.0) {
-    const unsigned long long cap = (unsigned long long)(ctx->mg_rate[rate_key] * (double)s->total * pool_scale) + (env_scale ? 64ull : 65536ull);
-    // extent table, ORF heads and cursors live in the plane scratch (K3 does not read the planes)
-    const size_t avail = ctx->scratch_bytes[SCR_PLANES];
-    const size_t head_bytes = ((size_t)s->n_orfs * sizeof(int) + 64 + 15) & ~(size_t)15;
-    if (avail > head_bytes + (size_t)s->n_orfs * 2 * sizeof(MgExt)) {
-      void* d_pool;
-      if (gmg_scratch(ctx, SCR_TMP2, (size_t)cap * sizeof(gmg_start), &d_pool)) return 1;
-      char* base = (char*)ctx->scratch[SCR_PLANES];
-      pool.pool = (gmg_start*)d_pool;
-      pool.cap = cap;
-      pool.cur = (unsigned long long*)base;
-      pool.orf_head = (int*)(base + 64);
-      pool.ext = (MgExt*)(base + head_bytes);
-      pool.ext_cap = (avail - head_bytes) / sizeof(MgExt);
-      GMG_CUDA(cudaMemsetAsync(pool.cur, 0, 64, ctx->stream));
-      single = true;
-    }
+  const uint32_t no = (uint32_t)s->n_orfs;
+  // Pass_Stop_Penalty with a quality file needs a log per root call: p_stop from the device, glibc's log here
+  if (p->allow_subs && p->have_quality_file) {
+    void* d_ps;
+    if (gmg_scratch(ctx, SCR_MISC, (size_t)no * sizeof(double), &d_ps)) return 1;
+    k_mg_sub_pstop<<<g3, 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, no, (double*)d_ps);
+    ctx->launches++;
+    std::vector<double> h((size_t)no);
+    GMG_CUDA(cudaMemcpyAsync(h.data(), d_ps, (size_t)no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < no; i++) h[i] = log(1.0 - h[i]) - log(h[i]);  // glimmer-mg.cc:993
+    GMG_CUDA(cudaMemcpyAsync(d_ps, h.data(), (size_t)no * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    B.sub_pen = (const double*)d_ps;
   }
-  if (single)
-    k3_mg_starts_warp<2><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                      counts, NULL, NULL, s->d_cbits, s->nwc, pool);
-  else if (k3mg_mode == 0)
-    k3_mg_starts_warp<0><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                      counts, NULL, NULL, s->d_cbits, s->nwc, pool);
-  else
-    k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                     (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                     counts, NULL, NULL);
+  MgfWork W;
+  memset(&W, 0, sizeof W);
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+  if (k3mg_mode == 0) {
+    // gates
+    const int64_t nblk = s->total / 32 + 2;
+    void* d_gate;
+    if (gmg_scratch(ctx, SCR_MG_GATE, (size_t)(3 * nblk + s->total + 8) * sizeof(uint32_t), &d_gate)) return 1;
+    uint32_t* gate_bits = (uint32_t*)d_gate;
+    uint32_t* gate_cnt = gate_bits + nblk;
+    uint32_t* gate_rank = gate_cnt + nblk;
+    uint32_t* gate_pos = gate_rank + nblk;
+    if (p->allow_indels) {
+      k_gate_bits<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_qual, s->total,
+                                                                          dp.indel_q_thresh, nblk, gate_bits, gate_cnt);
+      if (exclusive_sum_u32(ctx, gate_cnt, gate_rank, nblk)) return 1;
+      k_gate_pos<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(gate_bits, gate_rank, nblk, gate_pos);
+      ctx->launches += 2;
+    }
+    B.gate_bits = gate_bits;
+    B.gate_rank = gate_rank;
+    B.gate_pos = gate_pos;
+    // level 0
+    void *d_root, *d_l0;
+    if (gmg_scratch(ctx, SCR_MG_ROOT, (size_t)no * sizeof(MgfCall), &d_root)) return 1;
+    if (gmg_scratch(ctx, SCR_MG_L0, (size_t)(3 * ((size_t)no + 1)) * sizeof(uint32_t), &d_l0)) return 1;
+    W.orfs = s->d_orfs;
+    W.orf_seq = s->d_orf_seq;
+    W.n_orfs = no;
+    W.root = (MgfCall*)d_root;
+    W.n1 = (uint32_t*)d_l0;
+    W.off1 = W.n1 + no + 1;
+    W.own0 = W.off1 + no + 1;
+    W.counts = counts;
+    GMG_CUDA(cudaMemsetAsync(W.n1 + no, 0, sizeof(uint32_t), ctx->stream));
+    k_mgf_a<<<g3, 128, 0, ctx->stream>>>(B, dp, W);
+    ctx->launches++;
+    if (exclusive_sum_u32(ctx, W.n1, W.off1, (int64_t)no + 1)) return 1;
+    uint32_t* hs = (uint32_t*)&ctx->h_scalars[9];
+    GMG_CUDA(cudaMemcpyAsync(hs, W.off1 + no, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    W.c1 = hs[0];
+    GMG_CHECK(W.c1 < 0x7ffffff0u, "gmg_score_orfs_mg: %u level-1 candidate calls -- split the batch", W.c1);
+    // level 1
+    void *d_call1, *d_l1;
+    if (gmg_scratch(ctx, SCR_MG_CALL1, ((size_t)W.c1 + 1) * sizeof(MgfCall), &d_call1)) return 1;
+    if (gmg_scratch(ctx, SCR_MG_L1, (size_t)(5 * ((size_t)W.c1 + 1)) * sizeof(uint32_t), &d_l1)) return 1;
+    W.call1 = (MgfCall*)d_call1;
+    W.n2 = (uint32_t*)d_l1;
+    W.off2 = W.n2 + W.c1 + 1;
+    W.own1 = W.off2 + W.c1 + 1;
+    W.t1 = W.own1 + W.c1 + 1;
+    W.s1 = W.t1 + W.c1 + 1;
+    GMG_CUDA(cudaMemsetAsync(W.n2 + W.c1, 0, sizeof(uint32_t), ctx->stream));
+    GMG_CUDA(cudaMemsetAsync(W.t1 + W.c1, 0, sizeof(uint32_t), ctx->stream));
+    if (W.c1) {
+      k_mgf_b<<<(W.c1 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, W);
+      ctx->launches++;
+    }
+    if (exclusive_sum_u32(ctx, W.n2, W.off2, (int64_t)W.c1 + 1)) return 1;
+    GMG_CUDA(cudaMemcpyAsync(hs, W.off2 + W.c1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    W.c2 = hs[0];
+    GMG_CHECK(W.c2 < 0x7ffffff0u, "gmg_score_orfs_mg: %u level-2 candidate calls -- split the batch", W.c2);
+    // level 2
+    void* d_l2;
+    if (gmg_scratch(ctx, SCR_MG_L2, (size_t)(2 * ((size_t)W.c2 + 1)) * sizeof(uint32_t), &d_l2)) return 1;
+    W.cnt3 = (uint32_t*)d_l2;
+    W.s3 = W.cnt3 + W.c2 + 1;
+    GMG_CUDA(cudaMemsetAsync(W.cnt3 + W.c2, 0, sizeof(uint32_t), ctx->stream));
+    if (W.c2) {
+      k_mgf_c<<<(W.c2 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, W);
+      ctx->launches++;
+    }
+    if (exclusive_sum_u32(ctx, W.cnt3, W.s3, (int64_t)W.c2 + 1)) return 1;
+    if (W.c1) {
+      k_mgf_d<<<(W.c1 + 255) / 256, 256, 0, ctx->stream>>>(W);
+      ctx->launches++;
+    }
+    if (exclusive_sum_u32(ctx, W.t1, W.s1, (int64_t)W.c1 + 1)) return 1;
+    k_mgf_e<<<(no + 255) / 256, 256, 0, ctx->stream>>>(W);
+    ctx->launches++;
+    // sequences without a certificate: counted (and later written) in the reference's serial order
+    k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(B, s->n_orfs, s->d_orfs, s->d_orf_seq, cs, dp, 1, planes, s->d_bktidx,
+                                                     indep->dev, counts, NULL, NULL);
+    ctx->launches++;
+  } else {
+    k3_mg_starts<false><<<g3, 128, 0, ctx->stream>>>(B, s->n_orfs, s->d_orfs, s->d_orf_seq, cs, dp, 0, planes, s->d_bktidx,
+                                                     indep->dev, counts, NULL, NULL);
+    ctx->launches++;
+  }
   gmg_prof_end(ctx, GMG_PROF_K3);
+  GMG_CUDA(cudaGetLastError());
   k_count_zero_flags<<<(unsigned)((s->n + 255) / 256), 256, 0, ctx->stream>>>(cert, s->n,
                                                                              (unsigned long long*)(counts + s->n_orfs + 1));
-  ctx->launches += 2;
-  GMG_CUDA(cudaGetLastError());
+  ctx->launches++;
   if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
-  ctx->h_scalars[6] = ctx->h_scalars[7] = ctx->h_scalars[8] = 0;
+  ctx->h_scalars[6] = ctx->h_scalars[7] = 0;
   GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[6], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[7], counts + s->n_orfs + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (single)
-    GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[8], pool.cur + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   const int64_t total_starts = ctx->h_scalars[6], bad = ctx->h_scalars[7];
-  const bool overflow = single && ctx->h_scalars[8] != 0;
   s->uncertified = bad;
-  ctx->mg_rate[rate_key] = s->total > 0 ? (double)total_starts / (double)s->total : 0.0;
+  GMG_CHECK(total_starts < 0xfffffff0ll || k3mg_mode != 0, "gmg_score_orfs_mg: %lld start records -- split the batch",
+            (long long)total_starts);
   if (ensure_start_capacity(s, total_starts)) return 1;
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  if (single && !overflow) {
-    if (total_starts > 0)
-      k3_mg_compact<<<g3w, 128, 0, ctx->stream>>>(pool, s->d_start_off, s->n_orfs, s->d_starts);
-  } else if (k3mg_mode == 0) {
-    k3_mg_starts_warp<1><<<g3w, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                      (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                      NULL, s->d_start_off, s->d_starts, s->d_cbits, s->nwc, pool);
-  } else {
-    k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(s->d_words, s->d_off, s->d_orfs, s->d_orf_seq, s->n_orfs, s->total,
-                                                    (double*)d_cum, fwd_prev, rev_next, (uint8_t*)d_qual, d_tables, cs, dp,
-                                                    NULL, s->d_start_off, s->d_starts);
+  if (total_starts > 0) {
+    if (k3mg_mode == 0) {
+      W.start_off = s->d_start_off;
+      W.starts = s->d_starts;
+      k_mgf_w0<<<g3, 128, 0, ctx->stream>>>(B, dp, cs, W);
+      ctx->launches++;
+      if (W.c1) {
+        k_mgf_w1<<<(W.c1 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, cs, W);
+        ctx->launches++;
+      }
+      if (W.c2) {
+        k_mgf_w2<<<(W.c2 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, cs, W);
+        ctx->launches++;
+      }
+      if (bad > 0) {
+        k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(B, s->n_orfs, s->d_orfs, s->d_orf_seq, cs, dp, 1, planes, s->d_bktidx,
+                                                        indep->dev, NULL, s->d_start_off, s->d_starts);
+        ctx->launches++;
+      }
+    } else {
+      k3_mg_starts<true><<<g3, 128, 0, ctx->stream>>>(B, s->n_orfs, s->d_orfs, s->d_orf_seq, cs, dp, 0, planes, s->d_bktidx,
+                                                      indep->dev, NULL, s->d_start_off, s->d_starts);
+      ctx->launches++;
+    }
   }
   gmg_prof_end(ctx, GMG_PROF_K3);
-  ctx->launches++;
   GMG_CUDA(cudaGetLastError());
   s->n_starts = total_starts;
   if (n_starts) *n_starts = total_starts;
+  return 0;
+}
+
+extern "C" int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, const gmg_event_model* em,
+                                    int64_t* n_kept, int64_t* n_fallback_orfs) {
+  GMG_CHECK(ctx && s && p && em, "gmg_reduce_starts_mg: NULL argument");
+  GMG_CHECK(em->n_start >= 0 && em->n_start <= 8 && em->n_class >= 1 && em->n_len >= 1 && em->len_lo,
+            "gmg_reduce_starts_mg: bad event model (n_start %d, n_class %d, n_len %d)", em->n_start, em->n_class, em->n_len);
+  s->n_red = s->n_red_fallback = 0;
+  s->d_red = NULL;
+  if (n_kept) *n_kept = 0;
+  if (n_fallback_orfs) *n_fallback_orfs = 0;
+  if (s->n_orfs == 0) return 0;
+  const size_t len_bytes = (size_t)em->n_class * 4 * em->n_len * sizeof(double);
+  const size_t cls_bytes = em->seq_class ? (size_t)s->n * sizeof(int32_t) : 0;
+  const size_t hdr = ((len_bytes + cls_bytes + 128 + 255) / 256) * 256;
+  const size_t per_orf = sizeof(int64_t) + sizeof(int32_t) + 1;
+  const size_t meta = (((size_t)s->n_orfs * per_orf + 64 + 255) / 256) * 256;
+  void* d_red;
+  if (gmg_scratch(ctx, SCR_RED, hdr + meta + ((size_t)s->n_starts + 1) * sizeof(gmg_start), &d_red)) return 1;
+  char* base = (char*)d_red;
+  double* d_len = (double*)base;
+  int32_t* d_cls = em->seq_class ? (int32_t*)(base + ((len_bytes + 15) & ~(size_t)15)) : NULL;
+  unsigned long long* d_cursor = (unsigned long long*)(base + hdr - 64);
+  int64_t* d_first = (int64_t*)(base + hdr);
+  int32_t* d_cnt = (int32_t*)(d_first + s->n_orfs);
+  uint8_t* d_status = (uint8_t*)(d_cnt + s->n_orfs);
+  gmg_start* d_out = (gmg_start*)(base + hdr + meta);
+  GMG_CUDA(cudaMemcpyAsync(d_len, em->len_lo, len_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (d_cls) GMG_CUDA(cudaMemcpyAsync(d_cls, em->seq_class, cls_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaMemsetAsync(d_cursor, 0, 64, ctx->stream));
+  DevEventModel M;
+  M.prior = em->prior;
+  M.start_threshold = em->start_threshold;
+  M.event_threshold = em->event_threshold;
+  M.pwm_bonus_max = em->pwm_bonus_max;
+  for (int i = 0; i < 8; i++) M.start_lo[i] = i < em->n_start ? em->start_lo[i] : 0.0;
+  M.n_len = em->n_len;
+  M.n_class = em->n_class;
+  M.min_gene_len = p->min_gene_len;
+  M.len_lo = d_len;
+  M.seq_class = d_cls;
+  // one table slot per start position of a sequence (start records lie inside it); capped at 2 048 per warp
+  int slots = (int)(s->max_len + 8);
+  if (slots > 2048) slots = 2048;
+  const size_t smem = (size_t)4 * slots * sizeof(RedSlot);
+  if (smem > 48 * 1024) GMG_CUDA(cudaFuncSetAttribute(k3_mg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+  k3_mg_reduce<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, smem, ctx->stream>>>(
+      s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, slots, d_out, d_cursor, d_first, d_cnt,
+      d_status);
+  gmg_prof_end(ctx, GMG_PROF_K3);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  ctx->h_scalars[10] = 0;
+  GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[10], d_cursor, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->n_red = ctx->h_scalars[10];
+  s->d_red = d_out;
+  s->d_red_first = d_first;
+  s->d_red_cnt = d_cnt;
+  s->d_red_status = d_status;
+  if (n_kept) *n_kept = s->n_red;
+  if (n_fallback_orfs) *n_fallback_orfs = -1;  // counted by the caller from the status bytes
+  return 0;
+}
+
+extern "C" int gmg_get_reduced_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_first, int32_t* h_count,
+                                      uint8_t* h_status) {
+  GMG_CHECK(ctx && s, "gmg_get_reduced_starts: NULL argument");
+  GMG_CHECK(s->d_red != NULL || s->n_orfs == 0, "gmg_get_reduced_starts: no gmg_reduce_starts_mg result on this set");
+  if (s->n_orfs == 0) return 0;
+  if (h_starts && s->n_red)
+    GMG_CUDA(cudaMemcpyAsync(h_starts, s->d_red, (size_t)s->n_red * sizeof(gmg_start), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_first)
+    GMG_CUDA(cudaMemcpyAsync(h_first, s->d_red_first, (size_t)s->n_orfs * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_count)
+    GMG_CUDA(cudaMemcpyAsync(h_count, s->d_red_cnt, (size_t)s->n_orfs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_status)
+    GMG_CUDA(cudaMemcpyAsync(h_status, s->d_red_status, (size_t)s->n_orfs, cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int gmg_get_orf_starts(gmg_ctx* ctx, gmg_seqset* s, int64_t orf, gmg_start* h_out, int64_t cap, int64_t* n) {
+  GMG_CHECK(ctx && s && n && orf >= 0 && orf < s->n_orfs, "gmg_get_orf_starts: bad argument");
+  int64_t lim[2];
+  GMG_CUDA(cudaMemcpyAsync(lim, s->d_start_off + orf, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n = lim[1] - lim[0];
+  if (h_out && *n > 0) {
+    GMG_CHECK(*n <= cap, "gmg_get_orf_starts: ORF %lld has %lld records, buffer holds %lld", (long long)orf, (long long)*n,
+              (long long)cap);
+    GMG_CUDA(cudaMemcpyAsync(h_out, s->d_starts + lim[0], (size_t)*n * sizeof(gmg_start), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   return 0;
 }
 

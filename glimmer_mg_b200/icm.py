@@ -35,6 +35,12 @@ class _Params(C.Structure):
                 ("stop_codon", (C.c_char * 4) * 8)]
 
 
+class _EventModel(C.Structure):
+    _fields_ = [("prior", C.c_double), ("start_threshold", C.c_double), ("event_threshold", C.c_double),
+                ("pwm_bonus_max", C.c_double), ("n_start", C.c_int32), ("start_lo", C.c_double * 8),
+                ("n_class", C.c_int32), ("n_len", C.c_int32), ("len_lo", C.c_void_p), ("seq_class", C.c_void_p)]
+
+
 ORF_DTYPE = np.dtype([("frame", "<i4"), ("stop_position", "<i4"), ("orf_len", "<i4"), ("gene_len", "<i4")])
 START_DTYPE = np.dtype([("j", "<i4"), ("pos", "<i4"), ("score", "<f8"), ("which", "<i4"), ("truncated", "<i4"),
                         ("first", "<i4"), ("n_err", "<i4"), ("err_pos", "<i4", (2,)), ("err_type", "<i4", (2,))])
@@ -104,6 +110,9 @@ def lib():
         "gmg_score_orfs_g3": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
         "gmg_score_orfs_mg": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
         "gmg_get_starts": (i32, [vp, vp, vp, vp]),
+        "gmg_reduce_starts_mg": (i32, [vp, vp, P(_Params), P(_EventModel), P(i64), P(i64)]),
+        "gmg_get_reduced_starts": (i32, [vp, vp, vp, vp, vp, vp]),
+        "gmg_get_orf_starts": (i32, [vp, vp, i64, vp, i64, P(i64)]),
         "gmg_uncertified_count": (i64, [vp]),
         "gmg_ordered_fallback_count": (i32, [vp, P(i64)]),
         "gmg_trainer_create": (i32, [vp, vp, i32, i32, i32, i32, P(vp)]),
@@ -155,6 +164,40 @@ class Params:
         """Set_Ignore_Score_Len (glimmer_base.cc:2597)."""
         self.c.ignore_score_len = lib().gmg_ignore_score_len(gc, C.byref(self.c))
         return self.c.ignore_score_len
+
+
+class EventModel:
+    """What Add_Events_Fwd / Add_Events_Rev (glimmer_base.cc:43-235) add to a start's score, for the device-side
+    start-list reduction: prior, start-codon log-odds, the gene-length log-odds table
+    ``len_lo[class, truncated_5p, truncated_3p, length]`` and the two thresholds.  Defaults = glimmer-mg without a
+    feature file (-u 0): length log-odds 0, default start-codon probabilities."""
+
+    def __init__(self, prior=-1.0, start_threshold=-6.0, event_threshold=-3.0, pwm_bonus_max=0.0,
+                 start_lo=None, len_lo=None, seq_class=None):
+        import math
+        if start_lo is None:  # Start_Dist_t(DEFAULT_START_PROB): log(p) - log(1/n) (Common/gene.cc, glimmer_base.hh:27)
+            probs = (0.60, 0.30, 0.10)
+            start_lo = [math.log(x) - math.log(1.0 / len(probs)) for x in probs]
+        self.start_lo = [float(x) for x in start_lo]
+        # default Length_Dist_t: log-odds 0 for every length (Common/gene.cc:369-382); the device wants a table that
+        # covers every gene length of the batch
+        self.len_lo = np.ascontiguousarray(np.zeros((1, 2, 2, 4096)) if len_lo is None else len_lo, np.float64)
+        assert self.len_lo.ndim == 4 and self.len_lo.shape[1:3] == (2, 2)
+        self.seq_class = None if seq_class is None else np.ascontiguousarray(seq_class, np.int32)
+        self.prior, self.start_threshold, self.event_threshold = float(prior), float(start_threshold), float(event_threshold)
+        self.pwm_bonus_max = float(pwm_bonus_max)
+
+    def c(self):
+        m = _EventModel()
+        m.prior, m.start_threshold, m.event_threshold, m.pwm_bonus_max = (self.prior, self.start_threshold,
+                                                                          self.event_threshold, self.pwm_bonus_max)
+        m.n_start = len(self.start_lo)
+        for i, x in enumerate(self.start_lo):
+            m.start_lo[i] = x
+        m.n_class, m.n_len = self.len_lo.shape[0], self.len_lo.shape[3]
+        m.len_lo = self.len_lo.ctypes.data
+        m.seq_class = None if self.seq_class is None else self.seq_class.ctypes.data
+        return m
 
 
 class Context:
@@ -281,7 +324,8 @@ class SeqSet:
 
     def close(self):
         if self.h:
-            lib().gmg_seqset_free(self.h)
+            if self.ctx.h:  # a set outliving its context has nothing left to free (the context owned the device)
+                lib().gmg_seqset_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
@@ -362,6 +406,37 @@ class SeqSet:
         _check(lib().gmg_get_starts(self.ctx.h, self.h, starts.ctypes.data, off.ctypes.data))
         return starts, off
 
+    # ---- start-list reduction (row a11b) ----
+    def reduce_starts_mg(self, params, model):
+        """Reduce the raw start lists of the last score_orfs_mg call on the device -> number of surviving records."""
+        n, nf = C.c_int64(), C.c_int64()
+        cm = model.c()
+        _check(lib().gmg_reduce_starts_mg(self.ctx.h, self.h, C.byref(params.c), C.byref(cm), C.byref(n), C.byref(nf)))
+        self.n_red = n.value
+        return self.n_red
+
+    def get_reduced_starts(self, pinned=False):
+        """-> (records, first[n_orfs], count[n_orfs], status[n_orfs]); status 0 dropped, 1 reduced, 2 take the raw list."""
+        if pinned:
+            st = self.ctx.pinned("red_starts", self.n_red, START_DTYPE)
+            first = self.ctx.pinned("red_first", self.n_orfs, np.int64)
+            cnt = self.ctx.pinned("red_cnt", self.n_orfs, np.int32)
+            status = self.ctx.pinned("red_status", self.n_orfs, np.uint8)
+        else:
+            st = np.zeros(self.n_red, START_DTYPE)
+            first, cnt, status = np.zeros(self.n_orfs, np.int64), np.zeros(self.n_orfs, np.int32), np.zeros(self.n_orfs, np.uint8)
+        _check(lib().gmg_get_reduced_starts(self.ctx.h, self.h, st.ctypes.data, first.ctypes.data, cnt.ctypes.data,
+                                            status.ctypes.data))
+        return st, first, cnt, status
+
+    def get_orf_starts(self, orf):
+        n = C.c_int64()
+        _check(lib().gmg_get_orf_starts(self.ctx.h, self.h, orf, None, 0, C.byref(n)))
+        out = np.zeros(n.value, START_DTYPE)
+        if n.value:
+            _check(lib().gmg_get_orf_starts(self.ctx.h, self.h, orf, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
     @property
     def ordered_fallbacks(self):
         n = C.c_int64()
@@ -412,7 +487,8 @@ class ICM:
 
     def close(self):
         if self.h:
-            lib().gmg_icm_free(self.h)
+            if self.ctx.h:
+                lib().gmg_icm_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
@@ -553,7 +629,8 @@ class _Trainer:
 
     def close(self):
         if self.h:
-            lib().gmg_trainer_free(self.h)
+            if self.ctx.h:
+                lib().gmg_trainer_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -200,6 +200,39 @@ int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, g
  * Score_Orf_Starts / Score_Indels / Pass_Stop_Penalty recursion for every ORF. */
 int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, gmg_seqset* s,
                       const gmg_params* p, int64_t* n_starts);
+/* ---- start-list reduction (the consumer side of Score_Orfs_Errors, glimmer-mg.cc:1656-1684, and the per-position
+ * arg-max of Add_Events_Fwd / Add_Events_Rev, glimmer_base.cc:65-128, 175-235) ------------------------------------
+ * With -i nearly every raw start record is dominated by another candidate at the same start position; the
+ * reduction keeps, per ORF that passes the reference's two gates (first_j + 1 >= Min_Gene_Len, best score >
+ * Start_Threshold), the one record per start position that can win Add_Events' `ne->score > best->score` test, so
+ * that only survivors cross PCIe.  Candidates are ranked by the reference's event score without the RBS term
+ * (score + prior [+ LogOdds_Start(which)] + LogOdds_Length(...), added in the reference's order); the RBS term is the
+ * same for all candidates of a position.  The host then runs the reference's own Add_Events on the survivors.
+ * Whenever the decision could depend on the last bits (two candidates of a position within 1e-9, records sharing the
+ * extreme position with different j around Min_Gene_Len, a length beyond the table) the ORF gets status 2 and the host
+ * fetches its raw list (gmg_get_orf_starts) and proceeds exactly as the reference does. */
+typedef struct {
+  double prior;            /* LogOdds_Prior (a float in the reference, glimmer-mg.cc:119), widened */
+  double start_threshold;  /* Start_Threshold, -6 (glimmer-mg.cc:123) */
+  double event_threshold;  /* Event_Threshold, -3 (glimmer-mg.cc:107) */
+  double pwm_bonus_max;    /* upper bound of what Add_PWM_Score can add (glimmer_base.cc:267-295); 0 without an RBS
+                              model, INFINITY if unknown (then no candidate is dropped by the threshold) */
+  int32_t n_start;
+  double start_lo[8];      /* LogOdds_Start.Score(which) */
+  int32_t n_class;         /* fragment-length classes of LogOdds_Length (Length_Dist_t::Choose_Frag_Dist) */
+  int32_t n_len;           /* table length: gene lengths (1 + j) / 3 below n_len */
+  const double* len_lo;    /* host, [n_class][2 truncated_5p][2 truncated_3p][n_len]: LogOdds_Length.Score(l, t5, t3, frag) */
+  const int32_t* seq_class; /* host, class of every sequence (from Sequence_Len / 3), or NULL: all class 0 */
+} gmg_event_model;
+/* Reduce the raw start lists of the last gmg_score_orfs_mg call on the device.  *n_kept = surviving records. */
+int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, const gmg_event_model* em, int64_t* n_kept,
+                         int64_t* n_fallback_orfs /* unused, set to -1 */);
+/* survivors: ORF i owns h_starts[h_first[i] .. h_first[i] + h_count[i]); h_status[i]: 0 = the ORF fails a gate or
+ * has no surviving candidate, 1 = reduced list, 2 = undecided (take the raw list).  Any output may be NULL. */
+int gmg_get_reduced_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_first, int32_t* h_count,
+                           uint8_t* h_status);
+/* the raw start_list of one ORF of the last gmg_score_orfs_* call (*n = its length; h_out may be NULL to query) */
+int gmg_get_orf_starts(gmg_ctx* ctx, gmg_seqset* s, int64_t orf, gmg_start* h_out, int64_t cap, int64_t* n);
 /* start lists of the last gmg_score_orfs_* call: h_start_off has n_orfs+1 entries */
 int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_start_off);
 /* number of sequences (mg) / ORFs (g3) whose sums could not be certified exact in FP64 (see

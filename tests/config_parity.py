@@ -18,7 +18,8 @@ import numpy as np
 import oracle_lib as O
 
 ROOT = O.ROOT
-REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")       # the unmodified reference (test infrastructure)
+HOSTBIN = os.path.join(ROOT, "glimmer_mg_b200", "host", "bin")  # the product's C++ hosts over the C-ABI
 
 
 class ParityError(AssertionError):
@@ -101,7 +102,7 @@ def file_sha256(path):
 
 
 def have_ref_bin(name):
-    return os.path.exists(os.path.join(REFBIN, name))
+    return os.path.exists(os.path.join(HOSTBIN if name.endswith("-gmg") else REFBIN, name))
 
 
 def run(cmd, stdin_path=None, timeout=3600):
@@ -116,11 +117,11 @@ def run(cmd, stdin_path=None, timeout=3600):
 
 
 def predict_pair(driver, args, fasta, workdir, tag="p"):
-    """Run oracle/_ref/bin/<driver> and <driver>-gmg (the reference driver compiled against the C-ABI) with the
-    same arguments -> (reference .predict bytes, GPU-path .predict bytes)."""
+    """Run oracle/_ref/bin/<driver> and glimmer_mg_b200/host/bin/<driver>-gmg (the reference driver compiled against
+    the C-ABI) with the same arguments -> (reference .predict bytes, GPU-path .predict bytes)."""
     out = []
-    for exe, name in ((driver, tag + "_ref"), (driver + "-gmg", tag + "_gmg")):
-        run([os.path.join(REFBIN, exe), *args, fasta, os.path.join(workdir, name)])
+    for exe, name in ((os.path.join(REFBIN, driver), tag + "_ref"), (os.path.join(HOSTBIN, driver + "-gmg"), tag + "_gmg")):
+        run([exe, *args, fasta, os.path.join(workdir, name)])
         with open(os.path.join(workdir, name + ".predict"), "rb") as fp:
             out.append(fp.read())
     return out[0], out[1]
@@ -135,3 +136,86 @@ def predict_identity(ref_bytes, got_bytes):
     sm = difflib.SequenceMatcher(None, a, b, autojunk=False)
     same = sum(m.size for m in sm.get_matching_blocks())
     return same / max(1, len(a))
+
+
+def reduce_reference(raw, frame, stop_position, seq_len, min_gene_len, model, seq_cls=0):
+    """What the reference keeps of one ORF's raw start_list (structured array in generation order): restatement of
+    Score_Orfs_Errors' filter (glimmer-mg.cc:1656-1684) and of the per-position arg-max of Add_Events_Fwd / _Rev
+    (glimmer_base.cc:65-128, 175-235) WITHOUT an RBS model, event scores added in the reference's order.
+    -> ("drop", None) | ("keep", {pos: record index}) | ("undecided", None) where the outcome hangs on std::sort's
+    order among equal positions or on an exact score tie (the device must hand such ORFs back with status 2)."""
+    n = len(raw)
+    if n == 0:
+        return "drop", None
+    pos = raw["pos"]
+    ext = pos.min() if frame > 0 else pos.max()
+    js = raw["j"][pos == ext]
+    ok = js + 1 >= min_gene_len
+    if ok.any() and not ok.all():
+        return "undecided", None
+    if not ok.all():
+        return "drop", None
+    if not (raw["score"].max() > model.start_threshold):
+        return "drop", None
+    t3 = (stop_position > seq_len - 2) if frame > 0 else (stop_position < 1)
+    n_len = model.len_lo.shape[3]
+    tol = 1e-9
+    cand = {}
+    for i in range(n):
+        r = raw[i]
+        if 1 + r["j"] < min_gene_len:
+            continue
+        length = (1 + int(r["j"])) // 3
+        if length >= n_len:
+            return "undecided", None
+        x = np.float64(r["score"]) + np.float64(model.prior)
+        if r["which"] >= 0:
+            x = x + np.float64(model.start_lo[int(r["which"])])
+        x = x + np.float64(model.len_lo[seq_cls, 1 if r["truncated"] else 0, 1 if t3 else 0, length])
+        # candidates that can pass `ne->score > Event_Threshold` once the (>= 0) RBS term is added; the band of width
+        # tol below the threshold is kept for the host's exact test
+        if x + model.pwm_bonus_max > model.event_threshold - tol:
+            cand.setdefault(int(r["pos"]), []).append((x, i))
+    win = {}
+    for p, lst in cand.items():
+        top = max(x for x, _ in lst)
+        near = [i for x, i in lst if x >= top - tol]
+        if len(near) > 1:  # a tie (or close enough for the RBS term's rounding to decide): std::sort's order matters
+            return "undecided", None
+        win[p] = near[0]
+    return "keep", win
+
+
+def check_reduction(orfs, ooff, seq_lens, raw_starts, soff, red, first, cnt, status, min_gene_len, model, orf_ids=None):
+    """Device reduction (gmg_reduce_starts_mg) against reduce_reference for the ORFs `orf_ids` (default: all).
+    Status 2 is always acceptable where the reference outcome is 'undecided'; elsewhere the survivors must be
+    exactly the reference's winners (same records, byte for byte)."""
+    seq_of = np.repeat(np.arange(len(ooff) - 1), np.diff(ooff))
+    stats = {"orfs": 0, "kept_orfs": 0, "dropped_orfs": 0, "handed_back": 0, "survivors": 0, "raw": 0}
+    ids = range(len(orfs)) if orf_ids is None else orf_ids
+    for o in ids:
+        raw = raw_starts[int(soff[o]):int(soff[o + 1])]
+        what, win = reduce_reference(raw, int(orfs[o]["frame"]), int(orfs[o]["stop_position"]), int(seq_lens[seq_of[o]]),
+                                     min_gene_len, model)
+        stats["orfs"] += 1
+        stats["raw"] += len(raw)
+        st = int(status[o])
+        if st == 2:
+            stats["handed_back"] += 1
+            _require(what == "undecided" or len(raw) > 0, f"ORF {o}: handed back without records")
+            continue
+        _require(what != "undecided", f"ORF {o}: the outcome depends on sort order / a tie but the device decided it (status {st})")
+        if what == "drop" or not win:
+            _require(st == 0 or int(cnt[o]) == 0, f"ORF {o}: reference drops it, device status {st} with {int(cnt[o])} survivors")
+            stats["dropped_orfs"] += 1
+            continue
+        _require(st == 1, f"ORF {o}: reference keeps {len(win)} starts, device status {st}")
+        got = red[int(first[o]):int(first[o]) + int(cnt[o])]
+        _require(len(got) == len(win), f"ORF {o}: {len(got)} survivors, reference {len(win)}")
+        bypos = {int(g["pos"]): g for g in got}
+        _require(len(bypos) == len(got), f"ORF {o}: two survivors at one position")
+        for p, i in win.items():
+            _require(p in bypos and bypos[p].tobytes() == raw[i].tobytes(), f"ORF {o}: survivor at position {p} differs")
+        stats["kept_orfs"] += 1
+        stats["survivors"] += len(got)
+    return stats

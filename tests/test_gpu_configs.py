@@ -90,14 +90,19 @@ def test_config3_reads400_indel_matches_oracle(gm, ctx, reads400):
     indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc, STOPS)
     ss.find_orfs(p)
     og = CP.oracle_model(path=ICM_PATH)
-    for rep in range(2):  # the first call of a context takes the two-pass form, the second the single pass with a pool
-        ss.score_orfs_mg(gene, indep, p)
-        orfs, ooff = ss.get_orfs()
-        starts, soff = ss.get_starts()
-        ids = list(range(len(off) - 1)) if rep == 0 else CP.sample_ids(len(off) - 1, 300)
-        st = CP.check_scoring("mg", a, off, ids, orfs, ooff, starts, soff, og, gc, STOPS, allow_indels=1,
-                              ignore_score_len=p.ignore_score_len)
-        assert st["starts"] > 100 * st["seqs"]
+    ss.score_orfs_mg(gene, indep, p)
+    orfs, ooff = ss.get_orfs()
+    starts, soff = ss.get_starts()
+    st = CP.check_scoring("mg", a, off, list(range(len(off) - 1)), orfs, ooff, starts, soff, og, gc, STOPS, allow_indels=1,
+                          ignore_score_len=p.ignore_score_len)
+    assert st["starts"] > 100 * st["seqs"]
+    # row a11b: the device-side reduction of those lists against the reference's filter restated on the raw lists
+    model = gm.EventModel(prior=0.0)
+    n_kept = ss.reduce_starts_mg(p, model)
+    red, first, cnt, status = ss.get_reduced_starts()
+    rs = CP.check_reduction(orfs, ooff, np.diff(off), starts, soff, red, first, cnt, status, p.min_gene_len, model,
+                            orf_ids=range(0, len(orfs), 7))
+    assert rs["kept_orfs"] > 100 and n_kept * 5 < len(starts), (rs, n_kept, len(starts))
     assert ss.uncertified == 0
 
 

@@ -1,7 +1,7 @@
 """Drop-in boundary, end to end on the GPU: the C++ hosts over the C-ABI.
 
-* oracle/_ref/bin/glimmer3-gmg and glimmer-mg-gmg are the reference's own drivers compiled (oracle/Makefile,
-  `dropin`) against glimmer_mg_b200/host/icm.hh and linked to libgmgicm.so instead of the reference's ICM
+* glimmer_mg_b200/host/bin/glimmer3-gmg and glimmer-mg-gmg are the reference's own drivers compiled
+  (glimmer_mg_b200/host/Makefile, `dropin`) against glimmer_mg_b200/host/icm.hh and linked to libgmgicm.so instead of the reference's ICM
   library, with the scoring half redirected to host/*_dropin.inc.  Their .predict output must equal, byte for
   byte, the reference's golden NC_000915.run1.predict (sample-run config, BASELINE.json configs[0]) and the
   .predict files the unmodified reference wrote for the committed read sets (plain / -i / -s).
@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 G = os.path.join(HERE, "golden")
 REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+HOSTBIN = os.path.join(ROOT, "glimmer_mg_b200", "host", "bin")
 ICM = os.path.join(G, "NC_000915.icm")
 
 pytestmark = pytest.mark.gpu
@@ -44,7 +45,7 @@ def _run(cmd, **kw):
 
 
 def test_glimmer3_dropin_reproduces_golden_predict(tmp_path):
-    exe = _need(os.path.join(REFBIN, "glimmer3-gmg"))
+    exe = _need(os.path.join(HOSTBIN, "glimmer3-gmg"))
     fna = _gunzip("NC_000915.fna.gz", str(tmp_path / "NC_000915.fna"))
     _run([exe, "-u", "-12", "-m", ICM, fna, str(tmp_path / "run")])
     got = open(tmp_path / "run.predict", "rb").read()
@@ -56,7 +57,7 @@ def test_glimmer3_dropin_reproduces_golden_predict(tmp_path):
 def test_glimmer3_dropin_option_variants(tmp_path):
     """Option variants (-X truncated ORFs, -g/-A, -z translation table, -l) on a 300 kbp prefix: equal the
     unmodified reference binary's .predict."""
-    exe = _need(os.path.join(REFBIN, "glimmer3-gmg"))
+    exe = _need(os.path.join(HOSTBIN, "glimmer3-gmg"))
     ref = _need(os.path.join(REFBIN, "glimmer3"))
     lines = gzip.open(os.path.join(G, "NC_000915.fna.gz"), "rt").readlines()
     fna = tmp_path / "p.fna"
@@ -72,7 +73,7 @@ def test_glimmer3_dropin_option_variants(tmp_path):
 
 @pytest.mark.parametrize("tag,n,flags", [("plain", 120, []), ("indel", 40, ["-i"]), ("sub", 80, ["-s"])])
 def test_glimmer_mg_dropin_reproduces_reference_predict(tmp_path, tag, n, flags):
-    exe = _need(os.path.join(REFBIN, "glimmer-mg-gmg"))
+    exe = _need(os.path.join(HOSTBIN, "glimmer-mg-gmg"))
     recs = O.read_fasta(os.path.join(G, "seqs.fa.gz"))[:n]
     fa = tmp_path / "reads.fa"
     with open(fa, "wb") as f:

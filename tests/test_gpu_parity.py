@@ -337,12 +337,15 @@ def test_mg_start_lists_match_oracle_more_reads(gm, ctx, reads):
                 assert starts_as_tuples(starts[soff[o]:soff[o + 1]]) == starts_as_tuples(wst[woff[k]:woff[k + 1]])
 
 
-@pytest.mark.parametrize("flags", [dict(allow_indels=1), dict(allow_subs=1)])
-def test_mg_single_pass_two_pass_and_overflow_agree(gm, ctx, reads, monkeypatch, flags):
-    """-i / -s start lists come from one pass over a record pool (sized from the previous call's rate) plus a
-    compaction; the two-pass form and the pool-overflow fallback must give the identical CSR."""
+@pytest.mark.parametrize("flags", [dict(allow_indels=1), dict(allow_subs=1), dict(allow_indels=1, allow_subs=1),
+                                   dict(allow_indels=1, indel_max=1)])
+def test_mg_flat_thread_and_ordered_paths_agree(gm, ctx, reads, monkeypatch, flags):
+    """-i / -s start lists come from the flat level-by-level enumeration (gmg_mg_flat.cuh).  The thread-per-ORF
+    recursion (GMG_K3MG_MODE=1) and the ordered path of sequences without an exactness certificate (forced for
+    every / every third sequence) must give the identical CSR, and all of them the oracle's lists."""
     rs = [s for _, s in reads[:150]]
-    gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+    gene_path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, gene_path)
     indep = gm.ICM.Build_Indep_WO_Stops(ctx, 0.39)
     p = gm.Params(True, **flags)
     p.set_ignore_score_len(0.39)
@@ -352,15 +355,70 @@ def test_mg_single_pass_two_pass_and_overflow_agree(gm, ctx, reads, monkeypatch,
         ss.find_orfs(p)
         ss.score_orfs_mg(gene, indep, p)
         st, off = ss.get_starts()
-        return st.tobytes(), off.tolist()
+        return st.tobytes(), off.tolist(), ss.uncertified
 
-    monkeypatch.setenv("GMG_K3MG_TWO_PASS", "1")
-    want = run()            # two passes (also primes the rate)
-    monkeypatch.delenv("GMG_K3MG_TWO_PASS")
-    assert run() == want    # single pass
-    monkeypatch.setenv("GMG_K3MG_POOL_SCALE", "0.05")
-    assert run() == want    # pool too small: counts from the single pass, records from the write pass
-    assert len(want[0]) > 48 * 5000
+    want = run()                                   # flat
+    assert want[2] == 0
+    monkeypatch.setenv("GMG_K3MG_MODE", "1")
+    assert run()[:2] == want[:2]                   # one thread per ORF, explicit stack
+    monkeypatch.delenv("GMG_K3MG_MODE")
+    monkeypatch.setenv("GMG_MG_FORCE_UNCERT", "1")
+    got = run()
+    assert got[:2] == want[:2] and got[2] == len(rs)   # every sequence re-summed in the reference's order
+    monkeypatch.setenv("GMG_MG_FORCE_UNCERT", "3")
+    got = run()
+    assert got[:2] == want[:2] and got[2] == (len(rs) + 2) // 3   # both paths in one batch
+    monkeypatch.delenv("GMG_MG_FORCE_UNCERT")
+    assert len(want[0]) > 48 * 3000
+    # and the oracle
+    og = O.lib().orc_icm_read(gene_path.encode())
+    oi = O.build_indep(0.39)
+    op = O.params(True, **flags)
+    op.ignore_score_len = p.ignore_score_len
+    starts = np.frombuffer(want[0], gm.START_DTYPE)
+    k = 0
+    for s0 in rs[:40]:
+        s = O.filter_lower(s0)
+        worfs = O.find_orfs(s, op)
+        woff, wst = O.mg_score_orfs(og, oi, s, op, worfs)
+        a, b = want[1][k], want[1][k + len(worfs)]
+        assert starts[a:b].tobytes() == wst.tobytes()
+        k += len(worfs)
+
+
+@pytest.mark.parametrize("flags,table", [(dict(allow_indels=1), "default"), (dict(allow_indels=1), "random"),
+                                         (dict(allow_indels=1, allow_subs=1), "random"), (dict(), "default")])
+def test_mg_start_list_reduction(gm, ctx, reads, flags, table):
+    """Row a11b: the per-(ORF, start position) arg-max of Add_Events and Score_Orfs_Errors' two gates on the device
+    (gmg_reduce_starts_mg) against a restatement of the reference's filter run on the raw lists."""
+    import config_parity as CP
+    rs = [s for _, s in reads[:200]] + [b"", b"acgtacgt"]
+    gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+    ss = gm.SeqSet(ctx, seqs=rs)
+    gc = ss.gc_fraction()
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+    p = gm.Params(True, **flags)
+    p.set_ignore_score_len(gc)
+    ss.find_orfs(p)
+    ss.score_orfs_mg(gene, indep, p)
+    orfs, ooff = ss.get_orfs()
+    raw, soff = ss.get_starts()
+    if table == "default":
+        model = gm.EventModel(prior=0.0)  # glimmer-mg -u 1.0: LogOdds_Prior = -1 + 1
+    else:
+        rng = np.random.default_rng(11)
+        model = gm.EventModel(prior=-0.25, start_lo=[0.3, -0.4, -1.1], len_lo=rng.normal(0.0, 1.5, (1, 2, 2, 200)))
+    n_kept = ss.reduce_starts_mg(p, model)
+    red, first, cnt, status = ss.get_reduced_starts()
+    assert n_kept == len(red) == int(cnt.sum())
+    st = CP.check_reduction(orfs, ooff, [len(s) for s in rs], raw, soff, red, first, cnt, status, p.min_gene_len, model)
+    assert st["kept_orfs"] > 50 and st["handed_back"] <= st["orfs"] // 20, st
+    assert n_kept < len(raw)
+    if flags.get("allow_indels"):
+        assert n_kept * 4 < len(raw), (n_kept, len(raw))   # the point of the exercise
+    # the raw list of a single ORF (what the host fetches for status 2)
+    o = int(np.argmax(np.diff(soff)))
+    assert ss.get_orf_starts(o).tobytes() == raw[soff[o]:soff[o + 1]].tobytes()
 
 
 def test_g3_start_lists_match_reference_dump(gm, ctx, genome):
