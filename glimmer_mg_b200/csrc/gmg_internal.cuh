@@ -114,7 +114,8 @@ struct gmg_icm {
   float* d_lut3;
   float* d_lutp;
   DevIcmFast fast;
-  // value statistics of `prob` (lazily computed, see gmg_icm_value_stats)
+  int ready;  // device views built (gmg_icm_ready)
+  // value statistics of `prob` (computed with the device views, see gmg_icm_value_stats)
   int stat_valid, stat_ulp_exp;
   float stat_max_abs;
 };
@@ -122,6 +123,8 @@ struct gmg_icm {
 // smallest ulp exponent (every entry is an integer multiple of 2^ulp_exp) and largest magnitude of the model's
 // log-probabilities: the inputs of the static FP64 exactness certificates
 void gmg_icm_value_stats(const gmg_icm* m, int* ulp_exp, float* max_abs);
+// build the model's device views on first use (no-op afterwards); every scoring entry point calls it
+int gmg_icm_ready(const gmg_icm* m);
 
 struct gmg_seqset {
   gmg_ctx* ctx;

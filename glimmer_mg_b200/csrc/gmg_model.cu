@@ -243,6 +243,11 @@ static int base_code(char ch) {
 }
 
 void gmg_icm_value_stats(const gmg_icm* m, int* ulp_exp, float* max_abs) {
+  if (gmg_icm_ready(m)) {  // cannot upload: nothing can be certified
+    *ulp_exp = -100000;
+    *max_abs = 0.f;
+    return;
+  }
   *ulp_exp = m->stat_ulp_exp;
   *max_abs = m->stat_max_abs;
 }
@@ -438,99 +443,114 @@ extern "C" int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int1
       delete m;
       return 1;
     }
-  if (icm_upload(m)) {
-    delete m;
-    return 1;
-  }
+  // the device views (walk tables, completed tree, merged words, leaf tables by predicted base) are built when a
+  // scoring call first needs them (gmg_icm_ready): a model that is only trained and written never pays for them
+  m->ready = 0;
   *out = m;
   return 0;
 }
 
-extern "C" int gmg_icm_load(gmg_ctx* ctx, const char* path, gmg_icm** out) {
-  GMG_CHECK(ctx && path && out, "gmg_icm_load: NULL argument");
-  FILE* fp = fopen(path, "rb");
-  GMG_CHECK(fp != NULL, "ERROR:  Could not open file  %s", path);
+int gmg_icm_ready(const gmg_icm* cm) {
+  gmg_icm* m = const_cast<gmg_icm*>(cm);
+  if (m->ready) return 0;
+  if (icm_upload(m)) return 1;
+  m->ready = 1;
+  return 0;
+}
+
+// ICM_t::Input (icm.cc:614-726) over a memory image of the build-icm binary format
+extern "C" int gmg_icm_load_mem(gmg_ctx* ctx, const void* image, size_t n_bytes, gmg_icm** out) {
+  GMG_CHECK(ctx && out && (image || n_bytes == 0), "gmg_icm_load_mem: NULL argument");
+  const unsigned char* cur = (const unsigned char*)image;
+  const unsigned char* const end = cur + n_bytes;
+  auto take = [&](void* dst, size_t nb) -> bool {
+    if ((size_t)(end - cur) < nb) return false;
+    memcpy(dst, cur, nb);
+    cur += nb;
+    return true;
+  };
   char line[150];
   int32_t param[6];
-  if (fread(line, 1, 150, fp) != 150) {
-    fclose(fp);
-    gmg_set_error("ERROR reading ICM header");
-    return 1;
-  }
-  if (fread(param, sizeof(int32_t), 6, fp) != 6) {
-    fclose(fp);
-    gmg_set_error("ERROR reading parameters");
-    return 1;
-  }
-  if (param[0] != 200) {
-    fclose(fp);
-    gmg_set_error("Bad ICM version = %d  should be %d", param[0], 200);
-    return 1;
-  }
-  if (param[1] != 150) {
-    fclose(fp);
-    gmg_set_error("Bad ID_STRING_LEN = %d  should be %d", param[1], 150);
-    return 1;
-  }
+  GMG_CHECK(take(line, 150), "ERROR reading ICM header");
+  GMG_CHECK(take(param, sizeof param), "ERROR reading parameters");
+  GMG_CHECK(param[0] == 200, "Bad ICM version = %d  should be %d", param[0], 200);
+  GMG_CHECK(param[1] == 150, "Bad ID_STRING_LEN = %d  should be %d", param[1], 150);
   const int w = param[2], d = param[3], p = param[4], n = param[5];
-  if (icm_validate(w, d, p, n)) {
-    fclose(fp);
-    return 1;
-  }
+  if (icm_validate(w, d, p, n)) return 1;
   std::vector<int16_t> mip((size_t)p * n, 0);
   std::vector<float> prob((size_t)p * n * 4, 0.0f);
   int period = -1, prev = 0;
   int32_t id;
-  while (fread(&id, sizeof id, 1, fp) == 1) {
+  while (take(&id, sizeof id)) {
     if (id < 0) break;
     if (id == 0) period++;
-    if (period < 0 || period >= p || id >= n) {
-      fclose(fp);
-      gmg_set_error("ERROR reading icm node = %d  period = %d", id, period);
-      return 1;
-    }
+    GMG_CHECK(!(period < 0 || period >= p || id >= n), "ERROR reading icm node = %d  period = %d", id, period);
     size_t at = (size_t)period * n + id;
-    if (fread(&prob[at * 4], sizeof(float), 4, fp) != 4) {
-      fclose(fp);
-      gmg_set_error("ERROR reading icm node = %d  period = %d", id, period);
-      return 1;
-    }
-    if (fread(&mip[at], sizeof(int16_t), 1, fp) != 1) {
-      fclose(fp);
-      gmg_set_error("ERROR reading mut_info_pos for node = %d  period = %d", id, period);
-      return 1;
-    }
+    GMG_CHECK(take(&prob[at * 4], 4 * sizeof(float)), "ERROR reading icm node = %d  period = %d", id, period);
+    GMG_CHECK(take(&mip[at], sizeof(int16_t)), "ERROR reading mut_info_pos for node = %d  period = %d", id, period);
     if (id != 0 && prev != id - 1)
       for (int i = prev + 1; i < id; i++) mip[(size_t)period * n + i] = -2;
     if (id == 0 && period > 0)
       for (int i = prev + 1; i < n; i++) mip[(size_t)(period - 1) * n + i] = -2;
     prev = id;
   }
-  fclose(fp);
   GMG_CHECK(period == p - 1, "ERROR:  Too few nodes for periodicity = %d", p);
   for (int i = prev + 1; i < n; i++) mip[(size_t)period * n + i] = -2;
   return gmg_icm_from_tables(ctx, w, d, p, mip.data(), prob.data(), out);
 }
 
-extern "C" int gmg_icm_write(const gmg_icm* m, const char* path) {
-  GMG_CHECK(m && path, "gmg_icm_write: NULL argument");
-  FILE* fp = fopen(path, "wb");
+extern "C" int gmg_icm_load(gmg_ctx* ctx, const char* path, gmg_icm** out) {
+  GMG_CHECK(ctx && path && out, "gmg_icm_load: NULL argument");
+  FILE* fp = fopen(path, "rb");
   GMG_CHECK(fp != NULL, "ERROR:  Could not open file  %s", path);
+  std::vector<unsigned char> image;
+  unsigned char buf[1 << 16];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof buf, fp)) > 0) image.insert(image.end(), buf, buf + got);
+  fclose(fp);
+  return gmg_icm_load_mem(ctx, image.data(), image.size(), out);
+}
+
+// ICM_t::Output(fp, binary = true) (icm.cc:729-803, 961-998) into memory: *n_bytes receives the image size; the image
+// is copied to h_out when it fits in `cap` (call with h_out = NULL to size the buffer)
+extern "C" int gmg_icm_write_mem(const gmg_icm* m, void* h_out, size_t cap, size_t* n_bytes) {
+  GMG_CHECK(m && n_bytes, "gmg_icm_write_mem: NULL argument");
+  std::string img;
+  img.reserve(174 + (size_t)m->P * m->N * 22 + 4);
   char line[150];
   memset(line, 0, sizeof line);
   snprintf(line, sizeof line, ">ver = %.2f  len = %d  depth = %d  periodicity = %d  nodes = %d\n", 2.00, m->W, m->D,
            m->P, m->N);
   int32_t param[6] = {200, 150, m->W, m->D, m->P, m->N};
-  bool ok = fwrite(line, 1, 150, fp) == 150 && fwrite(param, sizeof(int32_t), 6, fp) == 6;
-  for (int f = 0; ok && f < m->P; f++)
-    for (int32_t i = 0; ok && i < m->N; i++) {
+  img.append(line, 150);
+  img.append((const char*)param, sizeof param);
+  for (int f = 0; f < m->P; f++)
+    for (int32_t i = 0; i < m->N; i++) {
       size_t at = (size_t)f * m->N + i;
       if (i != 0 && m->mip[at] < -1) continue;  // cut nodes are not stored
-      ok = fwrite(&i, sizeof i, 1, fp) == 1 && fwrite(&m->prob[at * 4], sizeof(float), 4, fp) == 4 &&
-           fwrite(&m->mip[at], sizeof(int16_t), 1, fp) == 1;
+      img.append((const char*)&i, sizeof i);
+      img.append((const char*)&m->prob[at * 4], 4 * sizeof(float));
+      img.append((const char*)&m->mip[at], sizeof(int16_t));
     }
   int32_t end_marker = -1;
-  ok = ok && fwrite(&end_marker, sizeof end_marker, 1, fp) == 1;
+  img.append((const char*)&end_marker, sizeof end_marker);
+  *n_bytes = img.size();
+  if (h_out) {
+    GMG_CHECK(cap >= img.size(), "gmg_icm_write_mem: buffer of %zu bytes, image needs %zu", cap, img.size());
+    memcpy(h_out, img.data(), img.size());
+  }
+  return 0;
+}
+
+extern "C" int gmg_icm_write(const gmg_icm* m, const char* path) {
+  GMG_CHECK(m && path, "gmg_icm_write: NULL argument");
+  size_t nb = 0;
+  if (gmg_icm_write_mem(m, NULL, 0, &nb)) return 1;
+  std::vector<char> img(nb);
+  if (gmg_icm_write_mem(m, img.data(), nb, &nb)) return 1;
+  FILE* fp = fopen(path, "wb");
+  GMG_CHECK(fp != NULL, "ERROR:  Could not open file  %s", path);
+  bool ok = fwrite(img.data(), 1, nb, fp) == nb;
   ok = (fclose(fp) == 0) && ok;
   GMG_CHECK(ok, "ERROR writing ICM file %s", path);
   return 0;

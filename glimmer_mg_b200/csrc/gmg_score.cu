@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const
 
 static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** planes_out) {
   GMG_CHECK(gene->P == 3, "six-frame scoring needs a periodicity-3 gene model (got %d)", gene->P);
+  if (gmg_icm_ready(gene)) return 1;
   void* planes = NULL;
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
   *planes_out = (float*)planes;
@@ -563,6 +564,7 @@ extern "C" int gmg_score_all_frames(gmg_ctx* ctx, const gmg_icm* gene, const gmg
                                     double* out, int out_on_device) {
   GMG_CHECK(ctx && gene && indep && s && out, "gmg_score_all_frames: NULL argument");
   GMG_CHECK(indep->P == 3, "independent model must have periodicity 3");
+  if (gmg_icm_ready(indep)) return 1;
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
   if (s->total == 0) return 0;
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(128) k_string_scores(DevIcm m, const uint64_t*
 static int string_scores(gmg_ctx* ctx, const gmg_icm* m, gmg_seqset* s, int frame, int mode, double* h_out) {
   GMG_CHECK(ctx && m && s && h_out, "string score: NULL argument");
   GMG_CHECK(frame >= 0 && (frame < m->P || m->P == 1), "frame %d out of range for periodicity %d", frame, m->P);
+  if (gmg_icm_ready(m)) return 1;
   if (s->n == 0) return 0;
   size_t n_out = (mode == 0) ? (size_t)s->n : (size_t)s->total;
   if (n_out == 0) return 0;
@@ -737,6 +740,7 @@ extern "C" int gmg_icm_score_strings_many(gmg_ctx* ctx, const gmg_icm* const* mo
   for (int k = 0; k < n_models; k++) {
     const gmg_icm* m = models[k];
     GMG_CHECK(m != NULL, "gmg_icm_score_strings_many: model %d is NULL", k);
+    if (gmg_icm_ready(m)) return 1;
     GMG_CHECK(frame >= 0 && (frame < m->P || m->P == 1), "frame %d out of range for periodicity %d (model %d)", frame, m->P, k);
     dev[(size_t)k] = m->dev;
     const size_t need = (size_t)m->dev.P * m->dev.inner;
@@ -2931,6 +2935,7 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
                                  const gmg_params* p, int64_t* n_starts) {
   GMG_CHECK(ctx && gene && indep && s && p, "gmg_score_orfs_g3: NULL argument");
   GMG_CHECK(gene->P == 3 && indep->P == 3, "glimmer3 scoring needs periodicity-3 models");
+  if (gmg_icm_ready(gene) || gmg_icm_ready(indep)) return 1;
   CodonSets cs;
   DevParams dp;
   if (make_codon_sets(p, &cs, &dp)) return 1;
@@ -3049,6 +3054,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
                                  const gmg_params* p, int64_t* n_starts) {
   GMG_CHECK(ctx && gene && indep && s && p, "gmg_score_orfs_mg: NULL argument");
   GMG_CHECK(gene->P == 3 && indep->P == 3, "glimmer-mg scoring needs periodicity-3 models");
+  if (gmg_icm_ready(gene) || gmg_icm_ready(indep)) return 1;
   CodonSets cs;
   DevParams dp;
   if (make_codon_sets(p, &cs, &dp)) return 1;

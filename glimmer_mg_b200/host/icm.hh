@@ -100,19 +100,31 @@ class ICM_t {
     Adopt(h);
   }
   void Input(FILE* fp) {  // icm.cc:614-727: the model follows at the stream's current position
-    char tmpl[] = "/tmp/gmg_icm_XXXXXX";
-    int fd = mkstemp(tmpl);
-    if (fd < 0) {
+    // read exactly the model's bytes -- header, parameters, 22-byte node records up to the -1 terminator -- so that
+    // the stream is left where the reference leaves it, and hand the image to the library
+    std::vector<unsigned char> image(150 + 6 * sizeof(int32_t));
+    if (fread(image.data(), 1, 150, fp) != 150) {
       fprintf(stderr, "ERROR reading ICM header\n");
       exit(EXIT_FAILURE);
     }
-    FILE* out = fdopen(fd, "wb");
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof buf, fp)) > 0) fwrite(buf, 1, n, out);
-    fclose(out);
-    Read(tmpl);
-    unlink(tmpl);
+    if (fread(image.data() + 150, sizeof(int32_t), 6, fp) != 6) {
+      fprintf(stderr, "ERROR reading parameters\n");
+      exit(EXIT_FAILURE);
+    }
+    for (;;) {
+      unsigned char rec[22];
+      if (fread(rec, 1, 4, fp) != 4) break;
+      image.insert(image.end(), rec, rec + 4);
+      int32_t id;
+      memcpy(&id, rec, 4);
+      if (id < 0) break;
+      const size_t got = fread(rec + 4, 1, 18, fp);
+      image.insert(image.end(), rec + 4, rec + 4 + got);
+      if (got != 18) break;  // the library reports the truncated node
+    }
+    gmg_icm* h = NULL;
+    GMG_OR_DIE(gmg_icm_load_mem(Gmg_Context(), image.data(), image.size(), &h));
+    Adopt(h);
   }
   void Build_Indep_WO_Stops(double gc_frac, const std::vector<const char*>& stop_codon) {  // icm.cc:65-216
     gmg_icm* h = NULL;
@@ -165,20 +177,14 @@ class ICM_t {
 inline void ICM_t::Output(FILE* fp, bool binary_form) {
   Need_Model("Output");
   if (binary_form) {
-    char tmpl[] = "/tmp/gmg_icm_XXXXXX";
-    int fd = mkstemp(tmpl);
-    if (fd < 0) {
-      fprintf(stderr, "ERROR:  cannot create a temporary file for the model\n");
+    size_t nb = 0;
+    GMG_OR_DIE(gmg_icm_write_mem(handle, NULL, 0, &nb));
+    std::vector<char> image(nb);
+    GMG_OR_DIE(gmg_icm_write_mem(handle, image.data(), nb, &nb));
+    if (fwrite(image.data(), 1, nb, fp) != nb) {
+      fprintf(stderr, "ERROR writing ICM\n");
       exit(EXIT_FAILURE);
     }
-    close(fd);
-    GMG_OR_DIE(gmg_icm_write(handle, tmpl));
-    FILE* in = fopen(tmpl, "rb");
-    char buf[1 << 16];
-    size_t n;
-    while (in && (n = fread(buf, 1, sizeof buf, in)) > 0) fwrite(buf, 1, n, fp);
-    if (in) fclose(in);
-    unlink(tmpl);
     return;
   }
   int32_t d[4];

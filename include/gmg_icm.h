@@ -108,6 +108,9 @@ int gmg_ignore_score_len(double gc, const gmg_params* p);
 /* ---- models: ICM_t ---------------------------------------------------------------- */
 /* ICM_t::Read / Input (icm.cc:846, 614-726): build-icm binary format */
 int gmg_icm_load(gmg_ctx* ctx, const char* path, gmg_icm** out);
+/* ICM_t::Input(FILE*) (icm.cc:614-726) for callers that hold the model file's bytes (an open FILE* read to memory, an
+ * mmap, a network buffer): the same format from a memory image */
+int gmg_icm_load_mem(gmg_ctx* ctx, const void* image, size_t n_bytes, gmg_icm** out);
 /* ICM_t(w,d,p) filled from caller tables: mip int16 [p][nodes], prob float [p][nodes][4] */
 int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int16_t* h_mip, const float* h_prob,
                         gmg_icm** out);
@@ -115,6 +118,9 @@ int gmg_icm_from_tables(gmg_ctx* ctx, int w, int d, int p, const int16_t* h_mip,
 int gmg_icm_build_indep(gmg_ctx* ctx, double gc, const char* const* stops, int n_stops, gmg_icm** out);
 /* ICM_t::Output(fp, binary=true) (icm.cc:729-803, 961-998) */
 int gmg_icm_write(const gmg_icm* m, const char* path);
+/* the same image into caller memory (ICM_t::Output(FILE*, true) without a file): *n_bytes = image size; copied to
+ * h_out when cap >= *n_bytes (h_out = NULL sizes the buffer) */
+int gmg_icm_write_mem(const gmg_icm* m, void* h_out, size_t cap, size_t* n_bytes);
 /* {model_len, model_depth, periodicity, num_nodes}  (Get_Model_Len / Get_Periodicity) */
 int gmg_icm_dims(const gmg_icm* m, int32_t dims[4]);
 int gmg_icm_tables(const gmg_icm* m, int16_t* h_mip, float* h_prob);
