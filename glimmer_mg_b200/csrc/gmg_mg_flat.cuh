@@ -20,7 +20,7 @@
 // contiguous range of the output, so all places are differences of the scans plus popcounts.
 //
 // Everything here is __host__ __device__: gmg_score.cu wraps each pass in a kernel, and tests/mgflat_host_check.cu
-// (test infrastructure) runs the very same functions on the host against the oracle.
+// (test infrastructure) runs the very same functions on the host against the CPU checker.
 #pragma once
 
 #include <stdint.h>

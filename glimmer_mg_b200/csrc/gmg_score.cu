@@ -2641,8 +2641,8 @@ __global__ void __launch_bounds__(128) k3_mg_starts(MgfBatch B, int64_t n_orfs, 
 // ------------------------------------------------------------------------------------------------
 // K3 (glimmer-mg), flat form (the default for -i / -s): the reference's recursion enumerated level by level with
 // one thread per CANDIDATE call, see gmg_mg_flat.cuh for the passes.  The kernels below only map a thread to an
-// item; the bodies are the __host__ __device__ functions of that header (checked on the host against the oracle
-// by tests/test_mgflat_host.py, on the device by the start-list parity tests).
+// item; the bodies are the __host__ __device__ functions of that header (tests/test_mgflat_host.py runs them
+// on the host against the CPU checker, the start-list parity tests run them on the device).
 
 // gates: positions whose quality allows an indel branch (Score_Orf_Starts glimmer-mg.cc:1816)
 __global__ void __launch_bounds__(256) k_gate_bits(const uint8_t* __restrict__ qual, int64_t total, int thresh, int64_t nblk,

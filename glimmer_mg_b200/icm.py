@@ -79,6 +79,8 @@ def lib():
         "gmg_params_default": (None, [P(_Params), i32]),
         "gmg_ignore_score_len": (i32, [C.c_double, P(_Params)]),
         "gmg_icm_load": (i32, [vp, C.c_char_p, P(vp)]),
+        "gmg_icm_load_mem": (i32, [vp, vp, C.c_size_t, P(vp)]),
+        "gmg_icm_write_mem": (i32, [vp, vp, C.c_size_t, P(C.c_size_t)]),
         "gmg_icm_from_tables": (i32, [vp, i32, i32, i32, vp, vp, P(vp)]),
         "gmg_icm_build_indep": (i32, [vp, C.c_double, P(C.c_char_p), i32, P(vp)]),
         "gmg_icm_write": (i32, [vp, C.c_char_p]),
@@ -462,6 +464,22 @@ class ICM:
         h = C.c_void_p()
         _check(lib().gmg_icm_load(ctx.h, os.fsencode(path), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def Input(cls, ctx, image):
+        """ICM_t::Input (icm.cc:614) from the bytes of a model file."""
+        buf = bytes(image)
+        h = C.c_void_p()
+        _check(lib().gmg_icm_load_mem(ctx.h, buf, len(buf), C.byref(h)))
+        return cls(ctx, h)
+
+    def image(self):
+        """The build-icm binary form as bytes (ICM_t::Output(fp, true), icm.cc:729)."""
+        n = C.c_size_t()
+        _check(lib().gmg_icm_write_mem(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(lib().gmg_icm_write_mem(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
 
     @classmethod
     def from_tables(cls, ctx, w, d, p, mip, prob):

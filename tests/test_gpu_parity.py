@@ -59,6 +59,12 @@ def test_model_io_and_tables(gm, ctx, tmp_path):
         out = str(tmp_path / "w.icm")
         m.Output(out)
         assert open(out, "rb").read() == open(path, "rb").read()
+        assert m.image() == open(path, "rb").read()                      # buffer forms (no file)
+        m2 = gm.ICM.Input(ctx, open(path, "rb").read())
+        mip2, prob2 = m2.tables()
+        assert (mip2 == mip).all() and (prob2.view(np.uint32) == prob.view(np.uint32)).all()
+        with pytest.raises(gm.GmgError, match="ERROR reading"):
+            gm.ICM.Input(ctx, open(path, "rb").read()[:1000])
     with pytest.raises(gm.GmgError):
         gm.ICM.Read(ctx, str(tmp_path / "missing.icm"))
     bad = tmp_path / "bad.icm"
