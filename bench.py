@@ -956,7 +956,7 @@ def run_b200_train(args, env):
         trainer = g.ICMTraining(ctx, 12, 7, 3)
         model = None
         for _ in range(Wu):
-            model = trainer.Train_Model(ss, reverse=True, allreduce=ar)
+            model = trainer.Train_Model(ss, reverse=True, allreduce=ar, rank=rank, world=world, global_bases=total_bases)
         ctx.sync()
         ctx.profile(True)
         ctx.profile_read("k4")
@@ -970,7 +970,7 @@ def run_b200_train(args, env):
             flush.zero_()
             e0[k].record(stream)
             tw = time.perf_counter()
-            model = trainer.Train_Model(ss, reverse=True, allreduce=ar)
+            model = trainer.Train_Model(ss, reverse=True, allreduce=ar, rank=rank, world=world, global_bases=total_bases)
             e1[k].record(stream)
             if os.environ.get("GMG_BENCH_DEBUG"):
                 print(f"train step {k}: host wall {1e3 * (time.perf_counter() - tw):.1f} ms", file=sys.stderr)
@@ -989,7 +989,7 @@ def run_b200_train(args, env):
             torch.cuda.synchronize()
             x.record(stream)
             s2 = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
-            m2 = trainer.Train_Model(s2, reverse=True, allreduce=ar)
+            m2 = trainer.Train_Model(s2, reverse=True, allreduce=ar, rank=rank, world=world, global_bases=total_bases)
             mip, prob = m2.tables()
             y.record(stream)
             torch.cuda.synchronize()
@@ -1045,7 +1045,9 @@ def run_b200_train(args, env):
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": train_desc(n_seqs), "training_bases": total_bases, "bases_per_gpu": my_bases,
                            "model_sha256_16": digest, "l2": "256 MB flush write before every timed step",
-                           "sharding": "round-robin strings; NCCL all-reduce of each level's count slab" if world > 1
+                           "host_recomputed_nodes": int(getattr(trainer, "flagged_nodes", 0)),
+                           "sharding": "round-robin strings; window histogram all-reduced once (NCCL), every rank walks 1/N of "
+                                       "its cells per level, each level's count slab all-reduced" if world > 1
                            else "single GPU, no exchange"},
                 "roofline": {"bound": "hbm", "kernel": "k4_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -86,6 +86,7 @@ struct gmg_ctx {
   cudaStream_t side;   // second stream: small kernels that do not depend on the walks run beside K1 (gmg_score_orfs_g3)
   cudaEvent_t ev_fork, ev_join;
   double mg_rate[4];   // start records per base seen by the last gmg_score_orfs_mg call, by (indels, subs) mode
+  int64_t train_flagged;  // nodes of the last gmg_icm_train* call that the host recomputed (gmg_ctx_train_flagged)
   void* h_stage;       // pinned staging for larger device -> host results (training count slabs), grown on demand
   size_t h_stage_bytes;
   // per-kernel device timing (gmg_ctx_profile): event pairs around the launches of each kernel class

@@ -123,6 +123,9 @@ def lib():
         "gmg_trainer_finish_level": (i32, [vp, i32]),
         "gmg_trainer_finish": (i32, [vp, P(vp)]),
         "gmg_icm_train": (i32, [vp, vp, i32, i32, i32, i32, ALLREDUCE_FN, vp, P(vp)]),
+        "gmg_icm_train_sharded": (i32, [vp, vp, i32, i32, i32, i32, ALLREDUCE_FN, vp, i32, i32, i64, P(vp)]),
+        "gmg_trainer_set_shard": (i32, [vp, i32, i32, i64, ALLREDUCE_FN, vp]),
+        "gmg_ctx_train_flagged": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export what include/gmg_icm.h declares
@@ -599,10 +602,12 @@ class ICMTraining:
         self.ctx = ctx
         self.w, self.d, self.p = model_len, model_depth, periodicity
 
-    def Train_Model(self, data, reverse=False, allreduce=None):
+    def Train_Model(self, data, reverse=False, allreduce=None, rank=0, world=1, global_bases=-1):
         """Train_Model (icm.cc:1356).  ``data``: training strings (or a SeqSet); ``reverse`` = build-icm -r.
         ``allreduce(dptr, count, stream)``: sums ``count`` int32 at device address ``dptr`` across ranks
-        (ordered on ``stream``) -- the one exchange step of multi-GPU training."""
+        (ordered on ``stream``) -- the exchange step of multi-GPU training.  With ``world`` > 1 this rank holds
+        1 / world of the strings (``global_bases`` = training bases of all ranks): the window histogram is summed
+        once and every rank walks 1 / world of its cells per level (gmg_trainer_set_shard)."""
         ss = data if isinstance(data, SeqSet) else SeqSet(self.ctx, seqs=data)
         h = C.c_void_p()
         if allreduce is None:
@@ -617,7 +622,9 @@ class ICMTraining:
                     traceback.print_exc()
                     return 1
             cb = ALLREDUCE_FN(_cb)
-        _check(lib().gmg_icm_train(self.ctx.h, ss.h, self.w, self.d, self.p, 1 if reverse else 0, cb, None, C.byref(h)))
+        _check(lib().gmg_icm_train_sharded(self.ctx.h, ss.h, self.w, self.d, self.p, 1 if reverse else 0, cb, None,
+                                           rank, world, global_bases, C.byref(h)))
+        self.flagged_nodes = int(lib().gmg_ctx_train_flagged(self.ctx.h))
         return ICM(self.ctx, h)
 
     # split form, for callers that want to drive the levels themselves

@@ -263,13 +263,26 @@ int gmg_trainer_count_level(gmg_trainer* t, int level, void** d_counts, int64_t*
 /* mutual-information position choice + Interpolate_Probs for the level (icm.cc:1097-1176,
  * 1401-1439, 1260-1330) from the (all-reduced) counts. */
 int gmg_trainer_finish_level(gmg_trainer* t, int level);
+/* Multi-GPU: this rank's seqset holds 1 / world of the training strings.  For large sets (window histogram) the
+ * histogram is summed over the ranks once through `ar` and each rank then walks 1 / world of its cells per level, so
+ * the level passes shrink with the number of GPUs.  Call before the first gmg_trainer_count_level. */
+typedef int (*gmg_allreduce_fn)(void* user, void* d_buf, int64_t count, void* stream);
+int gmg_trainer_set_shard(gmg_trainer* t, int rank, int world, int64_t global_bases /* training bases of ALL ranks: every
+                          rank must choose the same counting path */, gmg_allreduce_fn ar, void* user);
 /* Take_Logs (icm.cc:1334-1352) and hand the trained model over as a gmg_icm */
 int gmg_trainer_finish(gmg_trainer* t, gmg_icm** out);
 /* convenience: all levels, optional all-reduce callback (NULL = single GPU).  The callback
  * must sum `count` int32 at d_buf across ranks, ordered on `stream`. */
-typedef int (*gmg_allreduce_fn)(void* user, void* d_buf, int64_t count, void* stream);
 int gmg_icm_train(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_allreduce_fn ar,
                   void* user, gmg_icm** out);
+/* the same with the strings dealt to `world` ranks (gmg_trainer_set_shard): `ar` sums the window histogram once and
+ * every level's count slab across the ranks; every rank returns the identical model */
+int gmg_icm_train_sharded(gmg_ctx* ctx, gmg_seqset* s, int w, int d, int p, int reverse, gmg_allreduce_fn ar, void* user,
+                          int rank, int world, int64_t global_bases, gmg_icm** out);
+/* Position choice and interpolation of a level run on the device; nodes whose choice lies within the error bound of the
+ * device's logarithm are recomputed on the host with the reference's own libm.  This returns how many nodes of the
+ * last gmg_icm_train* call on the context took that path (diagnostic). */
+int64_t gmg_ctx_train_flagged(const gmg_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -31,12 +31,21 @@ def main():
         # ---- (1) training ----
         strs = [s.lower() for _, s in O.read_fasta(os.path.join(G, "NC_000915.train.gz"))]
         mine = [strs[i] for i in shard.round_robin(len(strs), rank, world)]
-        m = g.ICMTraining(ctx, 12, 7, 3).Train_Model(mine, reverse=True, allreduce=shard.torch_allreduce(local))
+        total = sum(len(s) for s in strs)
+        m = g.ICMTraining(ctx, 12, 7, 3).Train_Model(mine, reverse=True, allreduce=shard.torch_allreduce(local), rank=rank,
+                                                     world=world, global_bases=total)
         mip, prob = m.tables()
         blob = mip.tobytes() + prob.tobytes()
         blobs = [None] * world
         dist.all_gather_object(blobs, blob)
         assert all(b == blobs[0] for b in blobs), "ranks hold different models after the all-reduce"
+        # the large-set path: window histogram summed over the ranks once, every rank walks 1 / world of its cells
+        os.environ["GMG_K4_HIST"] = "1"
+        mh = g.ICMTraining(ctx, 12, 7, 3).Train_Model(mine, reverse=True, allreduce=shard.torch_allreduce(local), rank=rank,
+                                                      world=world, global_bases=total)
+        del os.environ["GMG_K4_HIST"]
+        hmip, hprob = mh.tables()
+        assert hmip.tobytes() + hprob.tobytes() == blob, "cell-sharded histogram training differs from direct counting"
         if rank == 0:
             alone = g.ICMTraining(ctx, 12, 7, 3).Train_Model(strs, reverse=True)
             amip, aprob = alone.tables()

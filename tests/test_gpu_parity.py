@@ -593,6 +593,30 @@ def test_training_histogram_path_gives_the_same_model(gm, ctx, tmp_path, monkeyp
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+def tr_nodes(args):
+    w, d, p = args
+    return p * (4 ** (d + 1) - 1) // 3
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_training_level_finish_device_and_host_paths_agree(gm, ctx, tmp_path, monkeypatch, mode):
+    """Position choice + interpolation run on the device with error bounds on every mutual-information decision
+    (k4_finish_level); GMG_K4_MI=0 keeps every node on the host (glibc), GMG_K4_MI=2 flags every node so that the
+    host redoes all of them after the device pass.  Same model bytes on all three routes, for three training sets."""
+    for name, args in (("seqs.cluster-5.run1.filt.gene.fasta.gz", (12, 7, 3)), ("seqs.cluster-4.run1.filt.gene.fasta.gz", (12, 7, 3)),
+                       ("NC_000915.train.gz", (10, 5, 1))):
+        strs = [s.lower() for _, s in O.read_fasta(os.path.join(G, name))]
+        tr = gm.ICMTraining(ctx, *args)
+        want = tr.Train_Model(strs, reverse=True).image()
+        few = tr.flagged_nodes
+        monkeypatch.setenv("GMG_K4_MI", mode)
+        got = gm.ICMTraining(ctx, *args).Train_Model(strs, reverse=True).image()
+        monkeypatch.delenv("GMG_K4_MI")
+        assert got == want, (name, mode)
+        # small training sets have many exactly tied positions (equal count tables): those go to the host by design
+        assert few < tr_nodes(args) // 2, f"{name}: {few} nodes within the error bound -- the bound is too loose"
+
+
 def test_count_level_matches_oracle(gm, ctx):
     """K4 in isolation: the count slab of every level equals Count_Char_Pairs(_Restricted) of the oracle."""
     strs = [s[::-1] for s in _train_strings("seqs.cluster-5.run1.filt.gene.fasta.gz")]
