@@ -163,6 +163,8 @@ struct gmg_seqset {
   gmg_start* d_starts;
   int64_t* d_start_off;      // n_orfs+1
   int64_t uncertified;
+  unsigned long long* uncert_pending;  // device counter still to be read into `uncertified` (fused plain path)
+  int orfs_external;                   // ORF table came from gmg_set_orfs (not from the device finder)
   size_t cap_orfs, cap_starts;
   // reduced start lists of the last gmg_reduce_starts_mg call (they live in the context's SCR_RED scratch)
   int64_t n_red, n_red_fallback;

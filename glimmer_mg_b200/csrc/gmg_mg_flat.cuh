@@ -292,17 +292,17 @@ MGF_HD void mgf_put(gmg_start* dst, const DevParams& P, int jj, int k, double sc
 
 // Write the call's own records in the reference's order (j descending).  `extra(j)` = records of the call's
 // children at positions >= j (they precede the record of j); the i-th own record goes to out[extra(j) + i].
-template <class Extra>
-MGF_HD int mgf_own_write(const MgfBatch& B, const MgfSeq& S, const DevParams& P, const CodonSets& cs, const MgfOwn& f, bool fwd,
-                         double suffix_score, int suffix_j, double cbase, int n_err, const int* err_pos, const int* err_type,
-                         gmg_start* out, Extra extra) {
+// `score_before(j)` = score[j - 1] of the call.
+template <class Extra, class ScoreBefore>
+MGF_HD int mgf_own_write_with(const MgfBatch& B, const MgfSeq& S, const DevParams& P, const CodonSets& cs, const MgfOwn& f, bool fwd,
+                              double suffix_score, int suffix_j, int n_err, const int* err_pos, const int* err_type,
+                              gmg_start* out, Extra extra, ScoreBefore score_before) {
   if (f.j_hi < f.j_lo) return 0;
-  const double* row = mgf_row(B, S, fwd, f.lo, f.hi);
   int cnt = 0, jt = f.j_hi;
   bool state = true;
   auto emit = [&](int j, int which, int truncated, int first, int64_t ex) {
     const int k = fwd ? f.lo + f.m - 2 - j : f.lo + j + 2;
-    const double sc = (mgf_score(S, fwd, row, f.lo, f.hi, cbase, j - 1) - 0.0) + suffix_score;
+    const double sc = (score_before(j) - 0.0) + suffix_score;
     mgf_put(out + ex + cnt, P, j + 2 + suffix_j, k, sc, which, truncated, first, n_err, err_pos, err_type);
     cnt++;
   };
@@ -350,6 +350,16 @@ MGF_HD int mgf_own_write(const MgfBatch& B, const MgfSeq& S, const DevParams& P,
     }
   }
   return cnt;
+}
+
+// the same with score[] read off K2's prefix-sum rows (Cumulative_Frame_Score as a difference of two entries)
+template <class Extra>
+MGF_HD int mgf_own_write(const MgfBatch& B, const MgfSeq& S, const DevParams& P, const CodonSets& cs, const MgfOwn& f, bool fwd,
+                         double suffix_score, int suffix_j, double cbase, int n_err, const int* err_pos, const int* err_type,
+                         gmg_start* out, Extra extra) {
+  const double* row = mgf_row(B, S, fwd, f.lo, f.hi);
+  return mgf_own_write_with(B, S, P, cs, f, fwd, suffix_score, suffix_j, n_err, err_pos, err_type, out, extra,
+                            [&](int j) { return mgf_score(S, fwd, row, f.lo, f.hi, cbase, j - 1); });
 }
 
 // ---- children ---------------------------------------------------------------------------------------------------

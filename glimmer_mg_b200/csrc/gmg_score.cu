@@ -1192,6 +1192,7 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   ctx->launches += 2;
   GMG_CUDA(cudaGetLastError());
   s->n_orfs = total_orfs;
+  s->orfs_external = 0;
   s->orf_off.clear();
   if (n_orfs) *n_orfs = total_orfs;
   return 0;
@@ -1241,6 +1242,7 @@ extern "C" int gmg_set_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_orf* h_orfs, 
   GMG_CUDA(cudaStreamSynchronize(ctx->stream));
   s->n_orfs = n_orfs;
   s->n_starts = 0;
+  s->orfs_external = 1;  // caller's table: its lengths are not trusted to agree with the sequence's stop codons
   return 0;
 }
 
@@ -2026,7 +2028,8 @@ __global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint6
     return;
   }
   unsigned umin = 0x7fffffffu;
-  float asum = 0.f;
+  float asum = 0.f;      // magnitudes of one tile (<= 48 terms per lane) ...
+  double asum_d = 0.0;  // ... folded into FP64 tile by tile: a float sum over a long sequence would eat the margin
   const int shift = (int)(a & 3);  // tiles start at sequence position -shift: a + q0 is a multiple of 4
   const int ntile = (L + shift + 127) >> 7;
   const size_t T = (size_t)total;
@@ -2207,6 +2210,8 @@ __global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint6
           }
         }
       }
+      asum_d += (double)asum;
+      asum = 0.f;
     }
   }
   // ---- right to left: forward-strand suffix sums, next reverse stops ----
@@ -2358,18 +2363,20 @@ __global__ void __launch_bounds__(128) k2_prefix_lanes(DevIcm indep, const uint6
           }
         }
       }
+      asum_d += (double)asum;
+      asum = 0.f;
     }
   }
   // ---- certificate: every term is a multiple of 2^g, g from the smallest float exponent seen; every partial sum
   // of any association is bounded by the sum of magnitudes (accumulated in FP32, 0.1 % margin for its rounding) ----
   for (int d = 16; d > 0; d >>= 1) {
     umin = min(umin, __shfl_xor_sync(FULL, umin, d));
-    asum += __shfl_xor_sync(FULL, asum, d);
+    asum_d += __shfl_xor_sync(FULL, asum_d, d);
   }
   if (lane == 0) {
     const int e = (int)(umin >> 23);
     const int g = (e > 0 ? e : 1) - 150;
-    bool ok = (umin == 0x7fffffffu) || ((double)asum * 1.001 < ldexp(1.0, g + 52));
+    bool ok = (umin == 0x7fffffffu) || (asum_d * 1.001 < ldexp(1.0, g + 52));
     cert[s] = ok ? 1 : 0;
   }
 }
@@ -2739,6 +2746,134 @@ static int exclusive_sum_u32(gmg_ctx* ctx, const uint32_t* d_in, uint32_t* d_out
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 + K3 (glimmer-mg) FUSED for read sets without error branches (plain glimmer-mg, BASELINE configs[4]): the
+// segmented prefix sums of Cumulative_Frame_Score (glimmer-mg.cc:561-604) are formed only over the ORFs -- one warp
+// per ORF, the terms gene - indep straight from the K1 planes, codon-boundary prefixes kept in shared memory -- and
+// the ORF's start records are written from them in the same kernel.  Without indel / substitution branches every
+// call is a root call, so the six whole-read prefix planes (48 B/base), the stop tables and the qualities that K2
+// materialises for the branching modes are never needed: 1.3 ms of K2 + K3 per 31 Mbp become one 0.1 ms-class pass.
+// Exactness: the static certificate of the model pair (as in gmg_score_orfs_g3) bounds the ORF length up to which no
+// FP64 addition can round; longer ORFs are accumulated by one lane in the reference's serial order.
+#define MGP_SLOTS 512  // codon-boundary prefixes per warp: sequences up to 3 * (MGP_SLOTS - 1) bases
+
+__device__ __forceinline__ void mgp_term(const DevIcm& indep, const float* __restrict__ s_lut, const float* __restrict__ planes,
+                                         const uint32_t* __restrict__ bktidx, const MgfBatch& B, const MgfSeq& S, bool fwd, int f,
+                                         int q, float* g_out, float* n_out) {
+  const int64_t p = S.a + q;
+  *g_out = __ldg(planes + (size_t)(fwd ? f : 3 + f) * (size_t)B.total + gmg_plane_index(B.words, bktidx, p));
+  float n;
+  if (indep.lut3 != NULL) {
+    if (fwd) {
+      const int raw = (int)(gmg_extract32(B.words, p) & 63);  // bases q, q+1, q+2
+      n = q <= S.L - 3 ? s_lut[f * 64 + raw] : __ldg(indep.lutp + (q - (S.L - 2)) * 192 + f * 64 + raw);
+    } else {
+      const int raw = (int)(gmg_extract32(B.words, p - 2) & 63);  // bases q-2, q-1, q
+      n = q >= 2 ? s_lut[192 + f * 64 + raw] : __ldg(indep.lutp + 384 + (1 - q) * 192 + f * 64 + raw);
+    }
+  } else {
+    n = fwd ? icm_fwd(indep, B.words, p, q, S.L, f) : icm_rev(indep, B.words, p, q, 0, f);
+  }
+  *n_out = n;
+}
+
+__global__ void __launch_bounds__(128) k3_mg_plain_count(MgfBatch B, DevParams P, const gmg_orf* __restrict__ orfs,
+                                                         const int32_t* __restrict__ orf_seq, int64_t n_orfs,
+                                                         int64_t* __restrict__ counts) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_orfs) return;
+  const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+  const gmg_orf orf = orfs[o];
+  const bool fwd = orf.frame > 0;
+  const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
+  const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
+  MgfOwn f;
+  mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+  counts[o] = mgf_own_count(f, fwd, -1);
+}
+
+__global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __restrict__ planes,
+                                                   const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, CodonSets cs,
+                                                   const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                   int64_t n_orfs, const int64_t* __restrict__ start_off,
+                                                   gmg_start* __restrict__ starts, int exact_len,
+                                                   unsigned long long* __restrict__ n_ordered) {
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ double s_pref[4][MGP_SLOTS];
+  __shared__ float s_lut[384];
+  if (indep.lut3 != NULL)
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (o >= n_orfs) return;  // warp-uniform
+  const int64_t so = start_off[o];
+  if (start_off[o + 1] == so) return;
+  const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+  const gmg_orf orf = orfs[o];
+  const bool fwd = orf.frame > 0;
+  const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
+  const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
+  MgfOwn f;
+  mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+  double* pref = s_pref[wid];
+  // score[j] for j < j_hi is all the records can ask for (score[j - 1] at their own j <= j_hi)
+  const int need = f.j_hi;  // terms j = 0 .. need - 1
+  if (lane == 0) pref[0] = 0.0;
+  // warp-parallel scan; its sums carry the reference's bits whenever the ORF's certificate holds: every term is a
+  // multiple of 2^g (g from the smallest float exponent the ORF meets) and the sum of magnitudes stays below 2^(g+52),
+  // so no addition of ANY association can round
+  unsigned umin = 0x7fffffffu;
+  float asum = 0.f;
+  double carry = 0.0;
+  for (int base = 0; base < need; base += 32) {
+    const int j = base + lane;
+    double x = 0.0;
+    if (j < need) {
+      float g, n;
+      mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+      k2_cert_term(g, umin, asum);
+      k2_cert_term(n, umin, asum);
+      x = (double)g - (double)n;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(FULL, x, d);
+      if (lane >= d) x += t;
+    }
+    x += carry;
+    if (j < need && (j + 1) % 3 == 0) pref[(j + 1) / 3] = x;
+    carry = __shfl_sync(FULL, x, 31);
+  }
+  double asum_d = (double)asum;  // <= need / 32 + 1 float additions per lane: the 0.1 % margin covers their rounding
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    umin = min(umin, __shfl_xor_sync(FULL, umin, d));
+    asum_d += __shfl_xor_sync(FULL, asum_d, d);
+  }
+  const int e = (int)(umin >> 23);
+  const bool exact = exact_len >= 0 && (umin == 0x7fffffffu || asum_d * 1.001 < ldexp(1.0, (e > 0 ? e : 1) - 150 + 52));
+  if (!exact) {  // no certificate: the reference's own order, one lane
+    __syncwarp();
+    if (lane == 0) {
+      atomicAdd(n_ordered, 1ull);
+      double run = 0.0;
+      for (int j = 0; j < need; j++) {
+        float g, n;
+        mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+        run = run + ((double)g - (double)n);
+        if ((j + 1) % 3 == 0) pref[(j + 1) / 3] = run;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int ep[2] = {0, 0}, et[2] = {0, 0};
+    mgf_own_write_with(B, S, P, cs, f, fwd, 0.0, 0, 0, ep, et, starts + so, [](int) { return (int64_t)0; },
+                       [&](int j) { return pref[j / 3]; });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Start-list reduction: what Score_Orfs_Errors' filter (glimmer-mg.cc:1656-1684) and
 // Add_Events_Fwd / Add_Events_Rev (glimmer_base.cc:65-128, 175-235) keep of an ORF's raw start_list -- at most one
 // candidate per start position -- decided on the device so that only survivors cross PCIe.
@@ -2911,6 +3046,79 @@ __global__ void __launch_bounds__(128) k3_mg_reduce(const gmg_start* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// All_Frame_Score (glimmer3.cc:328-359), batched: for every item -- a region [lo, lo + len) of a sequence -- the six
+// ICM_t::Score_String sums the reference forms for the `.detail` log: the region read downwards (context = the bases to
+// its right, the orientation of a forward gene's buff) with first-base periods 0, 1, 2, and the region's complement
+// read upwards (context = the complemented bases to its left) with first-base periods 0, 1, 2.  Positions past the
+// first W-1 are K1 plane entries; the first W-1 of either direction see only the region itself (Partial_Window_Prob,
+// icm.cc:807-842).  One warp per item; every sum is accumulated in the reference's serial order (icm.cc:886-900).
+// out[item][0..2] = downward sums (period of the first base 0, 1, 2), out[item][3..5] = upward sums.
+__global__ void __launch_bounds__(128) k_all_frame_scores(DevIcm gene, const uint64_t* __restrict__ words,
+                                                          const int64_t* __restrict__ off, const uint32_t* __restrict__ bktidx,
+                                                          int64_t total, const float* __restrict__ planes, int64_t n,
+                                                          const int32_t* __restrict__ it_seq, const int32_t* __restrict__ it_lo,
+                                                          const int32_t* __restrict__ it_len, double* __restrict__ out) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (it >= n) return;
+  const int64_t a = off[it_seq[it]];
+  const int lo = it_lo[it], len = it_len[it], hi = lo + len;
+  double tot[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (i < len) {
+      const int qd = hi - 1 - i, qu = lo + i;
+      const size_t pd = gmg_plane_index(words, bktidx, a + qd), pu = gmg_plane_index(words, bktidx, a + qu);
+#pragma unroll
+      for (int f0 = 0; f0 < 3; f0++) {
+        const int f = (f0 + i) % 3;
+        v[f0] = i < gene.W - 1 ? icm_fwd(gene, words, a + qd, qd, hi, f) : __ldg(planes + (size_t)f * total + pd);
+        v[3 + f0] = i < gene.W - 1 ? icm_rev(gene, words, a + qu, qu, lo, f) : __ldg(planes + (size_t)(3 + f) * total + pu);
+      }
+    }
+    const int cnt = min(32, len - base);
+    for (int l = 0; l < cnt; l++)
+#pragma unroll
+      for (int k = 0; k < 6; k++) tot[k] += (double)__shfl_sync(FULL, v[k], l);
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[it * 6 + k] = tot[k];
+}
+
+extern "C" int gmg_all_frame_scores(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, int64_t n, const int32_t* h_seq,
+                                    const int32_t* h_lo, const int32_t* h_len, double* h_out) {
+  GMG_CHECK(ctx && gene && s && (n == 0 || (h_seq && h_lo && h_len && h_out)), "gmg_all_frame_scores: NULL argument");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; i++) {
+    GMG_CHECK(h_seq[i] >= 0 && h_seq[i] < s->n, "gmg_all_frame_scores: item %lld: sequence %d out of range", (long long)i, h_seq[i]);
+    const int64_t L = s->off[(size_t)h_seq[i] + 1] - s->off[(size_t)h_seq[i]];
+    GMG_CHECK(h_lo[i] >= 0 && h_len[i] >= 0 && (int64_t)h_lo[i] + h_len[i] <= L, "gmg_all_frame_scores: item %lld: region [%d, %d) "
+              "outside its %lld bp sequence", (long long)i, h_lo[i], h_lo[i] + h_len[i], (long long)L);
+  }
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  void* d_it;
+  if (gmg_scratch(ctx, SCR_MISC, (size_t)n * (3 * sizeof(int32_t) + 6 * sizeof(double)) + 64, &d_it)) return 1;
+  double* d_out = (double*)d_it;
+  int32_t* d_seq = (int32_t*)(d_out + 6 * n);
+  int32_t* d_lo = d_seq + n;
+  int32_t* d_len = d_lo + n;
+  GMG_CUDA(cudaMemcpyAsync(d_seq, h_seq, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(d_lo, h_lo, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(d_len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  k_all_frame_scores<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(gene->dev, s->d_words, s->d_off, s->d_bktidx, s->total,
+                                                                                planes, n, d_seq, d_lo, d_len, d_out);
+  ctx->launches++;
+  GMG_CUDA(cudaGetLastError());
+  GMG_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host drivers of the two scoring halves
 
 static int ensure_start_capacity(gmg_seqset* s, int64_t n) {
@@ -3061,6 +3269,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CHECK(!(p->have_quality_file && !s->d_qual), "have_quality_file set but the seqset has no quality values");
   s->n_starts = 0;
   s->uncertified = 0;
+  s->uncert_pending = NULL;
   s->n_red = s->n_red_fallback = 0;
   s->d_red = NULL;
   if (n_starts) *n_starts = 0;
@@ -3070,6 +3279,50 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   if (ensure_codon_bits(ctx, s, cs)) return 1;  // start-codon bitmaps: the own starts of every call
   float* planes;
   if (launch_k1(ctx, gene, s, &planes)) return 1;
+  // flat form (0) when calls can branch (-i / -s); without error branches the fused per-ORF scan (2) -- or, for very
+  // long sequences and caller-supplied ORF tables, K2 + one thread per ORF (1).  GMG_K3MG_MODE forces a form (tests).
+  const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
+  const bool branching = p->allow_indels || p->allow_subs;
+  const bool fused_ok = !branching && !s->orfs_external && s->max_len <= 3 * (MGP_SLOTS - 1);
+  const int k3mg_mode = k3mg_env >= 0 && !(k3mg_env == 2 && !fused_ok) ? k3mg_env : (branching ? 0 : (fused_ok ? 2 : 1));
+  if (k3mg_mode == 2) {
+    // exactness is certified per ORF inside the kernel; the test hook withdraws every certificate
+    const int exact_len = (getenv("GMG_MG_FORCE_UNCERT") && atoi(getenv("GMG_MG_FORCE_UNCERT")) > 0) ? -1 : INT_MAX;
+    MgfBatch B;
+    memset(&B, 0, sizeof B);
+    B.words = s->d_words;
+    B.off = s->d_off;
+    B.total = s->total;
+    B.cb = s->d_cbits;
+    B.nwc = s->nwc;
+    void* d_counts;
+    if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
+    int64_t* counts = (int64_t*)d_counts;
+    GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
+    if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+    k3_mg_plain_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, s->n_orfs, counts);
+    gmg_prof_end(ctx, GMG_PROF_K3);
+    ctx->launches++;
+    if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
+    ctx->h_scalars[6] = 0;
+    GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[6], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t total_starts = ctx->h_scalars[6];
+    if (ensure_start_capacity(s, total_starts)) return 1;
+    if (total_starts > 0) {
+      if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+      k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+          indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
+          (unsigned long long*)(counts + s->n_orfs + 1));
+      gmg_prof_end(ctx, GMG_PROF_K3);
+      ctx->launches++;
+      GMG_CUDA(cudaGetLastError());
+    }
+    s->n_starts = total_starts;
+    s->uncert_pending = (unsigned long long*)(counts + s->n_orfs + 1);  // ORFs summed in serial order; read on demand
+    if (n_starts) *n_starts = total_starts;
+    return 0;
+  }
   // K2
   void *d_cum, *d_tab, *d_qual, *d_cert;
   if (gmg_scratch(ctx, SCR_CUM, (size_t)6 * s->total * sizeof(double), &d_cum)) return 1;
@@ -3140,10 +3393,6 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   int64_t* counts = (int64_t*)d_counts;
   GMG_CUDA(cudaMemsetAsync(counts, 0, (size_t)(s->n_orfs + 2) * sizeof(int64_t), ctx->stream));
   const unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
-  // flat form when calls can branch (-i / -s); without error branches an ORF is one short linear walk and the
-  // thread-per-ORF kernel does it directly.  GMG_K3MG_MODE = 0 / 1 forces the flat / thread-per-ORF form (tests).
-  const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
-  const int k3mg_mode = k3mg_env >= 0 ? k3mg_env : ((p->allow_indels || p->allow_subs) ? 0 : 1);
   const uint32_t no = (uint32_t)s->n_orfs;
   // Pass_Stop_Penalty with a quality file needs a log per root call: p_stop from the device, glibc's log here
   if (p->allow_subs && p->have_quality_file) {
@@ -3410,7 +3659,18 @@ extern "C" int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, 
   return 0;
 }
 
-extern "C" int64_t gmg_uncertified_count(const gmg_seqset* s) { return s ? s->uncertified : 0; }
+extern "C" int64_t gmg_uncertified_count(const gmg_seqset* cs) {
+  gmg_seqset* s = const_cast<gmg_seqset*>(cs);
+  if (!s) return 0;
+  if (s->uncert_pending) {  // the fused plain path leaves the counter on the device until somebody asks
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, s->uncert_pending, sizeof v, cudaMemcpyDeviceToHost, s->ctx->stream) == cudaSuccess &&
+        cudaStreamSynchronize(s->ctx->stream) == cudaSuccess)
+      s->uncertified = (int64_t)v;
+    s->uncert_pending = NULL;
+  }
+  return s->uncertified;
+}
 
 extern "C" int gmg_ordered_fallback_count(gmg_seqset* s, int64_t* out) {
   GMG_CHECK(s && out, "gmg_ordered_fallback_count: NULL argument");

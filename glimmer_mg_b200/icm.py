@@ -112,6 +112,7 @@ def lib():
         "gmg_score_orfs_g3": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
         "gmg_score_orfs_mg": (i32, [vp, vp, vp, vp, P(_Params), P(i64)]),
         "gmg_get_starts": (i32, [vp, vp, vp, vp]),
+        "gmg_all_frame_scores": (i32, [vp, vp, vp, i64, vp, vp, vp, vp]),
         "gmg_reduce_starts_mg": (i32, [vp, vp, P(_Params), P(_EventModel), P(i64), P(i64)]),
         "gmg_get_reduced_starts": (i32, [vp, vp, vp, vp, vp, vp]),
         "gmg_get_orf_starts": (i32, [vp, vp, i64, vp, i64, P(i64)]),
@@ -410,6 +411,15 @@ class SeqSet:
             off = np.zeros(self.n_orfs + 1, np.int64)
         _check(lib().gmg_get_starts(self.ctx.h, self.h, starts.ctypes.data, off.ctypes.data))
         return starts, off
+
+    def all_frame_scores(self, gene, seq, lo, length):
+        """All_Frame_Score (glimmer3.cc:328) of regions [lo, lo + length) of sequences `seq` -> float64 [n, 6]: columns
+        0..2 the region read downwards with first-base period 0, 1, 2; 3..5 its complement read upwards."""
+        seq, lo, length = (np.ascontiguousarray(x, np.int32) for x in (seq, lo, length))
+        out = np.zeros((len(seq), 6), np.float64)
+        _check(lib().gmg_all_frame_scores(self.ctx.h, gene.h, self.h, len(seq), seq.ctypes.data, lo.ctypes.data,
+                                          length.ctypes.data, out.ctypes.data))
+        return out
 
     # ---- start-list reduction (row a11b) ----
     def reduce_starts_mg(self, params, model):

@@ -201,6 +201,12 @@ int gmg_set_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_orf* h_orfs, const int64
  * Needs ORFs (gmg_find_orfs / gmg_set_orfs).  *n_starts = total. async until gmg_get_starts. */
 int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_icm* indep, gmg_seqset* s,
                       const gmg_params* p, int64_t* n_starts);
+/* All_Frame_Score (glimmer3.cc:328-359), batched, for the `.detail` log: for each of n regions [lo, lo + len) (0-based)
+ * of sequence h_seq[i] the six Score_String sums of the gene ICM the reference forms -- h_out[6 i + k], k = 0..2: the
+ * region read downwards (a forward gene's buff) with the first base in period k; k = 3..5: the region's complement
+ * read upwards (a reverse gene's buff) with the first base in period k - 3.  Sums in the reference's serial order. */
+int gmg_all_frame_scores(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, int64_t n, const int32_t* h_seq,
+                         const int32_t* h_lo, const int32_t* h_len, double* h_out);
 /* glimmer-mg Score_Orfs_Errors up to the boost (glimmer-mg.cc:1605-1651): Score_All_Frames,
  * Save_Prev_Stops, Set_Quality_454 / Clean_Quality_454, Cumulative_Frame_Score and the
  * Score_Orf_Starts / Score_Indels / Pass_Stop_Penalty recursion for every ORF. */
@@ -241,9 +247,10 @@ int gmg_get_reduced_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int
 int gmg_get_orf_starts(gmg_ctx* ctx, gmg_seqset* s, int64_t orf, gmg_start* h_out, int64_t cap, int64_t* n);
 /* start lists of the last gmg_score_orfs_* call: h_start_off has n_orfs+1 entries */
 int gmg_get_starts(gmg_ctx* ctx, gmg_seqset* s, gmg_start* h_starts, int64_t* h_start_off);
-/* number of sequences (mg) / ORFs (g3) whose sums could not be certified exact in FP64 (see
- * DESIGN.md "exactness certificate"); their scores are within 1e-12 relative instead of
- * bit-identical. */
+/* FP64 sums are formed by parallel scans where an exactness certificate proves them bit-identical to the reference's
+ * serial sums; sequences (glimmer-mg with -i / -s) or ORFs (plain glimmer-mg) without one are
+ * summed again in the reference's own serial order.  This returns how many took that route in the last call; results
+ * are exact either way. */
 int64_t gmg_uncertified_count(const gmg_seqset* s);
 /* gmg_score_orfs_g3 forms its FP64 sums with warp-parallel scans where an exactness certificate proves
  * them bit-identical to the reference's serial sums, and re-does every other ORF in the reference's

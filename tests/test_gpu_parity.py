@@ -392,6 +392,45 @@ def test_mg_flat_thread_and_ordered_paths_agree(gm, ctx, reads, monkeypatch, fla
         k += len(worfs)
 
 
+def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monkeypatch):
+    """Plain glimmer-mg (no -i / -s): K2 + K3 fused into one per-ORF scan over the K1 planes (k3_mg_plain).  Same CSR as
+    K2 + one thread per ORF (GMG_K3MG_MODE=1), also when every ORF longer than 30 bases is summed in the reference's
+    serial order (forced), for ragged / empty / tiny sequences, and equal to the oracle's lists."""
+    rs = [s for _, s in reads[:300]] + [b"", b"acgtacgtacgt", reads[5][1][:75], reads[6][1][:76], reads[7][1][:100]]
+    gene_path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, gene_path)
+    p = gm.Params(True)
+    ss0 = gm.SeqSet(ctx, seqs=rs)
+    gc = ss0.gc_fraction()
+    p.set_ignore_score_len(gc)
+    indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+
+    def run():
+        ss = gm.SeqSet(ctx, seqs=rs)
+        ss.find_orfs(p)
+        ss.score_orfs_mg(gene, indep, p)
+        st, off = ss.get_starts()
+        orfs, ooff = ss.get_orfs()
+        return st.tobytes(), off.tolist(), ss.uncertified, orfs, ooff
+
+    want = run()  # fused
+    assert want[2] == 0
+    monkeypatch.setenv("GMG_K3MG_MODE", "1")
+    assert run()[:2] == want[:2]
+    monkeypatch.delenv("GMG_K3MG_MODE")
+    monkeypatch.setenv("GMG_MG_FORCE_UNCERT", "1")
+    got = run()
+    assert got[:2] == want[:2] and got[2] > 100   # ORFs re-summed serially by one lane
+    monkeypatch.delenv("GMG_MG_FORCE_UNCERT")
+    import config_parity as CP
+    a = np.frombuffer(b"".join(rs), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in rs])]).astype(np.int64)
+    st = CP.check_scoring("mg", a, off, range(len(rs)), want[3], want[4], np.frombuffer(want[0], gm.START_DTYPE),
+                          np.asarray(want[1]), CP.oracle_model(path=gene_path), gc, ("taa", "tag", "tga"),
+                          ignore_score_len=p.ignore_score_len)
+    assert st["starts"] > 5000
+
+
 @pytest.mark.parametrize("flags,table", [(dict(allow_indels=1), "default"), (dict(allow_indels=1), "random"),
                                          (dict(allow_indels=1, allow_subs=1), "random"), (dict(), "default")])
 def test_mg_start_list_reduction(gm, ctx, reads, flags, table):
