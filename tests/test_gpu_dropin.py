@@ -71,6 +71,26 @@ def test_glimmer3_dropin_option_variants(tmp_path):
     assert open(tmp_path / "c.predict", "rb").read() == want
 
 
+def test_glimmer3_dropin_detail_log_opt_in(tmp_path):
+    """The `.detail` log (compiled off in the reference: `bool Detail_Log = false`, glimmer_base.cc:20) behind GMG_DETAIL=1:
+    every line -- ORF coordinates, gene scores and the six integerised All_Frame_Score columns, computed for all ORFs
+    in one device call -- equals what the reference writes when built with the flag on (oracle/_ref/bin/glimmer3-detail)."""
+    exe = _need(os.path.join(HOSTBIN, "glimmer3-gmg"))
+    ref = _need(os.path.join(REFBIN, "glimmer3-detail"))
+    lines = gzip.open(os.path.join(G, "NC_000915.fna.gz"), "rt").readlines()
+    fna = tmp_path / "p.fna"
+    fna.write_text(lines[0] + "".join(lines[1:1 + 200000 // 70]))
+    for flags in (["-u", "-12"], ["-u", "-12", "-X"]):
+        _run([ref, *flags, "-m", ICM, str(fna), str(tmp_path / "r")])
+        _run([exe, *flags, "-m", ICM, str(fna), str(tmp_path / "g")], env=dict(os.environ, GMG_DETAIL="1"))
+        want = [l for l in open(tmp_path / "r.detail") if not l.startswith("Command:")]
+        got = [l for l in open(tmp_path / "g.detail") if not l.startswith("Command:")]
+        assert len(want) > 1000 and got == want, flags
+        assert open(tmp_path / "g.predict", "rb").read() == open(tmp_path / "r.predict", "rb").read()
+    _run([exe, "-u", "-12", "-m", ICM, str(fna), str(tmp_path / "off")])
+    assert not os.path.exists(tmp_path / "off.detail")   # off by default, like the shipped reference binaries
+
+
 @pytest.mark.parametrize("tag,n,flags", [("plain", 120, []), ("indel", 40, ["-i"]), ("sub", 80, ["-s"])])
 def test_glimmer_mg_dropin_reproduces_reference_predict(tmp_path, tag, n, flags):
     exe = _need(os.path.join(HOSTBIN, "glimmer-mg-gmg"))

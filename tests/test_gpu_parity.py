@@ -201,6 +201,29 @@ def test_scalar_surface_matches_oracle(gm, ctx, reads):
     assert len(m.score_strings([b""], 0)) == 1 and m.score_strings([b""], 0)[0] == 0.0
 
 
+def test_all_frame_scores_match_oracle_score_string(gm, ctx, genome):
+    """gmg_all_frame_scores (All_Frame_Score glimmer3.cc:328-359, the `.detail` columns): for random regions the six
+    sums equal Score_String of the reversed region / its reverse complement under the oracle, bit for bit."""
+    path = os.path.join(G, "NC_000915.icm")
+    gene = gm.ICM.Read(ctx, path)
+    og = O.lib().orc_icm_read(path.encode())
+    seqs = [genome[:60000], genome[100000:100500], genome[7:40]]
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    rng = np.random.default_rng(3)
+    items = [(0, 0, 60000), (0, 59990, 10), (1, 0, 500), (2, 0, 33), (2, 5, 0), (1, 17, 1)]
+    for _ in range(60):
+        lo = int(rng.integers(0, 59000))
+        items.append((0, lo, int(rng.integers(1, 900))))
+    got = ss.all_frame_scores(gene, [i[0] for i in items], [i[1] for i in items], [i[2] for i in items])
+    comp = bytes.maketrans(b"acgt", b"tgca")
+    for (sq, lo, ln), row in zip(items, got):
+        region = O.filter_lower(seqs[sq])[lo:lo + ln]
+        down, up = region[::-1], region.translate(comp)
+        for f0 in range(3):
+            assert row[f0] == O.lib().orc_score_string(og, down, ln, f0), (sq, lo, ln, f0)
+            assert row[3 + f0] == O.lib().orc_score_string(og, up, ln, f0), (sq, lo, ln, f0)
+
+
 def test_score_all_frames_bit_exact(gm, ctx, reads):
     path = os.path.join(G, "NC_000915.icm")
     gene = gm.ICM.Read(ctx, path)
