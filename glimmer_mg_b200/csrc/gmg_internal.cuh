@@ -241,5 +241,6 @@ __device__ __forceinline__ uint64_t gmg_reverse_bases(uint64_t v, int W) {
   return v >> (2 * (32 - W));
 }
 
+int gmg_seqset_ensure_buckets(gmg_ctx* ctx, gmg_seqset* s);
 // kernel launchers implemented across the .cu files
 int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_t* d_words, unsigned long long* d_gc);

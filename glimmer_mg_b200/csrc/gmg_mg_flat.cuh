@@ -454,15 +454,11 @@ MGF_HD int mgf_n_candidates(const DevParams& P, const MgfCall& c) {
   return (mgf_may_sub(P, c.n_err) ? 1 : 0) + 2 * c.n_gates;
 }
 
-// first index i in [0, n] with off[i] > x, minus one: the segment that holds element x (off ascending, off[0] = 0)
-MGF_HD uint32_t mgf_segment_of(const uint32_t* off, uint32_t n, uint32_t x) {
-  uint32_t lo = 0, hi = n;  // invariant: off[lo] <= x < off[hi]
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (mgf_ld(off + mid) <= x) lo = mid;
-    else hi = mid;
-  }
-  return lo;
+// parent of every candidate: segment p of the scan `off` owns candidates [off[p], off[p + 1]).  Written once per level
+// (a binary search per candidate in each of the passes that need the parent cost a third of their time).
+MGF_HD void mgf_fill_parent(const uint32_t* off, uint32_t p, uint32_t* par) {
+  const uint32_t a = mgf_ld(off + p), b = mgf_ld(off + p + 1);
+  for (uint32_t i = a; i < b; i++) par[i] = p;
 }
 
 // ---- the passes ---------------------------------------------------------------------------------------------------
@@ -477,6 +473,7 @@ struct MgfWork {
   uint32_t* own0;   // [n_orfs]
   // level 1
   uint32_t c1;      // number of level-1 candidates (= off1[n_orfs]; known to the host before pass B)
+  uint32_t* par1;   // [c1] ORF of every level-1 candidate
   MgfCall* call1;   // [c1]
   uint32_t* n2;     // [c1 + 1]; off2 = its exclusive scan
   uint32_t* off2;
@@ -485,6 +482,7 @@ struct MgfWork {
   uint32_t* s1;
   // level 2
   uint32_t c2;      // number of level-2 candidates (= off2[c1])
+  uint32_t* par2;   // [c2] level-1 candidate (parent call) of every level-2 candidate
   uint32_t* cnt3;   // [c2 + 1] records of every level-2 candidate; s3 = its exclusive scan
   uint32_t* s3;
   // output
@@ -546,7 +544,7 @@ MGF_HD void mgf_pass_a(const MgfBatch& B, const DevParams& P, const MgfWork& W, 
 }
 
 MGF_HD void mgf_pass_b(const MgfBatch& B, const DevParams& P, const MgfWork& W, uint32_t i) {
-  const uint32_t o = mgf_segment_of(W.off1, W.n_orfs, i);
+  const uint32_t o = mgf_ld(W.par1 + i);
   const MgfCall r = W.root[o];
   const MgfSeq S = mgf_seq_of(B, W.orf_seq[o]);
   MgfCall ch;
@@ -574,7 +572,7 @@ MGF_HD void mgf_pass_b(const MgfBatch& B, const DevParams& P, const MgfWork& W, 
 }
 
 MGF_HD void mgf_pass_c(const MgfBatch& B, const DevParams& P, const MgfWork& W, uint32_t i) {
-  const uint32_t p = mgf_segment_of(W.off2, W.c1, i);
+  const uint32_t p = mgf_ld(W.par2 + i);
   const MgfCall c = W.call1[p];
   const MgfSeq S = mgf_seq_of(B, W.orf_seq[c.orf]);
   MgfCall ch;
@@ -644,7 +642,7 @@ MGF_HD void mgf_write_1(const MgfBatch& B, const DevParams& P, const CodonSets& 
 // records of a level-2 (leaf) call
 MGF_HD void mgf_write_2(const MgfBatch& B, const DevParams& P, const CodonSets& cs, const MgfWork& W, uint32_t i) {
   if (mgf_ld(W.s3 + i + 1) == mgf_ld(W.s3 + i)) return;  // no records (or the call does not exist)
-  const uint32_t p = mgf_segment_of(W.off2, W.c1, i);
+  const uint32_t p = mgf_ld(W.par2 + i);
   const MgfCall c = W.call1[p];
   const MgfSeq S = mgf_seq_of(B, W.orf_seq[c.orf]);
   const bool fwd = c.fwd != 0;

@@ -104,31 +104,45 @@ __device__ __forceinline__ int codon_rev_starting_at(const uint64_t* __restrict_
   return ((c & 3) << 4) | (c & 12) | (c >> 4);
 }
 
-static int code_of(char ch) {
+// Ch_Mask (Common/gene.cc:954-995): the set of bases an IUPAC letter stands for, bit b = base b (a c g t); 0 = none
+static unsigned iupac_mask(char ch) {
   switch (ch | 0x20) {
-    case 'a': return 0;
-    case 'c': return 1;
-    case 'g': return 2;
-    case 't': return 3;
-    default: return -1;
+    case 'a': return 0x1;
+    case 'c': return 0x2;
+    case 'g': return 0x4;
+    case 't': return 0x8;
+    case 'r': return 0x5;
+    case 'y': return 0xA;
+    case 's': return 0x6;
+    case 'w': return 0x9;
+    case 'm': return 0x3;
+    case 'k': return 0xC;
+    case 'b': return 0xE;
+    case 'd': return 0xD;
+    case 'h': return 0xB;
+    case 'v': return 0x7;
+    case 'n': return 0xF;
+    default: return 0x0;
   }
 }
 
+// Start / stop codon PATTERNS (Codon_t masks, gene.cc:39-161: letters may be IUPAC ambiguity codes) as sets of concrete
+// codons: a sequence codon (always a/c/g/t after Filter) matches pattern i iff each of its bases is in the pattern's
+// letter set; `which` = the first matching start pattern (Codon_t::Can_Be's order).
 static int make_codon_sets(const gmg_params* p, CodonSets* cs, DevParams* dp) {
   memset(cs, 0, sizeof *cs);
   GMG_CHECK(p->n_start >= 0 && p->n_start <= 8 && p->n_stop >= 0 && p->n_stop <= 8, "bad start/stop codon count");
   memset(cs->which, 0xFF, sizeof cs->which);
-  for (int i = 0; i < p->n_start; i++) {
-    int a = code_of(p->start_codon[i][0]), b = code_of(p->start_codon[i][1]), c = code_of(p->start_codon[i][2]);
-    GMG_CHECK(a >= 0 && b >= 0 && c >= 0, "start codon '%s': only a/c/g/t codons are supported", p->start_codon[i]);
-    int code = a * 16 + b * 4 + c;
-    if (!(cs->start_mask >> code & 1)) cs->which[code] = (unsigned char)i;
-    cs->start_mask |= 1ull << code;
-  }
-  for (int i = 0; i < p->n_stop; i++) {
-    int a = code_of(p->stop_codon[i][0]), b = code_of(p->stop_codon[i][1]), c = code_of(p->stop_codon[i][2]);
-    GMG_CHECK(a >= 0 && b >= 0 && c >= 0, "stop codon '%s': only a/c/g/t codons are supported", p->stop_codon[i]);
-    cs->stop_mask |= 1ull << (a * 16 + b * 4 + c);
+  for (int code = 0; code < 64; code++) {
+    const unsigned b0 = 1u << (code >> 4), b1 = 1u << ((code >> 2) & 3), b2 = 1u << (code & 3);
+    for (int i = 0; i < p->n_start; i++)
+      if ((iupac_mask(p->start_codon[i][0]) & b0) && (iupac_mask(p->start_codon[i][1]) & b1) && (iupac_mask(p->start_codon[i][2]) & b2)) {
+        if (!(cs->start_mask >> code & 1)) cs->which[code] = (unsigned char)i;
+        cs->start_mask |= 1ull << code;
+      }
+    for (int i = 0; i < p->n_stop; i++)
+      if ((iupac_mask(p->stop_codon[i][0]) & b0) && (iupac_mask(p->stop_codon[i][1]) & b1) && (iupac_mask(p->stop_codon[i][2]) & b2))
+        cs->stop_mask |= 1ull << code;
   }
   for (int raw = 0; raw < 64; raw++) {
     const int b0 = raw & 3, b1 = (raw >> 2) & 3, b2 = raw >> 4;
@@ -438,6 +452,7 @@ __global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const
 static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** planes_out) {
   GMG_CHECK(gene->P == 3, "six-frame scoring needs a periodicity-3 gene model (got %d)", gene->P);
   if (gmg_icm_ready(gene)) return 1;
+  if (gmg_seqset_ensure_buckets(ctx, s)) return 1;
   void* planes = NULL;
   if (gmg_scratch(ctx, SCR_PLANES, (size_t)6 * (s->total + 32) * sizeof(float), &planes)) return 1;
   *planes_out = (float*)planes;
@@ -2701,6 +2716,10 @@ __global__ void __launch_bounds__(128) k_mgf_a(MgfBatch B, DevParams P, MgfWork 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < W.n_orfs) mgf_pass_a(B, P, W, i);
 }
+__global__ void __launch_bounds__(256) k_mgf_fill(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ par) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) mgf_fill_parent(off, p, par);
+}
 __global__ void __launch_bounds__(128) k_mgf_b(MgfBatch B, DevParams P, MgfWork W) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < W.c1) mgf_pass_b(B, P, W, i);
@@ -2797,9 +2816,9 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
                                                    const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                    int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                    gmg_start* __restrict__ starts, int exact_len,
-                                                   unsigned long long* __restrict__ n_ordered) {
+                                                   unsigned long long* __restrict__ n_ordered, int slots) {
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ double s_pref[4][MGP_SLOTS];
+  extern __shared__ double s_pref_all[];  // [4 warps][slots]: sized for the batch's longest sequence (occupancy on short reads)
   __shared__ float s_lut[384];
   if (indep.lut3 != NULL)
     for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
@@ -2816,7 +2835,7 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
   MgfOwn f;
   mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
-  double* pref = s_pref[wid];
+  double* pref = s_pref_all + (size_t)wid * slots;
   // score[j] for j < j_hi is all the records can ask for (score[j - 1] at their own j <= j_hi)
   const int need = f.j_hi;  // terms j = 0 .. need - 1
   if (lane == 0) pref[0] = 0.0;
@@ -3145,6 +3164,7 @@ extern "C" int gmg_score_orfs_g3(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CHECK(ctx && gene && indep && s && p, "gmg_score_orfs_g3: NULL argument");
   GMG_CHECK(gene->P == 3 && indep->P == 3, "glimmer3 scoring needs periodicity-3 models");
   if (gmg_icm_ready(gene) || gmg_icm_ready(indep)) return 1;
+  if (gmg_seqset_ensure_buckets(ctx, s)) return 1;  // here, not inside K1: its scratch must not be touched once the side stream runs
   CodonSets cs;
   DevParams dp;
   if (make_codon_sets(p, &cs, &dp)) return 1;
@@ -3312,9 +3332,10 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     if (ensure_start_capacity(s, total_starts)) return 1;
     if (total_starts > 0) {
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-      k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+      const int slots = (int)(s->max_len / 3 + 4);
+      k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, (size_t)4 * slots * sizeof(double), ctx->stream>>>(
           indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
-          (unsigned long long*)(counts + s->n_orfs + 1));
+          (unsigned long long*)(counts + s->n_orfs + 1), slots);
       gmg_prof_end(ctx, GMG_PROF_K3);
       ctx->launches++;
       GMG_CUDA(cudaGetLastError());
@@ -3455,18 +3476,20 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     // level 1
     void *d_call1, *d_l1;
     if (gmg_scratch(ctx, SCR_MG_CALL1, ((size_t)W.c1 + 1) * sizeof(MgfCall), &d_call1)) return 1;
-    if (gmg_scratch(ctx, SCR_MG_L1, (size_t)(5 * ((size_t)W.c1 + 1)) * sizeof(uint32_t), &d_l1)) return 1;
+    if (gmg_scratch(ctx, SCR_MG_L1, (size_t)(6 * ((size_t)W.c1 + 1)) * sizeof(uint32_t), &d_l1)) return 1;
     W.call1 = (MgfCall*)d_call1;
     W.n2 = (uint32_t*)d_l1;
     W.off2 = W.n2 + W.c1 + 1;
     W.own1 = W.off2 + W.c1 + 1;
     W.t1 = W.own1 + W.c1 + 1;
     W.s1 = W.t1 + W.c1 + 1;
+    W.par1 = W.s1 + W.c1 + 1;
     GMG_CUDA(cudaMemsetAsync(W.n2 + W.c1, 0, sizeof(uint32_t), ctx->stream));
     GMG_CUDA(cudaMemsetAsync(W.t1 + W.c1, 0, sizeof(uint32_t), ctx->stream));
     if (W.c1) {
+      k_mgf_fill<<<(no + 255) / 256, 256, 0, ctx->stream>>>(W.off1, no, W.par1);
       k_mgf_b<<<(W.c1 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, W);
-      ctx->launches++;
+      ctx->launches += 2;
     }
     if (exclusive_sum_u32(ctx, W.n2, W.off2, (int64_t)W.c1 + 1)) return 1;
     GMG_CUDA(cudaMemcpyAsync(hs, W.off2 + W.c1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -3475,13 +3498,15 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     GMG_CHECK(W.c2 < 0x7ffffff0u, "gmg_score_orfs_mg: %u level-2 candidate calls -- split the batch", W.c2);
     // level 2
     void* d_l2;
-    if (gmg_scratch(ctx, SCR_MG_L2, (size_t)(2 * ((size_t)W.c2 + 1)) * sizeof(uint32_t), &d_l2)) return 1;
+    if (gmg_scratch(ctx, SCR_MG_L2, (size_t)(3 * ((size_t)W.c2 + 1)) * sizeof(uint32_t), &d_l2)) return 1;
     W.cnt3 = (uint32_t*)d_l2;
     W.s3 = W.cnt3 + W.c2 + 1;
+    W.par2 = W.s3 + W.c2 + 1;
     GMG_CUDA(cudaMemsetAsync(W.cnt3 + W.c2, 0, sizeof(uint32_t), ctx->stream));
     if (W.c2) {
+      k_mgf_fill<<<(W.c1 + 255) / 256, 256, 0, ctx->stream>>>(W.off2, W.c1, W.par2);
       k_mgf_c<<<(W.c2 + 127) / 128, 128, 0, ctx->stream>>>(B, dp, W);
-      ctx->launches++;
+      ctx->launches += 2;
     }
     if (exclusive_sum_u32(ctx, W.cnt3, W.s3, (int64_t)W.c2 + 1)) return 1;
     if (W.c1) {

@@ -148,7 +148,10 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
   ctxr[idx] = (r & ~15u) | (uint32_t)(q < 15 ? q : 15);
 }
 
-static int build_buckets(gmg_ctx* ctx, gmg_seqset* s) {
+// Base buckets and walk-ready contexts exist for K1 only: built on its first launch on a set (training and the
+// string-scoring calls never pay for them).
+int gmg_seqset_ensure_buckets(gmg_ctx* ctx, gmg_seqset* s) {
+  if (s->d_bktidx || s->total == 0) return 0;
   const int64_t nblk = (s->total + 31) >> 5;
   GMG_CHECK(s->total < (1ll << 32), "batches of 2^32 bases or more are not supported (got %lld)", (long long)s->total);
   GMG_CUDA(cudaMallocAsync(&s->d_bktidx, (size_t)(nblk + 1) * sizeof(uint4), ctx->stream));
@@ -223,7 +226,6 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
     k_blk2seq<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d_off, s->n, nblk, s->d_blk2seq);
     ctx->launches++;
     GMG_CUDA(cudaGetLastError());
-    if (build_buckets(ctx, s)) return 1;
     if (d_qual) {
       GMG_CUDA(cudaMallocAsync(&s->d_qual, (size_t)s->total, s->ctx->stream));
       GMG_CUDA(cudaMemcpyAsync(s->d_qual, d_qual, (size_t)s->total, cudaMemcpyDeviceToDevice, ctx->stream));

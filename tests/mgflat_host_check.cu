@@ -260,12 +260,18 @@ int main(int argc, char** argv) {
   W.call1 = call1.data();
   W.n2 = n2.data();
   W.own1 = own1.data();
+  std::vector<uint32_t> par1(W.c1 + 1, 0);
+  W.par1 = par1.data();
+  for (uint32_t o = 0; o < n_orfs; o++) mgf_fill_parent(W.off1, o, W.par1);
   for (uint32_t i = 0; i < W.c1; i++) mgf_pass_b(B, P, W, i);
   exscan(n2, off2);
   W.off2 = off2.data();
   W.c2 = off2[W.c1];
   std::vector<uint32_t> cnt3(W.c2 + 1, 0), s3;
   W.cnt3 = cnt3.data();
+  std::vector<uint32_t> par2(W.c2 + 1, 0);
+  W.par2 = par2.data();
+  for (uint32_t i = 0; i < W.c1; i++) mgf_fill_parent(W.off2, i, W.par2);
   for (uint32_t i = 0; i < W.c2; i++) mgf_pass_c(B, P, W, i);
   exscan(cnt3, s3);
   W.s3 = s3.data();

@@ -62,7 +62,9 @@ def test_glimmer3_dropin_option_variants(tmp_path):
     lines = gzip.open(os.path.join(G, "NC_000915.fna.gz"), "rt").readlines()
     fna = tmp_path / "p.fna"
     fna.write_text(lines[0] + "".join(lines[1:1 + 300000 // 70]))
-    for flags in (["-u", "-12"], ["-u", "-12", "-X"], ["-u", "-12", "-g", "90", "-A", "atg,gtg"], ["-u", "-8", "-z", "4", "-l"]):
+    # the last two: start / stop codon PATTERNS with IUPAC ambiguity codes (Codon_t masks, Common/gene.cc:39-161)
+    for flags in (["-u", "-12"], ["-u", "-12", "-X"], ["-u", "-12", "-g", "90", "-A", "atg,gtg"], ["-u", "-8", "-z", "4", "-l"],
+                  ["-u", "-12", "-Z", "tar,tga"], ["-u", "-12", "-A", "atg,ktg", "-P", "0.6,0.4", "-Z", "trr"]):
         _run([exe, *flags, "-m", ICM, str(fna), str(tmp_path / "a")])
         _run([ref, *flags, "-m", ICM, str(fna), str(tmp_path / "b")])
         assert open(tmp_path / "a.predict", "rb").read() == open(tmp_path / "b.predict", "rb").read(), flags

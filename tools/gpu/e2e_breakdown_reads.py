@@ -25,7 +25,9 @@ with torch.cuda.stream(stream):
         T("find_orfs", lambda: ss.find_orfs(p))
         T("score_orfs_mg", lambda: ss.score_orfs_mg(gene, indep, p))
         T("get_orfs", lambda: ss.get_orfs(pinned=True))
-        T("get_starts", lambda: ss.get_starts(pinned=True))
+        em = g.EventModel(prior=0.0, len_lo=np.zeros((1, 2, 2, 256)))
+        T("reduce_starts_mg", lambda: ss.reduce_starts_mg(p, em))
+        T("get_reduced_starts", lambda: ss.get_reduced_starts(pinned=True))
         T("close", ss.close)
     for k2, v in acc.items():
         print(f"{k2:22s} first {v[0]*1e3:8.3f} ms   steady {np.median(v[3:])*1e3:8.3f} ms")
