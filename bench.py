@@ -63,6 +63,7 @@ def parse_args():
                          "with the contig5m / train500m / reads400 lines of the same run nested under \"extra\"")
     ap.add_argument("--no-extra", action="store_true", help="default workload only, no nested lines")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the results (profiling runs)")
+    ap.add_argument("--no-pipeline", action="store_true", help="end to end with one batch at a time only")
     ap.add_argument("--scale", type=float, default=1.0,
                     help="shrink a non-default workload (fraction of its reads / training strings); 1.0 = BASELINE size")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
@@ -662,13 +663,14 @@ def run_b200_reads(args, env, kind):
             else:
                 ts, toff = cluster_training_strings(k)
                 genes[k] = g.ICMTraining(ctx, 12, 7, 3).Train_Model(g.SeqSet(ctx, ascii=ts, offsets=toff), reverse=True)
-        pinned, sets, indeps, params = [], [], [], []
+        pinned, sets, indeps, params, gcs = [], [], [], [], []
         for a, off, k in batches:
             h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
             h.numpy()[:] = a
             pinned.append(h)
             ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
             gc = ss.gc_fraction()
+            gcs.append(gc)
             p = g.Params(True, allow_indels=1 if indels else 0)
             p.set_ignore_score_len(gc)
             indeps.append(g.ICM.Build_Indep_WO_Stops(ctx, gc, p.stop_codons))
@@ -758,14 +760,66 @@ def run_b200_reads(args, env, kind):
                       "reduction": rs, "raw_starts": int(s2.n_starts), "surviving_starts": int(len(red)),
                       "uncertified_reads": int(s2.uncertified)}
         s2.close()
+        # ---- end to end with TWO batches in flight: the same call sequence from two host threads, each with its own
+        # context and stream, so that one batch's H2D / D2H copies overlap the other's kernels (what a streaming
+        # integration does with consecutive chunks).  Every step still copies its inputs from pinned host memory and its
+        # results back inside the timed region.
+        pipe_ms = None
+        if not args.no_pipeline:
+            import threading
+            stream_b = torch.cuda.Stream(device=dev)
+            ctx_b = g.Context(local, stream_b.cuda_stream)
+            genes_b = {k: g.ICM.from_tables(ctx_b, *m.dims()[:3], *m.tables()) for k, m in genes.items()}
+            indeps_b = [g.ICM.Build_Indep_WO_Stops(ctx_b, gcs[i], params[i].stop_codons) for i in range(nb)]
+            lanes = [(ctx, genes, indeps, stream), (ctx_b, genes_b, indeps_b, stream_b)]
 
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    tb = torch.tensor([done_bases, e2e_bases], dtype=torch.float64, device=dev)
+            def one(lane, jb):
+                c, gs, ins, _ = lanes[lane]
+                s3 = g.SeqSet(c, ascii=pinned[jb].numpy(), offsets=batches[jb][1])
+                s3.find_orfs(params[jb])
+                s3.get_orfs(pinned=True)
+                s3.score_orfs_mg(gs[batches[jb][2]], ins[jb], params[jb])
+                s3.reduce_starts_mg(params[jb], event_model)
+                s3.get_reduced_starts(pinned=True)
+                s3.close()
+
+            for lane in (0, 1):
+                for k in range(We):
+                    one(lane, k % nb)
+            barrier()
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ends = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+            ev0.record(stream)  # both streams are idle here
+            errs = []
+
+            def worker(lane):
+                try:
+                    torch.cuda.set_device(local)
+                    for k in range(lane, K, 2):
+                        one(lane, (We + k) % nb)
+                    ends[lane].record(lanes[lane][3])
+                except Exception as exc:  # pragma: no cover
+                    errs.append(exc)
+
+            th = [threading.Thread(target=worker, args=(lane,)) for lane in (0, 1)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            torch.cuda.synchronize()
+            if errs:
+                raise errs[0]
+            pipe_ms = max(ev0.elapsed_time(e) for e in ends)
+            pipe_bases = sum(bases[(We + k) % nb] for k in range(K))
+            ctx_b.close()
+
+    t = torch.tensor([ms, e2e_ms, pipe_ms or 0.0], dtype=torch.float64, device=dev)
+    tb = torch.tensor([done_bases, e2e_bases, pipe_bases if pipe_ms else 0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-    ms_max, e2e_max = t.tolist()
-    all_bases, all_e2e_bases = tb.tolist()
+    ms_max, e2e_max, pipe_max = t.tolist()
+    all_bases, all_e2e_bases, all_pipe_bases = tb.tolist()
     if rank == 0:
         value = all_bases / (ms_max / 1e3) / 1e9
         e2e = all_e2e_bases / (e2e_max / 1e3) / 1e9
@@ -792,9 +846,16 @@ def run_b200_reads(args, env, kind):
                              "note": "k3_mg_starts (per-ORF indel recursion) is latency/divergence-bound and has no "
                                      "HBM roofline; its time is listed beside the two streaming kernels"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_max / K},
+                        "ms_per_step": e2e_max / K, "in_flight": 1},
                 "gpu_launches": int(launches), "clocks": clk,
                 "parity_checked": parity is not None, "parity": parity}
+        if pipe_max > 0:
+            # headline e2e = the streaming form (two batches in flight); the one-batch-at-a-time figure stays beside it
+            line["e2e"].update({"value": all_pipe_bases / (pipe_max / 1e3) / 1e9, "ms_per_step": pipe_max / K, "in_flight": 2,
+                                "how": "two host threads, each with its own context / stream, alternate batches: copies of one batch "
+                                       "overlap the kernels of the other; every step copies its input from pinned host memory and "
+                                       "its ORF table + reduced start lists back", "one_batch_at_a_time": {"value": e2e,
+                                                                                                       "ms_per_step": e2e_max / K}})
         if world == 1 and not args.no_cpu_baseline:
             tmp = tempfile.mkdtemp(prefix="gmg_bench_")
             try:

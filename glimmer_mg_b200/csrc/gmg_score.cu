@@ -2893,6 +2893,52 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   }
 }
 
+// The same fused pass with ONE THREAD per ORF (the default for short reads): the ORF's records are laid out first
+// (positions, codons, flags from the codon bitmaps), then the thread walks the ORF string once, accumulating
+// gene - indep serially in the reference's own order (glimmer-mg.cc:577-586) and dropping each running sum into the
+// record that asks for it.  No scan, no certificate -- the order IS the reference's -- and with ~60 bases per ORF and
+// 300 k threads resident the serial walks hide each other's latency better than 32 lanes sharing one short ORF.
+__global__ void __launch_bounds__(128) k3_mg_plain_serial(DevIcm indep, const float* __restrict__ planes,
+                                                          const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P,
+                                                          CodonSets cs, const gmg_orf* __restrict__ orfs,
+                                                          const int32_t* __restrict__ orf_seq, int64_t n_orfs,
+                                                          const int64_t* __restrict__ start_off, gmg_start* __restrict__ starts) {
+  __shared__ float s_lut[384];
+  if (indep.lut3 != NULL)
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
+  __syncthreads();
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_orfs) return;
+  const int64_t so = start_off[o];
+  const int cnt = (int)(start_off[o + 1] - so);
+  if (cnt == 0) return;
+  const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+  const gmg_orf orf = orfs[o];
+  const bool fwd = orf.frame > 0;
+  const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
+  const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
+  MgfOwn f;
+  mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+  gmg_start* out = starts + so;
+  const int ep[2] = {0, 0}, et[2] = {0, 0};
+  DevParams Pn = P;
+  Pn.ignore_score_len = INT_MAX;  // the boost is applied when the score is known
+  mgf_own_write_with(B, S, Pn, cs, f, fwd, 0.0, 0, 0, ep, et, out, [](int) { return (int64_t)0; }, [](int) { return 0.0; });
+  // records are in descending j; walk j upwards and serve them from the last one
+  int r = cnt - 1;
+  double run = 0.0;
+  for (int j = 0; r >= 0; j++) {
+    float g, n;
+    mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+    run = run + ((double)g - (double)n);  // score[j]
+    while (r >= 0 && out[r].j - 2 == j + 1) {  // a start at j + 1 takes score[j] (glimmer-mg.cc:1826)
+      const double sc = (run - 0.0) + 0.0;
+      out[r].score = (out[r].j > P.ignore_score_len && 0.0 > sc) ? 0.0 : sc;
+      r--;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Start-list reduction: what Score_Orfs_Errors' filter (glimmer-mg.cc:1656-1684) and
 // Add_Events_Fwd / Add_Events_Rev (glimmer_base.cc:65-128, 175-235) keep of an ORF's raw start_list -- at most one
@@ -3330,7 +3376,15 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     const int64_t total_starts = ctx->h_scalars[6];
     if (ensure_start_capacity(s, total_starts)) return 1;
-    if (total_starts > 0) {
+    const int plain_warp = getenv("GMG_PLAIN_WARP") ? atoi(getenv("GMG_PLAIN_WARP")) : 0;  // A/B: warp-per-ORF scan
+    if (total_starts > 0 && !plain_warp && exact_len >= 0) {
+      if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
+      k3_mg_plain_serial<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(
+          indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts);
+      gmg_prof_end(ctx, GMG_PROF_K3);
+      ctx->launches++;
+      GMG_CUDA(cudaGetLastError());
+    } else if (total_starts > 0) {
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
       const int slots = (int)(s->max_len / 3 + 4);
       k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, (size_t)4 * slots * sizeof(double), ctx->stream>>>(
