@@ -1023,25 +1023,56 @@ __global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words
                                               const int32_t* __restrict__ blk2seq, int64_t total, DevParams P,
                                               int64_t* __restrict__ block_counts, const int64_t* __restrict__ block_base,
                                               gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq,
-                                              int* __restrict__ overflow) {
+                                              int* __restrict__ overflow, int64_t n_seq) {
   typedef cub::BlockScan<int, 256> Scan;
   __shared__ typename Scan::TempStorage tmp;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Per CTA, staged once: the sequence boundaries that fall into its 256 positions (the first warp reads 33 offsets) and
+  // the stop-bit words of its codons (6 streams x 4 words), so that a position that closes nothing -- most of them --
+  // touches no global memory at all (one thread per base used to pay 3 + 2 dependent loads each: 0.62 ms per 31 Mbp).
+  constexpr int NB = 33;
+  __shared__ long long s_bound[NB];
+  __shared__ unsigned s_stop[6][4];
+  __shared__ int s_s0;
+  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t p = p0 + threadIdx.x;
+  const uint32_t wbase = (uint32_t)((p0 >= 2 ? p0 - 2 : 0) / 3) >> 5;
+  if (threadIdx.x < NB) {
+    const int32_t s0 = __ldg(blk2seq + (p0 >> 5)) & 0x7FFFFFFF;  // p0 is a multiple of 32: the sequence that holds it
+    const int64_t k = (int64_t)s0 + threadIdx.x;
+    s_bound[threadIdx.x] = k <= n_seq ? (long long)__ldg(off + k) : LLONG_MAX;
+    if (threadIdx.x == 0) s_s0 = s0;
+  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + 24) {
+    const int t = threadIdx.x - 64, strm = t >> 2, w = t & 3;
+    s_stop[strm][w] = (int64_t)wbase + w < nwc ? __ldg(cb + (size_t)strm * nwc + wbase + w).y : 0u;
+  }
+  __syncthreads();
   gmg_orf rec[8];
   int n = 0;
   int32_t sq = 0;
   if (p < total) {
-    SeqView sv = locate(off, blk2seq, p, &sq);
-    const int64_t a = sv.a;
-    const int L = sv.len, q = (int)(p - a);
+    int64_t a;
+    int L;
+    if (s_bound[NB - 1] > p0 + 255) {  // all of the CTA's sequences are in the staged list
+      int k = 0;
+      while (s_bound[k + 1] <= p) k++;
+      sq = s_s0 + k;
+      a = s_bound[k];
+      L = (int)(s_bound[k + 1] - a);
+    } else {  // more than 32 sequences inside 256 bases: look it up
+      SeqView sv = locate(off, blk2seq, p, &sq);
+      a = sv.a;
+      L = sv.len;
+    }
+    const int q = (int)(p - a);
     if (L >= P.min_gene_len) {
       if (q >= 2) {  // the codon q-2 .. q: forward stop / reverse stop?
         const uint32_t c = (uint32_t)(p - 2);
         const int r = (int)(c % 3u);
         const uint32_t sl = c / 3u;
         const unsigned bit = 1u << (sl & 31u);
-        if (__ldg(cb + (size_t)r * nwc + (sl >> 5)).y & bit) n += orf_fwd_closed(cb, nwc, a, L, q, P, &rec[n]);
-        if (__ldg(cb + (size_t)(3 + r) * nwc + (sl >> 5)).y & bit) n += orf_rev_closed(cb, nwc, a, L, q, false, P, &rec[n]);
+        const uint32_t w = (sl >> 5) - wbase;  // 0 .. 3
+        if (s_stop[r][w] & bit) n += orf_fwd_closed(cb, nwc, a, L, q, P, &rec[n]);
+        if (s_stop[3 + r][w] & bit) n += orf_rev_closed(cb, nwc, a, L, q, false, P, &rec[n]);
       }
       if (q == L - 1) {
         for (int fr = 0; fr < 3; fr++) {
@@ -1182,7 +1213,7 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   GMG_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
   k_orfs<2><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total, dp,
-                                                     counts, NULL, st_orfs, st_seq, d_overflow);
+                                                     counts, NULL, st_orfs, st_seq, d_overflow, s->n);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -1202,7 +1233,7 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
                                                                                  s->d_orf_seq);
   else  // some CTA found more ORFs than it could stage: write pass over the whole batch
     k_orfs<1><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total,
-                                                       dp, NULL, bases, s->d_orfs, s->d_orf_seq, NULL);
+                                                       dp, NULL, bases, s->d_orfs, s->d_orf_seq, NULL, s->n);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
@@ -2893,11 +2924,11 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   }
 }
 
-// The same fused pass with ONE THREAD per ORF (the default for short reads): the ORF's records are laid out first
+// The same fused pass with ONE THREAD per ORF (an alternative, GMG_PLAIN_SERIAL=1): the ORF's records are laid out first
 // (positions, codons, flags from the codon bitmaps), then the thread walks the ORF string once, accumulating
 // gene - indep serially in the reference's own order (glimmer-mg.cc:577-586) and dropping each running sum into the
-// record that asks for it.  No scan, no certificate -- the order IS the reference's -- and with ~60 bases per ORF and
-// 300 k threads resident the serial walks hide each other's latency better than 32 lanes sharing one short ORF.
+// record that asks for it.  No scan, no certificate -- the order IS the reference's.  Measured slower than the warp form
+// on 100 bp reads (0.76 against 0.63 ms per 31 Mbp): kept as the simplest exact statement of the pass and for A/B runs.
 __global__ void __launch_bounds__(128) k3_mg_plain_serial(DevIcm indep, const float* __restrict__ planes,
                                                           const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P,
                                                           CodonSets cs, const gmg_orf* __restrict__ orfs,
@@ -3376,8 +3407,10 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     GMG_CUDA(cudaStreamSynchronize(ctx->stream));
     const int64_t total_starts = ctx->h_scalars[6];
     if (ensure_start_capacity(s, total_starts)) return 1;
-    const int plain_warp = getenv("GMG_PLAIN_WARP") ? atoi(getenv("GMG_PLAIN_WARP")) : 0;  // A/B: warp-per-ORF scan
-    if (total_starts > 0 && !plain_warp && exact_len >= 0) {
+    // A/B: one thread per ORF with serial sums (GMG_PLAIN_SERIAL=1; measured 0.76 ms per 31 Mbp against 0.63 ms for the
+    // warp-per-ORF scan below, which is the default)
+    const int plain_serial = getenv("GMG_PLAIN_SERIAL") ? atoi(getenv("GMG_PLAIN_SERIAL")) : 0;
+    if (total_starts > 0 && plain_serial && exact_len >= 0) {
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
       k3_mg_plain_serial<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(
           indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts);

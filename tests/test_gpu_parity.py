@@ -436,12 +436,12 @@ def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monk
         orfs, ooff = ss.get_orfs()
         return st.tobytes(), off.tolist(), ss.uncertified, orfs, ooff
 
-    want = run()  # fused, one thread per ORF (serial sums in the reference's order)
+    want = run()  # fused, one warp per ORF (parallel scan under the per-ORF certificate)
     assert want[2] == 0
-    monkeypatch.setenv("GMG_PLAIN_WARP", "1")
-    got = run()   # fused, one warp per ORF (parallel scan under the per-ORF certificate)
+    monkeypatch.setenv("GMG_PLAIN_SERIAL", "1")
+    got = run()   # fused, one thread per ORF (serial sums in the reference's order)
     assert got[:2] == want[:2] and got[2] == 0
-    monkeypatch.delenv("GMG_PLAIN_WARP")
+    monkeypatch.delenv("GMG_PLAIN_SERIAL")
     monkeypatch.setenv("GMG_K3MG_MODE", "1")
     assert run()[:2] == want[:2]
     monkeypatch.delenv("GMG_K3MG_MODE")
