@@ -615,9 +615,19 @@ def run_reference_reads(args, kind):
                 fastas.append(fa)
             else:
                 port_in = (sa, so)
+        model_path = W.gene_model_path()
+        if have and kind == "reads100" and ref_bin("build-icm"):
+            # the cluster's own ICM, trained by the reference's build-icm on the cluster's genes (not timed)
+            ts, toff = cluster_training_strings(batches[0][2])
+            tfa = os.path.join(tmp, "train.fa")
+            W.write_fasta(tfa, ts, toff, prefix="g")
+            model_path = os.path.join(tmp, "cluster.icm")
+            with open(tfa, "rb") as fin:
+                subprocess.run([ref_bin("build-icm"), "-r", model_path], stdin=fin, check=True, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL)
         times = []
         for k in range(args.warmup + args.steps):
-            sec = (ref_glimmer_mg_seconds(fastas, tmp, flags, [W.gene_model_path()] * len(fastas)) if have
+            sec = (ref_glimmer_mg_seconds(fastas, tmp, flags, [model_path] * len(fastas)) if have
                    else port_mg_seconds(port_in[0], port_in[1], kind == "reads400"))
             if k >= args.warmup:
                 times.append(sec)
@@ -626,7 +636,8 @@ def run_reference_reads(args, kind):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": desc, "model": "tests/golden/NC_000915.icm"},
+                "config": {"workload": desc, "model": "tests/golden/NC_000915.icm" if model_path == W.gene_model_path() else
+                           "the cluster's 12/7/3 ICM trained by the reference build-icm -r"},
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference" if have else "port",
                                  "sample": f"each step: {used} concurrent glimmer-mg {' '.join(flags)} processes, each on its own "
                                            f"{n_sample} reads of the workload (FASTA read + scoring + event DP + .predict)"},

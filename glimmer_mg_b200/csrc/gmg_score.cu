@@ -503,10 +503,12 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     k1_planes_bucketed<U, T><<<grid, T, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,  \
                                                             (float*)planes);                                            \
   } while (0)
-    // read sets: every window walked as full, the partial ones redone by k1_partial_fix (GMG_K1_FIX=0 disables)
+    // every window walked as full (no partial-window test, no slow path in the hot loop), the 2 (W-1) x 3 partial
+    // entries of every sequence redone by k1_partial_fix.  GMG_K1_FIX=0 disables, =2 restricts it to read sets (the
+    // round-1 behaviour: long sequences paid the test in every trip, 7 % of K1's instructions).
     static const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 1;
     const size_t fix_smem = (size_t)gene->dev.P * gene->dev.inner;
-    const bool fix = fix_env && !long_seqs && !ku_env && fix_smem <= 48 * 1024;
+    const bool fix = fix_env && !(fix_env == 2 && long_seqs) && !ku_env && fix_smem <= 48 * 1024;
     if (fix) {
       GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<6, 384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k1_planes_bucketed<6, 384, true><<<grid, 384, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr,

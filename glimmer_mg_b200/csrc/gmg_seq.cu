@@ -383,6 +383,23 @@ extern "C" int gmg_seqset_from_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t 
       GMG_CUDA(cudaMemcpyAsync(h_tab.data(), d_tab, h_tab.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
       GMG_CUDA(cudaStreamSynchronize(ctx->stream));
       n_chars = (int64_t)tot.x - h_tab[0];
+      // Fasta_Read skips the blanks after '>' and gives up if the file ends there (Common/fasta.cc:251-255): a last
+      // record whose '>' is followed by nothing but blanks does not exist; and the header text starts after the blanks
+      for (int64_t r = 0; r < n_rec; r++) {
+        int64_t& ho = h_tab[(size_t)(n_rec + r)];
+        const int64_t he = h_tab[(size_t)(2 * n_rec + r)];
+        while (ho < he && h_bytes[ho] == ' ') ho++;
+      }
+      {
+        int64_t q = h_tab[(size_t)(2 * n_rec - 1)];  // header text of the last record
+        while (q < n && h_bytes[q] == ' ') q++;
+        if (q == n) {  // it has no characters either: drop it
+          std::vector<int64_t> t2;
+          for (int part = 0; part < 3; part++) t2.insert(t2.end(), h_tab.begin() + part * n_rec, h_tab.begin() + part * n_rec + (n_rec - 1));
+          h_tab.swap(t2);
+          n_rec--;
+        }
+      }
     }
   }
   // sequence offsets: characters counted before each record, relative to the first record

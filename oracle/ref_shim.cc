@@ -7,6 +7,7 @@
 // Nothing here is part of the product.
 
 #include "icm.hh"
+#include "fasta.hh"
 #include <string>
 #include <vector>
 #include <cstring>
@@ -94,6 +95,30 @@ int ref_icm_write(void* h, const char* path) {
   static_cast<ICM_t*>(h)->Output(fp, true);
   fclose(fp);
   return 0;
+}
+
+// Fasta_Read (Common/fasta.cc:236-283) over a whole file: the records the reference's reader sees.  Returns the number
+// of records; *seqs / *hdrs are malloc'd buffers of NUL-separated strings (sequence characters as read, header text).
+int ref_fasta_read_file(const char* path, char** seqs, long* seqs_bytes, char** hdrs, long* hdrs_bytes) {
+  FILE* fp = fopen(path, "r");
+  if (!fp) return -1;
+  std::string s, h, all_s, all_h;
+  int n = 0;
+  while (Fasta_Read(fp, s, h)) {
+    all_s += s;
+    all_s.push_back('\0');
+    all_h += h;
+    all_h.push_back('\0');
+    n++;
+  }
+  fclose(fp);
+  *seqs = (char*)malloc(all_s.size() + 1);
+  memcpy(*seqs, all_s.data(), all_s.size());
+  *seqs_bytes = (long)all_s.size();
+  *hdrs = (char*)malloc(all_h.size() + 1);
+  memcpy(*hdrs, all_h.data(), all_h.size());
+  *hdrs_bytes = (long)all_h.size();
+  return n;
 }
 
 }  // extern "C"

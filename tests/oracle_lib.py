@@ -207,8 +207,27 @@ def ref():
     R.ref_icm_train.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int]
     R.ref_icm_train_free.argtypes = [C.c_void_p]
     R.ref_icm_write.argtypes = [C.c_void_p, C.c_char_p]
+    if hasattr(R, "ref_fasta_read_file"):
+        R.ref_fasta_read_file.restype = C.c_int
+        R.ref_fasta_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_long)]
     _ref = R
     return R
+
+
+def ref_fasta_records(path):
+    """[(header bytes, sequence bytes)] as the UNMODIFIED reference reader sees a file (Fasta_Read, Common/fasta.cc:236)."""
+    R = ref()
+    sp, hp, sn, hn = C.c_void_p(), C.c_void_p(), C.c_long(), C.c_long()
+    n = R.ref_fasta_read_file(os.fsencode(path), C.byref(sp), C.byref(sn), C.byref(hp), C.byref(hn))
+    assert n >= 0, path
+    seqs = C.string_at(sp, sn.value).split(b"\0")[:n]
+    hdrs = C.string_at(hp, hn.value).split(b"\0")[:n]
+    free = C.CDLL(None).free
+    free.argtypes = [C.c_void_p]
+    free(sp)
+    free(hp)
+    return list(zip(hdrs, seqs))
 
 
 def ref_tables(h):

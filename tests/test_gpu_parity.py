@@ -92,21 +92,28 @@ def test_filter_pack_gc(gm, ctx):
 
 
 def _py_fasta(image):
-    """Fasta_Read (Common/fasta.cc:236-283) restated: [(header text, sequence bytes)]."""
+    """Fasta_Read (Common/fasta.cc:236-283) restated: [(header text, sequence bytes)] -- used only where the reference
+    build (oracle/_ref) is absent; the test below pins the device parser to the reference's own reader."""
     recs, i, n = [], image.find(b">"), len(image)
     while i != -1:
-        e = image.find(b"\n", i)
+        h = i + 1
+        while h < n and image[h:h + 1] == b" ":
+            h += 1
+        if h == n:
+            break  # '>' followed by blanks and the end of the file: no record (fasta.cc:251-255)
+        e = image.find(b"\n", h)
         e = n if e == -1 else e
         nxt = image.find(b">", e)
         body = image[e:(n if nxt == -1 else nxt)]
-        recs.append((image[i + 1:e], bytes(c for c in body if c not in b" \t\n\v\f\r")))
+        recs.append((image[h:e], bytes(c for c in body if c not in b" \t\n\v\f\r")))
         i = nxt
     return recs
 
 
-@pytest.mark.parametrize("case", ["reads", "genome", "edge", "empty", "norecord"])
-def test_fasta_ingest_on_device(gm, ctx, case):
-    """gmg_seqset_from_fasta: records, headers, offsets and packed bases equal the reference reader's."""
+@pytest.mark.parametrize("case", ["reads", "genome", "edge", "edge2", "blank_tail", "empty", "norecord"])
+def test_fasta_ingest_on_device(gm, ctx, case, tmp_path):
+    """gmg_seqset_from_fasta: records, headers, offsets and packed bases equal what the UNMODIFIED reference reader
+    (Fasta_Read through oracle/_ref's shim) makes of the same bytes, incl. malformed input."""
     import gzip
     if case == "reads":
         image = gzip.open(os.path.join(G, "seqs.fa.gz"), "rb").read()
@@ -115,11 +122,19 @@ def test_fasta_ingest_on_device(gm, ctx, case):
     elif case == "edge":
         image = (b"junk before\nthe first record\n>r1 first  \r\nACGTNNacgt\r\n\r\nGG TT\tAA\n>empty\n>r3 > odd header\n"
                  b"acgRYKM>r4 starts mid line\nttt\n\n>last header without newline")
+    elif case == "edge2":
+        image = b">   leading blanks\nac gt\n>\nnoheader\n> \n\n>x\rcarriage\ronly\nGATTACA\n>tab\there\nN\n"
+    elif case == "blank_tail":
+        image = b">a\nacgt\n>   "
     elif case == "empty":
         image = b""
     else:
         image = b"no records here\nacgt\n"
     want = _py_fasta(image)
+    if O.have_ref() and hasattr(O.ref(), "ref_fasta_read_file"):
+        path = tmp_path / "in.fa"
+        path.write_bytes(image)
+        assert O.ref_fasta_records(str(path)) == want, "the restated reader disagrees with the reference's Fasta_Read"
     ss = gm.SeqSet.from_fasta(ctx, image)
     assert ss.n == len(want)
     assert [h.encode() for h in ss.headers] == [h for h, _ in want]
