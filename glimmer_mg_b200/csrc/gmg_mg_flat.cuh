@@ -352,6 +352,53 @@ MGF_HD int mgf_own_write_with(const MgfBatch& B, const MgfSeq& S, const DevParam
   return cnt;
 }
 
+// ---- the same records position by position (plain glimmer-mg: the fused K2 + K3 kernel gives every lane one position) --
+// What the serial loop above does at position j only depends on j, the call's geometry and on how many records with a
+// non-zero start coordinate came before it (`first_pos` of the reference, glimmer-mg.cc:1836-1853): the truncated records
+// sit at j_hi (and at j_hi - 3 when the coordinate at j_hi is 0); start-codon records follow at the eligible j <= jb.
+struct MgfPlan {
+  int nT;           // positions j_hi, j_hi - 3, ... that emit a truncated record
+  int state_after;  // first_pos is still 0 after them
+  int jb;           // start-codon records of the chain: eligible j <= jb with a start bit
+};
+MGF_HD int mgf_kpos(const MgfOwn& f, bool fwd, int j) { return fwd ? f.lo + f.m - 2 - j : f.lo + j + 2; }
+MGF_HD void mgf_plan(const MgfOwn& f, bool fwd, MgfPlan& pl) {
+  pl.nT = 0;
+  pl.state_after = 1;
+  int jt = f.j_hi;
+  if (f.trunc) {
+    bool state = true;
+    while (state && jt >= f.j_lo) {
+      pl.nT++;
+      if (mgf_kpos(f, fwd, jt) != 0) state = false;
+      jt -= 3;
+    }
+    pl.state_after = state ? 1 : 0;
+  }
+  pl.jb = jt < f.j_hs ? jt : f.j_hs;
+}
+// records at the eligible position j (a multiple of 3 in [j_lo, j_hi]): 0, 1 or 2.  *trunc_rec: the first of them is the
+// truncated record (which = -1, truncated, first); *chain: the position's only record is a start-codon record of the
+// chain, whose `first` flag is state_after && "no chain record with a non-zero coordinate at a higher j".
+MGF_HD int mgf_recs_at(const MgfOwn& f, const MgfPlan& pl, bool fwd, int j, bool* trunc_rec, bool* chain) {
+  const bool tpos = j > f.j_hi - 3 * pl.nT;
+  const bool bit = j <= f.j_hs && mgf_own_bit(f, fwd, j);
+  *trunc_rec = tpos;
+  *chain = !tpos && j <= pl.jb && bit;
+  if (tpos) return bit ? 2 : 1;
+  return *chain ? 1 : 0;
+}
+// index of the start codon at position j (Can_Be order), as which_at above
+MGF_HD int mgf_which_at(const MgfBatch& B, const MgfSeq& S, const unsigned char* which, const MgfOwn& f, bool fwd, int j) {
+  const int bidx = fwd ? f.hi - 1 - j : f.lo - 1 + j;
+  int cd = mgf_codon6_at(B.words, S.a + (fwd ? bidx - 2 : bidx));
+  if (!fwd) {
+    cd = 63 - cd;
+    cd = ((cd & 3) << 4) | (cd & 12) | (cd >> 4);
+  }
+  return (int)which[cd];
+}
+
 // the same with score[] read off K2's prefix-sum rows (Cumulative_Frame_Score as a difference of two entries)
 template <class Extra>
 MGF_HD int mgf_own_write(const MgfBatch& B, const MgfSeq& S, const DevParams& P, const CodonSets& cs, const MgfOwn& f, bool fwd,

@@ -245,14 +245,21 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
 // bucketed kernel would meet one and fall to its tested path, so for read sets that kernel walks EVERY window as if
 // it were full and this kernel then overwrites the 2 (W-1) x 3 partial entries of every sequence with the generic
 // walk (branch table in shared memory, leaf gathers from L2).  One thread per (sequence, end, offset).
+// kStage = false (a handful of long sequences: a few dozen items): the branch table is read from global memory instead
+// of being staged, so the kernel costs a launch and a few dependent loads rather than a 16 KB copy per CTA.
+template <bool kStage>
 __global__ void __launch_bounds__(256) k1_partial_fix(DevIcm gene, const uint64_t* __restrict__ words,
                                                       const int64_t* __restrict__ off, int64_t n_seq,
                                                       const uint32_t* __restrict__ bktidx, int64_t total,
                                                       float* __restrict__ planes) {
-  extern __shared__ int8_t s_mip[];
-  const int nmip = gene.P * gene.inner;
-  for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip[i] = gene.mip[i];
-  __syncthreads();
+  extern __shared__ int8_t s_mip_buf[];
+  const int8_t* s_mip = gene.mip;
+  if (kStage) {
+    const int nmip = gene.P * gene.inner;
+    for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip_buf[i] = gene.mip[i];
+    __syncthreads();
+    s_mip = s_mip_buf;
+  }
   const int W = gene.W, D = gene.D, per = 2 * (W - 1);
   const int64_t items = n_seq * per;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
@@ -503,10 +510,11 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     k1_planes_bucketed<U, T><<<grid, T, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr, (unsigned)s->total, segs,  \
                                                             (float*)planes);                                            \
   } while (0)
-    // every window walked as full (no partial-window test, no slow path in the hot loop), the 2 (W-1) x 3 partial
-    // entries of every sequence redone by k1_partial_fix.  GMG_K1_FIX=0 disables, =2 restricts it to read sets (the
-    // round-1 behaviour: long sequences paid the test in every trip, 7 % of K1's instructions).
-    static const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 1;
+    // read sets: every window walked as full (no partial-window test, no slow path in the hot loop), the 2 (W-1) x 3
+    // partial entries of every sequence redone by k1_partial_fix.  GMG_K1_FIX=0 disables, =1 extends it to long sequences
+    // (measured on the 5 Mbp contig: the test costs 7 % of K1's instructions, the second launch as much: 78.9 against
+    // 71.6 us, so long sequences keep the tested kernel).
+    static const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 2;
     const size_t fix_smem = (size_t)gene->dev.P * gene->dev.inner;
     const bool fix = fix_env && !(fix_env == 2 && long_seqs) && !ku_env && fix_smem <= 48 * 1024;
     if (fix) {
@@ -515,8 +523,12 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
                                                                          (unsigned)s->total, segs, (float*)planes);
       const int64_t items = s->n * 2 * (gene->W - 1);
       int64_t fg = (items + 255) / 256, fcap = (int64_t)ctx->sm_count * 8;
-      k1_partial_fix<<<(unsigned)(fg < fcap ? fg : fcap), 256, fix_smem, ctx->stream>>>(
-          gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
+      if (items >= 8192)
+        k1_partial_fix<true><<<(unsigned)(fg < fcap ? fg : fcap), 256, fix_smem, ctx->stream>>>(
+            gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
+      else  // 32 threads per CTA: the items spread over the SMs
+        k1_partial_fix<false><<<(unsigned)((items + 31) / 32), 32, 0, ctx->stream>>>(
+            gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
       ctx->launches++;
     } else if (ku == 1) GMG_K1_LAUNCH(1, 1024);
     else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
@@ -896,19 +908,37 @@ static int ensure_codon_bits(gmg_ctx* ctx, gmg_seqset* s, const CodonSets& cs) {
   return 0;
 }
 
+// One stream of the codon bitmaps as the ORF finder sees it: a CTA stages the words its tile can ask for (its own
+// 12 plus ORF_HALO below them) in shared memory; anything further down comes from global memory.
+#define ORF_TILE 1024      // bases per CTA, four consecutive bases per thread
+#define ORF_STAGE_CAP 256  // ORF records a CTA can stage in the single-pass mode
+#define ORF_HALO 2         // 2 words = 64 codons = 192 bases: every look-back of a short read stays in shared memory
+#define ORF_SW (ORF_HALO + 12)
+#define ORF_NB 129         // sequence bounds staged per CTA
+struct CbView {
+  const uint2* g;  // the six streams' words in global memory [6][nwc]
+  const uint2* s;  // staged copy of words [w0, w0 + ORF_SW) of every stream [6][ORF_SW]
+  int64_t nwc;
+  int w0;
+  __device__ __forceinline__ uint2 at(int strm, int w) const {
+    const unsigned d = (unsigned)(w - w0);
+    return d < (unsigned)ORF_SW ? s[strm * ORF_SW + d] : __ldg(g + (size_t)strm * nwc + w);
+  }
+};
+
 // Scan one stream's codon bits downwards over the slots [s_lo, s_hi]: the highest slot with a stop bit
 // (-1 = none) and, among the slots above it, the lowest (`far`) and highest (`near`) one with a start bit.
 struct BackScan {
   int stop, far, near;  // slot numbers (< 2^32 / 3: batches hold fewer than 2^32 bases), -1 = none
 };
-__device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int s_hi, int s_lo) {
+__device__ __forceinline__ BackScan scan_back(const CbView& cb, int strm, int s_hi, int s_lo) {
   BackScan r;
   r.stop = r.far = r.near = -1;
   if (s_hi < s_lo) return r;
   const int w_hi = s_hi >> 5, w_lo = s_lo >> 5;
   const unsigned m_hi = (2u << (s_hi & 31)) - 1u, m_lo = ~0u << (s_lo & 31);
   for (int w = w_hi; w >= w_lo; --w) {
-    const uint2 x = __ldg(cb + w);
+    const uint2 x = cb.at(strm, w);
     const unsigned m = (w == w_hi ? m_hi : ~0u) & (w == w_lo ? m_lo : ~0u);
     unsigned st = x.x & m;
     const unsigned sp = x.y & m;
@@ -932,22 +962,20 @@ __device__ __forceinline__ BackScan scan_back(const uint2* __restrict__ cb, int 
 // ------------------------------------------------------------------------------------------------
 // Device ORF finder (Find_Orfs, glimmer_base.cc:638-817; linear sequences, no ignore regions).
 //
-// Every ORF is created by the stop codon that closes it.  One thread per base: a base that closes an ORF (at
-// most one forward and one reverse stop, plus the Finish_Orfs reverse ORFs and the three virtual forward stops
-// at a sequence's last base) looks up the previous in-frame stop and the relevant start codon in the codon
-// bitmaps (32 codons per word).  Two passes (count, device scan of the CTA totals, write) give the
-// reference's output order deterministically: by closing base; forward before reverse; then the
-// end-of-sequence extras.
+// Every ORF is created by the stop codon that closes it.  A base that closes an ORF (at most one forward and one
+// reverse stop, plus the Finish_Orfs reverse ORFs and the three virtual forward stops at a sequence's last base)
+// looks up the previous in-frame stop and the relevant start codon in the codon bitmaps (32 codons per word).
+// The reference's output order -- by closing base; forward before reverse; then the end-of-sequence extras -- is
+// kept by ranks: count, block scan, emit inside a CTA; a device scan of the CTA totals between CTAs.
 
 // forward ORF closed by the (possibly virtual) stop codon whose last base is i (sequence coordinates).
-__device__ bool orf_fwd_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i,
-                               const DevParams& P, gmg_orf* o) {
+__device__ bool orf_fwd_closed(const CbView& cbv, int64_t a, int L, int i, const DevParams& P, gmg_orf* o) {
   // candidate codons end at t = i-3, i-6, ... >= 2, i.e. start at i-5, i-8, ... >= 0
   // 32-bit arithmetic: global base indices are below 2^32 (build_buckets checks the batch size)
   const uint32_t a32 = (uint32_t)a;
   const int r = (int)((a32 + (uint32_t)i + 1u) % 3u);
   const int s_hi = i >= 5 ? (int)((a32 + (uint32_t)i - 5u) / 3u) : -1, s_lo = (int)((a32 - (uint32_t)r + 2u) / 3u);
-  const BackScan f = scan_back(cb + (size_t)r * nwc, s_hi, s_lo);
+  const BackScan f = scan_back(cbv, r, s_hi, s_lo);
   const int prev = f.stop >= 0 ? (int)(3u * (uint32_t)f.stop + (uint32_t)r - a32) + 1 : 0;  // 1-based first base of the previous stop
   const int first_start = f.far >= 0 ? (int)(3u * (uint32_t)f.far + (uint32_t)r - a32) + 1 : INT_MAX;
   int gene_len, orf_len;
@@ -972,13 +1000,13 @@ __device__ bool orf_fwd_closed(const uint2* __restrict__ cb, int64_t nwc, int64_
 
 // reverse ORF closed at i (real reverse stop whose highest base is i), or with finish = true the
 // Finish_Orfs ORF of frame class fr = i % 3 where i is the last position of that class (< L).
-__device__ bool orf_rev_closed(const uint2* __restrict__ cb, int64_t nwc, int64_t a, int L, int i, bool finish,
-                               const DevParams& P, gmg_orf* o) {
+__device__ bool orf_rev_closed(const CbView& cbv, int64_t a, int L, int i, bool finish, const DevParams& P,
+                               gmg_orf* o) {
   const int t0 = finish ? i : i - 3;  // candidate codons end at t0, t0-3, ... >= 2
   const uint32_t a32 = (uint32_t)a;
   const int r = (int)((a32 + (uint32_t)(t0 + 1)) % 3u);  // t0 >= -1 in every call
   const int s_hi = t0 >= 2 ? (int)((a32 + (uint32_t)t0 - 2u) / 3u) : -1, s_lo = (int)((a32 - (uint32_t)r + 2u) / 3u);
-  const BackScan f = scan_back(cb + (size_t)(3 + r) * nwc, s_hi, s_lo);
+  const BackScan f = scan_back(cbv, 3 + r, s_hi, s_lo);
   const int prev = f.stop >= 0 ? (int)(3u * (uint32_t)f.stop + (uint32_t)r - a32) + 1 : 0;
   const int last_start = f.near >= 0 ? (int)(3u * (uint32_t)f.near + (uint32_t)r - a32) + 1 : 0;  // nearest to i
   int gene_len, orf_len, orf_stop;
@@ -1014,102 +1042,192 @@ __device__ bool orf_rev_closed(const uint2* __restrict__ cb, int64_t nwc, int64_
   return true;
 }
 
-// kMode 0: per-CTA ORF counts only.  kMode 1: ORF records at block_base[blockIdx] + in-block rank (second pass).
-// kMode 2: single pass -- per-CTA counts AND the records staged at slot blockIdx * ORF_STAGE_CAP + rank (a CTA with
-// more than ORF_STAGE_CAP ORFs raises *overflow and the caller re-runs the batch as two passes); k_orfs_compact
-// then moves the staged records to their final, scan-ordered places.
-#define ORF_STAGE_CAP 64
+// One CTA per tile of ORF_TILE bases.  Staged once per CTA: the sequence bounds that fall into the tile and the codon
+// bitmap words its look-backs can reach (ORF_SW per stream), so that on read sets no thread touches global memory
+// between the staging and its records.
+//   phase A  every thread tests the stop bits of its four bases and the "last base of a sequence" condition: a mask of
+//            CANDIDATE events (base x 8 kinds: forward stop, reverse stop, the three Finish_Orfs reverse ORFs, the three
+//            virtual forward stops -- the reference's order within a base); a block scan numbers them in output order
+//            and they are written, as 16-bit descriptors, to a shared-memory list;
+//   phase B  one thread per candidate evaluates it (orf_fwd_closed / orf_rev_closed), a block scan per 256 candidates
+//            ranks the ORFs that exist, and they are written at their ranks.
+// Evaluating events where they are found (one thread per base, 2-3 lanes of a warp inside the divergent look-back at any
+// time) cost 25 warp instructions per BASE: 0.65-0.8 ms per 31 Mbp, all of it instruction issue; compacted, the same
+// look-backs run with full warps.
+// kMode 1: records at block_base[blockIdx] + rank (write pass after an overflow).  kMode 2: single pass -- per-CTA
+// counts AND the records staged at slot blockIdx * ORF_STAGE_CAP + rank (a CTA with more than ORF_STAGE_CAP ORFs raises
+// *overflow and the caller re-runs the batch with kMode 1); k_orfs_compact then moves the staged records to their final,
+// scan-ordered places.
+#define ORF_CAND_CAP 4096  // candidate descriptors per round (a tile holds at most 2 * ORF_TILE + 6 * its sequence ends)
 template <int kMode>
-__global__ void __launch_bounds__(256) k_orfs(const uint64_t* __restrict__ words, const uint2* __restrict__ cb,
-                                              int64_t nwc, const int64_t* __restrict__ off,
+__global__ void __launch_bounds__(256) k_orfs(const uint2* __restrict__ cb, int64_t nwc, const int64_t* __restrict__ off,
                                               const int32_t* __restrict__ blk2seq, int64_t total, DevParams P,
                                               int64_t* __restrict__ block_counts, const int64_t* __restrict__ block_base,
                                               gmg_orf* __restrict__ orfs, int32_t* __restrict__ orf_seq,
                                               int* __restrict__ overflow, int64_t n_seq) {
   typedef cub::BlockScan<int, 256> Scan;
   __shared__ typename Scan::TempStorage tmp;
-  // Per CTA, staged once: the sequence boundaries that fall into its 256 positions (the first warp reads 33 offsets) and
-  // the stop-bit words of its codons (6 streams x 4 words), so that a position that closes nothing -- most of them --
-  // touches no global memory at all (one thread per base used to pay 3 + 2 dependent loads each: 0.62 ms per 31 Mbp).
-  constexpr int NB = 33;
-  __shared__ long long s_bound[NB];
-  __shared__ unsigned s_stop[6][4];
+  __shared__ uint2 s_cb[6][ORF_SW];
+  __shared__ long long s_bound[ORF_NB];
   __shared__ int s_s0;
-  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
-  const int64_t p = p0 + threadIdx.x;
-  const uint32_t wbase = (uint32_t)((p0 >= 2 ? p0 - 2 : 0) / 3) >> 5;
-  if (threadIdx.x < NB) {
+  __shared__ unsigned short s_cand[ORF_CAND_CAP];
+  __shared__ unsigned char s_blk[ORF_TILE / 32];
+  const int64_t p0 = (int64_t)blockIdx.x * ORF_TILE;
+  const int w0 = (int)(((p0 >= 2 ? p0 - 2 : 0) / 3) >> 5) - ORF_HALO;
+  const int t = threadIdx.x;
+  if (t < 6 * ORF_SW) {
+    const int strm = t / ORF_SW, k = t - strm * ORF_SW;
+    const int64_t w = (int64_t)w0 + k;
+    s_cb[strm][k] = (w >= 0 && w < nwc) ? __ldg(cb + (size_t)strm * nwc + w) : make_uint2(0u, 0u);
+  } else if (t >= 96 && t < 96 + ORF_NB) {
+    const int k = t - 96;
     const int32_t s0 = __ldg(blk2seq + (p0 >> 5)) & 0x7FFFFFFF;  // p0 is a multiple of 32: the sequence that holds it
-    const int64_t k = (int64_t)s0 + threadIdx.x;
-    s_bound[threadIdx.x] = k <= n_seq ? (long long)__ldg(off + k) : LLONG_MAX;
-    if (threadIdx.x == 0) s_s0 = s0;
-  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + 24) {
-    const int t = threadIdx.x - 64, strm = t >> 2, w = t & 3;
-    s_stop[strm][w] = (int64_t)wbase + w < nwc ? __ldg(cb + (size_t)strm * nwc + wbase + w).y : 0u;
+    const int64_t idx = (int64_t)s0 + k;
+    s_bound[k] = idx <= n_seq ? (long long)__ldg(off + idx) : LLONG_MAX;
+    if (k == 0) s_s0 = s0;
   }
   __syncthreads();
-  gmg_orf rec[8];
-  int n = 0;
-  int32_t sq = 0;
-  if (p < total) {
+  CbView cbv;
+  cbv.g = cb;
+  cbv.s = &s_cb[0][0];
+  cbv.nwc = nwc;
+  cbv.w0 = w0;
+  const bool staged = s_bound[ORF_NB - 1] > p0 + ORF_TILE - 1;  // all of the tile's sequences are in the staged list
+  // staged bound index of the sequence holding the first base of each 32-base block of the tile (one binary search per
+  // block instead of one per thread and candidate)
+  if (staged && t < ORF_TILE / 32) {
+    const int64_t p = p0 + 32 * t;
+    int lo = 0, hi = ORF_NB - 1;  // s_bound[lo] <= p < s_bound[hi]; empty sequences repeat a bound: the last one holds the base
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_bound[mid] <= p) lo = mid;
+      else hi = mid;
+    }
+    s_blk[t] = (unsigned char)lo;
+  }
+  __syncthreads();
+  // the sequence holding global base p: index, first base, length
+  auto seq_of = [&](int64_t p, int32_t* sq, int64_t* a, int* L) {
+    if (staged) {  // largest k with s_bound[k] <= p
+      int k = s_blk[(int)(p - p0) >> 5];
+      while (s_bound[k + 1] <= p) k++;
+      *sq = s_s0 + k;
+      *a = s_bound[k];
+      *L = (int)(s_bound[k + 1] - s_bound[k]);
+    } else {
+      SeqView sv = locate(off, blk2seq, p, sq);
+      *a = sv.a;
+      *L = sv.len;
+    }
+  };
+  // ---- phase A: candidate mask of this thread's bases pt .. pt + 3 (bit 8 m + kind)
+  const int64_t pt = p0 + 4 * t;
+  unsigned cm = 0;
+  if (pt < total) {
+    int32_t sq;
     int64_t a;
     int L;
-    if (s_bound[NB - 1] > p0 + 255) {  // all of the CTA's sequences are in the staged list
-      int k = 0;
-      while (s_bound[k + 1] <= p) k++;
-      sq = s_s0 + k;
-      a = s_bound[k];
-      L = (int)(s_bound[k + 1] - a);
-    } else {  // more than 32 sequences inside 256 bases: look it up
-      SeqView sv = locate(off, blk2seq, p, &sq);
-      a = sv.a;
-      L = sv.len;
+    seq_of(pt, &sq, &a, &L);
+    int64_t next = a + L;
+    const uint32_t c0 = (uint32_t)(pt >= 2 ? pt - 2 : 0);
+    uint32_t r = c0 % 3u, sl = c0 / 3u;
+    if (pt < 2) {  // bases 0, 1 of the batch close no codon; the codon of base 2 is (r, sl) = (0, 0)
+      r = (uint32_t)((pt + 1) % 3);  // so that after (2 - pt) steps r == 0
+      sl = 0;
     }
-    const int q = (int)(p - a);
-    if (L >= P.min_gene_len) {
-      if (q >= 2) {  // the codon q-2 .. q: forward stop / reverse stop?
-        const uint32_t c = (uint32_t)(p - 2);
-        const int r = (int)(c % 3u);
-        const uint32_t sl = c / 3u;
-        const unsigned bit = 1u << (sl & 31u);
-        const uint32_t w = (sl >> 5) - wbase;  // 0 .. 3
-        if (s_stop[r][w] & bit) n += orf_fwd_closed(cb, nwc, a, L, q, P, &rec[n]);
-        if (s_stop[3 + r][w] & bit) n += orf_rev_closed(cb, nwc, a, L, q, false, P, &rec[n]);
-      }
-      if (q == L - 1) {
-        for (int fr = 0; fr < 3; fr++) {
-          int i = L - 1 - mod3(L - 1 - fr);  // last index of class fr that is < L
-          if (i < 0) i = fr;                 // degenerate; the search range is empty
-          if (orf_rev_closed(cb, nwc, a, L, i, true, P, &rec[n])) {
-            rec[n].frame = -1 - (fr + 1) % 3;  // only depends on fr (= i % 3 when i >= 0)
-            n++;
-          }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int64_t p = pt + m;
+      if (p < total) {
+        if (p >= next) {  // the next non-empty sequence
+          seq_of(p, &sq, &a, &L);
+          next = a + L;
         }
-        if (P.allow_truncated)
-          for (int i = L; i < L + 3; i++) n += orf_fwd_closed(cb, nwc, a, L, i, P, &rec[n]);
+        const int q = (int)(p - a);
+        if (L >= P.min_gene_len) {
+          if (q >= 2) {  // the codon q-2 .. q: forward stop / reverse stop?
+            const unsigned d = (unsigned)((int)(sl >> 5) - w0);  // < ORF_SW by construction of the stage
+            const unsigned bit = 1u << (sl & 31u);
+            if (s_cb[r][d].y & bit) cm |= 1u << (8 * m);
+            if (s_cb[3 + r][d].y & bit) cm |= 2u << (8 * m);
+          }
+          if (q == L - 1) cm |= (P.allow_truncated ? 0xFCu : 0x1Cu) << (8 * m);
+        }
+      }
+      if (p >= 2) {  // advance (r, sl) to the codon ending at p + 1
+        if (++r == 3u) {
+          r = 0;
+          sl++;
+        }
+      } else {
+        r = (r + 1u) % 3u;
       }
     }
   }
-  int rank, block_total;
-  Scan(tmp).ExclusiveSum(n, rank, block_total);
-  if (kMode == 1) {
-    const int64_t base = block_base[blockIdx.x] + rank;
-    for (int k = 0; k < n; k++) {
-      orfs[base + k] = rec[k];
-      orf_seq[base + k] = sq;
-    }
-  } else {
-    if (kMode == 2 && block_total <= ORF_STAGE_CAP) {
-      const int64_t base = (int64_t)blockIdx.x * ORF_STAGE_CAP + rank;
-      for (int k = 0; k < n; k++) {
-        orfs[base + k] = rec[k];
-        orf_seq[base + k] = sq;
+  int my_n = __popc(cm), my_off, n_cand;
+  Scan(tmp).ExclusiveSum(my_n, my_off, n_cand);
+  int64_t out_base = kMode == 1 ? block_base[blockIdx.x] : (int64_t)blockIdx.x * ORF_STAGE_CAP;
+  int placed = 0;  // ORFs of this tile written (or counted) so far
+  // ---- rounds of at most ORF_CAND_CAP candidates (one round unless the tile is full of tiny sequences)
+  for (int r0 = 0; r0 < n_cand; r0 += ORF_CAND_CAP) {
+    __syncthreads();  // the list (and the scan's storage) are free again
+    {
+      unsigned x = cm;
+      int i = my_off;
+      while (x) {
+        const int b = __ffs(x) - 1;
+        x &= x - 1u;
+        if (i >= r0 && i < r0 + ORF_CAND_CAP) s_cand[i - r0] = (unsigned short)(((4 * t + (b >> 3)) << 3) | (b & 7));
+        i++;
       }
     }
-    if (threadIdx.x == 0) {
-      block_counts[blockIdx.x] = block_total;
-      if (kMode == 2 && block_total > ORF_STAGE_CAP) *overflow = 1;
+    __syncthreads();
+    const int n_round = min(n_cand - r0, ORF_CAND_CAP);
+    // ---- phase B
+    for (int c0 = 0; c0 < n_round; c0 += 256) {
+      const int i = c0 + t;
+      gmg_orf rec;
+      int32_t sq = 0;
+      int ok = 0;
+      if (i < n_round) {
+        const unsigned dsc = s_cand[i];
+        const int kind = (int)(dsc & 7u);
+        const int64_t p = p0 + (int64_t)(dsc >> 3);
+        int64_t a;
+        int L;
+        seq_of(p, &sq, &a, &L);
+        const int q = (int)(p - a);
+        // two code paths for the eight kinds, so a warp of mixed candidates runs each look-back at most twice
+        if (kind == 0 || kind >= 5) {
+          ok = orf_fwd_closed(cbv, a, L, kind == 0 ? q : L + (kind - 5), P, &rec);
+        } else {
+          const bool finish = kind != 1;
+          const int fr = kind - 2;
+          int ii = q;
+          if (finish) {
+            ii = L - 1 - mod3(L - 1 - fr);  // last index of class fr that is < L
+            if (ii < 0) ii = fr;            // degenerate; the search range is empty
+          }
+          ok = orf_rev_closed(cbv, a, L, ii, finish, P, &rec);
+          if (finish) rec.frame = -1 - (fr + 1) % 3;  // only depends on fr (= ii % 3 when ii >= 0)
+        }
+      }
+      int rank, found;
+      __syncthreads();
+      Scan(tmp).ExclusiveSum(ok, rank, found);
+      if (ok) {
+        const int slot = placed + rank;
+        if (kMode == 1 || slot < ORF_STAGE_CAP) {
+          orfs[out_base + slot] = rec;
+          orf_seq[out_base + slot] = sq;
+        }
+      }
+      placed += found;
     }
+  }
+  if (kMode == 2 && t == 0) {
+    block_counts[blockIdx.x] = placed;
+    if (placed > ORF_STAGE_CAP) *overflow = 1;
   }
 }
 
@@ -1199,7 +1317,7 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
     return 0;
   }
   if (ensure_codon_bits(ctx, s, cs)) return 1;
-  int64_t nblk = (s->total + 255) / 256;
+  int64_t nblk = (s->total + ORF_TILE - 1) / ORF_TILE;
   void* d_counts;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(2 * (nblk + 1)) * sizeof(int64_t), &d_counts)) return 1;
   int64_t* counts = (int64_t*)d_counts;
@@ -1214,8 +1332,8 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
   int* d_overflow = (int*)(st_seq + stage_slots);
   GMG_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int), ctx->stream));
   if (gmg_prof_begin(ctx, GMG_PROF_ORF)) return 1;
-  k_orfs<2><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total, dp,
-                                                     counts, NULL, st_orfs, st_seq, d_overflow, s->n);
+  k_orfs<2><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total, dp, counts, NULL,
+                                                     st_orfs, st_seq, d_overflow, s->n);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());
@@ -1234,8 +1352,8 @@ extern "C" int gmg_find_orfs(gmg_ctx* ctx, gmg_seqset* s, const gmg_params* p, i
     k_orfs_compact<<<(unsigned)((stage_slots + 255) / 256), 256, 0, ctx->stream>>>(st_orfs, st_seq, bases, nblk, s->d_orfs,
                                                                                  s->d_orf_seq);
   else  // some CTA found more ORFs than it could stage: write pass over the whole batch
-    k_orfs<1><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_words, s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total,
-                                                       dp, NULL, bases, s->d_orfs, s->d_orf_seq, NULL, s->n);
+    k_orfs<1><<<(unsigned)nblk, 256, 0, ctx->stream>>>(s->d_cbits, s->nwc, s->d_off, s->d_blk2seq, s->total, dp, NULL, bases,
+                                                       s->d_orfs, s->d_orf_seq, NULL, s->n);
   gmg_prof_end(ctx, GMG_PROF_ORF);
   k_orf_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->d_orf_seq, total_orfs, s->n, s->d_orf_off);
   ctx->launches += 2;
@@ -2849,7 +2967,7 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
                                                    const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                    int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                    gmg_start* __restrict__ starts, int exact_len,
-                                                   unsigned long long* __restrict__ n_ordered, int slots) {
+                                                   unsigned long long* __restrict__ n_ordered, int slots, int lanes) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double s_pref_all[];  // [4 warps][slots]: sized for the batch's longest sequence (occupancy on short reads)
   __shared__ float s_lut[384];
@@ -2871,6 +2989,7 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   double* pref = s_pref_all + (size_t)wid * slots;
   // score[j] for j < j_hi is all the records can ask for (score[j - 1] at their own j <= j_hi)
   const int need = f.j_hi;  // terms j = 0 .. need - 1
+  if (lanes && need <= 96 * 4 && f.j_lo >= 3) return;  // k3_mg_plain_lanes has written this ORF (mgl_takes)
   if (lane == 0) pref[0] = 0.0;
   // warp-parallel scan; its sums carry the reference's bits whenever the ORF's certificate holds: every term is a
   // multiple of 2^g (g from the smallest float exponent the ORF meets) and the sum of magnitudes stays below 2^(g+52),
@@ -2923,6 +3042,134 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
     const int ep[2] = {0, 0}, et[2] = {0, 0};
     mgf_own_write_with(B, S, P, cs, f, fwd, 0.0, 0, 0, ep, et, starts + so, [](int) { return (int64_t)0; },
                        [&](int j) { return pref[j / 3]; });
+  }
+}
+
+// The fused pass with ONE CODON PER LANE -- the default for ORFs of up to 96 * MGL_K scored bases (every ORF of a
+// short-read set).  The warp-per-ORF kernel above spends a 5-step FP64 scan on every 32 bases and a serial record
+// writer on lane 0: ~1 200 warp instructions per ORF, 0.60 ms per 31 Mbp batch, all of it instruction issue.  Here a lane
+// sums the three terms of one codon, ONE scan per 96 bases gives every codon-boundary prefix, and the lanes write the
+// records of their own positions (mgf_plan / mgf_recs_at: the position-by-position form of the reference's start loop,
+// held to the oracle on the host by tests/mgflat_host_check.cu).
+// Exactness as above: the per-ORF certificate (smallest term exponent, sum of magnitudes); an ORF without one is summed
+// by lane 0 in the reference's serial order into a shared-memory row and the lanes take their prefixes from there.
+// ORFs with more than 96 * MGL_K scored bases, or with j_lo < 3, are left to k3_mg_plain.
+#define MGL_K 4
+__device__ __forceinline__ bool mgl_takes(int need, int j_lo) { return need <= 96 * MGL_K && j_lo >= 3; }
+
+__global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
+                                                         const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, CodonSets cs,
+                                                         const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                         int64_t n_orfs, const int64_t* __restrict__ start_off,
+                                                         gmg_start* __restrict__ starts, int exact_len,
+                                                         unsigned long long* __restrict__ n_ordered) {
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ float s_lut[384];
+  __shared__ unsigned char s_which[64];
+  __shared__ double s_serial[4][32 * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
+  if (indep.lut3 != NULL)
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
+  if (threadIdx.x < 64) s_which[threadIdx.x] = cs.which[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (o >= n_orfs) return;  // warp-uniform
+  const int64_t so = __ldg(start_off + o), so1 = __ldg(start_off + o + 1);
+  const int32_t sq = __ldg(orf_seq + o);
+  const gmg_orf orf = orfs[o];
+  if (so1 == so) return;
+  const MgfSeq S = mgf_seq_of(B, sq);
+  const bool fwd = orf.frame > 0;
+  const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
+  const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
+  MgfOwn f;
+  mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+  const int need = f.j_hi;  // terms j = 0 .. need - 1: score[j - 1] of the highest record position j_hi
+  if (!mgl_takes(need, f.j_lo)) return;
+  MgfPlan pl;
+  mgf_plan(f, fwd, pl);
+  const int ncod = need / 3, nch = (ncod + 31) >> 5;
+  double incl[MGL_K];
+  double carry = 0.0;
+  unsigned umin = 0x7fffffffu;
+  float asum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MGL_K; k++) {
+    incl[k] = 0.0;
+    if (k < nch) {  // warp-uniform
+      const int c = 32 * k + lane;
+      double x = 0.0;
+      if (c < ncod) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const int j = 3 * c + t;
+          float g, n;
+          mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + t) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+          k2_cert_term(g, umin, asum);
+          k2_cert_term(n, umin, asum);
+          x = x + ((double)g - (double)n);
+        }
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+      }
+      x += carry;
+      incl[k] = x;  // score[3 (c + 1) - 1]
+      carry = __shfl_sync(FULL, x, 31);
+    }
+  }
+  umin = __reduce_min_sync(FULL, umin);
+  double asum_d = (double)asum;  // at most 6 * MGL_K float additions per lane: the 0.1 % margin covers their rounding
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) asum_d += __shfl_xor_sync(FULL, asum_d, d);
+  const int e = (int)(umin >> 23);
+  const bool exact = exact_len >= 0 && (umin == 0x7fffffffu || asum_d * 1.001 < ldexp(1.0, (e > 0 ? e : 1) - 150 + 52));
+  if (!exact) {  // no certificate: the reference's own order, one lane
+    if (lane == 0) {
+      atomicAdd(n_ordered, 1ull);
+      double run = 0.0;
+      for (int j = 0; j < need; j++) {
+        float g, n;
+        mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+        run = run + ((double)g - (double)n);
+        if ((j + 1) % 3 == 0) s_serial[wid][j / 3] = run;
+      }
+    }
+    __syncwarp();
+  }
+  // records, from the highest position down: lane = position j = 3 (c + 1)
+  const unsigned higher = lane == 31 ? 0u : ~((2u << lane) - 1u);
+  int placed = 0;
+  bool seen_nonzero = false;
+  const int ep[2] = {0, 0}, et[2] = {0, 0};
+  gmg_start* out = starts + so;
+#pragma unroll
+  for (int k = MGL_K - 1; k >= 0; k--) {
+    if (k < nch) {  // warp-uniform
+      const int c = 32 * k + lane, j = 3 * (c + 1);
+      bool trunc_rec = false, chain = false;
+      int nr = 0;
+      if (c < ncod && j >= f.j_lo) nr = mgf_recs_at(f, pl, fwd, j, &trunc_rec, &chain);
+      const int kp = mgf_kpos(f, fwd, j);
+      const unsigned m1 = __ballot_sync(FULL, nr >= 1), m2 = __ballot_sync(FULL, nr == 2);
+      const unsigned mnz = __ballot_sync(FULL, chain && kp != 0);
+      if (nr) {
+        const int idx = placed + __popc(m1 & higher) + __popc(m2 & higher);
+        const double sum = exact ? incl[k] : s_serial[wid][c];
+        const double sc = (sum - 0.0) + 0.0;
+        if (trunc_rec) {
+          mgf_put(out + idx, P, j + 2, kp, sc, -1, 1, 1, 0, ep, et);
+          if (nr == 2) mgf_put(out + idx + 1, P, j + 2, kp, sc, mgf_which_at(B, S, s_which, f, fwd, j), 0, 0, 0, ep, et);
+        } else {
+          const int first = (pl.state_after && !seen_nonzero && (mnz & higher) == 0u) ? 1 : 0;
+          mgf_put(out + idx, P, j + 2, kp, sc, mgf_which_at(B, S, s_which, f, fwd, j), 0, first, 0, ep, et);
+        }
+      }
+      placed += __popc(m1) + __popc(m2);
+      seen_nonzero = seen_nonzero || mnz != 0u;
+    }
   }
 }
 
@@ -3014,14 +3261,19 @@ __global__ void __launch_bounds__(128) k3_mg_reduce(const gmg_start* __restrict_
                                                     const int64_t* __restrict__ off, int64_t n_orfs, DevEventModel M,
                                                     int slots_per_warp, gmg_start* __restrict__ out,
                                                     unsigned long long* __restrict__ cursor, int64_t* __restrict__ red_first,
-                                                    int32_t* __restrict__ red_cnt, uint8_t* __restrict__ status) {
+                                                    int32_t* __restrict__ red_cnt, uint8_t* __restrict__ status,
+                                                    const uint32_t* __restrict__ big,
+                                                    const unsigned long long* __restrict__ n_big) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr double TOL = 1e-9;
   extern __shared__ __align__(16) unsigned char s_red[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (o >= n_orfs) return;  // warp-uniform
   RedSlot* tab = reinterpret_cast<RedSlot*>(s_red) + (size_t)wid * slots_per_warp;
+  // the ORFs k3_mg_reduce_small left over (big != NULL: their list and its length on the device), else all of them
+  const int64_t n_items = big ? (int64_t)*n_big : n_orfs;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += n_warps) {  // warp-uniform
+  const int64_t o = big ? (int64_t)big[item] : item;
   const int64_t a = soff[o];
   const int n = (int)(soff[o + 1] - a);
   const gmg_start* rec = starts + a;
@@ -3142,6 +3394,143 @@ __global__ void __launch_bounds__(128) k3_mg_reduce(const gmg_start* __restrict_
     red_cnt[o] = st == 1 ? kept : 0;
     red_first[o] = first;
   }
+  __syncwarp();
+  }
+}
+
+// The same decisions for ORFs with at most RED_SMALL raw records, ONE THREAD per ORF, everything in registers: on plain
+// read sets nearly every ORF has one to three records and a warp per ORF spent 680 instructions on each (0.38 ms per
+// 31 Mbp batch, all of it instruction issue).  ORFs with more records are appended to `big` for k3_mg_reduce.
+#define RED_SMALL 4
+__global__ void __launch_bounds__(128) k3_mg_reduce_small(const gmg_start* __restrict__ starts, const int64_t* __restrict__ soff,
+                                                          const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
+                                                          const int64_t* __restrict__ off, int64_t n_orfs, DevEventModel M,
+                                                          gmg_start* __restrict__ out, unsigned long long* __restrict__ cursor,
+                                                          int64_t* __restrict__ red_first, int32_t* __restrict__ red_cnt,
+                                                          uint8_t* __restrict__ status, uint32_t* __restrict__ big,
+                                                          unsigned long long* __restrict__ n_big) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr double TOL = 1e-9;
+  const int lane = threadIdx.x & 31;
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n = 0, st = 0, kept = 0;
+  int64_t a = 0;
+  if (o < n_orfs) {
+    a = soff[o];
+    n = (int)(soff[o + 1] - a);
+  }
+  const bool is_big = n > RED_SMALL;
+  unsigned keep_mask = 0;  // bit i: record i survives
+  if (n > 0 && !is_big) {
+    const gmg_start* rec = starts + a;
+    const gmg_orf orf = orfs[o];
+    const bool fwd = orf.frame > 0;
+    const int32_t sq = orf_seq[o];
+    const int L = (int)(off[sq + 1] - off[sq]);
+    const int cls = M.seq_class ? M.seq_class[sq] : 0;
+    const bool t3 = fwd ? orf.stop_position > L - 2 : orf.stop_position < 1;
+    const double* lenrow = M.len_lo + (size_t)cls * 4 * M.n_len;
+    int pos[RED_SMALL], jj[RED_SMALL];
+    double x[RED_SMALL];
+    bool elig[RED_SMALL];
+    int pmin = INT_MAX, pmax = INT_MIN;
+    double best = -DBL_MAX;
+    bool too_long = false;
+#pragma unroll
+    for (int i = 0; i < RED_SMALL; i++) {
+      pos[i] = 0;
+      jj[i] = 0;
+      x[i] = 0.0;
+      elig[i] = false;
+      if (i < n) {
+        const gmg_start r = rec[i];
+        pos[i] = r.pos;
+        jj[i] = r.j;
+        pmin = min(pmin, r.pos);
+        pmax = max(pmax, r.pos);
+        best = fmax(best, r.score);
+        if (1 + r.j >= M.min_gene_len) {
+          const int l = (1 + r.j) / 3;
+          if (l >= M.n_len) {
+            too_long = true;
+          } else {
+            double v = r.score + M.prior;
+            if (r.which >= 0) v += M.start_lo[r.which & 7];
+            v += lenrow[(size_t)((r.truncated ? 2 : 0) + (t3 ? 1 : 0)) * M.n_len + l];
+            x[i] = v;
+            elig[i] = v + M.pwm_bonus_max > M.event_threshold - TOL;
+          }
+        }
+      }
+    }
+    const int ext = fwd ? pmin : pmax;
+    bool pass_any = false, fail_any = false;
+#pragma unroll
+    for (int i = 0; i < RED_SMALL; i++)
+      if (i < n && pos[i] == ext) {
+        if (jj[i] + 1 >= M.min_gene_len) pass_any = true;
+        else fail_any = true;
+      }
+    if (too_long || (pass_any && fail_any)) {
+      st = 2;
+    } else if (!pass_any || !(best > M.start_threshold)) {
+      st = 0;
+    } else {
+      st = 1;
+      bool amb = false;
+#pragma unroll
+      for (int i = 0; i < RED_SMALL; i++) {
+        if (i < n && elig[i]) {
+          double mx = x[i];
+#pragma unroll
+          for (int k = 0; k < RED_SMALL; k++)
+            if (k < n && elig[k] && pos[k] == pos[i]) mx = fmax(mx, x[k]);
+          if (x[i] >= mx - TOL) {  // within TOL of its position's maximum
+#pragma unroll
+            for (int k = 0; k < RED_SMALL; k++)
+              if (k != i && k < n && elig[k] && pos[k] == pos[i] && x[k] >= mx - TOL) amb = true;
+            keep_mask |= 1u << i;
+          }
+        }
+      }
+      if (amb) {
+        st = 2;
+        keep_mask = 0;
+      }
+      kept = __popc(keep_mask);
+    }
+  }
+  // one cursor bump and one list bump per warp
+  int incl = kept;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int warp_kept = __shfl_sync(FULL, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && warp_kept) base = atomicAdd(cursor, (unsigned long long)warp_kept);
+  base = __shfl_sync(FULL, base, 31);
+  const unsigned bigs = __ballot_sync(FULL, is_big);
+  unsigned long long bbase = 0;
+  if (lane == 0 && bigs) bbase = atomicAdd(n_big, (unsigned long long)__popc(bigs));
+  bbase = __shfl_sync(FULL, bbase, 0);
+  if (o >= n_orfs) return;
+  if (is_big) {
+    big[bbase + (unsigned)__popc(bigs & ((1u << lane) - 1u))] = (uint32_t)o;
+    return;
+  }
+  long long first = 0;
+  if (kept) {
+    first = (long long)(base + (unsigned long long)(incl - kept));
+    const gmg_start* rec = starts + a;
+    long long at = first;
+    for (int i = 0; i < n; i++)
+      if (keep_mask >> i & 1u) out[at++] = rec[i];
+  }
+  status[o] = (uint8_t)st;
+  red_cnt[o] = st == 1 ? kept : 0;
+  red_first[o] = first;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3420,13 +3809,26 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
       ctx->launches++;
       GMG_CUDA(cudaGetLastError());
     } else if (total_starts > 0) {
+      // one codon per lane for ORFs of up to 96 * MGL_K scored bases; the warp-per-ORF scan for whatever is left.
+      // GMG_PLAIN_LANES=0: all of them through the latter (A/B runs, tests).
+      static const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 1;
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-      const int slots = (int)(s->max_len / 3 + 4);
-      k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, (size_t)4 * slots * sizeof(double), ctx->stream>>>(
-          indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
-          (unsigned long long*)(counts + s->n_orfs + 1), slots);
+      if (plain_lanes) {
+        k3_mg_plain_lanes<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+            indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
+            (unsigned long long*)(counts + s->n_orfs + 1));
+        ctx->launches++;
+      }
+      // every ORF taken above?  (need <= orf_len <= max_len; j_lo >= 3 whenever min_gene_len >= 6)
+      const bool all_taken = plain_lanes && s->max_len <= 96 * 4 && p->min_gene_len >= 6;
+      if (!all_taken) {
+        const int slots = (int)(s->max_len / 3 + 4);
+        k3_mg_plain<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, (size_t)4 * slots * sizeof(double), ctx->stream>>>(
+            indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
+            (unsigned long long*)(counts + s->n_orfs + 1), slots, plain_lanes);
+        ctx->launches++;
+      }
       gmg_prof_end(ctx, GMG_PROF_K3);
-      ctx->launches++;
       GMG_CUDA(cudaGetLastError());
     }
     s->n_starts = total_starts;
@@ -3675,7 +4077,7 @@ extern "C" int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_param
   const size_t len_bytes = (size_t)em->n_class * 4 * em->n_len * sizeof(double);
   const size_t cls_bytes = em->seq_class ? (size_t)s->n * sizeof(int32_t) : 0;
   const size_t hdr = ((len_bytes + cls_bytes + 128 + 255) / 256) * 256;
-  const size_t per_orf = sizeof(int64_t) + sizeof(int32_t) + 1;
+  const size_t per_orf = sizeof(int64_t) + sizeof(int32_t) + sizeof(uint32_t) + 1;
   const size_t meta = (((size_t)s->n_orfs * per_orf + 64 + 255) / 256) * 256;
   void* d_red;
   if (gmg_scratch(ctx, SCR_RED, hdr + meta + ((size_t)s->n_starts + 1) * sizeof(gmg_start), &d_red)) return 1;
@@ -3685,7 +4087,8 @@ extern "C" int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_param
   unsigned long long* d_cursor = (unsigned long long*)(base + hdr - 64);
   int64_t* d_first = (int64_t*)(base + hdr);
   int32_t* d_cnt = (int32_t*)(d_first + s->n_orfs);
-  uint8_t* d_status = (uint8_t*)(d_cnt + s->n_orfs);
+  uint32_t* d_big = (uint32_t*)(d_cnt + s->n_orfs);
+  uint8_t* d_status = (uint8_t*)(d_big + s->n_orfs);
   gmg_start* d_out = (gmg_start*)(base + hdr + meta);
   GMG_CUDA(cudaMemcpyAsync(d_len, em->len_lo, len_bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (d_cls) GMG_CUDA(cudaMemcpyAsync(d_cls, em->seq_class, cls_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -3707,9 +4110,23 @@ extern "C" int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_param
   const size_t smem = (size_t)4 * slots * sizeof(RedSlot);
   if (smem > 48 * 1024) GMG_CUDA(cudaFuncSetAttribute(k3_mg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-  k3_mg_reduce<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, smem, ctx->stream>>>(
-      s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, slots, d_out, d_cursor, d_first, d_cnt,
-      d_status);
+  // GMG_RED_SMALL=0: every ORF through the warp-per-ORF kernel (A/B and test hook)
+  static const int red_small = getenv("GMG_RED_SMALL") ? atoi(getenv("GMG_RED_SMALL")) : 1;
+  if (red_small) {
+    k3_mg_reduce_small<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(
+        s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, d_out, d_cursor, d_first, d_cnt, d_status,
+        d_big, d_cursor + 1);
+    // the ORFs with more than RED_SMALL records: a warp each, as many warps as the machine holds
+    int64_t ctas = (s->n_orfs * 32 + 127) / 128, cap = (int64_t)ctx->sm_count * 12;
+    k3_mg_reduce<<<(unsigned)(ctas < cap ? ctas : cap), 128, smem, ctx->stream>>>(
+        s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, slots, d_out, d_cursor, d_first, d_cnt,
+        d_status, d_big, d_cursor + 1);
+    ctx->launches++;
+  } else {
+    k3_mg_reduce<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, smem, ctx->stream>>>(
+        s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, slots, d_out, d_cursor, d_first, d_cnt,
+        d_status, NULL, NULL);
+  }
   gmg_prof_end(ctx, GMG_PROF_K3);
   ctx->launches++;
   GMG_CUDA(cudaGetLastError());

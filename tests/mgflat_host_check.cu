@@ -320,6 +320,68 @@ int main(int argc, char** argv) {
         break;
       }
   }
+  // plain mode: the position-by-position form of a root call's records (mgf_plan / mgf_recs_at, what the lanes of the
+  // fused kernel evaluate) against the same oracle lists
+  if (!op.allow_indels && !op.allow_subs) {
+    for (uint32_t o = 0; o < n_orfs && bad < 10; o++) {
+      const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+      const gmg_orf orf = orfs[o];
+      const bool fwd = orf.frame > 0;
+      const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
+      const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
+      MgfOwn f;
+      mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+      MgfPlan pl;
+      mgf_plan(f, fwd, pl);
+      const double* row = mgf_row(B, S, fwd, lo, hi);
+      const double cbase = mgf_cbase(B, S, fwd, lo, hi);
+      std::vector<gmg_start> got;
+      bool seen_nonzero = false;
+      const int ep[2] = {0, 0}, et[2] = {0, 0};
+      if (f.j_hi >= f.j_lo)
+        for (int j = f.j_hi; j >= f.j_lo; j -= 3) {
+          bool trunc_rec, chain;
+          const int nr = mgf_recs_at(f, pl, fwd, j, &trunc_rec, &chain);
+          if (nr == 0) continue;
+          const double sc = (mgf_score(S, fwd, row, lo, hi, cbase, j - 1) - 0.0) + 0.0;
+          const int k = mgf_kpos(f, fwd, j);
+          gmg_start st;
+          memset(&st, 0, sizeof st);
+          if (trunc_rec) {
+            mgf_put(&st, P, j + 2, k, sc, -1, 1, 1, 0, ep, et);
+            got.push_back(st);
+            if (nr == 2) {
+              mgf_put(&st, P, j + 2, k, sc, mgf_which_at(B, S, cs.which, f, fwd, j), 0, 0, 0, ep, et);
+              got.push_back(st);
+            }
+          } else {
+            mgf_put(&st, P, j + 2, k, sc, mgf_which_at(B, S, cs.which, f, fwd, j), 0, (pl.state_after && !seen_nonzero) ? 1 : 0, 0, ep,
+                    et);
+            got.push_back(st);
+            if (k != 0) seen_nonzero = true;
+          }
+        }
+      const int64_t wa = want_off[o], wb = want_off[o + 1];
+      if ((int64_t)got.size() != wb - wa) {
+        printf("lane form: ORF %u: %zu records, oracle %lld\n", o, got.size(), (long long)(wb - wa));
+        bad++;
+        continue;
+      }
+      for (size_t k = 0; k < got.size(); k++) {
+        gmg_start w;
+        memcpy(&w, &want[wa + k], sizeof w);
+        // padding bytes of the host-built record are zero as in mgf_put's full assignment: compare field by field
+        const gmg_start& g = got[k];
+        if (g.j != w.j || g.pos != w.pos || memcmp(&g.score, &w.score, 8) != 0 || g.which != w.which || g.truncated != w.truncated ||
+            g.first != w.first || g.n_err != w.n_err) {
+          printf("lane form: ORF %u record %zu: got j=%d pos=%d sc=%.17g w=%d t=%d f=%d  want j=%d pos=%d sc=%.17g w=%d t=%d f=%d\n", o, k,
+                 g.j, g.pos, g.score, g.which, g.truncated, g.first, w.j, w.pos, w.score, w.which, w.truncated, w.first);
+          bad++;
+          break;
+        }
+      }
+    }
+  }
   printf("%s: %lld reads, %u ORFs, %u level-1 candidates, %u level-2 candidates, %lld starts (oracle %zu)\n", bad ? "MISMATCH" : "OK",
          (long long)n, n_orfs, W.c1, W.c2, (long long)n_starts, want.size());
   return bad ? 1 : 0;

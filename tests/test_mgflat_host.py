@@ -34,7 +34,9 @@ def harness():
 
 # (reads, allow_indels, allow_subs, indel_max, truncate_len)
 @pytest.mark.parametrize("args", [(400, 1, 0, 2, 0), (400, 0, 1, 2, 0), (300, 1, 1, 2, 0), (400, 1, 0, 1, 0), (400, 0, 0, 2, 0),
-                                  (999, 1, 0, 2, 100), (300, 1, 1, 2, 76), (200, 1, 1, 2, 13)])
+                                  (999, 1, 0, 2, 100), (300, 1, 1, 2, 76), (200, 1, 1, 2, 13),
+                                  (999, 0, 0, 2, 100), (999, 0, 0, 2, 99), (999, 0, 0, 2, 98), (600, 0, 0, 2, 77),
+                                  (300, 0, 0, 2, 13)])
 def test_flat_enumeration_equals_oracle_on_the_host(harness, args):
     n, ai, asub, imax, trunc = args
     r = subprocess.run([EXE, os.path.join(ROOT, "tests", "golden", "NC_000915.icm"), harness, str(n), str(ai), str(asub),
