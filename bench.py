@@ -674,11 +674,14 @@ def run_b200_reads(args, env, kind):
             else:
                 ts, toff = cluster_training_strings(k)
                 genes[k] = g.ICMTraining(ctx, 12, 7, 3).Train_Model(g.SeqSet(ctx, ascii=ts, offsets=toff), reverse=True)
-        pinned, sets, indeps, params, gcs = [], [], [], [], []
+        pinned, pinned_off, sets, indeps, params, gcs = [], [], [], [], [], []
         for a, off, k in batches:
             h = torch.empty(len(a), dtype=torch.uint8).pin_memory()
             h.numpy()[:] = a
             pinned.append(h)
+            ho = torch.empty(len(off), dtype=torch.int64).pin_memory()  # the sequence offsets travel with the bases
+            ho.numpy()[:] = off
+            pinned_off.append(ho)
             ss = g.SeqSet(ctx, ascii=h.numpy(), offsets=off)
             gc = ss.gc_fraction()
             gcs.append(gc)
@@ -734,7 +737,7 @@ def run_b200_reads(args, env, kind):
             a.record(stream)
             # the call sequence of the chunk-level glimmer-mg binding (host/mg_score_orfs_dropin.inc): ORF table and the
             # REDUCED start lists (one candidate per ORF and start position, row a11b) come back to the host
-            s2 = g.SeqSet(ctx, ascii=pinned[j].numpy(), offsets=batches[j][1])
+            s2 = g.SeqSet(ctx, ascii=pinned[j].numpy(), offsets=pinned_off[j].numpy())
             s2.find_orfs(params[j])
             orfs, ooff = s2.get_orfs(pinned=True)
             s2.score_orfs_mg(genes[batches[j][2]], indeps[j], params[j])
@@ -771,22 +774,26 @@ def run_b200_reads(args, env, kind):
                       "reduction": rs, "raw_starts": int(s2.n_starts), "surviving_starts": int(len(red)),
                       "uncertified_reads": int(s2.uncertified)}
         s2.close()
-        # ---- end to end with TWO batches in flight: the same call sequence from two host threads, each with its own
+        # ---- end to end with N_LANES batches in flight: the same call sequence from N_LANES host threads, each with its own
         # context and stream, so that one batch's H2D / D2H copies overlap the other's kernels (what a streaming
         # integration does with consecutive chunks).  Every step still copies its inputs from pinned host memory and its
         # results back inside the timed region.
         pipe_ms = None
         if not args.no_pipeline:
             import threading
-            stream_b = torch.cuda.Stream(device=dev)
-            ctx_b = g.Context(local, stream_b.cuda_stream)
-            genes_b = {k: g.ICM.from_tables(ctx_b, *m.dims()[:3], *m.tables()) for k, m in genes.items()}
-            indeps_b = [g.ICM.Build_Indep_WO_Stops(ctx_b, gcs[i], params[i].stop_codons) for i in range(nb)]
-            lanes = [(ctx, genes, indeps, stream), (ctx_b, genes_b, indeps_b, stream_b)]
+            lanes = [(ctx, genes, indeps, stream)]
+            extra_ctx = []
+            for _ in range(N_LANES - 1):
+                stream_b = torch.cuda.Stream(device=dev)
+                ctx_b = g.Context(local, stream_b.cuda_stream)
+                genes_b = {k: g.ICM.from_tables(ctx_b, *m.dims()[:3], *m.tables()) for k, m in genes.items()}
+                indeps_b = [g.ICM.Build_Indep_WO_Stops(ctx_b, gcs[i], params[i].stop_codons) for i in range(nb)]
+                lanes.append((ctx_b, genes_b, indeps_b, stream_b))
+                extra_ctx.append(ctx_b)
 
             def one(lane, jb):
                 c, gs, ins, _ = lanes[lane]
-                s3 = g.SeqSet(c, ascii=pinned[jb].numpy(), offsets=batches[jb][1])
+                s3 = g.SeqSet(c, ascii=pinned[jb].numpy(), offsets=pinned_off[jb].numpy())
                 s3.find_orfs(params[jb])
                 s3.get_orfs(pinned=True)
                 s3.score_orfs_mg(gs[batches[jb][2]], ins[jb], params[jb])
@@ -794,25 +801,25 @@ def run_b200_reads(args, env, kind):
                 s3.get_reduced_starts(pinned=True)
                 s3.close()
 
-            for lane in (0, 1):
+            for lane in range(N_LANES):
                 for k in range(We):
                     one(lane, k % nb)
             barrier()
             ev0 = torch.cuda.Event(enable_timing=True)
-            ends = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(N_LANES)]
             ev0.record(stream)  # both streams are idle here
             errs = []
 
             def worker(lane):
                 try:
                     torch.cuda.set_device(local)
-                    for k in range(lane, K, 2):
+                    for k in range(lane, K, N_LANES):
                         one(lane, (We + k) % nb)
                     ends[lane].record(lanes[lane][3])
                 except Exception as exc:  # pragma: no cover
                     errs.append(exc)
 
-            th = [threading.Thread(target=worker, args=(lane,)) for lane in (0, 1)]
+            th = [threading.Thread(target=worker, args=(lane,)) for lane in range(N_LANES)]
             for t_ in th:
                 t_.start()
             for t_ in th:
@@ -822,7 +829,8 @@ def run_b200_reads(args, env, kind):
                 raise errs[0]
             pipe_ms = max(ev0.elapsed_time(e) for e in ends)
             pipe_bases = sum(bases[(We + k) % nb] for k in range(K))
-            ctx_b.close()
+            for c_ in extra_ctx:
+                c_.close()
 
     t = torch.tensor([ms, e2e_ms, pipe_ms or 0.0], dtype=torch.float64, device=dev)
     tb = torch.tensor([done_bases, e2e_bases, pipe_bases if pipe_ms else 0], dtype=torch.float64, device=dev)
@@ -861,12 +869,12 @@ def run_b200_reads(args, env, kind):
                 "gpu_launches": int(launches), "clocks": clk,
                 "parity_checked": parity is not None, "parity": parity}
         if pipe_max > 0:
-            # headline e2e = the streaming form (two batches in flight); the one-batch-at-a-time figure stays beside it
-            line["e2e"].update({"value": all_pipe_bases / (pipe_max / 1e3) / 1e9, "ms_per_step": pipe_max / K, "in_flight": 2,
-                                "how": "two host threads, each with its own context / stream, alternate batches: copies of one batch "
-                                       "overlap the kernels of the other; every step copies its input from pinned host memory and "
-                                       "its ORF table + reduced start lists back", "one_batch_at_a_time": {"value": e2e,
-                                                                                                       "ms_per_step": e2e_max / K}})
+            # headline e2e = the streaming form (N_LANES batches in flight); the one-batch-at-a-time figure stays beside it
+            line["e2e"].update({"value": all_pipe_bases / (pipe_max / 1e3) / 1e9, "ms_per_step": pipe_max / K, "in_flight": N_LANES,
+                                "how": f"{N_LANES} host threads, each with its own context / stream, take batches in turn: copies of "
+                                       "one batch overlap the kernels of the others; every step copies its input from pinned host "
+                                       "memory and its ORF table + reduced start lists back",
+                                "one_batch_at_a_time": {"value": e2e, "ms_per_step": e2e_max / K}})
         if world == 1 and not args.no_cpu_baseline:
             tmp = tempfile.mkdtemp(prefix="gmg_bench_")
             try:
@@ -1342,6 +1350,9 @@ def run_b200_simple(args, env):
                 "gpu_launches": int(launches), "clocks": clk, "parity_checked": parity is not None, "parity": parity}
         return line
     return None
+
+
+N_LANES = int(os.environ.get("GMG_BENCH_LANES", "4"))  # batches in flight of the streaming end-to-end measurement
 
 
 def main():

@@ -388,15 +388,18 @@ MGF_HD int mgf_recs_at(const MgfOwn& f, const MgfPlan& pl, bool fwd, int j, bool
   if (tpos) return bit ? 2 : 1;
   return *chain ? 1 : 0;
 }
-// index of the start codon at position j (Can_Be order), as which_at above
-MGF_HD int mgf_which_at(const MgfBatch& B, const MgfSeq& S, const unsigned char* which, const MgfOwn& f, bool fwd, int j) {
+// 6-bit code of the (sense-strand) codon at position j, and the index of that start codon (Can_Be order), as which_at above
+MGF_HD int mgf_codon_at(const MgfBatch& B, const MgfSeq& S, const MgfOwn& f, bool fwd, int j) {
   const int bidx = fwd ? f.hi - 1 - j : f.lo - 1 + j;
   int cd = mgf_codon6_at(B.words, S.a + (fwd ? bidx - 2 : bidx));
   if (!fwd) {
     cd = 63 - cd;
     cd = ((cd & 3) << 4) | (cd & 12) | (cd >> 4);
   }
-  return (int)which[cd];
+  return cd;
+}
+MGF_HD int mgf_which_at(const MgfBatch& B, const MgfSeq& S, const unsigned char* which, const MgfOwn& f, bool fwd, int j) {
+  return (int)which[mgf_codon_at(B, S, f, fwd, j)];
 }
 
 // the same with score[] read off K2's prefix-sum rows (Cumulative_Frame_Score as a difference of two entries)

@@ -240,65 +240,6 @@ __global__ void __launch_bounds__(256) k1_planes(DevIcm gene, const uint64_t* __
   }
 }
 
-// Partial windows of short sequences, separately: the W-1 first positions of a sequence have a partial reverse-strand
-// window and the W-1 last ones a partial forward window (icm.cc:807-842).  In bucket order nearly every warp of the
-// bucketed kernel would meet one and fall to its tested path, so for read sets that kernel walks EVERY window as if
-// it were full and this kernel then overwrites the 2 (W-1) x 3 partial entries of every sequence with the generic
-// walk (branch table in shared memory, leaf gathers from L2).  One thread per (sequence, end, offset).
-// kStage = false (a handful of long sequences: a few dozen items): the branch table is read from global memory instead
-// of being staged, so the kernel costs a launch and a few dependent loads rather than a 16 KB copy per CTA.
-template <bool kStage>
-__global__ void __launch_bounds__(256) k1_partial_fix(DevIcm gene, const uint64_t* __restrict__ words,
-                                                      const int64_t* __restrict__ off, int64_t n_seq,
-                                                      const uint32_t* __restrict__ bktidx, int64_t total,
-                                                      float* __restrict__ planes) {
-  extern __shared__ int8_t s_mip_buf[];
-  const int8_t* s_mip = gene.mip;
-  if (kStage) {
-    const int nmip = gene.P * gene.inner;
-    for (int i = threadIdx.x; i < nmip; i += blockDim.x) s_mip_buf[i] = gene.mip[i];
-    __syncthreads();
-    s_mip = s_mip_buf;
-  }
-  const int W = gene.W, D = gene.D, per = 2 * (W - 1);
-  const int64_t items = n_seq * per;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t sq = it / per;
-    const int k = (int)(it - sq * per);
-    const int64_t a = __ldg(off + sq);
-    const int L = (int)(__ldg(off + sq + 1) - a);
-    const bool tail = k >= W - 1;            // forward-strand partial windows at the end of the sequence
-    const int q = tail ? L - 1 - (k - (W - 1)) : k;
-    if (q < 0 || q >= L) continue;
-    const int64_t p = a + q;
-    int lf = q + W - L;
-    lf = lf > 0 ? lf : 0;
-    int lr = W - 1 - q;
-    lr = lr > 0 ? lr : 0;
-    // the strand whose window is partial at this end; the other strand's entry is a full window and already right
-    // (unless the sequence is so short that it is partial too: then the item of the other end rewrites it)
-    const bool rev = !tail;
-    if ((rev ? lr : lf) == 0) continue;
-    const uint64_t cx = rev ? ctx_rev(words, p, W) : ctx_fwd(words, p, W);
-    const int8_t* mipf[3];
-    const float* probf[3];
-    uint64_t ctx[3];
-    int lim[3];
-    float v[3];
-#pragma unroll
-    for (int f = 0; f < 3; f++) {
-      mipf[f] = s_mip + f * gene.inner;
-      probf[f] = gene.prob + (size_t)f * gene.N * 4;
-      ctx[f] = cx;
-      lim[f] = rev ? lr : lf;
-    }
-    walk_many<3>(mipf, probf, ctx, lim, W, D, v);
-    const size_t pi = gmg_plane_index(words, bktidx, p);
-#pragma unroll
-    for (int f = 0; f < 3; f++) planes[(size_t)(rev ? 3 + f : f) * total + pi] = v[f];
-  }
-}
-
 // K1, bucketed form (the default for W <= 16, D <= 7): role-persistent CTAs.  The planes are stored bucketed by
 // the base at each position (gmg_plane_index), so all positions whose PREDICTED base is pb -- the base itself on the
 // forward strand, its complement on the reverse strand -- are one dense run of plane indices.  A CTA keeps the
@@ -345,6 +286,62 @@ __device__ __forceinline__ bool k1_step2_tested(uint32_t w, uint32_t c, unsigned
   return false;
 }
 
+// Partial windows, separately: the W-1 first positions of a sequence have a partial reverse-strand window and the W-1
+// last ones a partial forward window (icm.cc:807-842).  In bucket order nearly every warp of the bucketed kernel would
+// meet one and fall to its tested path, so for read sets that kernel walks EVERY window as if it were full and this
+// kernel then overwrites the 2 (W-1) x 3 partial entries of every sequence.  One thread per (sequence, end, offset): the
+// entry's walk-ready context is read back from the context array, its three walks (one per period) go through the same
+// merged words as the main kernel -- read from global memory, 13 KB that stay in L1 -- and stop at the first node that
+// branches on an unavailable position.
+__global__ void __launch_bounds__(256) k1_partial_fix(DevIcmFast gm, const uint64_t* __restrict__ words,
+                                                      const int64_t* __restrict__ off, int64_t n_seq,
+                                                      const uint32_t* __restrict__ bktidx,
+                                                      const uint32_t* __restrict__ ctxf, const uint32_t* __restrict__ ctxr,
+                                                      int64_t total, float* __restrict__ planes) {
+  constexpr int NWORDS = 4 + 64 + 1024;
+  constexpr uint32_t OFF7 = (16384 - 1) / 3;
+  const int W = gm.W, per = 2 * (W - 1), wsh = 32 - 2 * W;
+  const int64_t items = n_seq * per;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t sq = it / per;
+    const int k = (int)(it - sq * per);
+    const int64_t a = __ldg(off + sq);
+    const int L = (int)(__ldg(off + sq + 1) - a);
+    const bool tail = k >= W - 1;  // forward-strand partial windows at the end of the sequence
+    const int q = tail ? L - 1 - (k - (W - 1)) : k;
+    if (q < 0 || q >= L) continue;
+    // the strand whose window is partial at this end; the other strand's entry is a full window and already right
+    // (unless the sequence is so short that it is partial too: then the item of the other end rewrites it)
+    const bool rev = !tail;
+    const int64_t p = a + q;
+    const uint32_t pi = gmg_plane_index(words, bktidx, p);
+    const uint32_t c = __ldg((rev ? ctxr : ctxf) + pi);
+    if ((int)(c & 15u) >= W - 1) continue;  // a full window after all
+    const unsigned own = (unsigned)gmg_base_at(words, p), pb = rev ? 3u - own : own;
+    const int lim = W - 1 - (int)(c & 15u);  // first available window position (>= 1 here)
+    const unsigned lsh = 30 - 2 * lim;      // a node may be descended iff its shift <= this
+    const uint32_t cw = c >> wsh;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const uint32_t* __restrict__ mw = gm.mw + (size_t)f * NWORDS;
+      const unsigned s0 = f == 0 ? gm.s0[0] : (f == 1 ? gm.s0[1] : gm.s0[2]);
+      const bool stop0 = (f == 0 ? gm.stop0[0] : (f == 1 ? gm.stop0[1] : gm.stop0[2])) != 0;
+      uint32_t res = 0;
+      if (!(stop0 || s0 > lsh)) {
+        uint32_t i = (cw << s0) >> 30;
+        if (!k1_step2_tested(__ldg(mw + i), cw, lsh, 1, &i, &res))
+          if (!k1_step2_tested(__ldg(mw + 4 + i), cw, lsh, 21, &i, &res))
+            if (!k1_step2_tested(__ldg(mw + 68 + i), cw, lsh, 341, &i, &res)) res = OFF7 + i;
+      }
+      planes[(size_t)(rev ? 3 + f : f) * total + pi] = __ldg(gm.bleaf + (size_t)(f * 4 + (int)pb) * gm.np + res);
+    }
+  }
+}
+
+// kAllFull: the main loop walks EVERY window as a full one (no test, no slow path); k1_partial_fix then redoes the entries
+// whose window is partial.  (Tried and measured slower, 0.85 against 0.62 ms per 31 Mbp of 100 bp reads: a second phase
+// inside this kernel that scans a bitmap of the partial plane indices and walks them from the shared-memory tables --
+// with 24 warps per SM its dependent bitmap -> context loads are pure latency, and the extra registers slow the main loop.)
 template <int kU, int NT = 1024, bool kAllFull = false>
 __global__ void __launch_bounds__(NT, 2) k1_planes_bucketed(DevIcmFast gm, const uint32_t* __restrict__ ctxf,
                                                               const uint32_t* __restrict__ ctxr, unsigned total,
@@ -514,21 +511,16 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     // partial entries of every sequence redone by k1_partial_fix.  GMG_K1_FIX=0 disables, =1 extends it to long sequences
     // (measured on the 5 Mbp contig: the test costs 7 % of K1's instructions, the second launch as much: 78.9 against
     // 71.6 us, so long sequences keep the tested kernel).
-    static const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 2;
-    const size_t fix_smem = (size_t)gene->dev.P * gene->dev.inner;
-    const bool fix = fix_env && !(fix_env == 2 && long_seqs) && !ku_env && fix_smem <= 48 * 1024;
+    const int fix_env = getenv("GMG_K1_FIX") ? atoi(getenv("GMG_K1_FIX")) : 2;
+    const bool fix = fix_env && !(fix_env == 2 && long_seqs) && !ku_env;
     if (fix) {
       GMG_CUDA(cudaFuncSetAttribute(k1_planes_bucketed<6, 384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k1_planes_bucketed<6, 384, true><<<grid, 384, smem, ctx->stream>>>(gene->fast, s->d_ctxf, s->d_ctxr,
                                                                          (unsigned)s->total, segs, (float*)planes);
       const int64_t items = s->n * 2 * (gene->W - 1);
-      int64_t fg = (items + 255) / 256, fcap = (int64_t)ctx->sm_count * 8;
-      if (items >= 8192)
-        k1_partial_fix<true><<<(unsigned)(fg < fcap ? fg : fcap), 256, fix_smem, ctx->stream>>>(
-            gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
-      else  // 32 threads per CTA: the items spread over the SMs
-        k1_partial_fix<false><<<(unsigned)((items + 31) / 32), 32, 0, ctx->stream>>>(
-            gene->dev, s->d_words, s->d_off, s->n, s->d_bktidx, s->total, (float*)planes);
+      int64_t fg = (items + 255) / 256, fcap = (int64_t)ctx->sm_count * 16;
+      k1_partial_fix<<<(unsigned)(fg < fcap ? fg : fcap), 256, 0, ctx->stream>>>(
+          gene->fast, s->d_words, s->d_off, s->n, s->d_bktidx, s->d_ctxf, s->d_ctxr, s->total, (float*)planes);
       ctx->launches++;
     } else if (ku == 1) GMG_K1_LAUNCH(1, 1024);
     else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
@@ -3050,27 +3042,74 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
 // writer on lane 0: ~1 200 warp instructions per ORF, 0.60 ms per 31 Mbp batch, all of it instruction issue.  Here a lane
 // sums the three terms of one codon, ONE scan per 96 bases gives every codon-boundary prefix, and the lanes write the
 // records of their own positions (mgf_plan / mgf_recs_at: the position-by-position form of the reference's start loop,
-// held to the oracle on the host by tests/mgflat_host_check.cu).
+// held to the CPU checker on the host by tests/mgflat_host_check.cu).
 // Exactness as above: the per-ORF certificate (smallest term exponent, sum of magnitudes); an ORF without one is summed
 // by lane 0 in the reference's serial order into a shared-memory row and the lanes take their prefixes from there.
 // ORFs with more than 96 * MGL_K scored bases, or with j_lo < 3, are left to k3_mg_plain.
 #define MGL_K 4
 __device__ __forceinline__ bool mgl_takes(int need, int j_lo) { return need <= 96 * MGL_K && j_lo >= 3; }
 
+// CodonSets::which as four 64-bit words, one nibble per 6-bit codon (15 = not a start codon): indexing the byte array of a
+// kernel parameter with a run-time subscript makes the compiler copy the whole parameter block to local memory
+struct Which4 {
+  unsigned long long w[4];
+};
+__device__ __forceinline__ int which4_of(const Which4& t, int cd) {
+  const unsigned long long w = cd < 32 ? (cd < 16 ? t.w[0] : t.w[1]) : (cd < 48 ? t.w[2] : t.w[3]);
+  const int v = (int)((w >> (4 * (cd & 15))) & 15ull);
+  return v == 15 ? 255 : v;
+}
+
+// gene - indep of the three consecutive sequence positions q0, q0 + 1, q0 + 2 (one codon), summed in ascending order of
+// q, with the certificate inputs of the six floats.  per(i) = model period of position q0 + i.  One 64-bit window of the
+// packed bases serves the three independent-model codes and the three own bases; W == 3 independent models only.
+__device__ __forceinline__ double mgl_codon_sum(const DevIcm& indep, const float* __restrict__ planes,
+                                                const uint32_t* __restrict__ bktidx, const MgfBatch& B, const MgfSeq& S, bool fwd,
+                                                int q0, unsigned& umin, float& asum) {
+  const int64_t p0 = S.a + q0;
+  const uint64_t v = gmg_extract32(B.words, p0 - 2);  // base q0 - 2 + m at bits 2 m
+  const uint32_t pu = (uint32_t)p0;                   // batches hold fewer than 2^32 bases
+  const uint32_t blk0 = pu >> 5, blk2 = (pu + 2u) >> 5;
+  const uint64_t w0 = __ldg(B.words + blk0);
+  const uint64_t w2 = blk2 != blk0 ? __ldg(B.words + blk2) : w0;
+  double x = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int q = q0 + i;
+    const int f = fwd ? (3 - i) % 3 : (1 + i) % 3;
+    const uint32_t p = pu + (uint32_t)i, blk = p >> 5, ib = p & 31u;
+    const uint64_t w = blk == blk0 ? w0 : w2;
+    const unsigned b = (unsigned)(v >> (2 * (i + 2))) & 3u;
+    const uint64_t y = w ^ (0x5555555555555555ull * b);
+    const uint64_t eq = ~(y | (y >> 1)) & 0x5555555555555555ull & ((1ull << (2 * ib)) - 1ull);
+    const uint32_t idx = __ldg(bktidx + (blk << 2) + b) + (uint32_t)__popcll(eq);
+    const float g = __ldg(planes + (size_t)(fwd ? f : 3 + f) * (size_t)B.total + idx);
+    float n;
+    if (fwd) {
+      const int raw = (int)(v >> (2 * (i + 2))) & 63;  // bases q, q+1, q+2
+      const float* tb = q <= S.L - 3 ? indep.lut3 : indep.lutp + (q - (S.L - 2)) * 192;
+      n = __ldg(tb + f * 64 + raw);
+    } else {
+      const int raw = (int)(v >> (2 * i)) & 63;  // bases q-2, q-1, q
+      const float* tb = q >= 2 ? indep.lut3 + 192 : indep.lutp + 384 + (1 - q) * 192;
+      n = __ldg(tb + f * 64 + raw);
+    }
+    k2_cert_term(g, umin, asum);
+    k2_cert_term(n, umin, asum);
+    x = x + ((double)g - (double)n);
+  }
+  return x;
+}
+
 __global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
-                                                         const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, CodonSets cs,
+                                                         const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, Which4 which,
                                                          const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                          int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                          gmg_start* __restrict__ starts, int exact_len,
                                                          unsigned long long* __restrict__ n_ordered) {
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ float s_lut[384];
-  __shared__ unsigned char s_which[64];
   __shared__ double s_serial[4][32 * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
-  if (indep.lut3 != NULL)
-    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_lut[i] = indep.lut3[i];
-  if (threadIdx.x < 64) s_which[threadIdx.x] = cs.which[threadIdx.x];
-  __syncthreads();
+  const float* s_lut = indep.lut3;            // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (o >= n_orfs) return;  // warp-uniform
@@ -3100,14 +3139,18 @@ __global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const flo
       const int c = 32 * k + lane;
       double x = 0.0;
       if (c < ncod) {
+        if (indep.lut3 != NULL) {  // j = 3 c .. 3 c + 2: positions hi-1-3c-2 .. hi-1-3c (forward), lo-1+3c .. +2 (reverse)
+          x = mgl_codon_sum(indep, planes, bktidx, B, S, fwd, fwd ? hi - 3 - 3 * c : lo - 1 + 3 * c, umin, asum);
+        } else {
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
-          const int j = 3 * c + t;
-          float g, n;
-          mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + t) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
-          k2_cert_term(g, umin, asum);
-          k2_cert_term(n, umin, asum);
-          x = x + ((double)g - (double)n);
+          for (int t = 0; t < 3; t++) {
+            const int j = 3 * c + t;
+            float g, n;
+            mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + t) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+            k2_cert_term(g, umin, asum);
+            k2_cert_term(n, umin, asum);
+            x = x + ((double)g - (double)n);
+          }
         }
       }
 #pragma unroll
@@ -3161,10 +3204,10 @@ __global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const flo
         const double sc = (sum - 0.0) + 0.0;
         if (trunc_rec) {
           mgf_put(out + idx, P, j + 2, kp, sc, -1, 1, 1, 0, ep, et);
-          if (nr == 2) mgf_put(out + idx + 1, P, j + 2, kp, sc, mgf_which_at(B, S, s_which, f, fwd, j), 0, 0, 0, ep, et);
+          if (nr == 2) mgf_put(out + idx + 1, P, j + 2, kp, sc, which4_of(which, mgf_codon_at(B, S, f, fwd, j)), 0, 0, 0, ep, et);
         } else {
           const int first = (pl.state_after && !seen_nonzero && (mnz & higher) == 0u) ? 1 : 0;
-          mgf_put(out + idx, P, j + 2, kp, sc, mgf_which_at(B, S, s_which, f, fwd, j), 0, first, 0, ep, et);
+          mgf_put(out + idx, P, j + 2, kp, sc, which4_of(which, mgf_codon_at(B, S, f, fwd, j)), 0, first, 0, ep, et);
         }
       }
       placed += __popc(m1) + __popc(m2);
@@ -3811,11 +3854,15 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     } else if (total_starts > 0) {
       // one codon per lane for ORFs of up to 96 * MGL_K scored bases; the warp-per-ORF scan for whatever is left.
       // GMG_PLAIN_LANES=0: all of them through the latter (A/B runs, tests).
-      static const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 1;
+      const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 1;
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
       if (plain_lanes) {
+        Which4 which;
+        memset(&which, 0, sizeof which);
+        for (int cd = 0; cd < 64; cd++)
+          which.w[cd >> 4] |= (unsigned long long)(cs.which[cd] < 15 ? cs.which[cd] : 15) << (4 * (cd & 15));
         k3_mg_plain_lanes<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-            indep->dev, planes, s->d_bktidx, B, dp, cs, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
+            indep->dev, planes, s->d_bktidx, B, dp, which, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
             (unsigned long long*)(counts + s->n_orfs + 1));
         ctx->launches++;
       }
@@ -4111,7 +4158,7 @@ extern "C" int gmg_reduce_starts_mg(gmg_ctx* ctx, gmg_seqset* s, const gmg_param
   if (smem > 48 * 1024) GMG_CUDA(cudaFuncSetAttribute(k3_mg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
   // GMG_RED_SMALL=0: every ORF through the warp-per-ORF kernel (A/B and test hook)
-  static const int red_small = getenv("GMG_RED_SMALL") ? atoi(getenv("GMG_RED_SMALL")) : 1;
+  const int red_small = getenv("GMG_RED_SMALL") ? atoi(getenv("GMG_RED_SMALL")) : 1;
   if (red_small) {
     k3_mg_reduce_small<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(
         s->d_starts, s->d_start_off, s->d_orfs, s->d_orf_seq, s->d_off, s->n_orfs, M, d_out, d_cursor, d_first, d_cnt, d_status,

@@ -114,9 +114,18 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
                                                        uint4* __restrict__ bktidx, uint32_t* __restrict__ ctxf,
                                                        uint32_t* __restrict__ ctxr,
                                                        unsigned long long* __restrict__ n_base) {
+  // totals per base: once per CTA (every thread used to re-derive them: 10 % of the kernel's instructions)
+  __shared__ unsigned s_tot[4];
+  if (threadIdx.x == 0) {
+    const uint4 lp = prefix[nblk - 1], lc = cnt[nblk - 1];
+    s_tot[0] = lp.x + lc.x;
+    s_tot[1] = lp.y + lc.y;
+    s_tot[2] = lp.z + lc.z;
+    s_tot[3] = lp.w + lc.w;
+  }
+  __syncthreads();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint4 lp = prefix[nblk - 1], lc = cnt[nblk - 1];
-  const unsigned na = lp.x + lc.x, nc = lp.y + lc.y, ng = lp.z + lc.z, nt = lp.w + lc.w;
+  const unsigned na = s_tot[0], nc = s_tot[1], ng = s_tot[2], nt = s_tot[3];
   if (p == 0) {
     n_base[0] = na; n_base[1] = nc; n_base[2] = ng; n_base[3] = nt;
   }
@@ -127,7 +136,9 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
   pre.z += na + nc;
   pre.w += na + nc + ng;
   if ((p & 31) == 0) bktidx[blk] = pre;
-  const uint64_t w = __ldg(words + blk);
+  // the block's word and its neighbours (warp-uniform loads; zero padding either side of the batch): every window below
+  // is cut from these three
+  const uint64_t wm = __ldg(words + blk - 1), w = __ldg(words + blk), wp = __ldg(words + blk + 1);
   const int i = (int)(p & 31);
   const unsigned b = (unsigned)(w >> (2 * i)) & 3u;
   const uint64_t x = w ^ (0x5555555555555555ull * b);
@@ -135,15 +146,17 @@ __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restric
   const unsigned first = b == 0 ? pre.x : (b == 1 ? pre.y : (b == 2 ? pre.z : pre.w));
   const unsigned idx = first + (unsigned)__popcll(eq);
   // forward: bases p .. p+15, order reversed (base p in the top pair)
-  uint32_t f = (uint32_t)gmg_extract32(words, p);
+  uint32_t f = (uint32_t)(i == 0 ? w : ((w >> (2 * i)) | (wp << (64 - 2 * i))));
   f = __brev(f);
   f = ((f >> 1) & 0x55555555u) | ((f & 0x55555555u) << 1);
-  const uint32_t r = ~(uint32_t)gmg_extract32(words, p - 15);
+  // reverse: complement of bases p-15 .. p (base p-15 in the low pair)
+  const uint32_t r = ~(uint32_t)(i >= 15 ? (w >> (2 * (i - 15))) : ((wm >> (64 - 2 * (15 - i))) | (w << (2 * (15 - i)))));
   // the low four bits (the two bases farthest from p; windows of up to 14 bases never see them) hold the distance
   // to the end / start of the sequence, clipped to 15: which window positions exist
   int32_t sq = __ldg(blk2seq + blk) & 0x7FFFFFFF;
-  while (p >= __ldg(off + sq + 1)) sq++;
-  const int64_t q = p - __ldg(off + sq), e = __ldg(off + sq + 1) - 1 - p;
+  int64_t nx = __ldg(off + sq + 1);
+  while (p >= nx) nx = __ldg(off + (++sq) + 1);
+  const int64_t q = p - __ldg(off + sq), e = nx - 1 - p;
   ctxf[idx] = (f & ~15u) | (uint32_t)(e < 15 ? e : 15);
   ctxr[idx] = (r & ~15u) | (uint32_t)(q < 15 ? q : 15);
 }
@@ -187,8 +200,11 @@ int gmg_launch_pack(gmg_ctx* ctx, const uint8_t* d_ascii, int64_t total, uint64_
   return 0;
 }
 
+// copy_off_from_caller: the device copy of the offsets is made straight from h_off (gmg_seqset_create synchronises before
+// it returns, so a page-locked caller buffer travels at PCIe rate and without the driver's staging copy); otherwise from
+// the set's own host copy.
 static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off, int64_t n, const void* d_qual,
-                        gmg_seqset** out) {
+                        gmg_seqset** out, bool copy_off_from_caller = false) {
   GMG_CHECK(n >= 0 && n < (1ll << 31), "gmg_seqset_create: %lld sequences unsupported", (long long)n);
   int64_t max_len = 0;
   for (int64_t i = 0; i < n; i++) {
@@ -216,8 +232,8 @@ static int seqset_build(gmg_ctx* ctx, const void* d_ascii, const int64_t* h_off,
   GMG_CUDA(cudaMemsetAsync(s->d_words_base, 0, wbytes, ctx->stream));
   s->d_words = s->d_words_base + GMG_PAD_WORDS;
   GMG_CUDA(cudaMallocAsync(&s->d_off, (size_t)(s->n + 1) * sizeof(int64_t), s->ctx->stream));
-  GMG_CUDA(cudaMemcpyAsync(s->d_off, s->off.data(), (size_t)(s->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                           ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(s->d_off, copy_off_from_caller && n > 0 ? h_off : s->off.data(), (size_t)(s->n + 1) * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, ctx->stream));
   GMG_CUDA(cudaMallocAsync(&s->d_blk2seq, (size_t)nblk * sizeof(int32_t), s->ctx->stream));
   GMG_CUDA(cudaMallocAsync(&s->d_gc, 6 * sizeof(unsigned long long), s->ctx->stream));
   GMG_CUDA(cudaMemsetAsync(s->d_gc, 0, 6 * sizeof(unsigned long long), ctx->stream));
@@ -257,7 +273,7 @@ extern "C" int gmg_seqset_create(gmg_ctx* ctx, const char* h_ascii, const int64_
       GMG_CUDA(cudaMemcpyAsync(d_q, h_qual, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
     }
   }
-  int rc = seqset_build(ctx, d_ascii, h_off, n, d_q, out);
+  int rc = seqset_build(ctx, d_ascii, h_off, n, d_q, out, true);
   if (rc == 0) GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // host buffers may be reused by the caller
   return rc;
 }

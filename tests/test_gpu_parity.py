@@ -239,7 +239,7 @@ def test_all_frame_scores_match_oracle_score_string(gm, ctx, genome):
             assert row[3 + f0] == O.lib().orc_score_string(og, up, ln, f0), (sq, lo, ln, f0)
 
 
-def test_score_all_frames_bit_exact(gm, ctx, reads):
+def test_score_all_frames_bit_exact(gm, ctx, reads, monkeypatch):
     path = os.path.join(G, "NC_000915.icm")
     gene = gm.ICM.Read(ctx, path)
     og = O.lib().orc_icm_read(path.encode())
@@ -254,6 +254,13 @@ def test_score_all_frames_bit_exact(gm, ctx, reads):
         want = O.score_all_frames(og, oi, O.filter_lower(s0))
         assert got.shape == want.shape
         assert (_bits(got) == _bits(want)).all()
+    # the other routes for partial windows: tested in the walk loop (0), fix-up kernel also for long sequences (1)
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GMG_K1_FIX", mode)
+        fs2 = gm.SeqSet(ctx, seqs=seqs).score_all_frames(gene, indep)
+        monkeypatch.delenv("GMG_K1_FIX")
+        for a, b in zip(fs, fs2):
+            assert (_bits(a) == _bits(b)).all(), mode
     # golden Frame_Scores of the unmodified reference (first 25 reads)
     recs = parse_dump(os.path.join(G, "mg_plain_120.dump.gz"))
     gc = _gc_oracle([s for _, s in reads[:120]])
@@ -451,12 +458,16 @@ def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monk
         orfs, ooff = ss.get_orfs()
         return st.tobytes(), off.tolist(), ss.uncertified, orfs, ooff
 
-    want = run()  # fused, one warp per ORF (parallel scan under the per-ORF certificate)
+    want = run()  # fused, one codon per lane (parallel scan under the per-ORF certificate)
     assert want[2] == 0
     monkeypatch.setenv("GMG_PLAIN_SERIAL", "1")
     got = run()   # fused, one thread per ORF (serial sums in the reference's order)
     assert got[:2] == want[:2] and got[2] == 0
     monkeypatch.delenv("GMG_PLAIN_SERIAL")
+    monkeypatch.setenv("GMG_PLAIN_LANES", "0")
+    got = run()   # fused, one warp per ORF with a scan per 32 bases (the route of ORFs beyond 384 scored bases)
+    assert got[:2] == want[:2] and got[2] == 0
+    monkeypatch.delenv("GMG_PLAIN_LANES")
     monkeypatch.setenv("GMG_K3MG_MODE", "1")
     assert run()[:2] == want[:2]
     monkeypatch.delenv("GMG_K3MG_MODE")
@@ -475,7 +486,7 @@ def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monk
 
 @pytest.mark.parametrize("flags,table", [(dict(allow_indels=1), "default"), (dict(allow_indels=1), "random"),
                                          (dict(allow_indels=1, allow_subs=1), "random"), (dict(), "default")])
-def test_mg_start_list_reduction(gm, ctx, reads, flags, table):
+def test_mg_start_list_reduction(gm, ctx, reads, monkeypatch, flags, table):
     """Row a11b: the per-(ORF, start position) arg-max of Add_Events and Score_Orfs_Errors' two gates on the device
     (gmg_reduce_starts_mg) against a restatement of the reference's filter run on the raw lists."""
     import config_parity as CP
@@ -495,9 +506,18 @@ def test_mg_start_list_reduction(gm, ctx, reads, flags, table):
     else:
         rng = np.random.default_rng(11)
         model = gm.EventModel(prior=-0.25, start_lo=[0.3, -0.4, -1.1], len_lo=rng.normal(0.0, 1.5, (1, 2, 2, 200)))
-    n_kept = ss.reduce_starts_mg(p, model)
+    monkeypatch.setenv("GMG_RED_SMALL", "0")  # every ORF through the warp-per-ORF kernel
+    n_kept_w = ss.reduce_starts_mg(p, model)
+    red_w, first_w, cnt_w, status_w = ss.get_reduced_starts()
+    monkeypatch.delenv("GMG_RED_SMALL")
+    n_kept = ss.reduce_starts_mg(p, model)  # lists of up to four records: one thread per ORF
     red, first, cnt, status = ss.get_reduced_starts()
     assert n_kept == len(red) == int(cnt.sum())
+    assert n_kept_w == n_kept and (cnt_w == cnt).all() and (status_w == status).all()
+    for o in np.flatnonzero(cnt):  # same survivors (their order within an ORF is free: one per start position)
+        a = red[first[o]:first[o] + cnt[o]]
+        b = red_w[first_w[o]:first_w[o] + cnt_w[o]]
+        assert sorted(x.tobytes() for x in a) == sorted(x.tobytes() for x in b), o
     st = CP.check_reduction(orfs, ooff, [len(s) for s in rs], raw, soff, red, first, cnt, status, p.min_gene_len, model)
     assert st["kept_orfs"] > 50 and st["handed_back"] <= st["orfs"] // 20, st
     assert n_kept < len(raw)
