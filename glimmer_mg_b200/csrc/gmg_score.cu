@@ -3809,27 +3809,28 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   GMG_CHECK(s->n_orfs < 0x7fffffffll && s->total < 0xffffffffll, "gmg_score_orfs_mg: batch too large (%lld ORFs): split it",
             (long long)s->n_orfs);
   if (ensure_codon_bits(ctx, s, cs)) return 1;  // start-codon bitmaps: the own starts of every call
-  float* planes;
-  if (launch_k1(ctx, gene, s, &planes)) return 1;
   // flat form (0) when calls can branch (-i / -s); without error branches the fused per-ORF scan (2) -- or, for very
   // long sequences and caller-supplied ORF tables, K2 + one thread per ORF (1).  GMG_K3MG_MODE forces a form (tests).
   const int k3mg_env = getenv("GMG_K3MG_MODE") ? atoi(getenv("GMG_K3MG_MODE")) : -1;
   const bool branching = p->allow_indels || p->allow_subs;
   const bool fused_ok = !branching && !s->orfs_external && s->max_len <= 3 * (MGP_SLOTS - 1);
   const int k3mg_mode = k3mg_env >= 0 && !(k3mg_env == 2 && !fused_ok) ? k3mg_env : (branching ? 0 : (fused_ok ? 2 : 1));
+  MgfBatch B;
+  memset(&B, 0, sizeof B);
+  B.words = s->d_words;
+  B.off = s->d_off;
+  B.total = s->total;
+  B.cb = s->d_cbits;
+  B.nwc = s->nwc;
+  int64_t* counts = NULL;
   if (k3mg_mode == 2) {
-    // exactness is certified per ORF inside the kernel; the test hook withdraws every certificate
-    const int exact_len = (getenv("GMG_MG_FORCE_UNCERT") && atoi(getenv("GMG_MG_FORCE_UNCERT")) > 0) ? -1 : INT_MAX;
-    MgfBatch B;
-    memset(&B, 0, sizeof B);
-    B.words = s->d_words;
-    B.off = s->d_off;
-    B.total = s->total;
-    B.cb = s->d_cbits;
-    B.nwc = s->nwc;
+    // The record counts only need the codon bitmaps: they are taken, scanned and their total sent to pinned memory BEFORE
+    // the walks are launched, so the host sizes the output while K1 runs and the emission kernel follows K1 without a gap
+    // (the stream used to drain between the count and the emission: a host round trip inside every step).
+    if (gmg_seqset_ensure_buckets(ctx, s)) return 1;  // here, not inside K1: one host synchronisation serves both
     void* d_counts;
     if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
-    int64_t* counts = (int64_t*)d_counts;
+    counts = (int64_t*)d_counts;
     GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
     k3_mg_plain_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, s->n_orfs, counts);
@@ -3838,7 +3839,14 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
     ctx->h_scalars[6] = 0;
     GMG_CUDA(cudaMemcpyAsync(&ctx->h_scalars[6], s->d_start_off + s->n_orfs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+    GMG_CUDA(cudaEventRecord(ctx->ev_scalars, ctx->stream));
+  }
+  float* planes;
+  if (launch_k1(ctx, gene, s, &planes)) return 1;
+  if (k3mg_mode == 2) {
+    // exactness is certified per ORF inside the kernel; the test hook withdraws every certificate
+    const int exact_len = (getenv("GMG_MG_FORCE_UNCERT") && atoi(getenv("GMG_MG_FORCE_UNCERT")) > 0) ? -1 : INT_MAX;
+    GMG_CUDA(cudaEventSynchronize(ctx->ev_scalars));
     const int64_t total_starts = ctx->h_scalars[6];
     if (ensure_start_capacity(s, total_starts)) return 1;
     // A/B: one thread per ORF with serial sums (GMG_PLAIN_SERIAL=1; measured 0.76 ms per 31 Mbp against 0.63 ms for the
@@ -3935,7 +3943,6 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   }
 
   // ---- K3 ----
-  MgfBatch B;
   memset(&B, 0, sizeof B);
   B.words = s->d_words;
   B.off = s->d_off;
@@ -3950,7 +3957,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   B.tables = d_tables;
   void* d_counts;
   if (gmg_scratch(ctx, SCR_FLAGS, (size_t)(s->n_orfs + 2) * sizeof(int64_t), &d_counts)) return 1;
-  int64_t* counts = (int64_t*)d_counts;
+  counts = (int64_t*)d_counts;
   GMG_CUDA(cudaMemsetAsync(counts, 0, (size_t)(s->n_orfs + 2) * sizeof(int64_t), ctx->stream));
   const unsigned g3 = (unsigned)((s->n_orfs + 127) / 128);
   const uint32_t no = (uint32_t)s->n_orfs;

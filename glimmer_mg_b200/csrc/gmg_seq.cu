@@ -432,6 +432,177 @@ extern "C" int gmg_seqset_from_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Quality-file ingest on the device (Fasta_Qual_Vec_Read, Common/fasta.cc:115-170): records
+// as in Fasta_Read -- a '>' outside a header line starts one, its header runs to the end of that line -- and in a
+// record's body a value is the number formed by ALL digits since the last white-space character, taken when the next
+// white-space character arrives (other characters are skipped; digits still pending at the next '>' or at the end of the
+// file are dropped).  One thread per byte: a white-space byte of a body looks back to the previous white space / header
+// byte for digits; the two scans of the FASTA ingest number the values and the records.
+__device__ __forceinline__ bool qual_is_space(unsigned ch) { return ch == ' ' || (ch >= 9 && ch <= 13); }
+
+// value ending at the white-space byte i (body byte): -1 if no digit since the previous reset point
+__device__ __forceinline__ long long qual_value_before(const uint8_t* __restrict__ in, const uint32_t* __restrict__ last,
+                                                       int64_t i, int* too_long) {
+  long long val = 0, mul = 1;
+  bool have = false;
+  int steps = 0;
+  for (int64_t j = i - 1; j >= 0; --j) {
+    const unsigned ch = in[j];
+    if ((last[j] & 1u) != 0 || qual_is_space(ch)) break;  // header byte (incl. the record's '>') or white space
+    if (ch >= '0' && ch <= '9') {
+      if (mul <= 1000000000ll) {
+        val += (long long)(ch - '0') * mul;
+        mul *= 10;
+      } else if (ch != '0') {
+        val = 0x7fffffffll;  // more than ten digits: saturate (the reference's int would overflow)
+      }
+      have = true;
+    }
+    if (++steps > 65536) {
+      *too_long = 1;
+      break;
+    }
+  }
+  if (val > 0x7fffffffll) val = 0x7fffffffll;
+  return have ? val : -1;
+}
+
+__global__ void __launch_bounds__(256) k_qual_flags(const uint8_t* __restrict__ in, int64_t n,
+                                                    const uint32_t* __restrict__ last, uint2* __restrict__ flags,
+                                                    int* __restrict__ too_long) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned ch = in[i];
+  const bool in_hdr = (last[i] & 1u) != 0;
+  const bool prev_hdr = i > 0 && (last[i - 1] & 1u) != 0;
+  const bool start = ch == '>' && !prev_hdr;
+  unsigned emit = 0;
+  if (!in_hdr && qual_is_space(ch)) emit = qual_value_before(in, last, i, too_long) >= 0 ? 1u : 0u;
+  flags[i] = make_uint2(emit, start ? 1u : 0u);
+}
+
+// values of all records, compacted (anything before the first record is dropped)
+__global__ void __launch_bounds__(256) k_qual_scatter(const uint8_t* __restrict__ in, int64_t n,
+                                                      const uint32_t* __restrict__ last, const uint2* __restrict__ incl,
+                                                      const int64_t* __restrict__ rec_vals, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 me = incl[i];
+  const uint32_t before = i > 0 ? incl[i - 1].x : 0u;
+  if (me.x != before && me.y > 0) {
+    int dummy = 0;
+    out[(int64_t)before - rec_vals[0]] = (int32_t)qual_value_before(in, last, i, &dummy);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_qual_clamp(const int32_t* __restrict__ v, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)(v[i] < 0 ? 0 : (v[i] > 255 ? 255 : v[i]));
+}
+
+// parse: *d_values = int32 values of all records (context scratch SCR_TMP2), off = values before each record
+static int quality_parse(gmg_ctx* ctx, const char* h_bytes, int64_t n, std::vector<int64_t>* off, int32_t** d_values) {
+  GMG_CHECK(n < (1ll << 30), "quality images of 1 GiB or more must be split at record boundaries (got %lld bytes)", (long long)n);
+  off->assign(1, 0);
+  *d_values = NULL;
+  if (n == 0) return 0;
+  void *d_in, *d_work;
+  if (gmg_scratch(ctx, SCR_TMP, (size_t)n + 64, &d_in)) return 1;
+  GMG_CUDA(cudaMemcpyAsync(d_in, h_bytes, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (gmg_scratch(ctx, SCR_CUM, (size_t)n * 12 + 256, &d_work)) return 1;
+  uint2* d_flags = (uint2*)d_work;
+  uint32_t* d_key = (uint32_t*)(d_flags + n);
+  int* d_err = (int*)(d_key + n);
+  GMG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  k_fasta_keys<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key);
+  size_t tb1 = 0, tb2 = 0;
+  GMG_CUDA(cub::DeviceScan::InclusiveScan(NULL, tb1, d_key, d_key, FastaMaxOp(), n, ctx->stream));
+  GMG_CUDA(cub::DeviceScan::InclusiveScan(NULL, tb2, d_flags, d_flags, FastaSumOp(), n, ctx->stream));
+  void* d_tmp;
+  if (gmg_scratch(ctx, SCR_TMP4, tb1 > tb2 ? tb1 : tb2, &d_tmp)) return 1;
+  GMG_CUDA(cub::DeviceScan::InclusiveScan(d_tmp, tb1, d_key, d_key, FastaMaxOp(), n, ctx->stream));
+  k_qual_flags<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key, d_flags, d_err);
+  GMG_CUDA(cub::DeviceScan::InclusiveScan(d_tmp, tb2, d_flags, d_flags, FastaSumOp(), n, ctx->stream));
+  ctx->launches += 4;
+  GMG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 4, d_flags + (n - 1), sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 5, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint2 tot;
+  memcpy(&tot, ctx->h_scalars + 4, sizeof tot);
+  GMG_CHECK((ctx->h_scalars[5] & 0xffffffff) == 0, "quality file: more than 65536 characters without white space");
+  int64_t n_rec = tot.y;
+  if (n_rec == 0) return 0;
+  void* d_tab;
+  if (gmg_scratch(ctx, SCR_TMP3, (size_t)3 * n_rec * sizeof(int64_t), &d_tab)) return 1;
+  int64_t* rec_vals = (int64_t*)d_tab;
+  int64_t* hdr_off = rec_vals + n_rec;
+  int64_t* hdr_end = hdr_off + n_rec;
+  k_fill_i64<<<(unsigned)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(hdr_end, n_rec, n);
+  k_fasta_records<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key, d_flags, rec_vals, hdr_off, hdr_end);
+  void* d_out;
+  if (gmg_scratch(ctx, SCR_TMP2, ((size_t)tot.x + 16) * sizeof(int32_t), &d_out)) return 1;
+  k_qual_scatter<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n, d_key, d_flags, rec_vals, (int32_t*)d_out);
+  ctx->launches += 3;
+  GMG_CUDA(cudaGetLastError());
+  std::vector<int64_t> h_tab((size_t)3 * n_rec);
+  GMG_CUDA(cudaMemcpyAsync(h_tab.data(), d_tab, h_tab.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  // a last record whose '>' is followed by nothing but blanks does not exist (fasta.cc:137-141)
+  {
+    int64_t q = h_tab[(size_t)(2 * n_rec - 1)];
+    while (q < n && h_bytes[q] == ' ') q++;
+    if (q == n) n_rec--;
+  }
+  off->assign((size_t)n_rec + 1, 0);
+  for (int64_t r = 0; r < n_rec; r++) (*off)[(size_t)r] = h_tab[(size_t)r] - h_tab[0];
+  (*off)[(size_t)n_rec] = (int64_t)tot.x - h_tab[0];
+  *d_values = (int32_t*)d_out;
+  return 0;
+}
+
+extern "C" int gmg_quality_parse_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t n_bytes, int64_t* n_records,
+                                       int64_t* n_values, int64_t* h_off, int32_t* h_values, int64_t cap_records,
+                                       int64_t cap_values) {
+  GMG_CHECK(ctx && n_bytes >= 0 && (h_bytes || n_bytes == 0), "gmg_quality_parse_fasta: bad argument");
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int64_t> off;
+  int32_t* d_values;
+  if (quality_parse(ctx, h_bytes, n_bytes, &off, &d_values)) return 1;
+  const int64_t n_rec = (int64_t)off.size() - 1, n_val = off.back();
+  if (n_records) *n_records = n_rec;
+  if (n_values) *n_values = n_val;
+  if (h_off && cap_records >= n_rec) memcpy(h_off, off.data(), off.size() * sizeof(int64_t));
+  if (h_values && cap_values >= n_val && n_val > 0) {
+    GMG_CUDA(cudaMemcpyAsync(h_values, d_values, (size_t)n_val * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int gmg_seqset_quality_from_fasta(gmg_ctx* ctx, gmg_seqset* s, const char* h_bytes, int64_t n_bytes) {
+  GMG_CHECK(ctx && s && n_bytes >= 0 && (h_bytes || n_bytes == 0), "gmg_seqset_quality_from_fasta: bad argument");
+  GMG_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int64_t> off;
+  int32_t* d_values;
+  if (quality_parse(ctx, h_bytes, n_bytes, &off, &d_values)) return 1;
+  const int64_t n_rec = (int64_t)off.size() - 1;
+  GMG_CHECK(n_rec == s->n, "quality file holds %lld records, the sequence set %lld", (long long)n_rec, (long long)s->n);
+  for (int64_t r = 0; r < n_rec; r++)
+    GMG_CHECK(off[(size_t)r + 1] - off[(size_t)r] == s->off[(size_t)r + 1] - s->off[(size_t)r],
+              "ERROR:  record %lld sequence length does not match quality values length (%lld bases, %lld values)", (long long)r,
+              (long long)(s->off[(size_t)r + 1] - s->off[(size_t)r]), (long long)(off[(size_t)r + 1] - off[(size_t)r]));
+  if (s->total > 0) {
+    if (!s->d_qual) GMG_CUDA(cudaMallocAsync(&s->d_qual, (size_t)s->total, ctx->stream));
+    k_qual_clamp<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(d_values, s->total, s->d_qual);
+    ctx->launches++;
+    GMG_CUDA(cudaGetLastError());
+    GMG_CUDA(cudaStreamSynchronize(ctx->stream));  // the values live in context scratch
+  }
+  return 0;
+}
+
 extern "C" int64_t gmg_seqset_count(const gmg_seqset* s) { return s ? s->n : 0; }
 
 extern "C" int gmg_seqset_offsets(const gmg_seqset* s, int64_t* h_off) {

@@ -95,6 +95,8 @@ def lib():
         "gmg_seqset_count": (i64, [vp]),
         "gmg_seqset_offsets": (i32, [vp, vp]),
         "gmg_seqset_fasta_headers": (i32, [vp, vp, vp]),
+        "gmg_quality_parse_fasta": (i32, [vp, vp, i64, P(i64), P(i64), vp, vp, i64, i64]),
+        "gmg_seqset_quality_from_fasta": (i32, [vp, vp, vp, i64]),
         "gmg_seqset_total_bases": (i64, [vp]),
         "gmg_seqset_gc_fraction": (i32, [vp, P(C.c_double)]),
         "gmg_seqset_unpack": (i32, [vp, vp]),
@@ -327,6 +329,13 @@ class SeqSet:
         raw = buf.tobytes()
         self.headers = [raw[a:b].decode(errors="replace") for a, b in zip(ho.tolist(), he.tolist())]
         return self
+
+    def set_quality_fasta(self, image):
+        """Per-base qualities from the image of a quality file (Fasta_Qual_Vec_Read, Common/fasta.cc:115), parsed on the
+        device; records must match the set's sequences in number and length."""
+        buf = np.frombuffer(image, np.uint8) if isinstance(image, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(image, np.uint8)
+        _check(lib().gmg_seqset_quality_from_fasta(self.ctx.h, self.h, buf.ctypes.data if len(buf) else None, len(buf)))
 
     def close(self):
         if self.h:
@@ -587,6 +596,20 @@ class ICM:
         out = np.zeros(ss.total, np.float64)
         _check(lib().gmg_icm_frame_score(self.ctx.h, self.h, ss.h, frame, out.ctypes.data))
         return out
+
+
+def parse_quality_fasta(ctx, image):
+    """Quality file image -> (offsets[n_records + 1], values int32) as Fasta_Qual_Vec_Read (Common/fasta.cc:115) reads it;
+    parsed on the device."""
+    buf = np.frombuffer(image, np.uint8) if isinstance(image, (bytes, bytearray, memoryview)) else \
+        np.ascontiguousarray(image, np.uint8)
+    ptr = buf.ctypes.data if len(buf) else None
+    nr, nv = C.c_int64(), C.c_int64()
+    _check(lib().gmg_quality_parse_fasta(ctx.h, ptr, len(buf), C.byref(nr), C.byref(nv), None, None, 0, 0))
+    off, vals = np.zeros(nr.value + 1, np.int64), np.zeros(nv.value, np.int32)
+    _check(lib().gmg_quality_parse_fasta(ctx.h, ptr, len(buf), C.byref(nr), C.byref(nv), off.ctypes.data, vals.ctypes.data,
+                                         nr.value, nv.value))
+    return off, vals
 
 
 def score_strings_many(ctx, models, strings, frame=0, pinned=False):

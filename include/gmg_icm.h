@@ -151,6 +151,18 @@ int gmg_seqset_from_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t n_bytes, gm
 int64_t gmg_seqset_count(const gmg_seqset* s);
 int gmg_seqset_offsets(const gmg_seqset* s, int64_t* h_off);
 int gmg_seqset_fasta_headers(const gmg_seqset* s, int64_t* h_hdr_off, int64_t* h_hdr_end);
+/* Quality values from the image of a quality file (Fasta_Qual_Vec_Read, Common/fasta.cc:115-170: a '>' header line per
+ * record, then integers separated by white space; a value is taken when white space follows it, characters that are
+ * neither digits nor white space are skipped, digits still pending at the next '>' or at the end of the file are
+ * dropped), parsed on the device.
+ * gmg_quality_parse_fasta: *n_records / *n_values always; h_off (n_records + 1 entries: values before each record) and
+ *   h_values are filled when their capacities suffice (call once with NULL / 0 to size them).
+ * gmg_seqset_quality_from_fasta: attaches the values (clamped to 0..255, as the bindings pass them) to a set as its
+ *   per-base qualities -- what gmg_seqset_create's h_qual does; the records must match the set's sequences in number and
+ *   length (glimmer-mg.cc:534-537: "sequence length does not match quality values length"). */
+int gmg_quality_parse_fasta(gmg_ctx* ctx, const char* h_bytes, int64_t n_bytes, int64_t* n_records, int64_t* n_values,
+                            int64_t* h_off, int32_t* h_values, int64_t cap_records, int64_t cap_values);
+int gmg_seqset_quality_from_fasta(gmg_ctx* ctx, gmg_seqset* s, const char* h_bytes, int64_t n_bytes);
 int64_t gmg_seqset_total_bases(const gmg_seqset* s);
 /* Set_GC_Fraction (glimmer_base.cc:2564-2595): (#c + #g after Filter) / total */
 int gmg_seqset_gc_fraction(gmg_seqset* s, double* gc);

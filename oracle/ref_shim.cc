@@ -121,4 +121,30 @@ int ref_fasta_read_file(const char* path, char** seqs, long* seqs_bytes, char** 
   return n;
 }
 
+// Fasta_Qual_Vec_Read (Common/fasta.cc:115-170) over a whole file: *vals = all values (malloc'd), *counts = values per
+// record (malloc'd, n entries), headers as above.  Returns the number of records.
+int ref_fasta_qual_read_file(const char* path, int** vals, long* n_vals, long** counts, char** hdrs, long* hdrs_bytes) {
+  FILE* fp = fopen(path, "r");
+  if (!fp) return -1;
+  std::vector<int> q, all;
+  std::vector<long> cnt;
+  std::string h, all_h;
+  while (Fasta_Qual_Vec_Read(fp, q, h)) {
+    all.insert(all.end(), q.begin(), q.end());
+    cnt.push_back((long)q.size());
+    all_h += h;
+    all_h.push_back('\0');
+  }
+  fclose(fp);
+  *vals = (int*)malloc((all.size() + 1) * sizeof(int));
+  memcpy(*vals, all.data(), all.size() * sizeof(int));
+  *n_vals = (long)all.size();
+  *counts = (long*)malloc((cnt.size() + 1) * sizeof(long));
+  memcpy(*counts, cnt.data(), cnt.size() * sizeof(long));
+  *hdrs = (char*)malloc(all_h.size() + 1);
+  memcpy(*hdrs, all_h.data(), all_h.size());
+  *hdrs_bytes = (long)all_h.size();
+  return (int)cnt.size();
+}
+
 }  // extern "C"

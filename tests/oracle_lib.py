@@ -211,8 +211,33 @@ def ref():
         R.ref_fasta_read_file.restype = C.c_int
         R.ref_fasta_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_long)]
+    if hasattr(R, "ref_fasta_qual_read_file"):
+        R.ref_fasta_qual_read_file.restype = C.c_int
+        R.ref_fasta_qual_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long), C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_long)]
     _ref = R
     return R
+
+
+def ref_qual_records(path):
+    """[(header bytes, [values])] as the UNMODIFIED reference reader sees a quality file (Fasta_Qual_Vec_Read,
+    Common/fasta.cc:115)."""
+    R = ref()
+    vp, cp, hp, nv, hn = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_long(), C.c_long()
+    n = R.ref_fasta_qual_read_file(os.fsencode(path), C.byref(vp), C.byref(nv), C.byref(cp), C.byref(hp), C.byref(hn))
+    assert n >= 0, path
+    vals = np.frombuffer(C.string_at(vp, nv.value * 4), np.int32).tolist() if nv.value else []
+    cnt = np.frombuffer(C.string_at(cp, n * 8), np.int64).tolist() if n else []
+    hdrs = C.string_at(hp, hn.value).split(b"\0")[:n]
+    free = C.CDLL(None).free
+    free.argtypes = [C.c_void_p]
+    for ptr in (vp, cp, hp):
+        free(ptr)
+    out, k = [], 0
+    for h, c in zip(hdrs, cnt):
+        out.append((h, vals[k:k + c]))
+        k += c
+    return out
 
 
 def ref_fasta_records(path):
@@ -282,3 +307,41 @@ def golden_path(name):
         if os.path.exists(cand):
             return cand
     return None
+
+
+def py_qual_records(image):
+    """Fasta_Qual_Vec_Read (Common/fasta.cc:115-170) restated: [(header, [values])]."""
+    out, i, n = [], 0, len(image)
+    while True:
+        while i < n and image[i:i + 1] != b">":
+            i += 1
+        if i >= n:
+            return out
+        i += 1
+        while i < n and image[i:i + 1] == b" ":
+            i += 1
+        if i >= n:
+            return out
+        j = image.find(b"\n", i)
+        j = n if j < 0 else j
+        hdr, i = image[i:j], min(j + 1, n)
+        vals, have, val = [], False, 0
+        while i < n and image[i:i + 1] != b">":
+            ch = image[i:i + 1]
+            if ch.isspace():
+                if have:
+                    vals.append(val)
+                have, val = False, 0
+            elif ch.isdigit():
+                have, val = True, 10 * val + int(ch)
+            i += 1
+        out.append((hdr, vals))
+
+
+QUAL_EDGE_IMAGES = {
+    "edge": (b"12 13 junk\n>r1  first \r\n40 40\t7\n\n 0 -3 1x2 999999 0012\n5>r2 mid-line start > odd\n1 2 3\n4"
+             b">r3\n>r4\n 8 \x0b9\x0c10\r11 \n>last header only"),
+    "edge2": b">   blanks\n1\n2 \n>\n3 4\n> \n\n>x\r5 6\rstill header\n7 8 9\n>tail\n10 11\n>   ",
+    "empty": b"",
+    "norecord": b"1 2 3\nno records\n",
+}

@@ -146,6 +146,50 @@ def test_fasta_ingest_on_device(gm, ctx, case, tmp_path):
         assert abs(ss.gc_fraction() - ref.gc_fraction()) == 0.0
 
 
+@pytest.mark.parametrize("case", ["reads", "edge", "edge2", "empty", "norecord"])
+def test_quality_ingest_on_device(gm, ctx, reads, case, tmp_path):
+    """gmg_quality_parse_fasta: records and values equal what the UNMODIFIED reference reader (Fasta_Qual_Vec_Read through
+    oracle/_ref's shim) makes of the same bytes, incl. malformed input; gmg_seqset_quality_from_fasta attaches them to a set
+    exactly as a host-supplied quality array."""
+    rng = np.random.default_rng(3)
+    if case == "reads":
+        sub = reads[:200]
+        qs = [rng.integers(0, 41, len(s)) for _, s in sub]
+        image = b"".join(b">" + h.encode() + b"\n" + b"\n".join(b" ".join(b"%d" % v for v in q[k:k + 17]) for k in range(0, len(q), 17))
+                         + b"\n" for (h, _), q in zip(sub, qs))
+    else:
+        image = O.QUAL_EDGE_IMAGES[case]
+    want = O.py_qual_records(image)
+    if O.have_ref() and hasattr(O.ref(), "ref_fasta_qual_read_file"):
+        path = tmp_path / "in.qual"
+        path.write_bytes(image)
+        assert O.ref_qual_records(str(path)) == want, "the restated reader disagrees with the reference's Fasta_Qual_Vec_Read"
+    off, vals = gm.parse_quality_fasta(ctx, image)
+    assert len(off) - 1 == len(want)
+    assert np.diff(off).tolist() == [len(q) for _, q in want]
+    assert vals.tolist() == [v for _, q in want for v in q]
+    if case == "reads":
+        p = gm.Params(True, allow_indels=1, have_quality_file=1)
+        gene = gm.ICM.Read(ctx, os.path.join(G, "NC_000915.icm"))
+
+        def run(ss):
+            gc = ss.gc_fraction()
+            p.set_ignore_score_len(gc)
+            indep = gm.ICM.Build_Indep_WO_Stops(ctx, gc)
+            ss.find_orfs(p)
+            ss.score_orfs_mg(gene, indep, p)
+            st, so = ss.get_starts()
+            return st.tobytes(), so.tolist()
+
+        a = gm.SeqSet(ctx, seqs=[s for _, s in sub], qual=np.concatenate(qs).astype(np.uint8))
+        b = gm.SeqSet(ctx, seqs=[s for _, s in sub])
+        b.set_quality_fasta(image)
+        assert run(a) == run(b)
+        c = gm.SeqSet(ctx, seqs=[s for _, s in sub[:-1]])
+        with pytest.raises(gm.GmgError):
+            c.set_quality_fasta(image)
+
+
 @pytest.mark.parametrize("k", [4, 5])
 def test_score_string_known_answers(gm, ctx, reads, k):
     m = gm.ICM.Read(ctx, os.path.join(G, f"cluster-{k}.icm"))

@@ -218,3 +218,14 @@ def test_reference_build_reproduces_golden_predict(tmp_path):
                        capture_output=True, timeout=300)
     assert r.returncode == 0
     assert open(tmp_path / "out.predict", "rb").read() == gzip.open(os.path.join(g, "NC_000915.run1.predict.gz"), "rb").read()
+
+
+@pytest.mark.parametrize("case", sorted(O.QUAL_EDGE_IMAGES))
+def test_quality_reader_restatement_equals_reference(case, tmp_path):
+    """The restated quality-file reader the GPU tests check gmg_quality_parse_fasta against (py_qual_records) sees what the
+    UNMODIFIED Fasta_Qual_Vec_Read (Common/fasta.cc:115-170, through oracle/_ref's shim) sees, on malformed input too."""
+    if not (O.have_ref() and hasattr(O.ref(), "ref_fasta_qual_read_file")):
+        pytest.skip("oracle/_ref not built")
+    path = tmp_path / "in.qual"
+    path.write_bytes(O.QUAL_EDGE_IMAGES[case])
+    assert O.ref_qual_records(str(path)) == O.py_qual_records(O.QUAL_EDGE_IMAGES[case])
