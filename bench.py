@@ -505,7 +505,19 @@ K2_BYTES_PER_BASE = 24 + 48 + 8 + 1   # planes read; cum doubles, stop tables, q
 READS400_BATCH, READS400_TOTAL, READS400_LEN = 25_000, 1_000_000, 400
 READS100_BATCH, READS100_PER_CLUSTER, READS100_LEN, READS100_CLUSTERS = 312_500, 625_000, 100, 16
 TRAIN_SEQS, TRAIN_CODONS = 500_500, 333
-MAX_RESIDENT_BATCHES = 6
+MAX_RESIDENT_BATCHES = 8
+
+
+# Job order of the reads100 workload: batch b (two per cluster) belongs to cluster PERM[(b + 4 (b // 16)) % 16].  The ORF
+# density follows the GC content (0.30 .. 0.70 over the clusters; fewer stop codons at high GC), so a job list in GC order
+# gives the ranks of a multi-GPU run unlike work -- and the first few batches, all a single GPU keeps resident, are the
+# cheapest ones.  With this order the batches a rank is dealt (b = rank + world * i) have the same mean GC at every world
+# size: PERM[m] + PERM[m + 8] = 15, every stride-4 quadruple sums to 30, the first eight entries to 60.
+READS100_PERM = (0, 14, 2, 12, 11, 5, 9, 7, 15, 1, 13, 3, 4, 10, 6, 8)
+
+
+def reads100_cluster_of_batch(b):
+    return READS100_PERM[(b + 4 * (b // READS100_CLUSTERS)) % READS100_CLUSTERS]
 
 
 def reads_batches(kind, rank, world, scale, n_wanted):
@@ -531,7 +543,7 @@ def reads_batches(kind, rank, world, scale, n_wanted):
     genomes = {}
     for i in range(min(n_wanted, MAX_RESIDENT_BATCHES)):
         b = (rank + world * i) % n_batches
-        k = b % READS100_CLUSTERS
+        k = reads100_cluster_of_batch(b)
         if k not in genomes:
             gc = float(np.linspace(0.30, 0.70, READS100_CLUSTERS)[k])
             genomes[k] = W.contig(W.READS100_SEED * 1000 + k, 2_000_000, freq=W.reweight_gc(freq, gc), gc=gc)
@@ -839,6 +851,15 @@ def run_b200_reads(args, env, kind):
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
     ms_max, e2e_max, pipe_max = t.tolist()
     all_bases, all_e2e_bases, all_pipe_bases = tb.tolist()
+    # per-rank view (diagnostic): step, kernel and end-to-end times of every rank -- batches differ between ranks (GC
+    # 0.30 .. 0.70: the ORF density varies) and the headline takes the slowest
+    mine = torch.tensor([ms / K, kms["k1"][0] / K, kms["k2"][0] / K, kms["k3"][0] / K, e2e_ms / K, (pipe_ms or 0.0) / K],
+                        dtype=torch.float64, device=dev)
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(x, 4) for x in r.tolist()] for r in per_rank]
     if rank == 0:
         value = all_bases / (ms_max / 1e3) / 1e9
         e2e = all_e2e_bases / (e2e_max / 1e3) / 1e9
@@ -867,7 +888,8 @@ def run_b200_reads(args, env, kind):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / K, "in_flight": 1},
                 "gpu_launches": int(launches), "clocks": clk,
-                "parity_checked": parity is not None, "parity": parity}
+                "parity_checked": parity is not None, "parity": parity,
+                "per_rank_ms": {"columns": ["step", "k1", "k2", "k3", "e2e_one_batch", "e2e_in_flight"], "rows": per_rank}}
         if pipe_max > 0:
             # headline e2e = the streaming form (N_LANES batches in flight); the one-batch-at-a-time figure stays beside it
             line["e2e"].update({"value": all_pipe_bases / (pipe_max / 1e3) / 1e9, "ms_per_step": pipe_max / K, "in_flight": N_LANES,
@@ -1352,7 +1374,18 @@ def run_b200_simple(args, env):
     return None
 
 
-N_LANES = int(os.environ.get("GMG_BENCH_LANES", "4"))  # batches in flight of the streaming end-to-end measurement
+def _default_lanes():
+    """Batches in flight of the streaming end-to-end measurement: 4, fewer when the ranks of a node would otherwise hold
+    more synchronising host threads than the node has cores."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 4
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return max(2, min(4, cores // max(world, 1) - 1))
+
+
+N_LANES = int(os.environ.get("GMG_BENCH_LANES", "0")) or _default_lanes()
 
 
 def main():

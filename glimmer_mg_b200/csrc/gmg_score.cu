@@ -526,7 +526,6 @@ static int launch_k1(gmg_ctx* ctx, const gmg_icm* gene, gmg_seqset* s, float** p
     else if (ku == 2) GMG_K1_LAUNCH(2, 1024);
     else if (ku == 3 && knt == 768) GMG_K1_LAUNCH(3, 768);
     else if (ku == 8 && knt == 256) GMG_K1_LAUNCH(8, 256);
-    else if (ku == 4 && knt == 768) GMG_K1_LAUNCH(4, 768);
     else if (ku == 4) GMG_K1_LAUNCH(4, 512);
     else GMG_K1_LAUNCH(6, 384);
 #undef GMG_K1_LAUNCH
