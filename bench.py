@@ -879,7 +879,8 @@ def run_b200_reads(args, env, kind):
                            "l2": "256 MB flush write before every timed step",
                            "sharding": "batches dealt to ranks, no collective"},
                 "roofline": {"bound": "hbm", "kernel": {"k1": "k1_planes", "k2": "k2_prefix"}[dom], "achieved": achieved,
-                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": ncu_traffic({"k1": "k1_planes_reads100", "k2": "k2_prefix_reads400"}[dom], nb_avg),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": nb_avg * per_base[dom],
                              "kernel_ms": dom_ms, "kernel_share_of_step": kms[dom][0] / ms,
                              "ms_per_step_by_kernel": {k: v[0] / K for k, v in kms.items()},

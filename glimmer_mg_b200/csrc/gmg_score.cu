@@ -2940,10 +2940,11 @@ __device__ __forceinline__ void mgp_term(const DevIcm& indep, const float* __res
 
 __global__ void __launch_bounds__(128) k3_mg_plain_count(MgfBatch B, DevParams P, const gmg_orf* __restrict__ orfs,
                                                          const int32_t* __restrict__ orf_seq, int64_t n_orfs,
-                                                         int64_t* __restrict__ counts) {
+                                                         int64_t* __restrict__ counts, uint2* __restrict__ geom) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_orfs) return;
   const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
+  geom[o] = make_uint2((uint32_t)S.a, (uint32_t)S.L);  // the ORF's sequence (first base, length): saves the emission kernel a load round
   const gmg_orf orf = orfs[o];
   const bool fwd = orf.frame > 0;
   const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
@@ -3100,30 +3101,52 @@ __device__ __forceinline__ double mgl_codon_sum(const DevIcm& indep, const float
   return x;
 }
 
-__global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
+__global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
                                                          const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, Which4 which,
                                                          const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                          int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                          gmg_start* __restrict__ starts, int exact_len,
-                                                         unsigned long long* __restrict__ n_ordered) {
+                                                         unsigned long long* __restrict__ n_ordered,
+                                                         const uint2* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   __shared__ double s_serial[4][32 * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
   const float* s_lut = indep.lut3;            // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (o >= n_orfs) return;  // warp-uniform
-  const int64_t so = __ldg(start_off + o), so1 = __ldg(start_off + o + 1);
-  const int32_t sq = __ldg(orf_seq + o);
-  const gmg_orf orf = orfs[o];
-  if (so1 == so) return;
-  const MgfSeq S = mgf_seq_of(B, sq);
+  // Persistent warps: a warp's life used to be five dependent load rounds (CSR -> ORF -> sequence offsets -> packed bases ->
+  // bucket index -> planes) with nothing to overlap them.  The first two are now one (the count kernel leaves every ORF's
+  // sequence start and length in `geom`) and are fetched for the warp's NEXT ORF while it works on the current one.
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nx_so = 0, nx_so1 = 0;
+  int4 nx_orf = make_int4(0, 0, 0, 0);
+  uint2 nx_g = make_uint2(0u, 0u);
+  if (o < n_orfs) {
+    nx_so = __ldg(start_off + o);
+    nx_so1 = __ldg(start_off + o + 1);
+    nx_orf = __ldg(reinterpret_cast<const int4*>(orfs + o));
+    nx_g = __ldg(geom + o);
+  }
+  for (; o < n_orfs; o += n_warps) {  // warp-uniform
+  const int64_t so = nx_so, so1 = nx_so1;
+  gmg_orf orf;
+  memcpy(&orf, &nx_orf, sizeof orf);
+  MgfSeq S;
+  S.a = (int64_t)nx_g.x;
+  S.L = (int)nx_g.y;
+  if (o + n_warps < n_orfs) {
+    nx_so = __ldg(start_off + o + n_warps);
+    nx_so1 = __ldg(start_off + o + n_warps + 1);
+    nx_orf = __ldg(reinterpret_cast<const int4*>(orfs + o + n_warps));
+    nx_g = __ldg(geom + o + n_warps);
+  }
+  if (so1 == so) continue;
   const bool fwd = orf.frame > 0;
   const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
   const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
   MgfOwn f;
   mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
   const int need = f.j_hi;  // terms j = 0 .. need - 1: score[j - 1] of the highest record position j_hi
-  if (!mgl_takes(need, f.j_lo)) return;
+  if (!mgl_takes(need, f.j_lo)) continue;
   MgfPlan pl;
   mgf_plan(f, fwd, pl);
   const int ncod = need / 3, nch = (ncod + 31) >> 5;
@@ -3212,6 +3235,8 @@ __global__ void __launch_bounds__(128) k3_mg_plain_lanes(DevIcm indep, const flo
       placed += __popc(m1) + __popc(m2);
       seen_nonzero = seen_nonzero || mnz != 0u;
     }
+  }
+  __syncwarp();  // the serial row is free for the warp's next ORF
   }
 }
 
@@ -3822,6 +3847,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   B.cb = s->d_cbits;
   B.nwc = s->nwc;
   int64_t* counts = NULL;
+  uint2* geom = NULL;
   if (k3mg_mode == 2) {
     // The record counts only need the codon bitmaps: they are taken, scanned and their total sent to pinned memory BEFORE
     // the walks are launched, so the host sizes the output while K1 runs and the emission kernel follows K1 without a gap
@@ -3832,7 +3858,11 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     counts = (int64_t*)d_counts;
     GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
-    k3_mg_plain_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, s->n_orfs, counts);
+    void* d_geom;
+    if (gmg_scratch(ctx, SCR_MISC, (size_t)(s->n_orfs + 1) * sizeof(uint2), &d_geom)) return 1;
+    geom = (uint2*)d_geom;
+    k3_mg_plain_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, s->n_orfs, counts,
+                                                                                   geom);
     gmg_prof_end(ctx, GMG_PROF_K3);
     ctx->launches++;
     if (exclusive_sum_i64(ctx, counts, s->d_start_off, s->n_orfs + 1)) return 1;
@@ -3868,9 +3898,10 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
         memset(&which, 0, sizeof which);
         for (int cd = 0; cd < 64; cd++)
           which.w[cd >> 4] |= (unsigned long long)(cs.which[cd] < 15 ? cs.which[cd] : 15) << (4 * (cd & 15));
-        k3_mg_plain_lanes<<<(unsigned)((s->n_orfs * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        const int64_t lanes_need = (s->n_orfs * 32 + 127) / 128, lanes_cap = (int64_t)ctx->sm_count * 8;  // 8 CTAs per SM resident
+        k3_mg_plain_lanes<<<(unsigned)(lanes_need < lanes_cap ? lanes_need : lanes_cap), 128, 0, ctx->stream>>>(
             indep->dev, planes, s->d_bktidx, B, dp, which, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
-            (unsigned long long*)(counts + s->n_orfs + 1));
+            (unsigned long long*)(counts + s->n_orfs + 1), geom);
         ctx->launches++;
       }
       // every ORF taken above?  (need <= orf_len <= max_len; j_lo >= 3 whenever min_gene_len >= 6)
