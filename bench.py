@@ -884,8 +884,11 @@ def run_b200_reads(args, env, kind):
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": nb_avg * per_base[dom],
                              "kernel_ms": dom_ms, "kernel_share_of_step": kms[dom][0] / ms,
                              "ms_per_step_by_kernel": {k: v[0] / K for k, v in kms.items()},
-                             "note": "k3_mg_starts (per-ORF indel recursion) is latency/divergence-bound and has no "
-                                     "HBM roofline; its time is listed beside the two streaming kernels"},
+                             "note": ("k3 = the flat start enumeration of -i (one thread per candidate call, L2-latency / issue "
+                                      "bound): no HBM roofline; its time is listed beside the two streaming kernels") if indels else
+                                     ("k1 = the bucketed walk kernel + the partial-window fix kernel (shared-memory gather wavefronts "
+                                      "at 77 % of the pipe, not HBM, bind it); k3 = the fused K2 + K3 pass (k3_mg_plain_lanes: DRAM "
+                                      "sector gathers through the bucket index, latency bound): its time is listed beside K1")},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / K, "in_flight": 1},
                 "gpu_launches": int(launches), "clocks": clk,
