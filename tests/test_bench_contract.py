@@ -47,3 +47,20 @@ def test_b200_arm_needs_a_gpu():
         pytest.skip("a GPU is present")
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reads100_job_order_balances_clusters_over_ranks():
+    """The batches a rank is dealt (b = rank + world * i) must have the same mean cluster index -- i.e. the same mean GC
+    content, which sets the ORF density and so the cost of a step -- at every world size, and every cluster appears twice
+    in the job list (BASELINE configs[4]: 16 clusters x 625 000 reads = two batches each)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    n_batches = b.READS100_CLUSTERS * (b.READS100_PER_CLUSTER // b.READS100_BATCH)
+    clusters = [b.reads100_cluster_of_batch(i) for i in range(n_batches)]
+    assert sorted(clusters) == sorted(list(range(b.READS100_CLUSTERS)) * 2)
+    for world in (1, 2, 4, 8):
+        for rank in range(world):
+            mine = [b.reads100_cluster_of_batch((rank + world * i) % n_batches) for i in range(b.MAX_RESIDENT_BATCHES)]
+            assert sum(mine) * 2 == (b.READS100_CLUSTERS - 1) * len(mine), (world, rank, mine)

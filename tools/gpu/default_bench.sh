@@ -1,4 +1,4 @@
-# round 2, GPU call Y: the default bench (N=1, everything on) and the reference arm, as the driver runs them
+# the default bench (N=1, everything on) and the reference arm, as the driver runs them
 mkdir -p gpurun_out
 ( timeout 900 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/r2y_bench_ref.json 2> gpurun_out/r2y_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/r2y_bench_ref.json
 ( timeout 1200 python bench.py ) > gpurun_out/r2y_bench_n1.json 2> gpurun_out/r2y_bench_n1.err; echo "bench n1 rc=$?"; tail -c 600 gpurun_out/r2y_bench_n1.err

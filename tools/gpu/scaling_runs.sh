@@ -1,4 +1,4 @@
-# round 2, GPU call Z (8 GPUs): scaling of the default workload (reads100) at N = 8, 4, 2 and of training at N = 8, final code
+# scaling of the default workload (reads100) at N = 8, 4, 2 and of training at N = 8, final code
 mkdir -p gpurun_out
 for n in 8 4 2; do
 ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2975$n bench.py --gpus $n --steps 40 --warmup 5 --no-cpu-baseline --no-extra ) > gpurun_out/r2z_reads100_n$n.json 2> gpurun_out/r2z_reads100_n$n.err; echo "reads100 n$n rc=$?"; tail -c 200 gpurun_out/r2z_reads100_n$n.err

@@ -1,4 +1,4 @@
-# round 2, GPU call X: persistent lanes kernel with next-ORF prefetch; representative reads100 job order
+# the GPU test suite, then reads100 with and without the codon-per-lane kernel (A/B)
 mkdir -p gpurun_out
 ( timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 --durations=3 ) > gpurun_out/r2x_tests.log 2>&1; echo "tests rc=$?"; tail -6 gpurun_out/r2x_tests.log
 ( timeout 600 python bench.py --workload reads100 --steps 32 --warmup 5 --no-cpu-baseline --no-extra ) > gpurun_out/r2x_reads100.json 2> gpurun_out/r2x_reads100.err; echo "reads100 rc=$?"; tail -c 300 gpurun_out/r2x_reads100.err
