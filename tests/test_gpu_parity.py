@@ -352,6 +352,39 @@ def test_find_orfs_reads(gm, ctx, reads, flags):
         assert got.tolist() == want.tolist(), i
 
 
+@pytest.mark.parametrize("flags", [dict(min_gene_len=6), dict(min_gene_len=9, allow_indels=1, min_indel_orf_len=6),
+                                   dict(min_gene_len=12, allow_truncated=0)])
+def test_find_orfs_tiny_and_ragged_sequences(gm, ctx, genome, flags):
+    """The tiled ORF finder on what its staging does not cover: thousands of sequences of 0 .. 12 bases (more than 128
+    sequence bounds inside a 1 024-base tile: the per-base lookup path), sequences that straddle tiles, a long one whose
+    look-backs leave the staged bitmap words, and ORFs that close exactly at tile edges -- each table equal to the
+    checker's for that sequence alone."""
+    rng = np.random.default_rng(17)
+    g = O.filter_lower(genome[:300000])
+    seqs, pos = [], 0
+    for _ in range(6000):  # tiny: the bounds of a tile overflow the staged list
+        n = int(rng.integers(0, 13))
+        seqs.append(g[pos:pos + n])
+        pos += n
+    for n in (1024, 1023, 1025, 2048, 3, 0, 1, 2, 5000, 7, 1024 * 3 - 1):  # tile-sized and straddling
+        seqs.append(g[pos:pos + n])
+        pos += n
+    seqs.append(b"atg" + b"gcc" * 900 + b"taa" + b"a" * 50)  # one ORF of 2.7 kbp: look-backs far beyond the halo
+    for _ in range(300):  # read-like
+        n = int(rng.integers(30, 400))
+        seqs.append(g[pos:pos + n])
+        pos += n
+    p = gm.Params(True, **flags)
+    op = O.params(True, **flags)
+    ss = gm.SeqSet(ctx, seqs=seqs)
+    n = ss.find_orfs(p)
+    orfs, off = ss.get_orfs()
+    assert off[-1] == n and n > 1000
+    for i, s0 in enumerate(seqs):
+        want = O.find_orfs(s0, op)
+        assert orfs[off[i]:off[i + 1]].tolist() == want.tolist(), (i, len(s0))
+
+
 @pytest.mark.parametrize("truncated", [0, 1])
 def test_find_orfs_genome(gm, ctx, genome, truncated):
     s0 = genome[:400000]
