@@ -5,6 +5,7 @@
 //                                                      anything else incl. 'n' -> 'c')
 //   tolower(Filter(c))     Glimmer/glimmer-mg.cc:381-382, glimmer3.cc:270-271
 //   Set_GC_Fraction        Glimmer/glimmer_base.cc:2564-2595
+#include <limits.h>
 #include <string.h>
 
 #include <cub/device/device_scan.cuh>
@@ -107,58 +108,95 @@ struct Uint4Add {
 };
 
 // exclusive per-base prefix -> absolute plane index of each block's first a / c / g / t, and the walk-ready
-// contexts of every position stored at its plane index
+// contexts of every position stored at its plane index.  One CTA per tile of BKT_TILE bases (a warp takes four 32-base
+// blocks); staged once per CTA: the per-base totals and the sequence bounds that fall into the tile, so that a position
+// finds its distance to the ends of its sequence without dependent global loads (they were 40 % of the kernel's stalls).
+#define BKT_TILE 1024
+#define BKT_NB 129
 __global__ void __launch_bounds__(256) k_bucket_finish(const uint64_t* __restrict__ words, int64_t total, int64_t nblk,
-                                                       const int64_t* __restrict__ off, const int32_t* __restrict__ blk2seq,
+                                                       const int64_t* __restrict__ off, int64_t n_seq,
+                                                       const int32_t* __restrict__ blk2seq,
                                                        const uint4* __restrict__ prefix, const uint4* __restrict__ cnt,
                                                        uint4* __restrict__ bktidx, uint32_t* __restrict__ ctxf,
                                                        uint32_t* __restrict__ ctxr,
                                                        unsigned long long* __restrict__ n_base) {
-  // totals per base: once per CTA (every thread used to re-derive them: 10 % of the kernel's instructions)
   __shared__ unsigned s_tot[4];
-  if (threadIdx.x == 0) {
+  __shared__ long long s_bound[BKT_NB];
+  __shared__ unsigned char s_blk[BKT_TILE / 32];
+  const int64_t p0 = (int64_t)blockIdx.x * BKT_TILE;
+  const int t = threadIdx.x;
+  if (t == 0) {
     const uint4 lp = prefix[nblk - 1], lc = cnt[nblk - 1];
     s_tot[0] = lp.x + lc.x;
     s_tot[1] = lp.y + lc.y;
     s_tot[2] = lp.z + lc.z;
     s_tot[3] = lp.w + lc.w;
+  } else if (t >= 32 && t < 32 + BKT_NB) {
+    const int k = t - 32;
+    const int32_t s0 = __ldg(blk2seq + (p0 >> 5)) & 0x7FFFFFFF;  // the sequence that holds the tile's first base
+    const int64_t idx = (int64_t)s0 + k;
+    s_bound[k] = idx <= n_seq ? (long long)__ldg(off + idx) : LLONG_MAX;
   }
   __syncthreads();
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool staged = s_bound[BKT_NB - 1] > p0 + BKT_TILE - 1;  // all of the tile's sequences are in the staged list
+  if (staged && t < BKT_TILE / 32) {  // staged bound index of the sequence holding the first base of each block
+    const int64_t p = p0 + 32 * t;
+    int lo = 0, hi = BKT_NB - 1;  // s_bound[lo] <= p < s_bound[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_bound[mid] <= p) lo = mid;
+      else hi = mid;
+    }
+    s_blk[t] = (unsigned char)lo;
+  }
+  __syncthreads();
   const unsigned na = s_tot[0], nc = s_tot[1], ng = s_tot[2], nt = s_tot[3];
-  if (p == 0) {
+  if (blockIdx.x == 0 && t == 0) {
     n_base[0] = na; n_base[1] = nc; n_base[2] = ng; n_base[3] = nt;
   }
-  if (p >= total) return;
-  const int64_t blk = p >> 5;
-  uint4 pre = prefix[blk];
-  pre.y += na;
-  pre.z += na + nc;
-  pre.w += na + nc + ng;
-  if ((p & 31) == 0) bktidx[blk] = pre;
-  // the block's word and its neighbours (warp-uniform loads; zero padding either side of the batch): every window below
-  // is cut from these three
-  const uint64_t wm = __ldg(words + blk - 1), w = __ldg(words + blk), wp = __ldg(words + blk + 1);
-  const int i = (int)(p & 31);
-  const unsigned b = (unsigned)(w >> (2 * i)) & 3u;
-  const uint64_t x = w ^ (0x5555555555555555ull * b);
-  const uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull & ((1ull << (2 * i)) - 1ull);
-  const unsigned first = b == 0 ? pre.x : (b == 1 ? pre.y : (b == 2 ? pre.z : pre.w));
-  const unsigned idx = first + (unsigned)__popcll(eq);
-  // forward: bases p .. p+15, order reversed (base p in the top pair)
-  uint32_t f = (uint32_t)(i == 0 ? w : ((w >> (2 * i)) | (wp << (64 - 2 * i))));
-  f = __brev(f);
-  f = ((f >> 1) & 0x55555555u) | ((f & 0x55555555u) << 1);
-  // reverse: complement of bases p-15 .. p (base p-15 in the low pair)
-  const uint32_t r = ~(uint32_t)(i >= 15 ? (w >> (2 * (i - 15))) : ((wm >> (64 - 2 * (15 - i))) | (w << (2 * (15 - i)))));
-  // the low four bits (the two bases farthest from p; windows of up to 14 bases never see them) hold the distance
-  // to the end / start of the sequence, clipped to 15: which window positions exist
-  int32_t sq = __ldg(blk2seq + blk) & 0x7FFFFFFF;
-  int64_t nx = __ldg(off + sq + 1);
-  while (p >= nx) nx = __ldg(off + (++sq) + 1);
-  const int64_t q = p - __ldg(off + sq), e = nx - 1 - p;
-  ctxf[idx] = (f & ~15u) | (uint32_t)(e < 15 ? e : 15);
-  ctxr[idx] = (r & ~15u) | (uint32_t)(q < 15 ? q : 15);
+  const int warp = t >> 5, i = t & 31;
+#pragma unroll 1
+  for (int k = 0; k < BKT_TILE / 256; k++) {
+    const int bt = warp + 8 * k;  // block of the tile
+    const int64_t blk = (p0 >> 5) + bt, p = (blk << 5) + i;
+    if (p >= total) continue;
+    uint4 pre = prefix[blk];
+    pre.y += na;
+    pre.z += na + nc;
+    pre.w += na + nc + ng;
+    if (i == 0) bktidx[blk] = pre;
+    // the block's word and its neighbours (warp-uniform loads; zero padding either side of the batch): every window
+    // below is cut from these three
+    const uint64_t wm = __ldg(words + blk - 1), w = __ldg(words + blk), wp = __ldg(words + blk + 1);
+    const unsigned b = (unsigned)(w >> (2 * i)) & 3u;
+    const uint64_t x = w ^ (0x5555555555555555ull * b);
+    const uint64_t eq = ~(x | (x >> 1)) & 0x5555555555555555ull & ((1ull << (2 * i)) - 1ull);
+    const unsigned first = b == 0 ? pre.x : (b == 1 ? pre.y : (b == 2 ? pre.z : pre.w));
+    const unsigned idx = first + (unsigned)__popcll(eq);
+    // forward: bases p .. p+15, order reversed (base p in the top pair)
+    uint32_t f = (uint32_t)(i == 0 ? w : ((w >> (2 * i)) | (wp << (64 - 2 * i))));
+    f = __brev(f);
+    f = ((f >> 1) & 0x55555555u) | ((f & 0x55555555u) << 1);
+    // reverse: complement of bases p-15 .. p (base p-15 in the low pair)
+    const uint32_t r = ~(uint32_t)(i >= 15 ? (w >> (2 * (i - 15))) : ((wm >> (64 - 2 * (15 - i))) | (w << (2 * (15 - i)))));
+    // the low four bits (the two bases farthest from p; windows of up to 14 bases never see them) hold the distance
+    // to the end / start of the sequence, clipped to 15: which window positions exist
+    int64_t a, nx;
+    if (staged) {
+      int kb = s_blk[bt];
+      while (s_bound[kb + 1] <= p) kb++;
+      a = s_bound[kb];
+      nx = s_bound[kb + 1];
+    } else {
+      int32_t sq = __ldg(blk2seq + blk) & 0x7FFFFFFF;
+      nx = __ldg(off + sq + 1);
+      while (p >= nx) nx = __ldg(off + (++sq) + 1);
+      a = __ldg(off + sq);
+    }
+    const int64_t q = p - a, e = nx - 1 - p;
+    ctxf[idx] = (f & ~15u) | (uint32_t)(e < 15 ? e : 15);
+    ctxr[idx] = (r & ~15u) | (uint32_t)(q < 15 ? q : 15);
+  }
 }
 
 // Base buckets and walk-ready contexts exist for K1 only: built on its first launch on a set (training and the
@@ -181,8 +219,8 @@ int gmg_seqset_ensure_buckets(gmg_ctx* ctx, gmg_seqset* s) {
   GMG_CUDA(cub::DeviceScan::ExclusiveScan(NULL, tmp_bytes, cnt, prefix, Uint4Add(), make_uint4(0, 0, 0, 0), nblk, ctx->stream));
   if (gmg_scratch(ctx, SCR_TMP4, tmp_bytes, &d_tmp)) return 1;
   GMG_CUDA(cub::DeviceScan::ExclusiveScan(d_tmp, tmp_bytes, cnt, prefix, Uint4Add(), make_uint4(0, 0, 0, 0), nblk, ctx->stream));
-  k_bucket_finish<<<(unsigned)((s->total + 255) / 256), 256, 0, ctx->stream>>>(
-      s->d_words, s->total, nblk, s->d_off, s->d_blk2seq, prefix, cnt, (uint4*)s->d_bktidx, s->d_ctxf, s->d_ctxr,
+  k_bucket_finish<<<(unsigned)((s->total + BKT_TILE - 1) / BKT_TILE), 256, 0, ctx->stream>>>(
+      s->d_words, s->total, nblk, s->d_off, s->n, s->d_blk2seq, prefix, cnt, (uint4*)s->d_bktidx, s->d_ctxf, s->d_ctxr,
       s->d_gc + 2);
   ctx->launches += 4;
   GMG_CUDA(cudaGetLastError());
