@@ -2938,13 +2938,23 @@ __device__ __forceinline__ void mgp_term(const DevIcm& indep, const float* __res
   *n_out = n;
 }
 
+// What the emission kernel needs of an ORF's root call, worked out once by the count kernel (one thread per ORF) instead of
+// by every emission warp: sequence (first base, length), lo / hi, the eligible j range and the plan of the truncated
+// records (mgf_own_open, mgf_plan).  32 bytes: two 16-byte loads, prefetched one ORF ahead.
+struct PlainDesc {
+  uint32_t a;    // global index of the sequence's first base (batches hold fewer than 2^32 bases)
+  int32_t L;     // its length
+  int32_t lo, hi;
+  int32_t j_lo, j_hi, j_hs;
+  uint32_t bits;  // bit 0 fwd, bit 1 trunc, bit 2 state_after, bits 4.. nT
+};
+
 __global__ void __launch_bounds__(128) k3_mg_plain_count(MgfBatch B, DevParams P, const gmg_orf* __restrict__ orfs,
                                                          const int32_t* __restrict__ orf_seq, int64_t n_orfs,
-                                                         int64_t* __restrict__ counts, uint2* __restrict__ geom) {
+                                                         int64_t* __restrict__ counts, PlainDesc* __restrict__ desc) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_orfs) return;
   const MgfSeq S = mgf_seq_of(B, orf_seq[o]);
-  geom[o] = make_uint2((uint32_t)S.a, (uint32_t)S.L);  // the ORF's sequence (first base, length): saves the emission kernel a load round
   const gmg_orf orf = orfs[o];
   const bool fwd = orf.frame > 0;
   const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
@@ -2952,6 +2962,18 @@ __global__ void __launch_bounds__(128) k3_mg_plain_count(MgfBatch B, DevParams P
   MgfOwn f;
   mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
   counts[o] = mgf_own_count(f, fwd, -1);
+  MgfPlan pl;
+  mgf_plan(f, fwd, pl);
+  PlainDesc d;
+  d.a = (uint32_t)S.a;
+  d.L = S.L;
+  d.lo = lo;
+  d.hi = hi;
+  d.j_lo = f.j_lo;
+  d.j_hi = f.j_hi;
+  d.j_hs = f.j_hs;
+  d.bits = (fwd ? 1u : 0u) | (f.trunc ? 2u : 0u) | (pl.state_after ? 4u : 0u) | ((uint32_t)pl.nT << 4);
+  desc[o] = d;
 }
 
 __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __restrict__ planes,
@@ -3107,48 +3129,59 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
                                                          int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                          gmg_start* __restrict__ starts, int exact_len,
                                                          unsigned long long* __restrict__ n_ordered,
-                                                         const uint2* __restrict__ geom) {
+                                                         const PlainDesc* __restrict__ desc) {
   constexpr unsigned FULL = 0xffffffffu;
   __shared__ double s_serial[4][32 * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
   const float* s_lut = indep.lut3;            // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // Persistent warps: a warp's life used to be five dependent load rounds (CSR -> ORF -> sequence offsets -> packed bases ->
-  // bucket index -> planes) with nothing to overlap them.  The first two are now one (the count kernel leaves every ORF's
-  // sequence start and length in `geom`) and are fetched for the warp's NEXT ORF while it works on the current one.
+  // bucket index -> planes) with nothing to overlap them, and ~100 instructions of call geometry that every warp derived
+  // again.  The count kernel now leaves a 32-byte descriptor per ORF (sequence, lo / hi, eligible j range, plan of the
+  // truncated records), fetched together with the CSR pair for the warp's NEXT ORF while it works on the current one.
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nx_so = 0, nx_so1 = 0;
-  int4 nx_orf = make_int4(0, 0, 0, 0);
-  uint2 nx_g = make_uint2(0u, 0u);
+  uint4 nx_d0 = make_uint4(0u, 0u, 0u, 0u), nx_d1 = make_uint4(0u, 0u, 0u, 0u);
   if (o < n_orfs) {
     nx_so = __ldg(start_off + o);
     nx_so1 = __ldg(start_off + o + 1);
-    nx_orf = __ldg(reinterpret_cast<const int4*>(orfs + o));
-    nx_g = __ldg(geom + o);
+    nx_d0 = __ldg(reinterpret_cast<const uint4*>(desc + o));
+    nx_d1 = __ldg(reinterpret_cast<const uint4*>(desc + o) + 1);
   }
   for (; o < n_orfs; o += n_warps) {  // warp-uniform
   const int64_t so = nx_so, so1 = nx_so1;
-  gmg_orf orf;
-  memcpy(&orf, &nx_orf, sizeof orf);
-  MgfSeq S;
-  S.a = (int64_t)nx_g.x;
-  S.L = (int)nx_g.y;
+  const uint4 d0 = nx_d0, d1 = nx_d1;
   if (o + n_warps < n_orfs) {
     nx_so = __ldg(start_off + o + n_warps);
     nx_so1 = __ldg(start_off + o + n_warps + 1);
-    nx_orf = __ldg(reinterpret_cast<const int4*>(orfs + o + n_warps));
-    nx_g = __ldg(geom + o + n_warps);
+    nx_d0 = __ldg(reinterpret_cast<const uint4*>(desc + o + n_warps));
+    nx_d1 = __ldg(reinterpret_cast<const uint4*>(desc + o + n_warps) + 1);
   }
   if (so1 == so) continue;
-  const bool fwd = orf.frame > 0;
-  const int hi = fwd ? orf.stop_position - 1 : orf.stop_position + 3 + orf.orf_len;
-  const int lo = fwd ? hi - orf.orf_len : orf.stop_position + 3;
-  MgfOwn f;
-  mgf_own_open(B, S, P, fwd, lo, hi, 0, f);
+  MgfSeq S;
+  S.a = (int64_t)d0.x;
+  S.L = (int)d0.y;
+  const int lo = (int)d0.z, hi = (int)d0.w;
+  const bool fwd = (d1.w & 1u) != 0;
+  MgfOwn f;  // as mgf_own_open leaves it
+  f.lo = lo;
+  f.hi = hi;
+  f.m = hi - lo > 0 ? hi - lo : 0;
+  f.trunc = (d1.w >> 1) & 1u;
+  f.j_lo = (int)d1.x;
+  f.j_hi = (int)d1.y;
+  f.j_hs = (int)d1.z;
+  f.cpos = fwd ? d0.x + (uint32_t)(hi - 3) : d0.x + (uint32_t)(lo - 1);
+  f.st = B.cb + (size_t)((fwd ? 0u : 3u) + f.cpos % 3u) * (size_t)B.nwc;
   const int need = f.j_hi;  // terms j = 0 .. need - 1: score[j - 1] of the highest record position j_hi
   if (!mgl_takes(need, f.j_lo)) continue;
-  MgfPlan pl;
-  mgf_plan(f, fwd, pl);
+  MgfPlan pl;  // as mgf_plan leaves it
+  pl.nT = (int)(d1.w >> 4);
+  pl.state_after = (int)((d1.w >> 2) & 1u);
+  {
+    const int jt = f.j_hi - 3 * pl.nT;
+    pl.jb = jt < f.j_hs ? jt : f.j_hs;
+  }
   const int ncod = need / 3, nch = (ncod + 31) >> 5;
   double incl[MGL_K];
   double carry = 0.0;
@@ -3847,7 +3880,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
   B.cb = s->d_cbits;
   B.nwc = s->nwc;
   int64_t* counts = NULL;
-  uint2* geom = NULL;
+  PlainDesc* geom = NULL;
   if (k3mg_mode == 2) {
     // The record counts only need the codon bitmaps: they are taken, scanned and their total sent to pinned memory BEFORE
     // the walks are launched, so the host sizes the output while K1 runs and the emission kernel follows K1 without a gap
@@ -3859,8 +3892,8 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
     GMG_CUDA(cudaMemsetAsync(counts + s->n_orfs, 0, 2 * sizeof(int64_t), ctx->stream));
     if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
     void* d_geom;
-    if (gmg_scratch(ctx, SCR_MISC, (size_t)(s->n_orfs + 1) * sizeof(uint2), &d_geom)) return 1;
-    geom = (uint2*)d_geom;
+    if (gmg_scratch(ctx, SCR_MISC, (size_t)(s->n_orfs + 1) * sizeof(PlainDesc), &d_geom)) return 1;
+    geom = (PlainDesc*)d_geom;
     k3_mg_plain_count<<<(unsigned)((s->n_orfs + 127) / 128), 128, 0, ctx->stream>>>(B, dp, s->d_orfs, s->d_orf_seq, s->n_orfs, counts,
                                                                                    geom);
     gmg_prof_end(ctx, GMG_PROF_K3);
