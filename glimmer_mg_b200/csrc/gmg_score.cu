@@ -3123,23 +3123,30 @@ __device__ __forceinline__ double mgl_codon_sum(const DevIcm& indep, const float
   return x;
 }
 
+// G = lanes per ORF.  G = 32: one ORF per warp, up to 96 * MGL_K scored bases.  G = 16: TWO ORFs per warp, up to
+// 48 * MGL_K scored bases each -- the kernel is bound by the latency of a warp's dependent rounds (6 us per ORF, 40 %
+// issue utilisation at 32 warps per SM), so two ORFs in flight per warp at the same register count is what raises the
+// throughput on short reads.  An instance takes the ORFs with need_lo < need <= 3 * G * MGL_K (and j_lo >= 3).
+template <int G>
 __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
                                                          const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, Which4 which,
-                                                         const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                          int64_t n_orfs, const int64_t* __restrict__ start_off,
                                                          gmg_start* __restrict__ starts, int exact_len,
                                                          unsigned long long* __restrict__ n_ordered,
-                                                         const PlainDesc* __restrict__ desc) {
+                                                         const PlainDesc* __restrict__ desc, int need_lo) {
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ double s_serial[4][32 * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
-  const float* s_lut = indep.lut3;            // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
+  constexpr int HPW = 32 / G;                                       // ORFs per warp
+  constexpr unsigned GMASK = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  __shared__ double s_serial[4][HPW][G * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
+  const float* s_lut = indep.lut3;                // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gshift = grp * G;
   // Persistent warps: a warp's life used to be five dependent load rounds (CSR -> ORF -> sequence offsets -> packed bases ->
   // bucket index -> planes) with nothing to overlap them, and ~100 instructions of call geometry that every warp derived
   // again.  The count kernel now leaves a 32-byte descriptor per ORF (sequence, lo / hi, eligible j range, plan of the
-  // truncated records), fetched together with the CSR pair for the warp's NEXT ORF while it works on the current one.
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // truncated records), fetched together with the CSR pair for the group's NEXT ORF while it works on the current one.
+  const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * HPW;
+  int64_t o = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * HPW + grp;
   int64_t nx_so = 0, nx_so1 = 0;
   uint4 nx_d0 = make_uint4(0u, 0u, 0u, 0u), nx_d1 = make_uint4(0u, 0u, 0u, 0u);
   if (o < n_orfs) {
@@ -3148,16 +3155,16 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
     nx_d0 = __ldg(reinterpret_cast<const uint4*>(desc + o));
     nx_d1 = __ldg(reinterpret_cast<const uint4*>(desc + o) + 1);
   }
-  for (; o < n_orfs; o += n_warps) {  // warp-uniform
+  for (; o - grp < n_orfs; o += stride) {  // warp-uniform: o - grp is the warp's first ORF of this round
   const int64_t so = nx_so, so1 = nx_so1;
   const uint4 d0 = nx_d0, d1 = nx_d1;
-  if (o + n_warps < n_orfs) {
-    nx_so = __ldg(start_off + o + n_warps);
-    nx_so1 = __ldg(start_off + o + n_warps + 1);
-    nx_d0 = __ldg(reinterpret_cast<const uint4*>(desc + o + n_warps));
-    nx_d1 = __ldg(reinterpret_cast<const uint4*>(desc + o + n_warps) + 1);
+  const bool have = o < n_orfs;
+  if (o + stride < n_orfs) {
+    nx_so = __ldg(start_off + o + stride);
+    nx_so1 = __ldg(start_off + o + stride + 1);
+    nx_d0 = __ldg(reinterpret_cast<const uint4*>(desc + o + stride));
+    nx_d1 = __ldg(reinterpret_cast<const uint4*>(desc + o + stride) + 1);
   }
-  if (so1 == so) continue;
   MgfSeq S;
   S.a = (int64_t)d0.x;
   S.L = (int)d0.y;
@@ -3174,7 +3181,8 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
   f.cpos = fwd ? d0.x + (uint32_t)(hi - 3) : d0.x + (uint32_t)(lo - 1);
   f.st = B.cb + (size_t)((fwd ? 0u : 3u) + f.cpos % 3u) * (size_t)B.nwc;
   const int need = f.j_hi;  // terms j = 0 .. need - 1: score[j - 1] of the highest record position j_hi
-  if (!mgl_takes(need, f.j_lo)) continue;
+  // this group's ORF is worked on here iff it has records and its length is this instance's
+  const bool act = have && so1 != so && f.j_lo >= 3 && need > need_lo && need <= 3 * G * MGL_K;
   MgfPlan pl;  // as mgf_plan leaves it
   pl.nT = (int)(d1.w >> 4);
   pl.state_after = (int)((d1.w >> 2) & 1u);
@@ -3182,7 +3190,9 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
     const int jt = f.j_hi - 3 * pl.nT;
     pl.jb = jt < f.j_hs ? jt : f.j_hs;
   }
-  const int ncod = need / 3, nch = (ncod + 31) >> 5;
+  const int ncod = act ? need / 3 : 0, nch = (ncod + G - 1) / G;
+  const int nch_w = G == 32 ? nch : __reduce_max_sync(FULL, nch);  // chunks the warp runs (warp-uniform)
+  if (nch_w == 0) continue;
   double incl[MGL_K];
   double carry = 0.0;
   unsigned umin = 0x7fffffffu;
@@ -3190,8 +3200,8 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
 #pragma unroll
   for (int k = 0; k < MGL_K; k++) {
     incl[k] = 0.0;
-    if (k < nch) {  // warp-uniform
-      const int c = 32 * k + lane;
+    if (k < nch_w) {  // warp-uniform
+      const int c = G * k + sub;
       double x = 0.0;
       if (c < ncod) {
         if (indep.lut3 != NULL) {  // j = 3 c .. 3 c + 2: positions hi-1-3c-2 .. hi-1-3c (forward), lo-1+3c .. +2 (reverse)
@@ -3209,53 +3219,54 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
         }
       }
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double y = __shfl_up_sync(FULL, x, d);
-        if (lane >= d) x += y;
+      for (int d = 1; d < G; d <<= 1) {
+        const double y = __shfl_up_sync(FULL, x, d, G);
+        if (sub >= d) x += y;
       }
       x += carry;
       incl[k] = x;  // score[3 (c + 1) - 1]
-      carry = __shfl_sync(FULL, x, 31);
+      carry = __shfl_sync(FULL, x, G - 1, G);
     }
   }
-  umin = __reduce_min_sync(FULL, umin);
   double asum_d = (double)asum;  // at most 6 * MGL_K float additions per lane: the 0.1 % margin covers their rounding
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) asum_d += __shfl_xor_sync(FULL, asum_d, d);
+  for (int d = G / 2; d > 0; d >>= 1) {  // within the group (xor with d < G stays inside it)
+    umin = min(umin, __shfl_xor_sync(FULL, umin, d));
+    asum_d += __shfl_xor_sync(FULL, asum_d, d);
+  }
   const int e = (int)(umin >> 23);
   const bool exact = exact_len >= 0 && (umin == 0x7fffffffu || asum_d * 1.001 < ldexp(1.0, (e > 0 ? e : 1) - 150 + 52));
-  if (!exact) {  // no certificate: the reference's own order, one lane
-    if (lane == 0) {
-      atomicAdd(n_ordered, 1ull);
-      double run = 0.0;
-      for (int j = 0; j < need; j++) {
-        float g, n;
-        mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
-        run = run + ((double)g - (double)n);
-        if ((j + 1) % 3 == 0) s_serial[wid][j / 3] = run;
-      }
+  if (!exact && act && sub == 0) {  // no certificate: the reference's own order, one lane of the group
+    atomicAdd(n_ordered, 1ull);
+    double run = 0.0;
+    for (int j = 0; j < need; j++) {
+      float g, n;
+      mgp_term(indep, s_lut, planes, bktidx, B, S, fwd, (1 + j) % 3, fwd ? hi - 1 - j : lo - 1 + j, &g, &n);
+      run = run + ((double)g - (double)n);
+      if ((j + 1) % 3 == 0) s_serial[wid][grp][j / 3] = run;
     }
-    __syncwarp();
   }
-  // records, from the highest position down: lane = position j = 3 (c + 1)
-  const unsigned higher = lane == 31 ? 0u : ~((2u << lane) - 1u);
+  __syncwarp();
+  // records, from the highest position down: lane = position j = 3 (c + 1); ballots are taken by the whole warp, a group
+  // reads its own G bits
+  const unsigned higher = sub == G - 1 ? 0u : (~((2u << sub) - 1u)) & GMASK;
   int placed = 0;
   bool seen_nonzero = false;
   const int ep[2] = {0, 0}, et[2] = {0, 0};
   gmg_start* out = starts + so;
 #pragma unroll
   for (int k = MGL_K - 1; k >= 0; k--) {
-    if (k < nch) {  // warp-uniform
-      const int c = 32 * k + lane, j = 3 * (c + 1);
+    if (k < nch_w) {  // warp-uniform
+      const int c = G * k + sub, j = 3 * (c + 1);
       bool trunc_rec = false, chain = false;
       int nr = 0;
       if (c < ncod && j >= f.j_lo) nr = mgf_recs_at(f, pl, fwd, j, &trunc_rec, &chain);
       const int kp = mgf_kpos(f, fwd, j);
-      const unsigned m1 = __ballot_sync(FULL, nr >= 1), m2 = __ballot_sync(FULL, nr == 2);
-      const unsigned mnz = __ballot_sync(FULL, chain && kp != 0);
+      const unsigned m1 = (__ballot_sync(FULL, nr >= 1) >> gshift) & GMASK, m2 = (__ballot_sync(FULL, nr == 2) >> gshift) & GMASK;
+      const unsigned mnz = (__ballot_sync(FULL, chain && kp != 0) >> gshift) & GMASK;
       if (nr) {
         const int idx = placed + __popc(m1 & higher) + __popc(m2 & higher);
-        const double sum = exact ? incl[k] : s_serial[wid][c];
+        const double sum = exact ? incl[k] : s_serial[wid][grp][c];
         const double sc = (sum - 0.0) + 0.0;
         if (trunc_rec) {
           mgf_put(out + idx, P, j + 2, kp, sc, -1, 1, 1, 0, ep, et);
@@ -3269,7 +3280,7 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
       seen_nonzero = seen_nonzero || mnz != 0u;
     }
   }
-  __syncwarp();  // the serial row is free for the warp's next ORF
+  __syncwarp();  // the serial rows are free for the warp's next ORFs
   }
 }
 
@@ -3922,20 +3933,32 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
       ctx->launches++;
       GMG_CUDA(cudaGetLastError());
     } else if (total_starts > 0) {
-      // one codon per lane for ORFs of up to 96 * MGL_K scored bases; the warp-per-ORF scan for whatever is left.
-      // GMG_PLAIN_LANES=0: all of them through the latter (A/B runs, tests).
-      const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 1;
+      // one codon per lane for ORFs of up to 96 * MGL_K scored bases (two ORFs per warp up to 48 * MGL_K); the warp-per-ORF
+      // scan for whatever is left.  GMG_PLAIN_LANES=0: all of them through the latter, =1: one ORF per warp throughout
+      // (A/B runs, tests).
+      const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 2;
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
       if (plain_lanes) {
         Which4 which;
         memset(&which, 0, sizeof which);
         for (int cd = 0; cd < 64; cd++)
           which.w[cd >> 4] |= (unsigned long long)(cs.which[cd] < 15 ? cs.which[cd] : 15) << (4 * (cd & 15));
-        const int64_t lanes_need = (s->n_orfs * 32 + 127) / 128, lanes_cap = (int64_t)ctx->sm_count * 8;  // 8 CTAs per SM resident
-        k3_mg_plain_lanes<<<(unsigned)(lanes_need < lanes_cap ? lanes_need : lanes_cap), 128, 0, ctx->stream>>>(
-            indep->dev, planes, s->d_bktidx, B, dp, which, s->d_orfs, s->d_orf_seq, s->n_orfs, s->d_start_off, s->d_starts, exact_len,
-            (unsigned long long*)(counts + s->n_orfs + 1), geom);
-        ctx->launches++;
+        // two ORFs per warp up to 192 scored bases (every ORF of a 100 bp read set), one per warp up to 384
+        const int64_t lanes_cap = (int64_t)ctx->sm_count * 8;  // 8 CTAs per SM resident
+        unsigned long long* d_nord = (unsigned long long*)(counts + s->n_orfs + 1);
+        if (plain_lanes >= 2) {
+          const int64_t need_ctas = (s->n_orfs * 16 + 127) / 128;
+          k3_mg_plain_lanes<16><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
+              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom, -1);
+          ctx->launches++;
+        }
+        if (plain_lanes < 2 || s->max_len > 48 * 4) {
+          const int64_t need_ctas = (s->n_orfs * 32 + 127) / 128;
+          k3_mg_plain_lanes<32><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
+              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom,
+              plain_lanes >= 2 ? 48 * 4 : -1);
+          ctx->launches++;
+        }
       }
       // every ORF taken above?  (need <= orf_len <= max_len; j_lo >= 3 whenever min_gene_len >= 6)
       const bool all_taken = plain_lanes && s->max_len <= 96 * 4 && p->min_gene_len >= 6;

@@ -535,16 +535,17 @@ def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monk
         orfs, ooff = ss.get_orfs()
         return st.tobytes(), off.tolist(), ss.uncertified, orfs, ooff
 
-    want = run()  # fused, one codon per lane (parallel scan under the per-ORF certificate)
+    want = run()  # fused, one codon per lane, two ORFs per warp up to 192 scored bases (parallel scan under the per-ORF certificate)
     assert want[2] == 0
     monkeypatch.setenv("GMG_PLAIN_SERIAL", "1")
     got = run()   # fused, one thread per ORF (serial sums in the reference's order)
     assert got[:2] == want[:2] and got[2] == 0
     monkeypatch.delenv("GMG_PLAIN_SERIAL")
-    monkeypatch.setenv("GMG_PLAIN_LANES", "0")
-    got = run()   # fused, one warp per ORF with a scan per 32 bases (the route of ORFs beyond 384 scored bases)
-    assert got[:2] == want[:2] and got[2] == 0
-    monkeypatch.delenv("GMG_PLAIN_LANES")
+    for mode in ("0", "1"):  # one warp per ORF: a scan per 32 bases (ORFs beyond 384 scored bases) / one codon per lane
+        monkeypatch.setenv("GMG_PLAIN_LANES", mode)
+        got = run()
+        assert got[:2] == want[:2] and got[2] == 0, mode
+        monkeypatch.delenv("GMG_PLAIN_LANES")
     monkeypatch.setenv("GMG_K3MG_MODE", "1")
     assert run()[:2] == want[:2]
     monkeypatch.delenv("GMG_K3MG_MODE")
