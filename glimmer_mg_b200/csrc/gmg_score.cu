@@ -3123,11 +3123,13 @@ __device__ __forceinline__ double mgl_codon_sum(const DevIcm& indep, const float
   return x;
 }
 
-// G = lanes per ORF.  G = 32: one ORF per warp, up to 96 * MGL_K scored bases.  G = 16: TWO ORFs per warp, up to
-// 48 * MGL_K scored bases each -- the kernel is bound by the latency of a warp's dependent rounds (6 us per ORF, 40 %
-// issue utilisation at 32 warps per SM), so two ORFs in flight per warp at the same register count is what raises the
-// throughput on short reads.  An instance takes the ORFs with need_lo < need <= 3 * G * MGL_K (and j_lo >= 3).
-template <int G>
+// G = lanes per ORF, K = chunks of G codons: an instance takes the ORFs with need_lo < need <= 3 * G * K scored bases (and
+// j_lo >= 3).  <32, 4>: one ORF per warp up to 384 bases; <16, 4>: TWO per warp up to 192; <8, 6>: FOUR per warp up to 144.
+// The kernel is bound by the latency of a warp's dependent rounds (6 us per ORF with one ORF per warp, 40 % issue
+// utilisation at 32 warps per SM): more ORFs in flight per warp at the same register count is what raises the throughput
+// on short reads (0.61 -> 0.49 ms per 31 Mbp with two; four: 0.50 -- the lane's serial share grows and its prefix
+// registers spill).
+template <int G, int K>
 __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const float* __restrict__ planes,
                                                          const uint32_t* __restrict__ bktidx, MgfBatch B, DevParams P, Which4 which,
                                                          int64_t n_orfs, const int64_t* __restrict__ start_off,
@@ -3137,7 +3139,7 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int HPW = 32 / G;                                       // ORFs per warp
   constexpr unsigned GMASK = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-  __shared__ double s_serial[4][HPW][G * MGL_K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
+  __shared__ double s_serial[4][HPW][G * K];  // codon-boundary prefixes of an ORF summed in serial order (rare)
   const float* s_lut = indep.lut3;                // 1.5 KB: read through L1 (staging it cost 8 % of the kernel's instructions)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gshift = grp * G;
@@ -3182,7 +3184,7 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
   f.st = B.cb + (size_t)((fwd ? 0u : 3u) + f.cpos % 3u) * (size_t)B.nwc;
   const int need = f.j_hi;  // terms j = 0 .. need - 1: score[j - 1] of the highest record position j_hi
   // this group's ORF is worked on here iff it has records and its length is this instance's
-  const bool act = have && so1 != so && f.j_lo >= 3 && need > need_lo && need <= 3 * G * MGL_K;
+  const bool act = have && so1 != so && f.j_lo >= 3 && need > need_lo && need <= 3 * G * K;
   MgfPlan pl;  // as mgf_plan leaves it
   pl.nT = (int)(d1.w >> 4);
   pl.state_after = (int)((d1.w >> 2) & 1u);
@@ -3193,12 +3195,12 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
   const int ncod = act ? need / 3 : 0, nch = (ncod + G - 1) / G;
   const int nch_w = G == 32 ? nch : __reduce_max_sync(FULL, nch);  // chunks the warp runs (warp-uniform)
   if (nch_w == 0) continue;
-  double incl[MGL_K];
+  double incl[K];
   double carry = 0.0;
   unsigned umin = 0x7fffffffu;
   float asum = 0.f;
 #pragma unroll
-  for (int k = 0; k < MGL_K; k++) {
+  for (int k = 0; k < K; k++) {
     incl[k] = 0.0;
     if (k < nch_w) {  // warp-uniform
       const int c = G * k + sub;
@@ -3228,7 +3230,7 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
       carry = __shfl_sync(FULL, x, G - 1, G);
     }
   }
-  double asum_d = (double)asum;  // at most 6 * MGL_K float additions per lane: the 0.1 % margin covers their rounding
+  double asum_d = (double)asum;  // at most 6 * K float additions per lane: the 0.1 % margin covers their rounding
 #pragma unroll
   for (int d = G / 2; d > 0; d >>= 1) {  // within the group (xor with d < G stays inside it)
     umin = min(umin, __shfl_xor_sync(FULL, umin, d));
@@ -3255,7 +3257,7 @@ __global__ void __launch_bounds__(128, 8) k3_mg_plain_lanes(DevIcm indep, const 
   const int ep[2] = {0, 0}, et[2] = {0, 0};
   gmg_start* out = starts + so;
 #pragma unroll
-  for (int k = MGL_K - 1; k >= 0; k--) {
+  for (int k = K - 1; k >= 0; k--) {
     if (k < nch_w) {  // warp-uniform
       const int c = G * k + sub, j = 3 * (c + 1);
       bool trunc_rec = false, chain = false;
@@ -3934,8 +3936,9 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
       GMG_CUDA(cudaGetLastError());
     } else if (total_starts > 0) {
       // one codon per lane for ORFs of up to 96 * MGL_K scored bases (two ORFs per warp up to 48 * MGL_K); the warp-per-ORF
-      // scan for whatever is left.  GMG_PLAIN_LANES=0: all of them through the latter, =1: one ORF per warp throughout
-      // (A/B runs, tests).
+      // scan for whatever is left.  GMG_PLAIN_LANES=0: all of them through the latter, =1: one ORF per warp throughout,
+      // =2 (default): two per warp up to 192 bases, =3: four per warp up to 144 bases (measured on 100 bp reads: 0.61 /
+      // 0.49 / 0.50 ms per 31 Mbp for 1 / 2 / 3; A/B runs, tests).
       const int plain_lanes = getenv("GMG_PLAIN_LANES") ? atoi(getenv("GMG_PLAIN_LANES")) : 2;
       if (gmg_prof_begin(ctx, GMG_PROF_K3)) return 1;
       if (plain_lanes) {
@@ -3943,20 +3946,28 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
         memset(&which, 0, sizeof which);
         for (int cd = 0; cd < 64; cd++)
           which.w[cd >> 4] |= (unsigned long long)(cs.which[cd] < 15 ? cs.which[cd] : 15) << (4 * (cd & 15));
-        // two ORFs per warp up to 192 scored bases (every ORF of a 100 bp read set), one per warp up to 384
+        // two ORFs per warp up to 192 scored bases (every ORF of a 100 bp read set), one up to 384; optionally four up to 144
         const int64_t lanes_cap = (int64_t)ctx->sm_count * 8;  // 8 CTAs per SM resident
         unsigned long long* d_nord = (unsigned long long*)(counts + s->n_orfs + 1);
-        if (plain_lanes >= 2) {
-          const int64_t need_ctas = (s->n_orfs * 16 + 127) / 128;
-          k3_mg_plain_lanes<16><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
-              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom, -1);
+        int done_to = -1;  // ORFs with need <= done_to are taken by an instance launched so far
+        if (plain_lanes >= 3) {
+          const int64_t need_ctas = (s->n_orfs * 8 + 127) / 128;
+          k3_mg_plain_lanes<8, 6><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
+              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom, done_to);
           ctx->launches++;
+          done_to = 3 * 8 * 6;
         }
-        if (plain_lanes < 2 || s->max_len > 48 * 4) {
+        if (plain_lanes >= 2 && s->max_len > done_to) {
+          const int64_t need_ctas = (s->n_orfs * 16 + 127) / 128;
+          k3_mg_plain_lanes<16, 4><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
+              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom, done_to);
+          ctx->launches++;
+          done_to = 3 * 16 * 4;
+        }
+        if (s->max_len > done_to) {
           const int64_t need_ctas = (s->n_orfs * 32 + 127) / 128;
-          k3_mg_plain_lanes<32><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
-              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom,
-              plain_lanes >= 2 ? 48 * 4 : -1);
+          k3_mg_plain_lanes<32, 4><<<(unsigned)(need_ctas < lanes_cap ? need_ctas : lanes_cap), 128, 0, ctx->stream>>>(
+              indep->dev, planes, s->d_bktidx, B, dp, which, s->n_orfs, s->d_start_off, s->d_starts, exact_len, d_nord, geom, done_to);
           ctx->launches++;
         }
       }

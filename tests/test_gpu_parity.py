@@ -541,7 +541,7 @@ def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monk
     got = run()   # fused, one thread per ORF (serial sums in the reference's order)
     assert got[:2] == want[:2] and got[2] == 0
     monkeypatch.delenv("GMG_PLAIN_SERIAL")
-    for mode in ("0", "1"):  # one warp per ORF: a scan per 32 bases (ORFs beyond 384 scored bases) / one codon per lane
+    for mode in ("0", "1", "3"):  # a scan per 32 bases (ORFs beyond 384 scored bases) / one codon per lane: one / up to four ORFs per warp
         monkeypatch.setenv("GMG_PLAIN_LANES", mode)
         got = run()
         assert got[:2] == want[:2] and got[2] == 0, mode
