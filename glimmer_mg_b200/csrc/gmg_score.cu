@@ -3003,7 +3003,7 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   double* pref = s_pref_all + (size_t)wid * slots;
   // score[j] for j < j_hi is all the records can ask for (score[j - 1] at their own j <= j_hi)
   const int need = f.j_hi;  // terms j = 0 .. need - 1
-  if (lanes && need <= 96 * 4 && f.j_lo >= 3) return;  // k3_mg_plain_lanes has written this ORF (mgl_takes)
+  if (lanes && need <= 384 && f.j_lo >= 3) return;  // an instance of k3_mg_plain_lanes has written this ORF (mgl_takes)
   if (lane == 0) pref[0] = 0.0;
   // warp-parallel scan; its sums carry the reference's bits whenever the ORF's certificate holds: every term is a
   // multiple of 2^g (g from the smallest float exponent the ORF meets) and the sum of magnitudes stays below 2^(g+52),
@@ -3059,17 +3059,16 @@ __global__ void __launch_bounds__(128) k3_mg_plain(DevIcm indep, const float* __
   }
 }
 
-// The fused pass with ONE CODON PER LANE -- the default for ORFs of up to 96 * MGL_K scored bases (every ORF of a
-// short-read set).  The warp-per-ORF kernel above spends a 5-step FP64 scan on every 32 bases and a serial record
-// writer on lane 0: ~1 200 warp instructions per ORF, 0.60 ms per 31 Mbp batch, all of it instruction issue.  Here a lane
-// sums the three terms of one codon, ONE scan per 96 bases gives every codon-boundary prefix, and the lanes write the
-// records of their own positions (mgf_plan / mgf_recs_at: the position-by-position form of the reference's start loop,
-// held to the CPU checker on the host by tests/mgflat_host_check.cu).
+// The fused pass with ONE CODON PER LANE -- the default for ORFs of up to 384 scored bases (every ORF of a short-read
+// set).  The warp-per-ORF kernel above spends a 5-step FP64 scan on every 32 bases and a serial record writer on lane 0:
+// ~1 200 warp instructions per ORF, 0.60 ms per 31 Mbp batch.  Here a lane sums the three terms of one codon, ONE scan
+// per group of lanes gives every codon-boundary prefix, and the lanes write the records of their own positions (mgf_plan /
+// mgf_recs_at: the position-by-position form of the reference's start loop, held to the CPU checker on the host by
+// tests/mgflat_host_check.cu).
 // Exactness as above: the per-ORF certificate (smallest term exponent, sum of magnitudes); an ORF without one is summed
-// by lane 0 in the reference's serial order into a shared-memory row and the lanes take their prefixes from there.
-// ORFs with more than 96 * MGL_K scored bases, or with j_lo < 3, are left to k3_mg_plain.
-#define MGL_K 4
-__device__ __forceinline__ bool mgl_takes(int need, int j_lo) { return need <= 96 * MGL_K && j_lo >= 3; }
+// by one lane in the reference's serial order into a shared-memory row and the lanes take their prefixes from there.
+// ORFs with more than 384 scored bases, or with j_lo < 3, are left to k3_mg_plain (its skip test is this one).
+__device__ __forceinline__ bool mgl_takes(int need, int j_lo) { return need <= 384 && j_lo >= 3; }
 
 // CodonSets::which as four 64-bit words, one nibble per 6-bit codon (15 = not a start codon): indexing the byte array of a
 // kernel parameter with a run-time subscript makes the compiler copy the whole parameter block to local memory
@@ -3935,7 +3934,7 @@ extern "C" int gmg_score_orfs_mg(gmg_ctx* ctx, const gmg_icm* gene, const gmg_ic
       ctx->launches++;
       GMG_CUDA(cudaGetLastError());
     } else if (total_starts > 0) {
-      // one codon per lane for ORFs of up to 96 * MGL_K scored bases (two ORFs per warp up to 48 * MGL_K); the warp-per-ORF
+      // one codon per lane for ORFs of up to 384 scored bases (two ORFs per warp up to 192); the warp-per-ORF
       // scan for whatever is left.  GMG_PLAIN_LANES=0: all of them through the latter, =1: one ORF per warp throughout,
       // =2 (default): two per warp up to 192 bases, =3: four per warp up to 144 bases (measured on 100 bp reads: 0.61 /
       // 0.49 / 0.50 ms per 31 Mbp for 1 / 2 / 3; A/B runs, tests).
