@@ -3513,7 +3513,7 @@ __global__ void __launch_bounds__(128) k3_mg_reduce(const gmg_start* __restrict_
 // The same decisions for ORFs with at most RED_SMALL raw records, ONE THREAD per ORF, everything in registers: on plain
 // read sets nearly every ORF has one to three records and a warp per ORF spent 680 instructions on each (0.38 ms per
 // 31 Mbp batch, all of it instruction issue).  ORFs with more records are appended to `big` for k3_mg_reduce.
-#define RED_SMALL 4
+#define RED_SMALL 8
 __global__ void __launch_bounds__(128) k3_mg_reduce_small(const gmg_start* __restrict__ starts, const int64_t* __restrict__ soff,
                                                           const gmg_orf* __restrict__ orfs, const int32_t* __restrict__ orf_seq,
                                                           const int64_t* __restrict__ off, int64_t n_orfs, DevEventModel M,

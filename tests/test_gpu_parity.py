@@ -588,7 +588,7 @@ def test_mg_start_list_reduction(gm, ctx, reads, monkeypatch, flags, table):
     n_kept_w = ss.reduce_starts_mg(p, model)
     red_w, first_w, cnt_w, status_w = ss.get_reduced_starts()
     monkeypatch.delenv("GMG_RED_SMALL")
-    n_kept = ss.reduce_starts_mg(p, model)  # lists of up to four records: one thread per ORF
+    n_kept = ss.reduce_starts_mg(p, model)  # lists of up to eight records: one thread per ORF
     red, first, cnt, status = ss.get_reduced_starts()
     assert n_kept == len(red) == int(cnt.sum())
     assert n_kept_w == n_kept and (cnt_w == cnt).all() and (status_w == status).all()
