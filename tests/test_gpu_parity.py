@@ -515,7 +515,7 @@ def test_mg_flat_thread_and_ordered_paths_agree(gm, ctx, reads, monkeypatch, fla
 
 
 def test_mg_plain_fused_scan_matches_thread_path_and_oracle(gm, ctx, reads, monkeypatch):
-    """Plain glimmer-mg (no -i / -s): K2 + K3 fused into one per-ORF scan over the K1 planes (k3_mg_plain).  Same CSR as
+    """Plain glimmer-mg (no -i / -s): K2 + K3 fused into one per-ORF scan over the K1 planes (k3_mg_plain_lanes, k3_mg_plain).  Same CSR as
     K2 + one thread per ORF (GMG_K3MG_MODE=1), also when every ORF longer than 30 bases is summed in the reference's
     serial order (forced), for ragged / empty / tiny sequences, and equal to the oracle's lists."""
     rs = [s for _, s in reads[:300]] + [b"", b"acgtacgtacgt", reads[5][1][:75], reads[6][1][:76], reads[7][1][:100]]
@@ -626,7 +626,7 @@ def test_g3_start_lists_match_reference_dump(gm, ctx, genome):
 
 
 def test_find_orfs_two_pass_path_gives_the_same_table(gm, ctx, reads, monkeypatch):
-    """The single-pass finder stages at most 64 ORFs per 256-base CTA; the overflow path (two passes) must give the
+    """The single-pass finder stages at most 256 ORFs per 1 024-base tile; the overflow path (two passes) must give the
     identical table."""
     p = gm.Params(True, allow_indels=1)
     rs = [s for _, s in reads[:300]]
